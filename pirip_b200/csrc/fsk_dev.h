@@ -1,0 +1,90 @@
+/*
+ * fsk_dev.h — structures shared by the host side (fsk_host.cu) and the demodulator
+ * kernel (fsk_kernel.cu).  Not part of the public C-ABI.
+ */
+#ifndef PIRIP_FSK_DEV_H
+#define PIRIP_FSK_DEV_H
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pirip_fsk.h"
+
+#define FSK_MAX_FFT_FACTORS 8
+#define FSK_MAX_MASK 12
+#define FSK_THREADS 256
+
+/* Everything the kernel needs to know about one modem configuration.  Passed by
+   value as a __grid_constant__ kernel parameter. */
+struct FskDevCfg {
+    int Fs, Rs, M, P, Nsym, Ts, N, Nmem, Ndft, Nbits, nint;
+    int st, en, f_zero; /* frequency-estimator search window / blanking, in bins */
+    int est_type, tone_spacing, f1_tx;
+    int burst_mode, lock_nin;
+    int fmt, soft;
+    int nmask, len_mask;
+    int mask_pos[FSK_MAX_MASK]; /* non-zero positions of the tone mask, ascending */
+    int nfac;                   /* FFT factor list, outermost first (kiss_fft order) */
+    int fac_p[FSK_MAX_FFT_FACTORS], fac_m[FSK_MAX_FFT_FACTORS], fac_fstride[FSK_MAX_FFT_FACTORS];
+    int fac_log2m[FSK_MAX_FFT_FACTORS];
+    float tc;
+    float fs_over_ndft;
+    const float *hann;     /* [Ndft] window, device */
+    const float2 *twiddle; /* [Ndft] FFT twiddles, device */
+    const float2 *phi_ft;  /* [nint] timing-line oscillator, device */
+    /* dynamic shared memory layout, byte offsets */
+    int off_fdc, off_A, off_B, off_Sf, off_tmp, off_tw, off_hann, off_misc;
+    int fft_slot_stride; /* float2 elements per FFT scratch slot (padded) */
+    int fft_slots;
+    int smem_bytes;
+};
+
+/* per-CTA scalars shared between the phases of one frame */
+struct FskFrameShared {
+    float2 phi_c[4];
+    float2 dphi[4];
+    float f_est[4];
+    float f2_est[4];
+    int freqi[4];
+    float norm_rx_timing, ppm, snr_est, EbNodB;
+    float tc_re, tc_im;
+    float fract, one_minus_fract;
+    int low, high;
+    int nin, nin_next;
+    int nan_flag;
+    float SNRest, v_est, rx_sig_pow, rx_nse_pow, foff, rx_timing;
+};
+
+/* demodulator state carried between frames — the serial state of SURVEY.md 3.1.
+   Layout in global memory: this header, then Sf[Ndft], then f_dc[M*Nmem] (float2). */
+struct FskDevStateHdr {
+    float2 phi_c[4];
+    float norm_rx_timing, ppm, snr_est, EbNodB;
+    int nin;
+    int pad[3];
+};
+
+struct FskBatchArgs {
+    const unsigned char *iq;     /* device */
+    size_t capture_stride_bytes; /* between captures */
+    size_t samples_per_capture;
+    size_t max_frames;
+    unsigned char *bits;              /* [ncap][max_frames*Nbits] or NULL */
+    float *llr;                       /* [ncap][max_frames*Nbits] or NULL */
+    float *rx_filt;                   /* [ncap][max_frames*M*Nsym] or NULL */
+    struct pirip_frame_stats *stats;  /* [ncap][max_frames] or NULL */
+    int32_t *nframes;                 /* [ncap] or NULL */
+    float *state;                     /* per-capture persistent state or NULL (fresh start) */
+    size_t state_stride_floats;
+    float *Sf_out;                    /* optional [ncap][Ndft] copy of Sf after the last frame */
+};
+
+static inline size_t fsk_state_floats(int Ndft, int M, int Nmem) {
+    return sizeof(FskDevStateHdr) / sizeof(float) + (size_t)Ndft + 2u * (size_t)M * (size_t)Nmem;
+}
+
+/* defined in fsk_kernel.cu */
+cudaError_t fsk_launch_demod(const FskDevCfg &cfg, const FskBatchArgs &args, size_t n_captures, cudaStream_t stream);
+cudaError_t fsk_kernel_prepare(const FskDevCfg &cfg);
+
+#endif

@@ -1,0 +1,728 @@
+/*
+ * fsk_host.cu — host side of the FSK demodulator: configuration validation, table
+ * generation, the batched C-ABI and codec2's `struct FSK` API on top of the
+ * persistent-CTA kernel (fsk_kernel.cu).  See include/pirip_fsk.h for the contract.
+ *
+ * The derived sizes follow codec2 fsk.c::fsk_create_core (SURVEY.md 8a row A6,
+ * App. A.1); invalid configurations abort through assert() in the codec2-named
+ * entry points, exactly as upstream does, and return NULL / a negative code in the
+ * batched extension.
+ */
+#include <assert.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "exact_math.h"
+#include "fsk_dev.h"
+#include "host_util.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ---------------------------------------------------------------- tables */
+
+namespace {
+
+struct cpx { float re, im; };
+static inline cpx cmulf(cpx a, cpx b) { return cpx{ a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re }; }
+static inline cpx cexpj(float phi) { return cpx{ em_cosf(phi), em_sinf(phi) }; }
+
+/* Hann window through the same recursive oscillator codec2 uses for its table
+   ([U fsk.c::fsk_generate_hann_table]) */
+static std::vector<float> make_hann(int Ndft) {
+    std::vector<float> h((size_t)Ndft);
+    const cpx d = cexpj((float)((2 * M_PI) / ((float)Ndft - 1)));
+    cpx r = { .5f, 0.0f };
+    r = cmulf(cpx{ d.re, -d.im }, r);
+    for (int i = 0; i < Ndft; ++i) {
+        r = cmulf(d, r);
+        h[(size_t)i] = (float)(.5 - r.re);
+    }
+    return h;
+}
+
+/* forward FFT twiddles, evaluated in double and rounded once ([U kiss_fft.c::kiss_fft_alloc]) */
+static std::vector<float2> make_twiddles(int n) {
+    std::vector<float2> t((size_t)n);
+    const double pi = 3.141592653589793238462643383279502884197169399375105820974944;
+    for (int i = 0; i < n; ++i) {
+        const double phase = -2 * pi * i / n;
+        t[(size_t)i] = make_float2((float)cos(phase), (float)sin(phase));
+    }
+    return t;
+}
+
+/* the timing-line oscillator e^{j 2 pi i / P} as the float recursion of
+   [U fsk.c::fsk_demod_core] produces it; it does not depend on the signal */
+static std::vector<float2> make_phi_ft(int Rs, int P, int nint) {
+    std::vector<float2> t((size_t)nint);
+    const cpx d = cexpj((float)(2 * M_PI * ((float)(Rs) / (float)(P * Rs))));
+    cpx ph = { 1.0f, 0.0f };
+    for (int i = 0; i < nint; ++i) {
+        t[(size_t)i] = make_float2(ph.re, ph.im);
+        ph = cmulf(ph, d);
+    }
+    return t;
+}
+
+static int ilog2(int v) {
+    int l = 0;
+    while ((1 << l) < v) ++l;
+    return l;
+}
+
+static inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+/* ---------------------------------------------------------------- plan */
+
+struct pirip_fsk_plan {
+    pirip_fsk_cfg user;
+    FskDevCfg dev;
+    int device;
+    float *d_hann = nullptr;
+    float2 *d_tw = nullptr;
+    float2 *d_phi_ft = nullptr;
+    std::vector<float> h_hann;
+};
+
+static bool cfg_valid(const pirip_fsk_cfg &c, std::string &why) {
+    char buf[160];
+#define REQ(cond)                                                   \
+    if (!(cond)) {                                                  \
+        snprintf(buf, sizeof buf, "invalid FSK config: %s", #cond); \
+        why = buf;                                                  \
+        return false;                                               \
+    }
+    REQ(c.Fs > 0);
+    REQ(c.Rs > 0);
+    REQ(c.P > 0);
+    REQ(c.Nsym > 0);
+    REQ((c.Fs % c.Rs) == 0);
+    REQ(((c.Fs / c.Rs) % c.P) == 0);
+    REQ(c.P >= 4);
+    REQ(c.M == 2 || c.M == 4);
+    REQ(c.fmt == PIRIP_FMT_U8 || c.fmt == PIRIP_FMT_S16 || c.fmt == PIRIP_FMT_F32);
+    if (c.have_limits) {
+        REQ(c.est_min >= -c.Fs / 2);
+        REQ(c.est_max <= c.Fs / 2);
+        REQ(c.est_max > c.est_min);
+    }
+#undef REQ
+    return true;
+}
+
+/* fill every derived field of FskDevCfg except the device pointers */
+static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, FskDevCfg &d, std::string &why) {
+    memset(&d, 0, sizeof d);
+    d.Fs = c.Fs;
+    d.Rs = c.Rs;
+    d.M = c.M;
+    d.P = c.P;
+    d.Nsym = c.Nsym;
+    d.Ts = c.Fs / c.Rs;
+    d.N = d.Ts * c.Nsym;
+    d.Nmem = d.N + 2 * d.Ts;
+    {
+        /* bins within 10% of the symbol rate, next power of two */
+        float bin_width_Hz = 0.1 * c.Rs;
+        float Ndft = (float)c.Fs / bin_width_Hz;
+        Ndft = pow(2.0, ceil(log2(Ndft)));
+        d.Ndft = (int)Ndft;
+    }
+    d.Nbits = c.M == 2 ? c.Nsym : 2 * c.Nsym;
+    d.nint = (c.Nsym + 1) * c.P;
+    d.tc = 0.1;
+    d.fs_over_ndft = (float)c.Fs / (float)d.Ndft;
+    d.est_type = c.freq_est_type;
+    d.tone_spacing = c.tone_spacing;
+    d.f1_tx = c.f1_tx;
+    d.burst_mode = burst_mode;
+    d.lock_nin = lock_nin;
+    d.fmt = c.fmt;
+    d.soft = c.soft;
+
+    if (d.Ndft < 32 || d.Ndft > 1024) {
+        why = "Ndft outside the supported 32..1024 range";
+        return false;
+    }
+    if ((long long)c.Fs * d.Ndft > 0x7fffffffLL) {
+        why = "Fs*Ndft overflows int (as it would upstream)";
+        return false;
+    }
+    /* estimator window: defaults are codec2's est_min = 0, est_max = Fs */
+    const int est_min = c.have_limits ? c.est_min : 0;
+    const int est_max = c.have_limits ? c.est_max : c.Fs;
+    const int est_space = 0.75 * c.Rs;
+    d.st = (est_min * d.Ndft) / c.Fs + d.Ndft / 2;
+    if (d.st < 0) d.st = 0;
+    d.en = (est_max * d.Ndft) / c.Fs + d.Ndft / 2;
+    if (d.en > d.Ndft) d.en = d.Ndft;
+    d.f_zero = (est_space * d.Ndft) / c.Fs;
+
+    /* tone mask: 3-bin teeth at multiples of the tone spacing */
+    std::vector<char> mask((size_t)d.Ndft, 0);
+    for (int i = 0; i < 3; ++i) mask[(size_t)i] = 1;
+    int bin = 0;
+    for (int m = 1; m <= c.M - 1; ++m) {
+        bin = round((float)m * c.tone_spacing * d.Ndft / c.Fs) - 1;
+        for (int i = bin; i <= bin + 2; ++i)
+            if (i >= 0 && i < d.Ndft) mask[(size_t)i] = 1;
+    }
+    d.len_mask = bin + 2 + 1;
+    d.nmask = 0;
+    for (int i = 0; i < d.len_mask && i < d.Ndft; ++i)
+        if (mask[(size_t)i]) {
+            if (d.nmask >= FSK_MAX_MASK) {
+                why = "tone mask has too many teeth";
+                return false;
+            }
+            d.mask_pos[d.nmask++] = i;
+        }
+
+    /* FFT factors in kiss_fft order: 4s first, then a 2 */
+    {
+        int n = d.Ndft, fstride = 1;
+        d.nfac = 0;
+        while (n > 1) {
+            const int p = (n % 4 == 0) ? 4 : 2;
+            n /= p;
+            d.fac_p[d.nfac] = p;
+            d.fac_m[d.nfac] = n;
+            d.fac_log2m[d.nfac] = ilog2(n);
+            d.fac_fstride[d.nfac] = fstride;
+            fstride *= p;
+            d.nfac++;
+        }
+    }
+
+    /* shared memory layout */
+    const int nin_max = d.N + d.Ts / 4;
+    d.fft_slots = nin_max / (d.Ndft / 2) - 1;
+    if (d.fft_slots < 1) d.fft_slots = 1;
+    d.fft_slot_stride = d.Ndft + d.Ndft / 4 + 2;
+    int off = 0;
+    d.off_fdc = off;
+    off += align_up(c.M * d.Nmem * 8, 16);
+    d.off_A = off;
+    {
+        const int fft_bytes = d.fft_slots * d.fft_slot_stride * 8;
+        const int fint_bytes = c.M * d.nint * 8;
+        off += align_up(fft_bytes > fint_bytes ? fft_bytes : fint_bytes, 16);
+    }
+    d.off_B = off;
+    {
+        const int in_bytes = nin_max * 8;
+        const int tl_bytes = (2 * d.nint + 3 * c.Nsym) * 4;
+        off += align_up(in_bytes > tl_bytes ? in_bytes : tl_bytes, 16);
+    }
+    d.off_Sf = off;
+    off += align_up(d.Ndft * 4, 16);
+    d.off_tmp = off;
+    off += align_up(d.Ndft * 4, 16);
+    d.off_tw = off;
+    off += align_up(d.Ndft * 8, 16);
+    d.off_hann = off;
+    off += align_up(d.Ndft * 4, 16);
+    d.off_misc = off;
+    off += align_up((int)sizeof(FskFrameShared), 16);
+    d.smem_bytes = off;
+    if (d.smem_bytes > 227 * 1024) {
+        why = "configuration needs more than 227 KB of shared memory per capture";
+        return false;
+    }
+    return true;
+}
+
+static void plan_free(pirip_fsk_plan *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_hann);
+    cudaFree(p->d_tw);
+    cudaFree(p->d_phi_ft);
+    delete p;
+}
+
+static pirip_fsk_plan *plan_build(const pirip_fsk_cfg &cfg, int device, int burst_mode, int lock_nin) {
+    std::string why;
+    if (!cfg_valid(cfg, why)) {
+        pirip::set_error(why);
+        return nullptr;
+    }
+    pirip_fsk_plan *p = new pirip_fsk_plan();
+    p->user = cfg;
+    p->device = device;
+    if (!derive_cfg(cfg, burst_mode, lock_nin, p->dev, why)) {
+        pirip::set_error(why);
+        delete p;
+        return nullptr;
+    }
+    p->h_hann = make_hann(p->dev.Ndft);
+    const std::vector<float2> tw = make_twiddles(p->dev.Ndft);
+    const std::vector<float2> pf = make_phi_ft(cfg.Rs, cfg.P, p->dev.nint);
+    if (!pirip::cuda_ok(cudaSetDevice(device), "cudaSetDevice") ||
+        !pirip::cuda_ok(cudaMalloc(&p->d_hann, sizeof(float) * p->h_hann.size()), "cudaMalloc hann") ||
+        !pirip::cuda_ok(cudaMalloc(&p->d_tw, sizeof(float2) * tw.size()), "cudaMalloc twiddles") ||
+        !pirip::cuda_ok(cudaMalloc(&p->d_phi_ft, sizeof(float2) * pf.size()), "cudaMalloc phi_ft") ||
+        !pirip::cuda_ok(cudaMemcpy(p->d_hann, p->h_hann.data(), sizeof(float) * p->h_hann.size(), cudaMemcpyHostToDevice), "copy hann") ||
+        !pirip::cuda_ok(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice), "copy twiddles") ||
+        !pirip::cuda_ok(cudaMemcpy(p->d_phi_ft, pf.data(), sizeof(float2) * pf.size(), cudaMemcpyHostToDevice), "copy phi_ft") ||
+        !pirip::cuda_ok(fsk_kernel_prepare(p->dev), "cudaFuncSetAttribute")) {
+        plan_free(p);
+        return nullptr;
+    }
+    p->dev.hann = p->d_hann;
+    p->dev.twiddle = p->d_tw;
+    p->dev.phi_ft = p->d_phi_ft;
+    return p;
+}
+
+extern "C" pirip_fsk_plan *pirip_fsk_plan_create(const pirip_fsk_cfg *cfg, int device) {
+    if (!cfg) {
+        pirip::set_error("cfg is NULL");
+        return nullptr;
+    }
+    return plan_build(*cfg, device, 0, 0);
+}
+
+extern "C" void pirip_fsk_plan_destroy(pirip_fsk_plan *plan) { plan_free(plan); }
+
+extern "C" int pirip_fsk_plan_nbits(const pirip_fsk_plan *plan) { return plan ? plan->dev.Nbits : -1; }
+extern "C" int pirip_fsk_plan_nfilt(const pirip_fsk_plan *plan) { return plan ? plan->dev.M * plan->dev.Nsym : -1; }
+
+extern "C" size_t pirip_fsk_plan_max_frames(const pirip_fsk_plan *plan, size_t samples_per_capture) {
+    if (!plan) return 0;
+    const size_t nin_min = (size_t)(plan->dev.N - plan->dev.Ts / 4);
+    return samples_per_capture / nin_min + 1;
+}
+
+static size_t bytes_per_sample(int fmt) { return fmt == PIRIP_FMT_U8 ? 2 : (fmt == PIRIP_FMT_S16 ? 4 : 8); }
+
+extern "C" int pirip_fsk_demod_batch_dev(pirip_fsk_plan *plan, const void *d_iq, size_t n_captures,
+                                         size_t samples_per_capture, size_t capture_stride_bytes, uint8_t *d_bits,
+                                         float *d_llr, float *d_rx_filt, struct pirip_frame_stats *d_stats,
+                                         int32_t *d_nframes, size_t max_frames, void *stream) {
+    if (!plan) return pirip::fail(-1, "plan is NULL");
+    if (n_captures == 0) return 0;
+    if (!d_iq) return pirip::fail(-2, "d_iq is NULL");
+    if (d_llr && !plan->dev.soft) return pirip::fail(-3, "LLR output requested but cfg.soft == 0");
+    if (capture_stride_bytes < samples_per_capture * bytes_per_sample(plan->dev.fmt))
+        return pirip::fail(-4, "capture_stride_bytes smaller than one capture");
+    if (n_captures > 0x7fffffffu) return pirip::fail(-5, "too many captures for one launch");
+    if (!pirip::cuda_ok(cudaSetDevice(plan->device), "cudaSetDevice")) return -10;
+    FskBatchArgs a;
+    memset(&a, 0, sizeof a);
+    a.iq = (const unsigned char *)d_iq;
+    a.capture_stride_bytes = capture_stride_bytes;
+    a.samples_per_capture = samples_per_capture;
+    a.max_frames = max_frames;
+    a.bits = d_bits;
+    a.llr = d_llr;
+    a.rx_filt = d_rx_filt;
+    a.stats = d_stats;
+    a.nframes = d_nframes;
+    if (!pirip::cuda_ok(fsk_launch_demod(plan->dev, a, n_captures, (cudaStream_t)stream), "fsk_demod_kernel launch"))
+        return -11;
+    pirip::count_launch();
+    return 0;
+}
+
+extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_t n_captures,
+                                     size_t samples_per_capture, uint8_t *bits, float *llr, float *rx_filt,
+                                     struct pirip_frame_stats *stats, int32_t *nframes, size_t max_frames) {
+    if (!plan) return pirip::fail(-1, "plan is NULL");
+    if (n_captures == 0) return 0;
+    if (!iq) return pirip::fail(-2, "iq is NULL");
+    if (!pirip::cuda_ok(cudaSetDevice(plan->device), "cudaSetDevice")) return -10;
+    const size_t cap_bytes = samples_per_capture * bytes_per_sample(plan->dev.fmt);
+    const size_t stride = (cap_bytes + 15) / 16 * 16;
+    const size_t nb = (size_t)plan->dev.Nbits, nf = (size_t)plan->dev.M * plan->dev.Nsym;
+    unsigned char *d_iq = nullptr;
+    uint8_t *d_bits = nullptr;
+    float *d_llr = nullptr, *d_filt = nullptr;
+    pirip_frame_stats *d_stats = nullptr;
+    int32_t *d_nf = nullptr;
+    int rc = 0;
+    cudaStream_t s = nullptr;
+#define CK(call, what)                 \
+    if (rc == 0 && !pirip::cuda_ok((call), what)) rc = -12;
+    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
+    CK(cudaMalloc(&d_iq, stride * n_captures), "cudaMalloc iq");
+    CK(cudaMalloc(&d_nf, sizeof(int32_t) * n_captures), "cudaMalloc nframes");
+    if (bits) CK(cudaMalloc(&d_bits, n_captures * max_frames * nb), "cudaMalloc bits");
+    if (llr) CK(cudaMalloc(&d_llr, sizeof(float) * n_captures * max_frames * nb), "cudaMalloc llr");
+    if (rx_filt) CK(cudaMalloc(&d_filt, sizeof(float) * n_captures * max_frames * nf), "cudaMalloc rx_filt");
+    if (stats) CK(cudaMalloc(&d_stats, sizeof(pirip_frame_stats) * n_captures * max_frames), "cudaMalloc stats");
+    if (bits) CK(cudaMemsetAsync(d_bits, 0, n_captures * max_frames * nb, s), "memset bits");
+    if (llr) CK(cudaMemsetAsync(d_llr, 0, sizeof(float) * n_captures * max_frames * nb, s), "memset llr");
+    if (rx_filt) CK(cudaMemsetAsync(d_filt, 0, sizeof(float) * n_captures * max_frames * nf, s), "memset rx_filt");
+    if (stats) CK(cudaMemsetAsync(d_stats, 0, sizeof(pirip_frame_stats) * n_captures * max_frames, s), "memset stats");
+    CK(cudaMemcpy2DAsync(d_iq, stride, iq, cap_bytes, cap_bytes, n_captures, cudaMemcpyHostToDevice, s), "H2D iq");
+    if (rc == 0)
+        rc = pirip_fsk_demod_batch_dev(plan, d_iq, n_captures, samples_per_capture, stride, d_bits, d_llr, d_filt, d_stats,
+                                       d_nf, max_frames, s);
+    if (bits) CK(cudaMemcpyAsync(bits, d_bits, n_captures * max_frames * nb, cudaMemcpyDeviceToHost, s), "D2H bits");
+    if (llr) CK(cudaMemcpyAsync(llr, d_llr, sizeof(float) * n_captures * max_frames * nb, cudaMemcpyDeviceToHost, s), "D2H llr");
+    if (rx_filt) CK(cudaMemcpyAsync(rx_filt, d_filt, sizeof(float) * n_captures * max_frames * nf, cudaMemcpyDeviceToHost, s), "D2H rx_filt");
+    if (stats) CK(cudaMemcpyAsync(stats, d_stats, sizeof(pirip_frame_stats) * n_captures * max_frames, cudaMemcpyDeviceToHost, s), "D2H stats");
+    if (nframes) CK(cudaMemcpyAsync(nframes, d_nf, sizeof(int32_t) * n_captures, cudaMemcpyDeviceToHost, s), "D2H nframes");
+    CK(cudaStreamSynchronize(s), "kernel execution");
+#undef CK
+    cudaFree(d_iq);
+    cudaFree(d_bits);
+    cudaFree(d_llr);
+    cudaFree(d_filt);
+    cudaFree(d_stats);
+    cudaFree(d_nf);
+    if (s) cudaStreamDestroy(s);
+    return rc;
+}
+
+/* ---------------------------------------------------------------- codec2 struct FSK API */
+
+namespace {
+
+struct FskDevice {
+    pirip_fsk_plan *plan = nullptr;
+    pirip_fsk_cfg cfg;
+    cudaStream_t stream = nullptr;
+    float *d_state = nullptr;
+    COMP *d_in = nullptr;
+    uint8_t *d_bits = nullptr;
+    float *d_filt = nullptr;
+    float *d_Sf = nullptr;
+    pirip_frame_stats *d_stats = nullptr;
+    /* pinned host staging */
+    COMP *h_in = nullptr;
+    uint8_t *h_bits = nullptr;
+    float *h_filt = nullptr;
+    float *h_Sf = nullptr;
+    pirip_frame_stats *h_stats = nullptr;
+    FskDevStateHdr *h_hdr = nullptr;
+    int nin_max = 0;
+    bool dirty_cfg = false;
+};
+
+[[noreturn]] void die(const char *what) {
+    fprintf(stderr, "libpirip_b200: %s: %s\n", what, pirip_last_error());
+    abort();
+}
+
+void ck(cudaError_t e, const char *what) {
+    if (!pirip::cuda_ok(e, what)) die(what);
+}
+
+void rebuild_plan(struct FSK *fsk) {
+    FskDevice *d = (FskDevice *)fsk->dev;
+    pirip_fsk_cfg c = d->cfg;
+    c.est_min = fsk->est_min;
+    c.est_max = fsk->est_max;
+    c.have_limits = !(fsk->est_min == 0 && fsk->est_max == fsk->Fs);
+    c.freq_est_type = fsk->freq_est_type;
+    c.tone_spacing = fsk->tone_spacing;
+    c.f1_tx = fsk->f1_tx;
+    pirip_fsk_plan *np = plan_build(c, d->plan ? d->plan->device : pirip::current_device(), fsk->burst_mode, fsk->lock_nin);
+    if (!np) die("fsk plan");
+    plan_free(d->plan);
+    d->plan = np;
+    d->cfg = c;
+    d->dirty_cfg = false;
+}
+
+void write_state_nin(struct FSK *fsk) {
+    /* push nin / Sf changes made through the API (clear_estimators, burst mode) to the device */
+    FskDevice *d = (FskDevice *)fsk->dev;
+    ck(cudaMemcpyAsync(d->h_hdr, d->d_state, sizeof(FskDevStateHdr), cudaMemcpyDeviceToHost, d->stream), "read state");
+    ck(cudaStreamSynchronize(d->stream), "sync");
+    d->h_hdr->nin = fsk->nin;
+    ck(cudaMemcpyAsync(d->d_state, d->h_hdr, sizeof(FskDevStateHdr), cudaMemcpyHostToDevice, d->stream), "write state");
+    ck(cudaStreamSynchronize(d->stream), "sync");
+}
+
+void demod_common(struct FSK *fsk, uint8_t *rx_bits, float *rx_filt, COMP *fsk_in) {
+    FskDevice *d = (FskDevice *)fsk->dev;
+    /* fields a caller may poke directly between calls */
+    if (d->dirty_cfg || d->plan->dev.burst_mode != fsk->burst_mode || d->plan->dev.lock_nin != fsk->lock_nin ||
+        d->plan->dev.est_type != fsk->freq_est_type || d->plan->dev.tone_spacing != fsk->tone_spacing)
+        rebuild_plan(fsk);
+    ck(cudaSetDevice(d->plan->device), "cudaSetDevice");
+    const int nin = fsk->nin;
+    const int M = fsk->mode, Nsym = fsk->Nsym, Nbits = fsk->Nbits;
+    memcpy(d->h_in, fsk_in, sizeof(COMP) * (size_t)nin);
+    ck(cudaMemcpyAsync(d->d_in, d->h_in, sizeof(COMP) * (size_t)nin, cudaMemcpyHostToDevice, d->stream), "H2D samples");
+    FskBatchArgs a;
+    memset(&a, 0, sizeof a);
+    a.iq = (const unsigned char *)d->d_in;
+    a.capture_stride_bytes = sizeof(COMP) * (size_t)d->nin_max;
+    a.samples_per_capture = (size_t)nin;
+    a.max_frames = 1;
+    a.bits = d->d_bits;
+    a.rx_filt = d->d_filt;
+    a.stats = d->d_stats;
+    a.state = d->d_state;
+    a.state_stride_floats = fsk_state_floats(fsk->Ndft, M, fsk->Nmem);
+    a.Sf_out = d->d_Sf;
+    ck(fsk_launch_demod(d->plan->dev, a, 1, d->stream), "fsk_demod_kernel launch");
+    pirip::count_launch();
+    ck(cudaMemcpyAsync(d->h_bits, d->d_bits, (size_t)Nbits, cudaMemcpyDeviceToHost, d->stream), "D2H bits");
+    ck(cudaMemcpyAsync(d->h_filt, d->d_filt, sizeof(float) * (size_t)(M * Nsym), cudaMemcpyDeviceToHost, d->stream), "D2H rx_filt");
+    ck(cudaMemcpyAsync(d->h_stats, d->d_stats, sizeof(pirip_frame_stats), cudaMemcpyDeviceToHost, d->stream), "D2H stats");
+    ck(cudaMemcpyAsync(d->h_Sf, d->d_Sf, sizeof(float) * (size_t)fsk->Ndft, cudaMemcpyDeviceToHost, d->stream), "D2H Sf");
+    ck(cudaMemcpyAsync(d->h_hdr, d->d_state, sizeof(FskDevStateHdr), cudaMemcpyDeviceToHost, d->stream), "D2H state");
+    ck(cudaStreamSynchronize(d->stream), "fsk_demod kernel");
+
+    if (rx_bits) memcpy(rx_bits, d->h_bits, (size_t)Nbits);
+    if (rx_filt) memcpy(rx_filt, d->h_filt, sizeof(float) * (size_t)(M * Nsym));
+    memcpy(fsk->Sf, d->h_Sf, sizeof(float) * (size_t)fsk->Ndft);
+    const pirip_frame_stats &s = *d->h_stats;
+    for (int m = 0; m < M; ++m) {
+        fsk->f_est[m] = s.f_est[m];
+        fsk->f2_est[m] = s.f2_est[m];
+        fsk->phi_c[m].real = d->h_hdr->phi_c[m].x;
+        fsk->phi_c[m].imag = d->h_hdr->phi_c[m].y;
+    }
+    fsk->norm_rx_timing = s.norm_rx_timing;
+    fsk->ppm = s.ppm;
+    fsk->SNRest = s.SNRest;
+    fsk->v_est = s.v_est;
+    fsk->rx_sig_pow = s.rx_sig_pow;
+    fsk->rx_nse_pow = s.rx_nse_pow;
+    fsk->EbNodB = s.EbNodB;
+    fsk->nin = s.nin_next;
+    fsk->stats->snr_est = s.snr_est;
+    fsk->stats->foff = s.foff;
+    fsk->stats->rx_timing = s.rx_timing;
+    fsk->stats->clock_offset = s.ppm;
+}
+
+}  // namespace
+
+extern "C" struct FSK *fsk_create_hbr(int Fs, int Rs, int M, int P, int Nsym, int f1_tx, int tone_spacing) {
+    /* same conditions upstream asserts ([U fsk.c::fsk_create_core]) */
+    assert(Fs > 0);
+    assert(Rs > 0);
+    assert(P > 0);
+    assert(Nsym > 0);
+    assert((Fs % Rs) == 0);
+    assert(((Fs / Rs) % P) == 0);
+    assert(P >= 4);
+    assert(M == 2 || M == 4);
+
+    struct FSK *fsk = (struct FSK *)calloc(1, sizeof(struct FSK));
+    assert(fsk != NULL);
+    FskDevice *d = new FskDevice();
+    fsk->dev = d;
+    pirip_fsk_cfg c;
+    memset(&c, 0, sizeof c);
+    c.Fs = Fs;
+    c.Rs = Rs;
+    c.M = M;
+    c.P = P;
+    c.Nsym = Nsym;
+    c.f1_tx = f1_tx;
+    c.tone_spacing = tone_spacing;
+    c.have_limits = 0;
+    c.fmt = PIRIP_FMT_F32;
+    d->cfg = c;
+    d->plan = plan_build(c, pirip::current_device(), 0, 0);
+    if (!d->plan) die("fsk_create_hbr");
+    const FskDevCfg &v = d->plan->dev;
+    fsk->Ndft = v.Ndft;
+    fsk->Fs = Fs;
+    fsk->N = v.N;
+    fsk->Rs = Rs;
+    fsk->Ts = v.Ts;
+    fsk->Nmem = v.Nmem;
+    fsk->P = P;
+    fsk->Nsym = Nsym;
+    fsk->Nbits = v.Nbits;
+    fsk->f1_tx = f1_tx;
+    fsk->tone_spacing = tone_spacing;
+    fsk->mode = M;
+    fsk->tc = v.tc;
+    fsk->est_min = 0;
+    fsk->est_max = Fs;
+    fsk->est_space = 0.75 * Rs;
+    fsk->freq_est_type = 0;
+    fsk->nin = v.N;
+    fsk->burst_mode = 0;
+    fsk->lock_nin = 0;
+    fsk->normalise_eye = 1;
+    fsk->hann_table = (float *)malloc(sizeof(float) * (size_t)v.Ndft);
+    memcpy(fsk->hann_table, d->plan->h_hann.data(), sizeof(float) * (size_t)v.Ndft);
+    fsk->Sf = (float *)calloc((size_t)v.Ndft, sizeof(float));
+    for (int m = 0; m < M; ++m) {
+        fsk->phi_c[m].real = 1.0f;
+        fsk->phi_c[m].imag = 0.0f;
+    }
+    fsk->tx_phase_c.real = 1.0f;
+    fsk->tx_phase_c.imag = 0.0f;
+    fsk->stats = (struct MODEM_STATS *)calloc(1, sizeof(struct MODEM_STATS));
+    fsk_setup_modem_stats(fsk, fsk->stats);
+
+    d->nin_max = v.N + v.Ts / 4 + 16;
+    const size_t sfl = fsk_state_floats(v.Ndft, M, v.Nmem);
+    ck(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    ck(cudaMalloc(&d->d_state, sizeof(float) * sfl), "cudaMalloc state");
+    ck(cudaMalloc(&d->d_in, sizeof(COMP) * (size_t)d->nin_max), "cudaMalloc in");
+    ck(cudaMalloc(&d->d_bits, (size_t)v.Nbits), "cudaMalloc bits");
+    ck(cudaMalloc(&d->d_filt, sizeof(float) * (size_t)(M * Nsym)), "cudaMalloc filt");
+    ck(cudaMalloc(&d->d_Sf, sizeof(float) * (size_t)v.Ndft), "cudaMalloc Sf");
+    ck(cudaMalloc(&d->d_stats, sizeof(pirip_frame_stats)), "cudaMalloc stats");
+    ck(cudaMallocHost(&d->h_in, sizeof(COMP) * (size_t)d->nin_max), "cudaMallocHost in");
+    ck(cudaMallocHost(&d->h_bits, (size_t)v.Nbits), "cudaMallocHost bits");
+    ck(cudaMallocHost(&d->h_filt, sizeof(float) * (size_t)(M * Nsym)), "cudaMallocHost filt");
+    ck(cudaMallocHost(&d->h_Sf, sizeof(float) * (size_t)v.Ndft), "cudaMallocHost Sf");
+    ck(cudaMallocHost(&d->h_stats, sizeof(pirip_frame_stats)), "cudaMallocHost stats");
+    ck(cudaMallocHost(&d->h_hdr, sizeof(FskDevStateHdr)), "cudaMallocHost hdr");
+    /* initial state: zero memory, unit oscillators, nin = N */
+    std::vector<float> st(sfl, 0.0f);
+    FskDevStateHdr *h = (FskDevStateHdr *)st.data();
+    for (int m = 0; m < 4; ++m) h->phi_c[m] = make_float2(1.0f, 0.0f);
+    h->nin = v.N;
+    ck(cudaMemcpy(d->d_state, st.data(), sizeof(float) * sfl, cudaMemcpyHostToDevice), "init state");
+    ck(cudaMemset(d->d_bits, 0, (size_t)v.Nbits), "memset bits");
+    return fsk;
+}
+
+extern "C" struct FSK *fsk_create(int Fs, int Rs, int M, int tx_f1, int tx_fs) {
+    return fsk_create_hbr(Fs, Rs, M, FSK_DEFAULT_P, FSK_DEFAULT_NSYM, tx_f1, tx_fs);
+}
+
+extern "C" void fsk_destroy(struct FSK *fsk) {
+    if (!fsk) return;
+    FskDevice *d = (FskDevice *)fsk->dev;
+    if (d) {
+        if (d->plan) cudaSetDevice(d->plan->device);
+        cudaFree(d->d_state);
+        cudaFree(d->d_in);
+        cudaFree(d->d_bits);
+        cudaFree(d->d_filt);
+        cudaFree(d->d_Sf);
+        cudaFree(d->d_stats);
+        cudaFreeHost(d->h_in);
+        cudaFreeHost(d->h_bits);
+        cudaFreeHost(d->h_filt);
+        cudaFreeHost(d->h_Sf);
+        cudaFreeHost(d->h_stats);
+        cudaFreeHost(d->h_hdr);
+        if (d->stream) cudaStreamDestroy(d->stream);
+        plan_free(d->plan);
+        delete d;
+    }
+    free(fsk->hann_table);
+    free(fsk->Sf);
+    free(fsk->stats);
+    free(fsk);
+}
+
+extern "C" uint32_t fsk_nin(struct FSK *fsk) { return (uint32_t)fsk->nin; }
+
+extern "C" void fsk_demod(struct FSK *fsk, uint8_t rx_bits[], COMP fsk_in[]) { demod_common(fsk, rx_bits, NULL, fsk_in); }
+
+extern "C" void fsk_demod_sd(struct FSK *fsk, float rx_filt[], COMP fsk_in[]) { demod_common(fsk, NULL, rx_filt, fsk_in); }
+
+extern "C" void fsk_set_freq_est_limits(struct FSK *fsk, int est_min, int est_max) {
+    assert(fsk != NULL);
+    assert(est_min >= -fsk->Fs / 2);
+    assert(est_max <= fsk->Fs / 2);
+    assert(est_max > est_min);
+    fsk->est_min = est_min;
+    fsk->est_max = est_max;
+    ((FskDevice *)fsk->dev)->dirty_cfg = true;
+}
+
+extern "C" void fsk_set_freq_est_alg(struct FSK *fsk, int est_type) {
+    assert(fsk != NULL);
+    fsk->freq_est_type = est_type;
+    ((FskDevice *)fsk->dev)->dirty_cfg = true;
+}
+
+extern "C" void fsk_clear_estimators(struct FSK *fsk) {
+    FskDevice *d = (FskDevice *)fsk->dev;
+    for (int i = 0; i < fsk->Ndft; ++i) fsk->Sf[i] = 0;
+    fsk->nin = fsk->N;
+    ck(cudaMemsetAsync(d->d_state + sizeof(FskDevStateHdr) / sizeof(float), 0, sizeof(float) * (size_t)fsk->Ndft, d->stream), "clear Sf");
+    write_state_nin(fsk);
+}
+
+extern "C" void fsk_enable_burst_mode(struct FSK *fsk) {
+    fsk->burst_mode = 1;
+    fsk->nin = fsk->N;
+    ((FskDevice *)fsk->dev)->dirty_cfg = true;
+    write_state_nin(fsk);
+}
+
+extern "C" void fsk_setup_modem_stats(struct FSK *fsk, struct MODEM_STATS *stats) {
+    /* [U fsk.c::stats_init] the members the demodulator maintains */
+    (void)fsk;
+    stats->Nc = 0;
+    stats->snr_est = 0;
+    stats->sync = 0;
+    stats->foff = 0;
+    stats->rx_timing = 0;
+    stats->clock_offset = 0;
+    stats->neyetr = 0;
+    stats->neyesamp = 0;
+}
+
+extern "C" void fsk_get_demod_stats(struct FSK *fsk, struct MODEM_STATS *stats) {
+    stats->clock_offset = fsk->stats->clock_offset;
+    stats->snr_est = fsk->stats->snr_est;
+    stats->rx_timing = fsk->stats->rx_timing;
+    stats->foff = fsk->stats->foff;
+    stats->neyesamp = fsk->stats->neyesamp;
+    stats->neyetr = fsk->stats->neyetr;
+    stats->sync = 0;
+    stats->nr = 0;
+    stats->Nc = 0;
+    for (int m = 0; m < MODE_M_MAX; ++m) stats->f_est[m] = fsk->f_est[m];
+}
+
+extern "C" void fsk_stats_normalise_eye(struct FSK *fsk, int normalise_enable) {
+    assert(fsk != NULL);
+    fsk->normalise_eye = normalise_enable;
+}
+
+/* Tx side, host only: continuous-phase M-FSK by a recursive complex oscillator
+   ([U fsk.c::fsk_mod_c]); tone index = symbol value as at [R tx/rpitx_fsk.cpp:127-143] */
+extern "C" void fsk_mod_c(struct FSK *fsk, COMP fsk_out[], uint8_t tx_bits[], int nbits) {
+    const int Ts = fsk->Ts, Fs = fsk->Fs, M = fsk->mode;
+    cpx ph = { fsk->tx_phase_c.real, fsk->tx_phase_c.imag };
+    cpx step[MODE_M_MAX];
+    for (int m = 0; m < M; ++m)
+        step[m] = cexpj((float)(2 * M_PI * ((float)(fsk->f1_tx + (fsk->tone_spacing * m)) / (float)(Fs))));
+    int bit_i = 0;
+    const int nsym = nbits / (M >> 1);
+    for (int i = 0; i < nsym; ++i) {
+        int sym = 0;
+        for (int m = M; m >>= 1;) {
+            sym = (sym << 1) | (tx_bits[bit_i] == 1 ? 1 : 0);
+            bit_i++;
+        }
+        for (int j = 0; j < Ts; ++j) {
+            ph = cmulf(ph, step[sym]);
+            fsk_out[i * Ts + j].real = 2.0f * ph.re;
+            fsk_out[i * Ts + j].imag = 2.0f * ph.im;
+        }
+    }
+    const float av = sqrtf((ph.re * ph.re) + (ph.im * ph.im));
+    fsk->tx_phase_c.real = ph.re / av;
+    fsk->tx_phase_c.imag = ph.im / av;
+}
+
+extern "C" void fsk_mod(struct FSK *fsk, float fsk_out[], uint8_t tx_bits[], int nbits) {
+    /* real output = real part of the complex modulator */
+    const int n = (nbits / (fsk->mode >> 1)) * fsk->Ts;
+    std::vector<COMP> tmp((size_t)n);
+    fsk_mod_c(fsk, tmp.data(), tx_bits, nbits);
+    for (int i = 0; i < n; ++i) fsk_out[i] = tmp[(size_t)i].real;
+}
