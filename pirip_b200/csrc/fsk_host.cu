@@ -92,6 +92,17 @@ struct pirip_fsk_plan {
     float2 *d_tw = nullptr;
     float2 *d_phi_ft = nullptr;
     std::vector<float> h_hann;
+    /* reusable device buffers of the host-buffer entry point */
+    struct Work {
+        static const int kStreams = 3;
+        cudaStream_t streams[kStreams] = { nullptr, nullptr, nullptr };
+        unsigned char *d_iq = nullptr;
+        uint8_t *d_bits = nullptr;
+        float *d_llr = nullptr, *d_filt = nullptr;
+        pirip_frame_stats *d_stats = nullptr;
+        int32_t *d_nf = nullptr;
+        size_t cap_iq = 0, cap_bits = 0, cap_llr = 0, cap_filt = 0, cap_stats = 0, cap_nf = 0;
+    } work;
 };
 
 static bool cfg_valid(const pirip_fsk_cfg &c, std::string &why) {
@@ -248,6 +259,14 @@ static void plan_free(pirip_fsk_plan *p) {
     cudaFree(p->d_hann);
     cudaFree(p->d_tw);
     cudaFree(p->d_phi_ft);
+    cudaFree(p->work.d_iq);
+    cudaFree(p->work.d_bits);
+    cudaFree(p->work.d_llr);
+    cudaFree(p->work.d_filt);
+    cudaFree(p->work.d_stats);
+    cudaFree(p->work.d_nf);
+    for (int i = 0; i < pirip_fsk_plan::Work::kStreams; ++i)
+        if (p->work.streams[i]) cudaStreamDestroy(p->work.streams[i]);
     delete p;
 }
 
@@ -335,54 +354,80 @@ extern "C" int pirip_fsk_demod_batch_dev(pirip_fsk_plan *plan, const void *d_iq,
     return 0;
 }
 
+/* Host-buffer variant.  Device buffers, streams and events are cached in the plan and
+   reused across calls; the captures are split into chunks that are copied in, demodulated
+   and copied out on alternating streams so PCIe transfers overlap the kernel. */
+namespace {
+template <typename T>
+bool ensure_cap(T *&ptr, size_t &cap_bytes, size_t need_bytes, const char *what) {
+    if (need_bytes <= cap_bytes && ptr) return true;
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap_bytes = 0;
+    if (!pirip::cuda_ok(cudaMalloc(&ptr, need_bytes), what)) return false;
+    cap_bytes = need_bytes;
+    return true;
+}
+}  // namespace
+
 extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_t n_captures,
                                      size_t samples_per_capture, uint8_t *bits, float *llr, float *rx_filt,
                                      struct pirip_frame_stats *stats, int32_t *nframes, size_t max_frames) {
     if (!plan) return pirip::fail(-1, "plan is NULL");
     if (n_captures == 0) return 0;
     if (!iq) return pirip::fail(-2, "iq is NULL");
+    if (llr && !plan->dev.soft) return pirip::fail(-3, "LLR output requested but cfg.soft == 0");
     if (!pirip::cuda_ok(cudaSetDevice(plan->device), "cudaSetDevice")) return -10;
+    pirip_fsk_plan::Work &w = plan->work;
     const size_t cap_bytes = samples_per_capture * bytes_per_sample(plan->dev.fmt);
     const size_t stride = (cap_bytes + 15) / 16 * 16;
     const size_t nb = (size_t)plan->dev.Nbits, nf = (size_t)plan->dev.M * plan->dev.Nsym;
-    unsigned char *d_iq = nullptr;
-    uint8_t *d_bits = nullptr;
-    float *d_llr = nullptr, *d_filt = nullptr;
-    pirip_frame_stats *d_stats = nullptr;
-    int32_t *d_nf = nullptr;
     int rc = 0;
-    cudaStream_t s = nullptr;
-#define CK(call, what)                 \
+#define CK(call, what) \
     if (rc == 0 && !pirip::cuda_ok((call), what)) rc = -12;
-    CK(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking), "cudaStreamCreate");
-    CK(cudaMalloc(&d_iq, stride * n_captures), "cudaMalloc iq");
-    CK(cudaMalloc(&d_nf, sizeof(int32_t) * n_captures), "cudaMalloc nframes");
-    if (bits) CK(cudaMalloc(&d_bits, n_captures * max_frames * nb), "cudaMalloc bits");
-    if (llr) CK(cudaMalloc(&d_llr, sizeof(float) * n_captures * max_frames * nb), "cudaMalloc llr");
-    if (rx_filt) CK(cudaMalloc(&d_filt, sizeof(float) * n_captures * max_frames * nf), "cudaMalloc rx_filt");
-    if (stats) CK(cudaMalloc(&d_stats, sizeof(pirip_frame_stats) * n_captures * max_frames), "cudaMalloc stats");
-    if (bits) CK(cudaMemsetAsync(d_bits, 0, n_captures * max_frames * nb, s), "memset bits");
-    if (llr) CK(cudaMemsetAsync(d_llr, 0, sizeof(float) * n_captures * max_frames * nb, s), "memset llr");
-    if (rx_filt) CK(cudaMemsetAsync(d_filt, 0, sizeof(float) * n_captures * max_frames * nf, s), "memset rx_filt");
-    if (stats) CK(cudaMemsetAsync(d_stats, 0, sizeof(pirip_frame_stats) * n_captures * max_frames, s), "memset stats");
-    CK(cudaMemcpy2DAsync(d_iq, stride, iq, cap_bytes, cap_bytes, n_captures, cudaMemcpyHostToDevice, s), "H2D iq");
-    if (rc == 0)
-        rc = pirip_fsk_demod_batch_dev(plan, d_iq, n_captures, samples_per_capture, stride, d_bits, d_llr, d_filt, d_stats,
-                                       d_nf, max_frames, s);
-    if (bits) CK(cudaMemcpyAsync(bits, d_bits, n_captures * max_frames * nb, cudaMemcpyDeviceToHost, s), "D2H bits");
-    if (llr) CK(cudaMemcpyAsync(llr, d_llr, sizeof(float) * n_captures * max_frames * nb, cudaMemcpyDeviceToHost, s), "D2H llr");
-    if (rx_filt) CK(cudaMemcpyAsync(rx_filt, d_filt, sizeof(float) * n_captures * max_frames * nf, cudaMemcpyDeviceToHost, s), "D2H rx_filt");
-    if (stats) CK(cudaMemcpyAsync(stats, d_stats, sizeof(pirip_frame_stats) * n_captures * max_frames, cudaMemcpyDeviceToHost, s), "D2H stats");
-    if (nframes) CK(cudaMemcpyAsync(nframes, d_nf, sizeof(int32_t) * n_captures, cudaMemcpyDeviceToHost, s), "D2H nframes");
-    CK(cudaStreamSynchronize(s), "kernel execution");
+    for (int i = 0; i < pirip_fsk_plan::Work::kStreams; ++i)
+        if (!w.streams[i]) CK(cudaStreamCreateWithFlags(&w.streams[i], cudaStreamNonBlocking), "cudaStreamCreate");
+    if (rc == 0 && !ensure_cap(w.d_iq, w.cap_iq, stride * n_captures, "cudaMalloc iq")) rc = -12;
+    if (rc == 0 && !ensure_cap(w.d_nf, w.cap_nf, sizeof(int32_t) * n_captures, "cudaMalloc nframes")) rc = -12;
+    if (rc == 0 && bits && !ensure_cap(w.d_bits, w.cap_bits, n_captures * max_frames * nb, "cudaMalloc bits")) rc = -12;
+    if (rc == 0 && llr && !ensure_cap(w.d_llr, w.cap_llr, sizeof(float) * n_captures * max_frames * nb, "cudaMalloc llr")) rc = -12;
+    if (rc == 0 && rx_filt && !ensure_cap(w.d_filt, w.cap_filt, sizeof(float) * n_captures * max_frames * nf, "cudaMalloc rx_filt")) rc = -12;
+    if (rc == 0 && stats && !ensure_cap(w.d_stats, w.cap_stats, sizeof(pirip_frame_stats) * n_captures * max_frames, "cudaMalloc stats")) rc = -12;
+
+    /* chunking: about one resident wave of CTAs per chunk, at most 8 chunks */
+    size_t nchunks = (n_captures + 295) / 296;
+    if (nchunks > 8) nchunks = 8;
+    if (nchunks < 1) nchunks = 1;
+    const size_t per = (n_captures + nchunks - 1) / nchunks;
+    for (size_t c0 = 0, ci = 0; rc == 0 && c0 < n_captures; c0 += per, ++ci) {
+        const size_t nc = (c0 + per <= n_captures) ? per : n_captures - c0;
+        cudaStream_t s = w.streams[ci % pirip_fsk_plan::Work::kStreams];
+        unsigned char *d_iq = w.d_iq + c0 * stride;
+        uint8_t *d_bits = bits ? w.d_bits + c0 * max_frames * nb : nullptr;
+        float *d_llr = llr ? w.d_llr + c0 * max_frames * nb : nullptr;
+        float *d_filt = rx_filt ? w.d_filt + c0 * max_frames * nf : nullptr;
+        pirip_frame_stats *d_stats = stats ? w.d_stats + c0 * max_frames : nullptr;
+        int32_t *d_nf = w.d_nf + c0;
+        /* frames past the end of a capture are never written by the kernel: define them as zero */
+        if (bits) CK(cudaMemsetAsync(d_bits, 0, nc * max_frames * nb, s), "memset bits");
+        if (llr) CK(cudaMemsetAsync(d_llr, 0, sizeof(float) * nc * max_frames * nb, s), "memset llr");
+        if (rx_filt) CK(cudaMemsetAsync(d_filt, 0, sizeof(float) * nc * max_frames * nf, s), "memset rx_filt");
+        if (stats) CK(cudaMemsetAsync(d_stats, 0, sizeof(pirip_frame_stats) * nc * max_frames, s), "memset stats");
+        CK(cudaMemcpy2DAsync(d_iq, stride, (const unsigned char *)iq + c0 * cap_bytes, cap_bytes, cap_bytes, nc,
+                             cudaMemcpyHostToDevice, s),
+           "H2D iq");
+        if (rc == 0)
+            rc = pirip_fsk_demod_batch_dev(plan, d_iq, nc, samples_per_capture, stride, d_bits, d_llr, d_filt, d_stats, d_nf,
+                                           max_frames, s);
+        if (bits) CK(cudaMemcpyAsync(bits + c0 * max_frames * nb, d_bits, nc * max_frames * nb, cudaMemcpyDeviceToHost, s), "D2H bits");
+        if (llr) CK(cudaMemcpyAsync(llr + c0 * max_frames * nb, d_llr, sizeof(float) * nc * max_frames * nb, cudaMemcpyDeviceToHost, s), "D2H llr");
+        if (rx_filt) CK(cudaMemcpyAsync(rx_filt + c0 * max_frames * nf, d_filt, sizeof(float) * nc * max_frames * nf, cudaMemcpyDeviceToHost, s), "D2H rx_filt");
+        if (stats) CK(cudaMemcpyAsync(stats + c0 * max_frames, d_stats, sizeof(pirip_frame_stats) * nc * max_frames, cudaMemcpyDeviceToHost, s), "D2H stats");
+        if (nframes) CK(cudaMemcpyAsync(nframes + c0, d_nf, sizeof(int32_t) * nc, cudaMemcpyDeviceToHost, s), "D2H nframes");
+    }
+    for (int i = 0; i < pirip_fsk_plan::Work::kStreams; ++i)
+        if (w.streams[i] && !pirip::cuda_ok(cudaStreamSynchronize(w.streams[i]), "kernel execution") && rc == 0) rc = -13;
 #undef CK
-    cudaFree(d_iq);
-    cudaFree(d_bits);
-    cudaFree(d_llr);
-    cudaFree(d_filt);
-    cudaFree(d_stats);
-    cudaFree(d_nf);
-    if (s) cudaStreamDestroy(s);
     return rc;
 }
 
