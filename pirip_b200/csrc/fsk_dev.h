@@ -12,7 +12,8 @@
 
 #define FSK_MAX_FFT_FACTORS 8
 #define FSK_MAX_MASK 12
-#define FSK_THREADS 256
+#define FSK_THREADS 128
+#define FSK_MIN_CTAS 4 /* resident CTAs per SM the register budget is sized for */
 
 /* Everything the kernel needs to know about one modem configuration.  Passed by
    value as a __grid_constant__ kernel parameter. */
@@ -33,7 +34,7 @@ struct FskDevCfg {
     const float2 *twiddle; /* [Ndft] FFT twiddles, device */
     const float2 *phi_ft;  /* [nint] timing-line oscillator, device */
     /* dynamic shared memory layout, byte offsets */
-    int off_fdc, off_A, off_B, off_Sf, off_tmp, off_tw, off_hann, off_misc;
+    int off_fdc, off_A, off_B, off_Sf, off_tmp, off_misc;
     int fft_slot_stride; /* float2 elements per FFT scratch slot (padded) */
     int fft_slots;
     int smem_bytes;
@@ -53,6 +54,7 @@ struct FskFrameShared {
     int nin, nin_next;
     int nan_flag;
     float SNRest, v_est, rx_sig_pow, rx_nse_pow, foff, rx_timing;
+    float sums[4];
 };
 
 /* demodulator state carried between frames — the serial state of SURVEY.md 3.1.

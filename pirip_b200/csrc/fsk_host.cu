@@ -232,16 +232,12 @@ static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, Fsk
     d.off_B = off;
     {
         const int in_bytes = nin_max * 8;
-        const int tl_bytes = (2 * d.nint + 3 * c.Nsym) * 4;
+        const int tl_bytes = (2 * d.nint + 3 * c.Nsym) * 4; /* float2 timing products + per-symbol sums */
         off += align_up(in_bytes > tl_bytes ? in_bytes : tl_bytes, 16);
     }
     d.off_Sf = off;
     off += align_up(d.Ndft * 4, 16);
     d.off_tmp = off;
-    off += align_up(d.Ndft * 4, 16);
-    d.off_tw = off;
-    off += align_up(d.Ndft * 8, 16);
-    d.off_hann = off;
     off += align_up(d.Ndft * 4, 16);
     d.off_misc = off;
     off += align_up((int)sizeof(FskFrameShared), 16);

@@ -68,7 +68,7 @@ __device__ void warp_fft_mag(const FskDevCfg &cfg, const float2 *x, float2 *buf,
                              int lane) {
     const int N = cfg.Ndft;
     for (int n = lane; n < N; n += 32) {
-        const float h = hann[n];
+        const float h = __ldg(hann + n);
         const float2 v = x[n];
         float2 w;
         w.x = h * v.x;
@@ -91,9 +91,9 @@ __device__ void warp_fft_mag(const FskDevCfg &cfg, const float2 *x, float2 *buf,
                 const int base = ((blk << 2) << lm) + k;
                 const int i0 = fpad(base), i1 = fpad(base + m), i2 = fpad(base + 2 * m), i3 = fpad(base + 3 * m);
                 float2 F0 = buf[i0];
-                const float2 s0 = cmul(buf[i1], tw[k * fs]);
-                const float2 s1 = cmul(buf[i2], tw[2 * k * fs]);
-                const float2 s2 = cmul(buf[i3], tw[3 * k * fs]);
+                const float2 s0 = cmul(buf[i1], __ldg(tw + k * fs));
+                const float2 s1 = cmul(buf[i2], __ldg(tw + 2 * k * fs));
+                const float2 s2 = cmul(buf[i3], __ldg(tw + 3 * k * fs));
                 const float2 s5 = csub(F0, s1);
                 F0 = cadd(F0, s1);
                 const float2 s3 = cadd(s0, s2);
@@ -108,7 +108,7 @@ __device__ void warp_fft_mag(const FskDevCfg &cfg, const float2 *x, float2 *buf,
                 const int blk = b >> lm, k = b & (m - 1);
                 const int base = ((blk << 1) << lm) + k;
                 const int i0 = fpad(base), i1 = fpad(base + m);
-                const float2 t = cmul(buf[i1], tw[k * fs]);
+                const float2 t = cmul(buf[i1], __ldg(tw + k * fs));
                 const float2 F0 = buf[i0];
                 buf[i1] = csub(F0, t);
                 buf[i0] = cadd(F0, t);
@@ -154,7 +154,7 @@ __device__ float max_star0(float delta1, float delta2) {
 }
 
 template <int kThreads>
-__global__ void __launch_bounds__(kThreads) fsk_demod_kernel(const __grid_constant__ FskDevCfg cfg,
+__global__ void __launch_bounds__(kThreads, FSK_MIN_CTAS) fsk_demod_kernel(const __grid_constant__ FskDevCfg cfg,
                                                              const __grid_constant__ FskBatchArgs args) {
     extern __shared__ __align__(16) unsigned char smem[];
     float2 *f_dc = reinterpret_cast<float2 *>(smem + cfg.off_fdc);  /* [M][Nmem] */
@@ -162,8 +162,8 @@ __global__ void __launch_bounds__(kThreads) fsk_demod_kernel(const __grid_consta
     float2 *xin = reinterpret_cast<float2 *>(smem + cfg.off_B);     /* frame input, then timing products */
     float *Sf = reinterpret_cast<float *>(smem + cfg.off_Sf);
     float *tmpS = reinterpret_cast<float *>(smem + cfg.off_tmp);
-    float2 *tw = reinterpret_cast<float2 *>(smem + cfg.off_tw);
-    float *hann = reinterpret_cast<float *>(smem + cfg.off_hann);
+    const float2 *tw = cfg.twiddle; /* read through L1 (__ldg): shared by every CTA on the SM */
+    const float *hann = cfg.hann;
     FrameShared *fs = reinterpret_cast<FrameShared *>(smem + cfg.off_misc);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -175,10 +175,6 @@ __global__ void __launch_bounds__(kThreads) fsk_demod_kernel(const __grid_consta
     float *state = args.state ? args.state + cap * args.state_stride_floats : nullptr;
 
     /* ---- load tables and state ------------------------------------------------ */
-    for (int i = tid; i < Ndft; i += kThreads) {
-        tw[i] = cfg.twiddle[i];
-        hann[i] = cfg.hann[i];
-    }
     if (state) {
         const FskDevStateHdr *h = reinterpret_cast<const FskDevStateHdr *>(state);
         const float *sSf = state + sizeof(FskDevStateHdr) / sizeof(float);
@@ -350,10 +346,8 @@ __global__ void __launch_bounds__(kThreads) fsk_demod_kernel(const __grid_consta
 
         /* ---- A8: shift memory, spin the oscillators, mix to DC ------------------ */
         if (nold <= nin) {
-            for (int idx = tid; idx < M * nold; idx += kThreads) {
-                const int m = idx / nold, i = idx - m * nold;
-                f_dc[m * Nmem + i] = f_dc[m * Nmem + i + nin];
-            }
+            for (int m = 0; m < M; ++m)
+                for (int i = tid; i < nold; i += kThreads) f_dc[m * Nmem + i] = f_dc[m * Nmem + i + nin];
         } else if (tid < M) {
             for (int i = 0; i < nold; ++i) f_dc[tid * Nmem + i] = f_dc[tid * Nmem + i + nin];
         }
@@ -370,7 +364,7 @@ __global__ void __launch_bounds__(kThreads) fsk_demod_kernel(const __grid_consta
             const float2 d = fs->dphi[tid];
             float2 ph = fs->phi_c[tid];
             float2 *dst = f_dc + tid * Nmem + nold;
-#pragma unroll 4
+#pragma unroll 8
             for (int j = 0; j < nin; ++j) {
                 ph = cmul(ph, d);
                 dst[j] = ph;
@@ -379,33 +373,80 @@ __global__ void __launch_bounds__(kThreads) fsk_demod_kernel(const __grid_consta
             fs->phi_c[tid] = make_float2(ph.x / av, ph.y / av);
         }
         __syncthreads();
-        for (int idx = tid; idx < M * nin; idx += kThreads) {
-            const int m = idx / nin, j = idx - m * nin;
-            const float2 o = f_dc[m * Nmem + nold + j];
+        for (int j = tid; j < nin; j += kThreads) {
             const float2 x = xin[j];
-            f_dc[m * Nmem + nold + j] = make_float2(x.x * o.x + x.y * o.y, x.y * o.x - x.x * o.y);
+            for (int m = 0; m < M; ++m) {
+                const float2 o = f_dc[m * Nmem + nold + j];
+                f_dc[m * Nmem + nold + j] = make_float2(x.x * o.x + x.y * o.y, x.y * o.x - x.x * o.y);
+            }
         }
         __syncthreads();
 
         /* ---- A9: integrate one symbol period at every timing offset -------------- */
         float2 *f_int = regA;
         const int step = Ts / P;
-        for (int idx = tid; idx < M * nint; idx += kThreads) {
-            const int m = idx / nint, i = idx - m * nint;
-            const float2 *src = f_dc + m * Nmem + i * step;
-            float ar = 0.0f, ai = 0.0f;
-            for (int j = 0; j < Ts; ++j) {
-                const float2 v = src[j];
-                ar += v.x;
-                ai += v.y;
+        if (step == 1 && Ts >= 4) {
+            /* P == Ts: four adjacent windows per thread share their loads; every window is
+               still accumulated in ascending sample order */
+            const int nquad = (nint + 3) >> 2;
+            for (int m = 0; m < M; ++m) {
+                for (int q = tid; q < nquad; q += kThreads) {
+                    const int i = q << 2;
+                    const float2 *src = f_dc + m * Nmem + i;
+                    float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
+                    float2 v = src[0];
+                    a0 = cadd(a0, v);
+                    v = src[1];
+                    a0 = cadd(a0, v);
+                    a1 = cadd(a1, v);
+                    v = src[2];
+                    a0 = cadd(a0, v);
+                    a1 = cadd(a1, v);
+                    a2 = cadd(a2, v);
+#pragma unroll 7
+                    for (int j = 3; j < Ts; ++j) {
+                        v = src[j];
+                        a0 = cadd(a0, v);
+                        a1 = cadd(a1, v);
+                        a2 = cadd(a2, v);
+                        a3 = cadd(a3, v);
+                    }
+                    f_int[m * nint + i] = a0;
+                    if (i + 1 < nint) {
+                        v = src[Ts];
+                        a1 = cadd(a1, v);
+                        f_int[m * nint + i + 1] = a1;
+                        if (i + 2 < nint) {
+                            const float2 w = src[Ts + 1];
+                            a2 = cadd(cadd(a2, v), w);
+                            f_int[m * nint + i + 2] = a2;
+                            if (i + 3 < nint) {
+                                a3 = cadd(cadd(cadd(a3, v), w), src[Ts + 2]);
+                                f_int[m * nint + i + 3] = a3;
+                            }
+                        }
+                    }
+                }
             }
-            f_int[idx] = make_float2(ar, ai);
+        } else {
+            for (int m = 0; m < M; ++m) {
+                for (int i = tid; i < nint; i += kThreads) {
+                    const float2 *src = f_dc + m * Nmem + i * step;
+                    float ar = 0.0f, ai = 0.0f;
+#pragma unroll 4
+                    for (int j = 0; j < Ts; ++j) {
+                        const float2 v = src[j];
+                        ar += v.x;
+                        ai += v.y;
+                    }
+                    f_int[m * nint + i] = make_float2(ar, ai);
+                }
+            }
         }
         __syncthreads();
 
         /* ---- A10: timing line ---------------------------------------------------- */
-        float *prod_re = reinterpret_cast<float *>(xin);
-        float *prod_im = prod_re + nint;
+        float2 *prod = xin;
         for (int i = tid; i < nint; i += kThreads) {
             float ft1 = 0.0f;
             for (int m = 0; m < M; ++m) {
@@ -413,24 +454,19 @@ __global__ void __launch_bounds__(kThreads) fsk_demod_kernel(const __grid_consta
                 ft1 += (v.x * v.x) + (v.y * v.y);
             }
             const float2 ph = __ldg(cfg.phi_ft + i);
-            prod_re[i] = ft1 * ph.x;
-            prod_im[i] = ft1 * ph.y;
-        }
-        __syncthreads();
-        if (lane == 0 && warp < 2) {
-            /* serial accumulation, real part on warp 0 and imaginary part on warp 1 */
-            const float *p = warp == 0 ? prod_re : prod_im;
-            float acc = 0.0f;
-#pragma unroll 8
-            for (int i = 0; i < nint; ++i) acc += p[i];
-            if (warp == 0)
-                fs->tc_re = acc;
-            else
-                fs->tc_im = acc;
+            prod[i] = make_float2(ft1 * ph.x, ft1 * ph.y);
         }
         __syncthreads();
         if (tid == 0) {
-            const float tre = fs->tc_re, tim = fs->tc_im;
+            /* the timing-line sum is a serial float accumulation: real and imaginary chains
+               interleaved on one lane, then the per-frame scalar estimates */
+            float tre = 0.0f, tim = 0.0f;
+#pragma unroll 8
+            for (int i = 0; i < nint; ++i) {
+                const float2 p = prod[i];
+                tre += p.x;
+                tim += p.y;
+            }
             if (tre != tre || tim != tim) {
                 fs->nan_flag = 1;
                 fs->nin_next = nin;
@@ -516,14 +552,16 @@ __global__ void __launch_bounds__(kThreads) fsk_demod_kernel(const __grid_consta
                 bits_out[frame * (size_t)Nbits + i] = frame ? bits_out[(frame - 1) * (size_t)Nbits + i] : 0;
         }
         __syncthreads();
+        if (tid < 4 && !fs->nan_flag) {
+            /* four independent serial sums over the symbols, one lane each */
+            const float *src = tid == 1 ? nse : (tid == 3 ? sqm : sig);
+            float acc = tid == 1 ? 1E-12f : 0.0f;
+            for (int i = 0; i < Nsym; ++i) acc += src[i];
+            fs->sums[tid] = acc;
+        }
+        __syncthreads();
         if (tid == 0 && !fs->nan_flag) {
-            float rx_nse_pow = 1E-12f, rx_sig_pow = 0.0f, meanebno = 0.0f, stdebno = 0.0f;
-            for (int i = 0; i < Nsym; ++i) {
-                rx_sig_pow += sig[i];
-                rx_nse_pow += nse[i];
-                stdebno += sig[i];
-                meanebno += sqm[i];
-            }
+            float rx_sig_pow = fs->sums[0], rx_nse_pow = fs->sums[1], stdebno = fs->sums[2], meanebno = fs->sums[3];
             rx_sig_pow = rx_sig_pow / (float)Nsym;
             rx_nse_pow = rx_nse_pow / (float)Nsym;
             fs->rx_sig_pow = rx_sig_pow;
