@@ -12,8 +12,7 @@
 
 #define FSK_MAX_FFT_FACTORS 8
 #define FSK_MAX_MASK 12
-#define FSK_THREADS 128
-#define FSK_MIN_CTAS 4 /* resident CTAs per SM the register budget is sized for */
+#define FSK_MAX_G 8 /* captures demodulated in lockstep by one CTA */
 
 /* Everything the kernel needs to know about one modem configuration.  Passed by
    value as a __grid_constant__ kernel parameter. */
@@ -33,28 +32,44 @@ struct FskDevCfg {
     const float *hann;     /* [Ndft] window, device */
     const float2 *twiddle; /* [Ndft] FFT twiddles, device */
     const float2 *phi_ft;  /* [nint] timing-line oscillator, device */
-    /* dynamic shared memory layout, byte offsets */
-    int off_fdc, off_A, off_B, off_Sf, off_tmp, off_misc;
-    int fft_slot_stride; /* float2 elements per FFT scratch slot (padded) */
-    int fft_slots;
+    /* launch geometry and dynamic shared memory layout (byte offsets) */
+    int G;               /* captures per CTA */
+    int threads;         /* threads per CTA */
+    int chunk;           /* samples per pipeline chunk of the streaming phase */
+    int fdc_tone_stride; /* float2 elements between the tones of one capture's f_dc */
+    int cap_stride;      /* bytes per capture block */
+    int off_fdc, off_xin, off_mag, off_Sf, off_scal; /* inside a capture block */
+    int off_fft, off_ctl;                            /* CTA-wide, after the G capture blocks */
+    int max_numffts;
     int smem_bytes;
 };
 
-/* per-CTA scalars shared between the phases of one frame */
-struct FskFrameShared {
+/* per-capture scalars kept in shared memory for the life of the CTA */
+struct FskCapShared {
     float2 phi_c[4];
     float2 dphi[4];
     float f_est[4];
     float f2_est[4];
     int freqi[4];
     float norm_rx_timing, ppm, snr_est, EbNodB;
-    float tc_re, tc_im;
     float fract, one_minus_fract;
     int low, high;
-    int nin, nin_next;
-    int nan_flag;
+    int nin, nin_next, nold, numffts;
+    int nan_flag, active;
     float SNRest, v_est, rx_sig_pow, rx_nse_pow, foff, rx_timing;
     float sums[4];
+    unsigned long long pos;
+    int frame;
+    int pad;
+};
+
+/* CTA-wide control words of the streaming phase */
+#define FSK_MAX_CHUNKS 64
+struct FskCtaShared {
+    unsigned long long bar_osc[FSK_MAX_CHUNKS]; /* mbarrier: oscillator warp finished chunk ck */
+    unsigned long long bar_int[FSK_MAX_CHUNKS]; /* mbarrier: every worker warp integrated chunk ck */
+    int any_active;
+    int max_nin;
 };
 
 /* demodulator state carried between frames — the serial state of SURVEY.md 3.1.
@@ -71,6 +86,7 @@ struct FskBatchArgs {
     size_t capture_stride_bytes; /* between captures */
     size_t samples_per_capture;
     size_t max_frames;
+    size_t n_captures;
     unsigned char *bits;              /* [ncap][max_frames*Nbits] or NULL */
     float *llr;                       /* [ncap][max_frames*Nbits] or NULL */
     float *rx_filt;                   /* [ncap][max_frames*M*Nsym] or NULL */

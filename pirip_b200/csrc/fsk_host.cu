@@ -132,7 +132,7 @@ static bool cfg_valid(const pirip_fsk_cfg &c, std::string &why) {
 }
 
 /* fill every derived field of FskDevCfg except the device pointers */
-static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, FskDevCfg &d, std::string &why) {
+static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, int max_g, FskDevCfg &d, std::string &why) {
     memset(&d, 0, sizeof d);
     d.Fs = c.Fs;
     d.Rs = c.Rs;
@@ -215,34 +215,66 @@ static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, Fsk
         }
     }
 
-    /* shared memory layout */
+    /* launch geometry and shared memory layout (see fsk_kernel.cu "PARALLEL STRUCTURE") */
     const int nin_max = d.N + d.Ts / 4;
-    d.fft_slots = nin_max / (d.Ndft / 2) - 1;
-    if (d.fft_slots < 1) d.fft_slots = 1;
-    d.fft_slot_stride = d.Ndft + d.Ndft / 4 + 2;
+    d.max_numffts = nin_max / (d.Ndft / 2) - 1;
+    if (d.max_numffts < 1) d.max_numffts = 1;
+    /* tones of one capture are 2 (mod 16) elements apart: even (16-byte vector loads) and on
+       different banks for the per-tone oscillator lanes; at least 2 spare elements */
+    d.fdc_tone_stride = d.Nmem + 2;
+    while ((d.fdc_tone_stride & 15) != 2) d.fdc_tone_stride++;
+    d.chunk = 64;
+    if (const char *e = getenv("PIRIP_FSK_CHUNK")) {
+        const int v = atoi(e);
+        if (v >= 16 && v <= 1024 && (v & (v - 1)) == 0) d.chunk = v;
+    }
+    while ((nin_max + d.chunk - 1) / d.chunk > FSK_MAX_CHUNKS) d.chunk *= 2;
     int off = 0;
     d.off_fdc = off;
-    off += align_up(c.M * d.Nmem * 8, 16);
-    d.off_A = off;
+    off += align_up(c.M * d.fdc_tone_stride * 8, 16);
+    d.off_xin = off;
     {
-        const int fft_bytes = d.fft_slots * d.fft_slot_stride * 8;
-        const int fint_bytes = c.M * d.nint * 8;
-        off += align_up(fft_bytes > fint_bytes ? fft_bytes : fint_bytes, 16);
+        const int in_elems = nin_max > d.nint ? nin_max : d.nint; /* frame input, then timing products */
+        off += align_up((in_elems + 2) * 8, 16);
     }
-    d.off_B = off;
+    d.off_mag = off;
     {
-        const int in_bytes = nin_max * 8;
-        const int tl_bytes = (2 * d.nint + 3 * c.Nsym) * 4; /* float2 timing products + per-symbol sums */
-        off += align_up(in_bytes > tl_bytes ? in_bytes : tl_bytes, 16);
+        const int fft_floats = d.max_numffts * d.Ndft;
+        const int dec_floats = d.Ndft + (3 + c.M) * c.Nsym; /* tmpS | sig | nse | sqm | rx_filt */
+        off += align_up((fft_floats > dec_floats ? fft_floats : dec_floats) * 4, 16);
     }
     d.off_Sf = off;
     off += align_up(d.Ndft * 4, 16);
-    d.off_tmp = off;
-    off += align_up(d.Ndft * 4, 16);
-    d.off_misc = off;
-    off += align_up((int)sizeof(FskFrameShared), 16);
-    d.smem_bytes = off;
-    if (d.smem_bytes > 227 * 1024) {
+    d.off_scal = off;
+    off += align_up((int)sizeof(FskCapShared), 16);
+    d.cap_stride = off;
+
+    /* captures per CTA and threads: as many captures as fit the 227 KB of one SM, 16 warps */
+    const int limit = 227 * 1024;
+    int want_g = max_g, want_threads = 512;
+    if (const char *e = getenv("PIRIP_FSK_G")) want_g = atoi(e);
+    if (const char *e = getenv("PIRIP_FSK_THREADS")) want_threads = atoi(e);
+    if (want_g < 1) want_g = 1;
+    if (want_g > FSK_MAX_G) want_g = FSK_MAX_G;
+    if (want_g == 7) want_g = 6;
+    want_threads = want_threads / 32 * 32;
+    if (want_threads < 96) want_threads = 96;
+    if (want_threads > 512) want_threads = 512;
+    for (int g = want_g; g >= 1; --g) {
+        if (g == 7) continue;
+        int threads = want_threads;
+        if (g == 1 && max_g == 1) threads = 128;
+        const int cta_bytes = align_up((threads / 32) * d.Ndft * 8, 16) + align_up((int)sizeof(FskCtaShared), 16);
+        if (g * d.cap_stride + cta_bytes <= limit) {
+            d.G = g;
+            d.threads = threads;
+            d.off_fft = 0;
+            d.off_ctl = align_up((threads / 32) * d.Ndft * 8, 16);
+            d.smem_bytes = g * d.cap_stride + cta_bytes;
+            break;
+        }
+    }
+    if (d.G == 0) {
         why = "configuration needs more than 227 KB of shared memory per capture";
         return false;
     }
@@ -266,7 +298,7 @@ static void plan_free(pirip_fsk_plan *p) {
     delete p;
 }
 
-static pirip_fsk_plan *plan_build(const pirip_fsk_cfg &cfg, int device, int burst_mode, int lock_nin) {
+static pirip_fsk_plan *plan_build(const pirip_fsk_cfg &cfg, int device, int burst_mode, int lock_nin, int max_g = FSK_MAX_G) {
     std::string why;
     if (!cfg_valid(cfg, why)) {
         pirip::set_error(why);
@@ -275,7 +307,7 @@ static pirip_fsk_plan *plan_build(const pirip_fsk_cfg &cfg, int device, int burs
     pirip_fsk_plan *p = new pirip_fsk_plan();
     p->user = cfg;
     p->device = device;
-    if (!derive_cfg(cfg, burst_mode, lock_nin, p->dev, why)) {
+    if (!derive_cfg(cfg, burst_mode, lock_nin, max_g, p->dev, why)) {
         pirip::set_error(why);
         delete p;
         return nullptr;
@@ -344,6 +376,7 @@ extern "C" int pirip_fsk_demod_batch_dev(pirip_fsk_plan *plan, const void *d_iq,
     a.rx_filt = d_rx_filt;
     a.stats = d_stats;
     a.nframes = d_nframes;
+    a.n_captures = n_captures;
     if (!pirip::cuda_ok(fsk_launch_demod(plan->dev, a, n_captures, (cudaStream_t)stream), "fsk_demod_kernel launch"))
         return -11;
     pirip::count_launch();
@@ -470,7 +503,7 @@ void rebuild_plan(struct FSK *fsk) {
     c.freq_est_type = fsk->freq_est_type;
     c.tone_spacing = fsk->tone_spacing;
     c.f1_tx = fsk->f1_tx;
-    pirip_fsk_plan *np = plan_build(c, d->plan ? d->plan->device : pirip::current_device(), fsk->burst_mode, fsk->lock_nin);
+    pirip_fsk_plan *np = plan_build(c, d->plan ? d->plan->device : pirip::current_device(), fsk->burst_mode, fsk->lock_nin, 1);
     if (!np) die("fsk plan");
     plan_free(d->plan);
     d->plan = np;
@@ -505,6 +538,7 @@ void demod_common(struct FSK *fsk, uint8_t *rx_bits, float *rx_filt, COMP *fsk_i
     a.capture_stride_bytes = sizeof(COMP) * (size_t)d->nin_max;
     a.samples_per_capture = (size_t)nin;
     a.max_frames = 1;
+    a.n_captures = 1;
     a.bits = d->d_bits;
     a.rx_filt = d->d_filt;
     a.stats = d->d_stats;
@@ -573,7 +607,7 @@ extern "C" struct FSK *fsk_create_hbr(int Fs, int Rs, int M, int P, int Nsym, in
     c.have_limits = 0;
     c.fmt = PIRIP_FMT_F32;
     d->cfg = c;
-    d->plan = plan_build(c, pirip::current_device(), 0, 0);
+    d->plan = plan_build(c, pirip::current_device(), 0, 0, 1);
     if (!d->plan) die("fsk_create_hbr");
     const FskDevCfg &v = d->plan->dev;
     fsk->Ndft = v.Ndft;
