@@ -32,14 +32,17 @@ struct FskDevCfg {
     const float *hann;     /* [Ndft] window, device */
     const float2 *twiddle; /* [Ndft] FFT twiddles, device */
     const float2 *phi_ft;  /* [nint] timing-line oscillator, device */
+    const unsigned short *perm; /* [Ndft] swizzled FFT input permutation, device */
+    int log2_ndft;
     /* launch geometry and dynamic shared memory layout (byte offsets) */
     int G;               /* captures per CTA */
     int threads;         /* threads per CTA */
     int chunk;           /* samples per pipeline chunk of the streaming phase */
     int fdc_tone_stride; /* float2 elements between the tones of one capture's f_dc */
     int cap_stride;      /* bytes per capture block */
-    int off_fdc, off_xin, off_mag, off_Sf, off_scal; /* inside a capture block */
-    int off_fft, off_ctl;                            /* CTA-wide, after the G capture blocks */
+    int off_fdc, off_xin, off_mag, off_Sf, off_stage, off_scal; /* inside a capture block */
+    int off_fft, off_tw, off_hann, off_phift, off_perm, off_ctl; /* CTA-wide, after the G capture blocks */
+    int stage_bytes;
     int max_numffts;
     int smem_bytes;
 };
@@ -59,6 +62,9 @@ struct FskCapShared {
     float SNRest, v_est, rx_sig_pow, rx_nse_pow, foff, rx_timing;
     float sums[4];
     unsigned long long pos;
+    unsigned long long stg_lo; /* global address the staged window starts at */
+    unsigned stg_bytes;
+    int stg_valid;
     int frame;
     int pad;
 };
@@ -68,6 +74,7 @@ struct FskCapShared {
 struct FskCtaShared {
     unsigned long long bar_osc[FSK_MAX_CHUNKS]; /* mbarrier: oscillator warp finished chunk ck */
     unsigned long long bar_int[FSK_MAX_CHUNKS]; /* mbarrier: every worker warp integrated chunk ck */
+    unsigned long long bar_in[FSK_MAX_G];       /* mbarrier: TMA copy of capture g's next frame landed */
     int any_active;
     int max_nin;
 };
@@ -95,6 +102,7 @@ struct FskBatchArgs {
     float *state;                     /* per-capture persistent state or NULL (fresh start) */
     size_t state_stride_floats;
     float *Sf_out;                    /* optional [ncap][Ndft] copy of Sf after the last frame */
+    int tma_ok;                       /* iq is 16-byte aligned: stage frames with TMA bulk copies */
 };
 
 static inline size_t fsk_state_floats(int Ndft, int M, int Nmem) {

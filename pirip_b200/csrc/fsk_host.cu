@@ -72,6 +72,22 @@ static std::vector<float2> make_phi_ft(int Rs, int P, int nint) {
     return t;
 }
 
+/* slot of FFT input n before the first butterfly level: kiss_fft's decimation-in-time digit
+   reversal for the factor list, then the bank swizzle of fsk_kernel.cu::fswz */
+static std::vector<unsigned short> make_perm(const FskDevCfg &d) {
+    std::vector<unsigned short> p((size_t)d.Ndft);
+    for (int n = 0; n < d.Ndft; ++n) {
+        int t = n, pos = 0;
+        for (int s = 0; s < d.nfac; ++s) {
+            const int digit = t % d.fac_p[s];
+            t /= d.fac_p[s];
+            pos += digit * d.fac_m[s];
+        }
+        p[(size_t)n] = (unsigned short)(pos ^ (5 * ((pos >> 4) & 3)));
+    }
+    return p;
+}
+
 static int ilog2(int v) {
     int l = 0;
     while ((1 << l) < v) ++l;
@@ -91,6 +107,7 @@ struct pirip_fsk_plan {
     float *d_hann = nullptr;
     float2 *d_tw = nullptr;
     float2 *d_phi_ft = nullptr;
+    unsigned short *d_perm = nullptr;
     std::vector<float> h_hann;
     /* reusable device buffers of the host-buffer entry point */
     struct Work {
@@ -153,6 +170,7 @@ static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, int
     d.nint = (c.Nsym + 1) * c.P;
     d.tc = 0.1;
     d.fs_over_ndft = (float)c.Fs / (float)d.Ndft;
+    d.log2_ndft = ilog2(d.Ndft);
     d.est_type = c.freq_est_type;
     d.tone_spacing = c.tone_spacing;
     d.f1_tx = c.f1_tx;
@@ -223,7 +241,7 @@ static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, int
        different banks for the per-tone oscillator lanes; at least 2 spare elements */
     d.fdc_tone_stride = d.Nmem + 2;
     while ((d.fdc_tone_stride & 15) != 2) d.fdc_tone_stride++;
-    d.chunk = 64;
+    d.chunk = 128;
     if (const char *e = getenv("PIRIP_FSK_CHUNK")) {
         const int v = atoi(e);
         if (v >= 16 && v <= 1024 && (v & (v - 1)) == 0) d.chunk = v;
@@ -245,8 +263,14 @@ static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, int
     }
     d.off_Sf = off;
     off += align_up(d.Ndft * 4, 16);
+    d.off_stage = off;
+    d.stage_bytes = align_up(nin_max * (c.fmt == PIRIP_FMT_U8 ? 2 : (c.fmt == PIRIP_FMT_S16 ? 4 : 8)) + 32, 16);
+    off += d.stage_bytes;
     d.off_scal = off;
     off += align_up((int)sizeof(FskCapShared), 16);
+    /* capture blocks 32 (mod 128) bytes apart: with tones 16 (mod 128) bytes apart the lanes
+       (capture, tone) of one quarter-warp hit distinct 16-byte bank groups (M = 2, G <= 4) */
+    while ((off & 127) != (c.M == 2 ? 32 : 64)) off += 16;
     d.cap_stride = off;
 
     /* captures per CTA and threads: as many captures as fit the 227 KB of one SM, 16 warps */
@@ -258,19 +282,35 @@ static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, int
     if (want_g > FSK_MAX_G) want_g = FSK_MAX_G;
     if (want_g == 7) want_g = 6;
     want_threads = want_threads / 32 * 32;
-    if (want_threads < 96) want_threads = 96;
+    if (want_threads < 256) want_threads = 256; /* two serial warps on sub-partition 3 need >= 8 warps */
     if (want_threads > 512) want_threads = 512;
     for (int g = want_g; g >= 1; --g) {
         if (g == 7) continue;
         int threads = want_threads;
-        if (g == 1 && max_g == 1) threads = 128;
-        const int cta_bytes = align_up((threads / 32) * d.Ndft * 8, 16) + align_up((int)sizeof(FskCtaShared), 16);
-        if (g * d.cap_stride + cta_bytes <= limit) {
+        if (g == 1 && max_g == 1) threads = 256;
+        int o = 0;
+        const int o_fft = o;
+        o += align_up((threads / 32) * d.Ndft * 8, 16);
+        const int o_tw = o;
+        o += align_up(d.Ndft * 8, 16);
+        const int o_hann = o;
+        o += align_up(d.Ndft * 4, 16);
+        const int o_phift = o;
+        o += align_up(d.nint * 8, 16);
+        const int o_perm = o;
+        o += align_up(d.Ndft * 2, 16);
+        const int o_ctl = o;
+        o += align_up((int)sizeof(FskCtaShared), 16);
+        if (g * d.cap_stride + o <= limit) {
             d.G = g;
             d.threads = threads;
-            d.off_fft = 0;
-            d.off_ctl = align_up((threads / 32) * d.Ndft * 8, 16);
-            d.smem_bytes = g * d.cap_stride + cta_bytes;
+            d.off_fft = o_fft;
+            d.off_tw = o_tw;
+            d.off_hann = o_hann;
+            d.off_phift = o_phift;
+            d.off_perm = o_perm;
+            d.off_ctl = o_ctl;
+            d.smem_bytes = g * d.cap_stride + o;
             break;
         }
     }
@@ -287,6 +327,7 @@ static void plan_free(pirip_fsk_plan *p) {
     cudaFree(p->d_hann);
     cudaFree(p->d_tw);
     cudaFree(p->d_phi_ft);
+    cudaFree(p->d_perm);
     cudaFree(p->work.d_iq);
     cudaFree(p->work.d_bits);
     cudaFree(p->work.d_llr);
@@ -315,6 +356,7 @@ static pirip_fsk_plan *plan_build(const pirip_fsk_cfg &cfg, int device, int burs
     p->h_hann = make_hann(p->dev.Ndft);
     const std::vector<float2> tw = make_twiddles(p->dev.Ndft);
     const std::vector<float2> pf = make_phi_ft(cfg.Rs, cfg.P, p->dev.nint);
+    const std::vector<unsigned short> pm = make_perm(p->dev);
     if (!pirip::cuda_ok(cudaSetDevice(device), "cudaSetDevice") ||
         !pirip::cuda_ok(cudaMalloc(&p->d_hann, sizeof(float) * p->h_hann.size()), "cudaMalloc hann") ||
         !pirip::cuda_ok(cudaMalloc(&p->d_tw, sizeof(float2) * tw.size()), "cudaMalloc twiddles") ||
@@ -322,6 +364,8 @@ static pirip_fsk_plan *plan_build(const pirip_fsk_cfg &cfg, int device, int burs
         !pirip::cuda_ok(cudaMemcpy(p->d_hann, p->h_hann.data(), sizeof(float) * p->h_hann.size(), cudaMemcpyHostToDevice), "copy hann") ||
         !pirip::cuda_ok(cudaMemcpy(p->d_tw, tw.data(), sizeof(float2) * tw.size(), cudaMemcpyHostToDevice), "copy twiddles") ||
         !pirip::cuda_ok(cudaMemcpy(p->d_phi_ft, pf.data(), sizeof(float2) * pf.size(), cudaMemcpyHostToDevice), "copy phi_ft") ||
+        !pirip::cuda_ok(cudaMalloc(&p->d_perm, sizeof(unsigned short) * pm.size()), "cudaMalloc perm") ||
+        !pirip::cuda_ok(cudaMemcpy(p->d_perm, pm.data(), sizeof(unsigned short) * pm.size(), cudaMemcpyHostToDevice), "copy perm") ||
         !pirip::cuda_ok(fsk_kernel_prepare(p->dev), "cudaFuncSetAttribute")) {
         plan_free(p);
         return nullptr;
@@ -329,6 +373,7 @@ static pirip_fsk_plan *plan_build(const pirip_fsk_cfg &cfg, int device, int burs
     p->dev.hann = p->d_hann;
     p->dev.twiddle = p->d_tw;
     p->dev.phi_ft = p->d_phi_ft;
+    p->dev.perm = p->d_perm;
     return p;
 }
 
@@ -377,6 +422,7 @@ extern "C" int pirip_fsk_demod_batch_dev(pirip_fsk_plan *plan, const void *d_iq,
     a.stats = d_stats;
     a.nframes = d_nframes;
     a.n_captures = n_captures;
+    a.tma_ok = (reinterpret_cast<size_t>(d_iq) & 15) == 0 && getenv("PIRIP_FSK_NO_TMA") == nullptr;
     if (!pirip::cuda_ok(fsk_launch_demod(plan->dev, a, n_captures, (cudaStream_t)stream), "fsk_demod_kernel launch"))
         return -11;
     pirip::count_launch();
@@ -539,6 +585,7 @@ void demod_common(struct FSK *fsk, uint8_t *rx_bits, float *rx_filt, COMP *fsk_i
     a.samples_per_capture = (size_t)nin;
     a.max_frames = 1;
     a.n_captures = 1;
+    a.tma_ok = 0;
     a.bits = d->d_bits;
     a.rx_filt = d->d_filt;
     a.stats = d->d_stats;

@@ -10,7 +10,7 @@
  * bits and maps soft decisions ([U fsk.c::fsk_demod_core],
  * [U mpdecode_core.c::fsk_rx_filt_to_llrs]).  All demodulator state (f_dc memory, Sf,
  * oscillator phases, nin) stays in shared memory between frames; HBM traffic is the u8 IQ
- * in and the bits out.
+ * in (TMA bulk copies, one frame ahead) and the bits out.
  *
  * NUMERICS CONTRACT.  The kernel performs the same IEEE-754 operations in the same order
  * as the reference algorithm: sequential accumulation where the reference accumulates
@@ -23,12 +23,15 @@
  * floating point: the per-tone oscillator phi *= dphi (nin steps), the timing-line sum
  * over (Nsym+1)*P integrator outputs, and the per-frame power sums.  They run on single
  * lanes, but (a) the lanes of one warp carry the recurrences of all G captures x M tones
- * at once, and (b) the frame is a streaming pipeline: warp 0 spins the oscillators and
- * publishes its progress, the worker warps mix and integrate chunk by chunk right behind
- * it, and warp 1 accumulates the timing line right behind them, so everything downstream
- * of the oscillator hides under its latency.  FFTs, IIR, peak search, decisions and LLRs
- * are ordinary data-parallel phases between CTA barriers.
+ * at once, and (b) the frame is a streaming pipeline: the oscillator warp publishes its
+ * progress chunk by chunk through mbarriers, the worker warps mix and integrate right
+ * behind it, and the timing warp accumulates the timing line right behind them, so
+ * everything downstream of the oscillator hides under its latency.  The two serial warps
+ * are the highest-numbered warps of the CTA (the issue arbiter favours high warp ids).
+ * FFTs, IIR, peak search, decisions and LLRs are data-parallel phases between CTA barriers.
  */
+#include <stdio.h>
+
 #include "exact_math.h"
 #include "fsk_dev.h"
 
@@ -43,8 +46,6 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
 
-__device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
-__device__ __forceinline__ void st_volatile(int *p, int v) { *reinterpret_cast<volatile int *>(p) = v; }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -58,16 +59,25 @@ __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
 __device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
     asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
         "@p bra DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t}" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+/* TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier */
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 /* FFT scratch index swizzle: XOR bits [5:4] of the element index into bits [3:2] and
@@ -75,49 +85,53 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
    distinct bank pairs; unit-stride stages are unaffected (constant XOR per 16-block) */
 __device__ __forceinline__ int fswz(int e) { return e ^ (5 * ((e >> 4) & 3)); }
 
-/* magnitude of the fft-shifted spectrum, written as N floats to out */
-template <int PER>
-__device__ __forceinline__ void fft_shift_mag(const float2 *buf, float *out, int N, int lane) {
+/* One warp: Hann-window N = 2^LOGN samples of x, FFT them in the warp's scratch slot with
+   kiss_fft's decimation-in-time factor order 4,4,..,(2), write the fft-shifted magnitudes.
+   perm[n] is the (swizzled) slot of input n before the first butterfly level. */
+template <int LOGN>
+__device__ __forceinline__ void warp_fft_mag(const float2 *x, float2 *buf, float *out, const float2 *tw,
+                                             const float *hann, const unsigned short *perm, int lane) {
+    constexpr int N = 1 << LOGN;
+    constexpr int N4 = LOGN / 2;          /* radix-4 levels */
+    constexpr bool HAS2 = (LOGN & 1) != 0; /* innermost radix-2 level */
 #pragma unroll
-    for (int q = 0; q < PER; ++q) {
-        const int i = lane + (q << 5);
-        const float2 X = buf[fswz((i + (N >> 1)) & (N - 1))];
-        out[i] = sqrtf((X.x * X.x) + (X.y * X.y));
-    }
-}
-
-/* One warp: Hann-window Ndft samples of x, FFT them (kiss_fft decimation-in-time factor
-   order 4,4,..,(2)) in the warp's scratch slot, write the fft-shifted magnitudes to out. */
-__device__ void warp_fft_mag(const FskDevCfg &cfg, const float2 *x, float2 *buf, float *out, int lane) {
-    const int N = cfg.Ndft;
-    const float2 *tw = cfg.twiddle; /* read through L1: shared by every warp on the SM */
-    for (int n = lane; n < N; n += 32) {
-        const float h = __ldg(cfg.hann + n);
+    for (int q = 0; q < N / 32; ++q) {
+        const int n = lane + (q << 5);
+        const float h = hann[n];
         const float2 v = x[n];
-        float2 w;
-        w.x = h * v.x;
-        w.y = h * v.y;
-        int t = n, pos = 0;
-        for (int s = 0; s < cfg.nfac; ++s) {
-            const int p = cfg.fac_p[s];
-            const int d = t & (p - 1);
-            t = (p == 4) ? (t >> 2) : (t >> 1);
-            pos += d << cfg.fac_log2m[s];
-        }
-        buf[fswz(pos)] = w;
+        buf[perm[n]] = make_float2(h * v.x, h * v.y);
     }
     __syncwarp();
-    for (int s = cfg.nfac - 1; s >= 0; --s) {
-        const int p = cfg.fac_p[s], m = cfg.fac_m[s], lm = cfg.fac_log2m[s], fs = cfg.fac_fstride[s];
-        if (p == 4) {
-            for (int b = lane; b < (N >> 2); b += 32) {
+    if (HAS2) {
+        /* m = 1, fstride = N/2: the only twiddle is tw[0] */
+        const float2 w0 = tw[0];
+#pragma unroll
+        for (int q = 0; q < N / 64; ++q) {
+            const int b = lane + (q << 5);
+            const int i0 = fswz(2 * b), i1 = fswz(2 * b + 1);
+            const float2 t = cmul(buf[i1], w0);
+            const float2 F0 = buf[i0];
+            buf[i1] = csub(F0, t);
+            buf[i0] = cadd(F0, t);
+        }
+        __syncwarp();
+    }
+#pragma unroll
+    for (int L = N4 - 1; L >= 0; --L) {
+        const int lm = (HAS2 ? 1 : 0) + 2 * (N4 - 1 - L); /* log2 m */
+        const int m = 1 << lm;
+        const int fs = N >> (lm + 2); /* fstride */
+#pragma unroll
+        for (int q = 0; q < (N / 128 > 0 ? N / 128 : 1); ++q) {
+            const int b = lane + (q << 5);
+            if (N / 4 >= 32 || b < N / 4) {
                 const int blk = b >> lm, k = b & (m - 1);
-                const int base = ((blk << 2) << lm) + k;
+                const int base = (blk << (lm + 2)) + k;
                 const int i0 = fswz(base), i1 = fswz(base + m), i2 = fswz(base + 2 * m), i3 = fswz(base + 3 * m);
                 float2 F0 = buf[i0];
-                const float2 s0 = cmul(buf[i1], __ldg(tw + k * fs));
-                const float2 s1 = cmul(buf[i2], __ldg(tw + 2 * k * fs));
-                const float2 s2 = cmul(buf[i3], __ldg(tw + 3 * k * fs));
+                const float2 s0 = cmul(buf[i1], tw[k * fs]);
+                const float2 s1 = cmul(buf[i2], tw[2 * k * fs]);
+                const float2 s2 = cmul(buf[i3], tw[3 * k * fs]);
                 const float2 s5 = csub(F0, s1);
                 F0 = cadd(F0, s1);
                 const float2 s3 = cadd(s0, s2);
@@ -127,26 +141,15 @@ __device__ void warp_fft_mag(const FskDevCfg &cfg, const float2 *x, float2 *buf,
                 buf[i1] = make_float2(s5.x + s4.y, s5.y - s4.x);
                 buf[i3] = make_float2(s5.x - s4.y, s5.y + s4.x);
             }
-        } else {
-            for (int b = lane; b < (N >> 1); b += 32) {
-                const int blk = b >> lm, k = b & (m - 1);
-                const int base = ((blk << 1) << lm) + k;
-                const int i0 = fswz(base), i1 = fswz(base + m);
-                const float2 t = cmul(buf[i1], __ldg(tw + k * fs));
-                const float2 F0 = buf[i0];
-                buf[i1] = csub(F0, t);
-                buf[i0] = cadd(F0, t);
-            }
         }
         __syncwarp();
     }
-    switch (N >> 5) {
-        case 1: fft_shift_mag<1>(buf, out, N, lane); break;
-        case 2: fft_shift_mag<2>(buf, out, N, lane); break;
-        case 4: fft_shift_mag<4>(buf, out, N, lane); break;
-        case 8: fft_shift_mag<8>(buf, out, N, lane); break;
-        case 16: fft_shift_mag<16>(buf, out, N, lane); break;
-        default: fft_shift_mag<32>(buf, out, N, lane); break;
+    /* fft shift (DC -> bin N/2) and magnitude */
+#pragma unroll
+    for (int q = 0; q < N / 32; ++q) {
+        const int i = lane + (q << 5);
+        const float2 X = buf[fswz((i + (N >> 1)) & (N - 1))];
+        out[i] = sqrtf((X.x * X.x) + (X.y * X.y));
     }
     __syncwarp();
 }
@@ -184,7 +187,7 @@ __device__ __forceinline__ float u8f(unsigned b) { return (float)((int)b - 127) 
 __device__ __forceinline__ int outputs_ready(int nold, int j, int Ts, int step, int nint) {
     const int have = nold + j - Ts;
     if (have < 0) return 0;
-    const int r = have / step + 1;
+    const int r = (step == 1 ? have : have / step) + 1;
     return r < nint ? r : nint;
 }
 
@@ -200,11 +203,27 @@ __device__ __forceinline__ float2 window_sum(const float2 *src, int Ts) {
     return make_float2(ar, ai);
 }
 
+/* two window sums at once (independent chains interleaved for latency) */
+__device__ __forceinline__ void window_sum2(const float2 *sa, const float2 *sb, int Ts, float2 &a, float2 &b) {
+    float ar = 0.0f, ai = 0.0f, br = 0.0f, bi = 0.0f;
+#pragma unroll 4
+    for (int j = 0; j < Ts; ++j) {
+        const float2 v = sa[j], w = sb[j];
+        ar += v.x;
+        ai += v.y;
+        br += w.x;
+        bi += w.y;
+    }
+    a = make_float2(ar, ai);
+    b = make_float2(br, bi);
+}
+
 struct CapPtrs {
     float2 *fdc;
     float2 *xin; /* frame input; later the timing-line products */
     float *mag;  /* FFT magnitudes; later tmpS | sig | nse | sqm | rx_filt */
     float *Sf;
+    unsigned char *stage; /* TMA landing zone for the next frame's raw samples */
     FskCapShared *cs;
 };
 
@@ -215,6 +234,7 @@ __device__ __forceinline__ CapPtrs cap_ptrs(unsigned char *smem, const FskDevCfg
     p.xin = reinterpret_cast<float2 *>(cb + cfg.off_xin);
     p.mag = reinterpret_cast<float *>(cb + cfg.off_mag);
     p.Sf = reinterpret_cast<float *>(cb + cfg.off_Sf);
+    p.stage = cb + cfg.off_stage;
     p.cs = reinterpret_cast<FskCapShared *>(cb + cfg.off_scal);
     return p;
 }
@@ -227,6 +247,35 @@ __device__ __forceinline__ float2 *prod_slot(const CapPtrs &c, int e, int D) {
     return e < D ? reinterpret_cast<float2 *>(c.mag) + e : c.xin + (e - D);
 }
 
+__device__ __forceinline__ size_t bytes_per_sample(int fmt) {
+    return fmt == PIRIP_FMT_U8 ? 2 : (fmt == PIRIP_FMT_S16 ? 4 : 8);
+}
+
+/* Issue the TMA bulk copy of the raw samples [pos, pos + nin_max) of capture `cap` into its
+   staging buffer (16-byte aligned superset, clipped to the batch allocation). */
+__device__ void stage_issue(const FskDevCfg &cfg, const FskBatchArgs &args, const CapPtrs &c, size_t cap,
+                            unsigned long long pos, unsigned long long *bar) {
+    FskCapShared *cs = c.cs;
+    cs->stg_valid = 0;
+    if (!args.tma_ok) return;
+    const size_t bps = bytes_per_sample(cfg.fmt);
+    if (pos >= args.samples_per_capture) return;
+    const size_t base = reinterpret_cast<size_t>(args.iq);
+    const size_t a = base + cap * args.capture_stride_bytes + pos * bps;
+    const size_t lo = a & ~(size_t)15;
+    size_t hi = (a + (size_t)(cfg.N + cfg.Ts / 4) * bps + 15) & ~(size_t)15;
+    const size_t safe = (base + (args.n_captures - 1) * args.capture_stride_bytes + args.samples_per_capture * bps) & ~(size_t)15;
+    if (hi > safe) hi = safe;
+    if (hi <= lo) return;
+    const unsigned bytes = (unsigned)(hi - lo);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive_expect_tx(bar, bytes);
+    tma_load_1d(c.stage, reinterpret_cast<const void *>(lo), bytes, bar);
+    cs->stg_lo = (unsigned long long)lo;
+    cs->stg_bytes = bytes;
+    cs->stg_valid = 1;
+}
+
 template <int G>
 __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant__ FskDevCfg cfg,
                                                            const __grid_constant__ FskBatchArgs args) {
@@ -236,20 +285,43 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
     const int M = cfg.M, Nmem = cfg.Nmem, Ndft = cfg.Ndft, nint = cfg.nint, Nsym = cfg.Nsym, P = cfg.P, Ts = cfg.Ts;
     const int Nbits = cfg.Nbits, TS = cfg.fdc_tone_stride, CH = cfg.chunk, step = Ts / P;
     const size_t cap0 = (size_t)blockIdx.x * G;
-    FskCtaShared *ctl = reinterpret_cast<FskCtaShared *>(smem + (size_t)G * cfg.cap_stride + cfg.off_ctl);
-    float2 *fft_slot = reinterpret_cast<float2 *>(smem + (size_t)G * cfg.cap_stride + cfg.off_fft) + (size_t)warp * Ndft;
+    unsigned char *cta = smem + (size_t)G * cfg.cap_stride;
+    FskCtaShared *ctl = reinterpret_cast<FskCtaShared *>(cta + cfg.off_ctl);
+    float2 *fft_slot = reinterpret_cast<float2 *>(cta + cfg.off_fft) + (size_t)warp * Ndft;
+    float2 *tw = reinterpret_cast<float2 *>(cta + cfg.off_tw);
+    float *hann = reinterpret_cast<float *>(cta + cfg.off_hann);
+    float2 *phi_ft = reinterpret_cast<float2 *>(cta + cfg.off_phift);
+    unsigned short *perm = reinterpret_cast<unsigned short *>(cta + cfg.off_perm);
     const float tc = cfg.tc;
     const float omtc = 1.0f - tc;
     const int D = Ts + Ts / 4 + 1;
-    unsigned long long par = 0; /* phase parity of every per-chunk mbarrier, bit ck */
+    /* Roles of the streaming phase.  Warp w issues on sub-partition w % 4.  The two serial
+       warps (oscillators, timing line) share sub-partition 3 and no worker runs there, so the
+       latency-bound recurrences never wait for an issue slot; the workers are the warps of
+       sub-partitions 0..2. */
+    const int osc_warp = nwarps - 1, tim_warp = nwarps - 5;
+    const bool is_worker = (warp & 3) != 3;
+    const int nww = nwarps - nwarps / 4;          /* worker warps */
+    const int nwt = nww * 32;                     /* worker threads */
+    const int wtid = (warp - (warp >> 2)) * 32 + lane; /* dense worker thread index */
+    unsigned long long par = 0;        /* phase parity of every per-chunk mbarrier, bit ck */
+    unsigned par_in = 0;               /* phase parity of the staging mbarriers, bit g */
+
+    /* ---- tables, barriers, initial state -------------------------------------------- */
+    for (int i = tid; i < Ndft; i += nthreads) {
+        tw[i] = cfg.twiddle[i];
+        hann[i] = cfg.hann[i];
+        perm[i] = cfg.perm[i];
+    }
+    for (int i = tid; i < nint; i += nthreads) phi_ft[i] = cfg.phi_ft[i];
     if (tid == 0) {
         for (int i = 0; i < FSK_MAX_CHUNKS; ++i) {
             mbar_init(&ctl->bar_osc[i], 1);
-            mbar_init(&ctl->bar_int[i], nwarps - 2);
+            mbar_init(&ctl->bar_int[i], nww);
         }
+        for (int g = 0; g < FSK_MAX_G; ++g) mbar_init(&ctl->bar_in[g], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-
-    /* ---- initial state ------------------------------------------------------------ */
     for (int g = 0; g < G; ++g) {
         const CapPtrs c = cap_ptrs(smem, cfg, g);
         const size_t cap = cap0 + g;
@@ -292,10 +364,40 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
             c.cs->frame = 0;
             c.cs->active = exists ? 1 : 0;
             c.cs->nan_flag = 0;
+            c.cs->stg_valid = 0;
         }
     }
     __syncthreads();
+    if (tid < G) {
+        const CapPtrs c = cap_ptrs(smem, cfg, tid);
+        if (c.cs->active) stage_issue(cfg, args, c, cap0 + tid, 0, &ctl->bar_in[tid]);
+    }
+    __syncthreads();
 
+#ifdef FSK_PHASE_TIMING
+    long long tph[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+    long long tlast = clock64();
+    int tsink = 0;
+#define PHASE_MARK(k)                     \
+    do {                                  \
+        /* a barrier only blocks at the next access to protected state: touch shared memory first */ \
+        tsink += *reinterpret_cast<volatile int *>(&ctl->max_nin); \
+        const long long tnow = clock64() + (tsink & 0); \
+        tph[k] += tnow - tlast;           \
+        tlast = tnow;                     \
+    } while (0)
+    long long wph[6] = { 0, 0, 0, 0, 0, 0 };
+    long long wlast = 0;
+#define WMARK(k)                                         \
+    do {                                                 \
+        const long long tnow = clock64();                \
+        if (k) wph[k] += tnow - wlast;                   \
+        wlast = tnow;                                    \
+    } while (0)
+#else
+#define PHASE_MARK(k)
+#define WMARK(k)
+#endif
     for (;;) {
         /* ---- frame bookkeeping: which captures still have a whole frame to read ------- */
         if (tid == 0) {
@@ -320,22 +422,33 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
         __syncthreads();
         if (!ctl->any_active) break;
         const int max_nin = ctl->max_nin;
+        PHASE_MARK(0);
 
         /* ---- A5: input conversion ([U fsk_demod.c]) + A8: slide the f_dc memory ---------- */
         for (int g = 0; g < G; ++g) {
             const CapPtrs c = cap_ptrs(smem, cfg, g);
-            if (!c.cs->active) continue;
-            const int nin = c.cs->nin, nold = c.cs->nold;
-            const unsigned char *iq = args.iq + (cap0 + g) * args.capture_stride_bytes;
+            FskCapShared *cs = c.cs;
+            if (cs->stg_valid) {
+                /* the staged copy issued one frame ago must have landed before anyone moves on,
+                   whether or not the capture still has a frame to demodulate */
+                mbar_wait(&ctl->bar_in[g], (par_in >> g) & 1u);
+                par_in ^= 1u << g;
+            }
+            if (!cs->active) continue;
+            const int nin = cs->nin, nold = cs->nold;
+            const size_t bps = bytes_per_sample(cfg.fmt);
+            const size_t a = reinterpret_cast<size_t>(args.iq) + (cap0 + g) * args.capture_stride_bytes + cs->pos * bps;
+            const unsigned char *src = reinterpret_cast<const unsigned char *>(a);
+            if (cs->stg_valid && a >= cs->stg_lo && a + (size_t)nin * bps <= cs->stg_lo + cs->stg_bytes)
+                src = c.stage + (a - cs->stg_lo); /* read the staged copy */
             if (cfg.fmt == PIRIP_FMT_U8) {
-                const unsigned char *src = iq + 2 * c.cs->pos;
-                /* 4-byte loads (two samples) over the aligned body, single samples at the ends */
+                /* 4-byte reads (two samples) over the aligned body, single samples at the ends */
                 const int mis = (int)((reinterpret_cast<size_t>(src) >> 1) & 1);
                 if (mis && tid == 0) c.xin[0] = make_float2(u8f(src[0]), u8f(src[1]));
                 const int npair = (nin - mis) >> 1;
                 const unsigned *s4 = reinterpret_cast<const unsigned *>(src + 2 * mis);
                 for (int k = tid; k < npair; k += nthreads) {
-                    const unsigned w = __ldg(s4 + k);
+                    const unsigned w = s4[k];
                     float2 *dst = c.xin + mis + 2 * k;
                     dst[0] = make_float2(u8f(w & 0xff), u8f((w >> 8) & 0xff));
                     dst[1] = make_float2(u8f((w >> 16) & 0xff), u8f(w >> 24));
@@ -345,12 +458,12 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
                     c.xin[j] = make_float2(u8f(src[2 * j]), u8f(src[2 * j + 1]));
                 }
             } else if (cfg.fmt == PIRIP_FMT_S16) {
-                const short *src = reinterpret_cast<const short *>(iq) + 2 * c.cs->pos;
+                const short *s2 = reinterpret_cast<const short *>(src);
                 float *xf = reinterpret_cast<float *>(c.xin);
-                for (int i = tid; i < 2 * nin; i += nthreads) xf[i] = (float)src[i] / 825.0f; /* FDMDV_SCALE */
+                for (int i = tid; i < 2 * nin; i += nthreads) xf[i] = (float)s2[i] / 825.0f; /* FDMDV_SCALE */
             } else {
-                const float2 *src = reinterpret_cast<const float2 *>(iq) + c.cs->pos;
-                for (int i = tid; i < nin; i += nthreads) c.xin[i] = src[i];
+                const float2 *s8 = reinterpret_cast<const float2 *>(src);
+                for (int i = tid; i < nin; i += nthreads) c.xin[i] = s8[i];
             }
             if (nold <= nin) {
                 for (int m = 0; m < M; ++m)
@@ -360,15 +473,33 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
             }
         }
         __syncthreads();
+        /* the staging buffers are free again: fetch the next frame's samples behind the compute */
+        if (tid < G) {
+            const CapPtrs c = cap_ptrs(smem, cfg, tid);
+            if (c.cs->active)
+                stage_issue(cfg, args, c, cap0 + tid, c.cs->pos + (unsigned long long)c.cs->nin, &ctl->bar_in[tid]);
+            else
+                c.cs->stg_valid = 0;
+        }
+        PHASE_MARK(1);
 
         /* ---- A7: tone frequency estimate --------------------------------------------- */
         for (int job = warp; job < G * cfg.max_numffts; job += nwarps) {
             const int g = job / cfg.max_numffts, j = job - g * cfg.max_numffts;
             const CapPtrs c = cap_ptrs(smem, cfg, g);
             if (!c.cs->active || j >= c.cs->numffts) continue;
-            warp_fft_mag(cfg, c.xin + j * (Ndft >> 1), fft_slot, c.mag + (size_t)j * Ndft, lane);
+            const float2 *x = c.xin + j * (Ndft >> 1);
+            float *out = c.mag + (size_t)j * Ndft;
+            switch (cfg.log2_ndft) {
+                case 6: warp_fft_mag<6>(x, fft_slot, out, tw, hann, perm, lane); break;
+                case 7: warp_fft_mag<7>(x, fft_slot, out, tw, hann, perm, lane); break;
+                case 8: warp_fft_mag<8>(x, fft_slot, out, tw, hann, perm, lane); break;
+                case 9: warp_fft_mag<9>(x, fft_slot, out, tw, hann, perm, lane); break;
+                default: warp_fft_mag<10>(x, fft_slot, out, tw, hann, perm, lane); break;
+            }
         }
         __syncthreads();
+        PHASE_MARK(2);
         for (int g = 0; g < G; ++g) {
             const CapPtrs c = cap_ptrs(smem, cfg, g);
             if (!c.cs->active) continue;
@@ -464,10 +595,11 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
             }
         }
         __syncthreads();
+        PHASE_MARK(3);
 
         /* ================= streaming phase: oscillators -> mix -> integrate -> timing line ===== */
         const int nchunks = (max_nin + CH - 1) / CH;
-        if (warp == 0) {
+        if (warp == osc_warp) {
             /* A8: the oscillator recursion phi *= dphi is serial; lane (g, m) carries tone m of
                capture g, all lanes step together and publish progress once per chunk */
             const int g = lane / M, m = lane - g * M;
@@ -484,12 +616,24 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
                 const int o = __shfl_xor_sync(0xffffffffu, lo, off);
                 lo = o < lo ? o : lo;
             }
-            for (int j0 = 0; j0 < max_nin; j0 += CH) {
+            for (int ck = 0; ck < nchunks; ++ck) {
+                const int j0 = ck * CH;
                 const int jend = j0 + CH < max_nin ? j0 + CH : max_nin;
                 if (jend <= lo) {
                     if (on) {
-#pragma unroll 8
-                        for (int j = j0; j < jend; ++j) {
+                        /* two steps per 16-byte store once the destination is 16-byte aligned */
+                        int j = j0;
+                        if ((reinterpret_cast<size_t>(dst + j) & 15) != 0) {
+                            ph = cmul(ph, d);
+                            dst[j++] = ph;
+                        }
+#pragma unroll 4
+                        for (; j + 1 < jend; j += 2) {
+                            const float2 p1 = cmul(ph, d);
+                            ph = cmul(p1, d);
+                            *reinterpret_cast<float4 *>(dst + j) = make_float4(p1.x, p1.y, ph.x, ph.y);
+                        }
+                        if (j < jend) {
                             ph = cmul(ph, d);
                             dst[j] = ph;
                         }
@@ -503,13 +647,13 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&ctl->bar_osc[j0 / CH]);
+                if (lane == 0) mbar_arrive(&ctl->bar_osc[ck]);
             }
             if (on) {
                 const float av = sqrtf((ph.x * ph.x) + (ph.y * ph.y));
                 c.cs->phi_c[m] = make_float2(ph.x / av, ph.y / av);
             }
-        } else if (warp == 1) {
+        } else if (warp == tim_warp) {
             /* A10: the timing-line sum is a serial float accumulation; lane g carries capture g
                (real and imaginary chains interleaved) right behind the integrating workers */
             const int g = lane;
@@ -524,10 +668,28 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
                 int jc = (ck + 1) * CH;
                 jc = jc < my_nin ? jc : my_nin;
                 const int avail = on ? outputs_ready(nold, jc, Ts, step, nint) : 0;
-                for (; done < avail; ++done) {
-                    const float2 p = *prod_slot(c, done, D);
-                    tre += p.x;
-                    tim += p.y;
+                /* the two product regions are contiguous: batch eight independent loads ahead of
+                   the sixteen dependent adds so the chain runs at FADD latency, not LDS latency */
+                while (done < avail) {
+                    const bool head = done < D;
+                    const float2 *src = head ? reinterpret_cast<const float2 *>(c.mag) + done : c.xin + (done - D);
+                    const int lim = head ? (avail < D ? avail : D) : avail;
+                    int n = lim - done;
+                    for (; n >= 8; n -= 8, src += 8, done += 8) {
+                        float2 v[8];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) v[k] = src[k];
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            tre += v[k].x;
+                            tim += v[k].y;
+                        }
+                    }
+                    for (; n > 0; --n, ++src, ++done) {
+                        const float2 v = *src;
+                        tre += v.x;
+                        tim += v.y;
+                    }
                 }
             }
             if (on) {
@@ -563,153 +725,189 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
                     cs->rx_timing = rx_timing;
                 }
             }
-        } else {
-            /* workers: A8 mix and A9 integrate, chunk by chunk behind the oscillator warp */
-            const int wt = tid - 64, nwt = nthreads - 64;
-            const int lch = 31 - __clz(CH); /* CH is a power of two */
+        } else if (is_worker) {
+            /* workers: A8 mix and A9 integrate, chunk by chunk behind the oscillator warp.
+               Lanes wt .. wt+M-1 share one (capture, slot): one tone each. */
+            const int wt = wtid;
+            const int m = wt & (M - 1);
+            const int q = wt / M;
+            const int g = q % G, slot = q / G;
+            const int nslots = (nwt / M) / G; /* slots per capture; threads beyond G*nslots*M idle */
+            const bool have_slot = slot < nslots;
+            const CapPtrs c = cap_ptrs(smem, cfg, g);
+            const bool on = have_slot && c.cs->active;
+            const int nin = c.cs->nin, nold = c.cs->nold;
+            float2 *ftone = c.fdc + m * TS;
+            const unsigned lane_base = lane & ~(M - 1);
             for (int ck = 0; ck < nchunks; ++ck) {
                 const int j0 = ck * CH;
                 const int jend = j0 + CH < max_nin ? j0 + CH : max_nin;
+                WMARK(0);
                 mbar_wait(&ctl->bar_osc[ck], (unsigned)(par >> ck) & 1u);
+                WMARK(1);
                 /* mix: f_dc = in * conj(phi), in place over the oscillator values */
-                for (int it = wt; it < (G << lch); it += nwt) {
-                    const int g = it >> lch, j = j0 + (it & (CH - 1));
-                    const CapPtrs c = cap_ptrs(smem, cfg, g);
-                    if (!c.cs->active || j >= c.cs->nin) continue;
-                    const float2 x = c.xin[j];
-                    float2 *f = c.fdc + c.cs->nold + j;
-                    for (int m = 0; m < M; ++m) {
-                        const float2 o = f[m * TS];
-                        f[m * TS] = make_float2(x.x * o.x + x.y * o.y, x.y * o.x - x.x * o.y);
+                if (on) {
+                    const int je = jend < nin ? jend : nin;
+                    for (int j = j0 + slot; j < je; j += nslots) {
+                        const float2 x = c.xin[j];
+                        const float2 o = ftone[nold + j];
+                        ftone[nold + j] = make_float2(x.x * o.x + x.y * o.y, x.y * o.x - x.x * o.y);
                     }
                 }
+                WMARK(2);
                 named_bar_sync(1, nwt);
+                WMARK(3);
                 /* integrate every output whose window became complete with this chunk, form
                    sum_m |f_int|^2 and multiply by the timing oscillator */
-                /* the first chunk also owns the outputs that lie entirely in the old samples */
-                const int extra = ck == 0 ? (Ts + Ts / 4 + 1) : 0;
+                const int lo = ck == 0 ? 0 : outputs_ready(nold, j0 < nin ? j0 : nin, Ts, step, nint);
+                const int hi = on ? outputs_ready(nold, jend < nin ? jend : nin, Ts, step, nint) : 0;
                 if (step == 1) {
-                    const int max_pairs = ((CH + extra) >> 1) + 2;
-                    for (int it = wt; it < max_pairs * G; it += nwt) {
-                        const int g = it % G, pr = it / G;
-                        const CapPtrs c = cap_ptrs(smem, cfg, g);
-                        if (!c.cs->active) continue;
-                        const int nin = c.cs->nin, nold = c.cs->nold;
-                        const int lo = ck == 0 ? 0 : outputs_ready(nold, j0 < nin ? j0 : nin, Ts, 1, nint);
-                        const int hi = outputs_ready(nold, jend < nin ? jend : nin, Ts, 1, nint);
-                        const int e = (lo & ~1) + 2 * pr;
-                        if (e >= hi) continue;
-                        float ft0 = 0.0f, ft1 = 0.0f;
-                        for (int m = 0; m < M; ++m) {
-                            const float4 *src = reinterpret_cast<const float4 *>(c.fdc + m * TS + e);
-                            float4 v = src[0];
-                            float2 a0 = make_float2(0.0f + v.x, 0.0f + v.y);
-                            a0 = cadd(a0, make_float2(v.z, v.w));
-                            float2 a1 = make_float2(0.0f + v.z, 0.0f + v.w);
-                            int r = 2;
-#pragma unroll 4
-                            for (; r + 1 < Ts; r += 2) {
-                                v = src[r >> 1];
+                    /* four adjacent windows per thread share their 16-byte loads; every window is
+                       still accumulated in ascending sample order from zero */
+                    for (int e = (lo & ~1) + 4 * slot; __any_sync(0xffffffffu, e < hi); e += 4 * nslots) {
+                        float en[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+                        if (e < hi) {
+                            const float2 *s2 = ftone + e;
+                            float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
+                            /* head: samples 0..3 enter the windows one by one */
+                            {
+                                const float4 v = *reinterpret_cast<const float4 *>(s2);
+                                const float4 w = *reinterpret_cast<const float4 *>(s2 + 2);
                                 a0 = cadd(a0, make_float2(v.x, v.y));
-                                a1 = cadd(a1, make_float2(v.x, v.y));
                                 a0 = cadd(a0, make_float2(v.z, v.w));
                                 a1 = cadd(a1, make_float2(v.z, v.w));
+                                a0 = cadd(a0, make_float2(w.x, w.y));
+                                a1 = cadd(a1, make_float2(w.x, w.y));
+                                a2 = cadd(a2, make_float2(w.x, w.y));
+                                a0 = cadd(a0, make_float2(w.z, w.w));
+                                a1 = cadd(a1, make_float2(w.z, w.w));
+                                a2 = cadd(a2, make_float2(w.z, w.w));
+                                a3 = cadd(a3, make_float2(w.z, w.w));
                             }
-                            v = src[r >> 1];
-                            if (r == Ts) { /* Ts even */
-                                a1 = cadd(a1, make_float2(v.x, v.y));
-                            } else {
+                            int r = 4;
+#pragma unroll 2
+                            for (; r + 1 < Ts; r += 2) {
+                                const float4 v = *reinterpret_cast<const float4 *>(s2 + r);
                                 a0 = cadd(a0, make_float2(v.x, v.y));
                                 a1 = cadd(a1, make_float2(v.x, v.y));
+                                a2 = cadd(a2, make_float2(v.x, v.y));
+                                a3 = cadd(a3, make_float2(v.x, v.y));
+                                a0 = cadd(a0, make_float2(v.z, v.w));
                                 a1 = cadd(a1, make_float2(v.z, v.w));
+                                a2 = cadd(a2, make_float2(v.z, v.w));
+                                a3 = cadd(a3, make_float2(v.z, v.w));
                             }
-                            ft0 += (a0.x * a0.x) + (a0.y * a0.y);
-                            ft1 += (a1.x * a1.x) + (a1.y * a1.y);
+                            /* tail: samples r .. Ts+2 leave the windows one by one */
+                            for (int t = r; t < Ts + 3; ++t) {
+                                const float2 x = s2[t];
+                                if (t < Ts) a0 = cadd(a0, x);
+                                if (t < Ts + 1) a1 = cadd(a1, x);
+                                if (t < Ts + 2) a2 = cadd(a2, x);
+                                a3 = cadd(a3, x);
+                            }
+                            en[0] = (a0.x * a0.x) + (a0.y * a0.y);
+                            en[1] = (a1.x * a1.x) + (a1.y * a1.y);
+                            en[2] = (a2.x * a2.x) + (a2.y * a2.y);
+                            en[3] = (a3.x * a3.x) + (a3.y * a3.y);
                         }
-                        if (e >= lo) {
-                            const float2 ph = __ldg(cfg.phi_ft + e);
-                            *prod_slot(c, e, D) = make_float2(ft0 * ph.x, ft0 * ph.y);
+                        /* sum the tone energies in tone order on the lane of tone 0 */
+                        float ft[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+                        for (int mm = 0; mm < M; ++mm) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) ft[k] += __shfl_sync(0xffffffffu, en[k], lane_base + mm);
                         }
-                        if (e + 1 < hi) {
-                            const float2 ph = __ldg(cfg.phi_ft + e + 1);
-                            *prod_slot(c, e + 1, D) = make_float2(ft1 * ph.x, ft1 * ph.y);
+                        if (m == 0 && e < hi) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                const int o = e + k;
+                                if (o >= lo && o < hi) {
+                                    const float2 ph = phi_ft[o];
+                                    *prod_slot(c, o, D) = make_float2(ft[k] * ph.x, ft[k] * ph.y);
+                                }
+                            }
                         }
                     }
                 } else {
-                    const int max_out = (CH + extra) / step + 2;
-                    for (int it = wt; it < max_out * G; it += nwt) {
-                        const int g = it % G, k = it / G;
-                        const CapPtrs c = cap_ptrs(smem, cfg, g);
-                        if (!c.cs->active) continue;
-                        const int nin = c.cs->nin, nold = c.cs->nold;
-                        const int lo = ck == 0 ? 0 : outputs_ready(nold, j0 < nin ? j0 : nin, Ts, step, nint);
-                        const int hi = outputs_ready(nold, jend < nin ? jend : nin, Ts, step, nint);
-                        const int i = lo + k;
-                        if (i >= hi) continue;
-                        float ft = 0.0f;
-                        for (int m = 0; m < M; ++m) {
-                            const float2 a = window_sum(c.fdc + m * TS + i * step, Ts);
-                            ft += (a.x * a.x) + (a.y * a.y);
+                    for (int i = lo + slot; __any_sync(0xffffffffu, i < hi); i += nslots) {
+                        float en = 0.0f;
+                        if (i < hi) {
+                            const float2 a = window_sum(ftone + i * step, Ts);
+                            en = (a.x * a.x) + (a.y * a.y);
                         }
-                        const float2 ph = __ldg(cfg.phi_ft + i);
-                        *prod_slot(c, i, D) = make_float2(ft * ph.x, ft * ph.y);
+                        float ft = 0.0f;
+                        for (int mm = 0; mm < M; ++mm) ft += __shfl_sync(0xffffffffu, en, lane_base + mm);
+                        if (m == 0 && i < hi) {
+                            const float2 ph = phi_ft[i];
+                            *prod_slot(c, i, D) = make_float2(ft * ph.x, ft * ph.y);
+                        }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&ctl->bar_int[ck]);
+                WMARK(4);
             }
         }
         par ^= nchunks >= 64 ? ~0ull : ((1ull << nchunks) - 1ull);
+        PHASE_MARK(4); /* own role's time in the streaming phase */
         __syncthreads();
+        PHASE_MARK(5); /* waiting for the slowest role */
 
-        /* ---- A11: resample at the timing instant, decide, per-symbol statistics ---------- */
-        for (int it = tid; it < G * Nsym; it += nthreads) {
-            const int g = it % G, i = it / G;
-            const CapPtrs c = cap_ptrs(smem, cfg, g);
+        /* ---- A11: resample at the timing instant, decide, per-symbol statistics ----------
+           lanes t .. t+M-1 share one (capture, symbol): one tone each */
+        for (int it = tid; __any_sync(0xffffffffu, it < G * Nsym * M); it += nthreads) {
+            const int m = it & (M - 1), q = it / M;
+            const int g = q % G, i = q / G;
+            const bool valid = it < G * Nsym * M;
+            const CapPtrs c = cap_ptrs(smem, cfg, valid ? g : 0);
             FskCapShared *cs = c.cs;
-            if (!cs->active || cs->nan_flag) continue;
-            const size_t cap = cap0 + g;
-            const size_t frame = (size_t)cs->frame;
-            float *sig = c.mag + Ndft, *nse = sig + Nsym, *sqm = nse + Nsym, *rfl = sqm + Nsym;
-            const float fract = cs->fract, omf = cs->one_minus_fract;
-            const int st = (i + 1) * P;
-            const int olo = (st + cs->low) * step, ohi = (st + cs->high) * step;
-            float tmax[4];
-            for (int m = 0; m < M; ++m) {
+            const bool on = valid && cs->active && !cs->nan_flag;
+            float tm = 0.0f;
+            if (on) {
                 /* the two integrator outputs around the timing instant, re-summed from f_dc in
                    the same ascending order as the streaming pass */
-                const float2 a = window_sum(c.fdc + m * TS + olo, Ts);
-                const float2 b = (ohi == olo) ? a : window_sum(c.fdc + m * TS + ohi, Ts);
+                const float fract = cs->fract, omf = cs->one_minus_fract;
+                const int st = (i + 1) * P;
+                const int olo = (st + cs->low) * step, ohi = (st + cs->high) * step;
+                float2 a, b;
+                window_sum2(c.fdc + m * TS + olo, c.fdc + m * TS + ohi, Ts, a, b);
                 float2 t = make_float2(omf * a.x, omf * a.y);
                 t = cadd(t, make_float2(fract * b.x, fract * b.y));
-                tmax[m] = (t.x * t.x) + (t.y * t.y);
+                tm = (t.x * t.x) + (t.y * t.y);
             }
-            float mx = tmax[0];
-            int sym = 0;
-            for (int m = 1; m < M; ++m)
-                if (tmax[m] > mx) {
-                    mx = tmax[m];
-                    sym = m;
-                }
-            if (args.bits) {
-                unsigned char *bo = args.bits + (cap * args.max_frames + frame) * (size_t)Nbits;
-                if (M == 2) {
-                    bo[i] = sym == 1;
-                } else {
-                    bo[2 * i + 1] = sym & 1;
-                    bo[2 * i] = (sym & 2) >> 1;
-                }
-            }
-            float sum = 0.0f;
-            for (int m = 0; m < M; ++m) {
-                const float rf = sqrtf(tmax[m]);
+            float tmax[4];
+            const unsigned lb = lane & ~(M - 1);
+            for (int mm = 0; mm < M; ++mm) tmax[mm] = __shfl_sync(0xffffffffu, tm, lb + mm);
+            if (on) {
+                const size_t cap = cap0 + g;
+                const size_t frame = (size_t)cs->frame;
+                float *sig = c.mag + Ndft, *nse = sig + Nsym, *sqm = nse + Nsym, *rfl = sqm + Nsym;
+                const float rf = sqrtf(tm);
                 rfl[m * Nsym + i] = rf; /* tone-major, as rx_filt */
                 if (args.rx_filt) args.rx_filt[(cap * args.max_frames + frame) * (size_t)(M * Nsym) + m * Nsym + i] = rf;
-                sum += tmax[m];
+                if (m == 0) {
+                    float mx = tmax[0];
+                    int sym = 0;
+                    for (int mm = 1; mm < M; ++mm)
+                        if (tmax[mm] > mx) {
+                            mx = tmax[mm];
+                            sym = mm;
+                        }
+                    if (args.bits) {
+                        unsigned char *bo = args.bits + (cap * args.max_frames + frame) * (size_t)Nbits;
+                        if (M == 2) {
+                            bo[i] = sym == 1;
+                        } else {
+                            bo[2 * i + 1] = sym & 1;
+                            bo[2 * i] = (sym & 2) >> 1;
+                        }
+                    }
+                    float sum = 0.0f;
+                    for (int mm = 0; mm < M; ++mm) sum += tmax[mm];
+                    sig[i] = mx;
+                    nse[i] = (sum - mx) / (float)(M - 1);
+                    sqm[i] = sqrtf(mx);
+                }
             }
-            sig[i] = mx;
-            nse[i] = (sum - mx) / (float)(M - 1);
-            sqm[i] = sqrtf(mx);
         }
         if (args.bits) {
             /* reference returns early on a NaN timing estimate and the CLI re-emits its bit
@@ -722,6 +920,7 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
             }
         }
         __syncthreads();
+        PHASE_MARK(6);
         if (warp == 0) {
             /* four serial sums over the symbols per capture, lane (g, s) */
             const int g = lane >> 2, s = lane & 3;
@@ -733,6 +932,7 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
                 const float *sig = c.mag + Ndft;
                 const float *src = s == 1 ? sig + Nsym : (s == 3 ? sig + 2 * Nsym : sig);
                 float acc = s == 1 ? 1E-12f : 0.0f;
+#pragma unroll 10
                 for (int i = 0; i < Nsym; ++i) acc += src[i];
                 cs->sums[s] = acc;
             }
@@ -761,6 +961,7 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
             }
         }
         __syncthreads();
+        PHASE_MARK(7);
 
         /* ---- A12: soft decisions ([U mpdecode_core.c::fsk_rx_filt_to_llrs]) ----------------- */
         if (args.llr) {
@@ -822,13 +1023,25 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
             }
         }
         __syncthreads();
+        PHASE_MARK(8);
     }
+#ifdef FSK_PHASE_TIMING
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == tim_warp || warp == osc_warp) && args.Sf_out == nullptr &&
+        args.stats == nullptr)
+        printf("w%d worker: wait-osc %lld mix %lld bar %lld integrate %lld\n", warp, wph[1], wph[2], wph[3], wph[4]);
+    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == tim_warp || warp == osc_warp) && args.Sf_out == nullptr &&
+        args.stats == nullptr)
+        printf("w%d load %lld fft %lld iir+peaks %lld stream-own %lld stream-wait %lld decide %lld sums %lld adv %lld book %lld\n",
+               warp, tph[1], tph[2], tph[3], tph[4], tph[5], tph[6], tph[7], tph[8], tph[0]);
+#endif
 
     /* ---- results and state ------------------------------------------------------------ */
     for (int g = 0; g < G; ++g) {
         const size_t cap = cap0 + g;
         if (cap >= args.n_captures) break;
         const CapPtrs c = cap_ptrs(smem, cfg, g);
+        /* drain a staged copy that will not be consumed before the CTA retires */
+        if (c.cs->stg_valid) mbar_wait(&ctl->bar_in[g], (par_in >> g) & 1u);
         if (args.nframes && tid == 0) args.nframes[cap] = (int32_t)c.cs->frame;
         if (args.Sf_out)
             for (int i = tid; i < Ndft; i += nthreads) args.Sf_out[cap * (size_t)Ndft + i] = c.Sf[i];

@@ -12,15 +12,23 @@ from collections import defaultdict
 rep, cubin = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 dis = subprocess.run(["nvdisasm", "--print-line-info", cubin], capture_output=True, text=True).stdout
-line_of = []  # per instruction, in order
+# split per function (.text.<name> sections); pick the one whose size matches the SASS page
+funcs = {}
+curf = None
 cur = None
 for l in dis.splitlines():
+    m = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
+    if m:
+        curf = m.group(1)
+        funcs[curf] = []
+        cur = None
+        continue
     m = re.search(r'//## File "([^"]+)", line (\d+)', l)
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2)))
         continue
-    if re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", l) and ".byte" not in l and ".dword" not in l and ".short" not in l and ".word" not in l:
-        line_of.append(cur)
+    if curf and re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+\S", l) and not any(x in l for x in (".byte", ".dword", ".short", ".word")):
+        funcs[curf].append(cur)
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = next(i for i, r in enumerate(rows) if "Instructions Executed" in r)
@@ -29,8 +37,9 @@ ie, ss, sc = hdr.index("Instructions Executed"), hdr.index("# Samples"), hdr.ind
 inst = defaultdict(int)
 smp = defaultdict(int)
 body = rows[hi + 1:]
-if len(body) != len(line_of):
-    print("warning: %d SASS rows vs %d disassembled instructions" % (len(body), len(line_of)))
+fname = min(funcs, key=lambda f: abs(len(funcs[f]) - len(body)))
+line_of = funcs[fname]
+print("function", fname[:80], len(line_of), "instructions; SASS rows", len(body))
 for k, r in enumerate(body):
     key = line_of[k] if k < len(line_of) else None
     inst[key] += int(r[ie])
@@ -38,7 +47,7 @@ for k, r in enumerate(body):
 ti, ts = sum(inst.values()), sum(smp.values())
 print("total warp-instructions %d, stall samples %d" % (ti, ts))
 src_cache = {}
-for key in sorted(inst, key=lambda k: -smp[k])[:top]:
+for key in sorted(inst, key=lambda k: -(inst[k] if len(sys.argv) > 4 else smp[k]))[:top]:
     text = ""
     if key:
         f, n = key
