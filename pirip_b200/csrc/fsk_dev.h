@@ -44,6 +44,7 @@ struct FskDevCfg {
     int off_fft, off_tw, off_hann, off_phift, off_perm, off_ctl; /* CTA-wide, after the G capture blocks */
     int stage_bytes;
     int max_numffts;
+    int mag_blocks;      /* FFT blocks per batch = capacity of the magnitude buffer */
     int smem_bytes;
 };
 

@@ -247,71 +247,86 @@ static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, int
         if (v >= 16 && v <= 1024 && (v & (v - 1)) == 0) d.chunk = v;
     }
     while ((nin_max + d.chunk - 1) / d.chunk > FSK_MAX_CHUNKS) d.chunk *= 2;
-    int off = 0;
-    d.off_fdc = off;
-    off += align_up(c.M * d.fdc_tone_stride * 8, 16);
-    d.off_xin = off;
-    {
-        const int in_elems = nin_max > d.nint ? nin_max : d.nint; /* frame input, then timing products */
-        off += align_up((in_elems + 2) * 8, 16);
-    }
-    d.off_mag = off;
-    {
-        const int fft_floats = d.max_numffts * d.Ndft;
-        const int dec_floats = d.Ndft + (3 + c.M) * c.Nsym; /* tmpS | sig | nse | sqm | rx_filt */
-        off += align_up((fft_floats > dec_floats ? fft_floats : dec_floats) * 4, 16);
-    }
-    d.off_Sf = off;
-    off += align_up(d.Ndft * 4, 16);
-    d.off_stage = off;
-    d.stage_bytes = align_up(nin_max * (c.fmt == PIRIP_FMT_U8 ? 2 : (c.fmt == PIRIP_FMT_S16 ? 4 : 8)) + 32, 16);
-    off += d.stage_bytes;
-    d.off_scal = off;
-    off += align_up((int)sizeof(FskCapShared), 16);
-    /* capture blocks 32 (mod 128) bytes apart: with tones 16 (mod 128) bytes apart the lanes
-       (capture, tone) of one quarter-warp hit distinct 16-byte bank groups (M = 2, G <= 4) */
-    while ((off & 127) != (c.M == 2 ? 32 : 64)) off += 16;
-    d.cap_stride = off;
-
-    /* captures per CTA and threads: as many captures as fit the 227 KB of one SM, 16 warps */
-    const int limit = 227 * 1024;
-    int want_g = max_g, want_threads = 512;
-    if (const char *e = getenv("PIRIP_FSK_G")) want_g = atoi(e);
-    if (const char *e = getenv("PIRIP_FSK_THREADS")) want_threads = atoi(e);
-    if (want_g < 1) want_g = 1;
-    if (want_g > FSK_MAX_G) want_g = FSK_MAX_G;
-    if (want_g == 7) want_g = 6;
-    want_threads = want_threads / 32 * 32;
-    if (want_threads < 256) want_threads = 256; /* two serial warps on sub-partition 3 need >= 8 warps */
-    if (want_threads > 512) want_threads = 512;
-    for (int g = want_g; g >= 1; --g) {
-        if (g == 7) continue;
-        int threads = want_threads;
-        if (g == 1 && max_g == 1) threads = 256;
+    /* Per-capture block for a given magnitude-buffer capacity; returns its size. */
+    auto layout_capture = [&](int mag_blocks) {
+        int off = 0;
+        d.off_fdc = off;
+        off += align_up(c.M * d.fdc_tone_stride * 8, 16);
+        d.off_xin = off;
+        {
+            const int in_elems = nin_max > d.nint ? nin_max : d.nint; /* frame input, then timing products */
+            off += align_up((in_elems + 2) * 8, 16);
+        }
+        d.off_mag = off;
+        {
+            const int fft_floats = mag_blocks * d.Ndft;
+            const int dec_floats = d.Ndft + (3 + c.M) * c.Nsym; /* tmpS | sig | nse | sqm | rx_filt */
+            off += align_up((fft_floats > dec_floats ? fft_floats : dec_floats) * 4, 16);
+        }
+        d.off_Sf = off;
+        off += align_up(d.Ndft * 4, 16);
+        d.off_stage = off;
+        d.stage_bytes = align_up(nin_max * (c.fmt == PIRIP_FMT_U8 ? 2 : (c.fmt == PIRIP_FMT_S16 ? 4 : 8)) + 32, 16);
+        off += d.stage_bytes;
+        d.off_scal = off;
+        off += align_up((int)sizeof(FskCapShared), 16);
+        /* capture blocks 32 (mod 128) bytes apart: with tones 16 (mod 128) bytes apart the lanes
+           (capture, tone) of one quarter-warp hit distinct 16-byte bank groups (M = 2, G <= 4) */
+        while ((off & 127) != (c.M == 2 ? 32 : 64)) off += 16;
+        d.cap_stride = off;
+        d.mag_blocks = mag_blocks;
+        return off;
+    };
+    auto layout_cta = [&](int threads) {
         int o = 0;
-        const int o_fft = o;
+        d.off_fft = o;
         o += align_up((threads / 32) * d.Ndft * 8, 16);
-        const int o_tw = o;
+        d.off_tw = o;
         o += align_up(d.Ndft * 8, 16);
-        const int o_hann = o;
+        d.off_hann = o;
         o += align_up(d.Ndft * 4, 16);
-        const int o_phift = o;
+        d.off_phift = o;
         o += align_up(d.nint * 8, 16);
-        const int o_perm = o;
+        d.off_perm = o;
         o += align_up(d.Ndft * 2, 16);
-        const int o_ctl = o;
+        d.off_ctl = o;
         o += align_up((int)sizeof(FskCtaShared), 16);
-        if (g * d.cap_stride + o <= limit) {
-            d.G = g;
-            d.threads = threads;
-            d.off_fft = o_fft;
-            d.off_tw = o_tw;
-            d.off_hann = o_hann;
-            d.off_phift = o_phift;
-            d.off_perm = o_perm;
-            d.off_ctl = o_ctl;
-            d.smem_bytes = g * d.cap_stride + o;
-            break;
+        return o;
+    };
+
+    /* Geometry.  Preferred: two 256-thread CTAs of G = 2 captures per SM (their phases overlap);
+       otherwise one 512-thread CTA with as many captures as fit 227 KB.  PIRIP_FSK_G forces G. */
+    int force_g = 0;
+    if (const char *e = getenv("PIRIP_FSK_G")) force_g = atoi(e);
+    if (force_g > FSK_MAX_G) force_g = FSK_MAX_G;
+    if (force_g == 7) force_g = 6;
+    d.G = 0;
+    const int sm_bytes = 228 * 1024, cta_reserve = 1024;
+    if (max_g >= 2 && (force_g == 0 || force_g == 2)) {
+        const int budget = sm_bytes / 2 - cta_reserve;
+        const int cta_bytes = layout_cta(256);
+        for (int mb = d.max_numffts; mb >= 1; --mb) {
+            if (2 * layout_capture(mb) + cta_bytes <= budget) {
+                d.G = 2;
+                d.threads = 256;
+                d.smem_bytes = 2 * d.cap_stride + cta_bytes;
+                break;
+            }
+        }
+    }
+    if (d.G == 0) {
+        const int limit = 227 * 1024;
+        const int gmax = force_g ? force_g : (max_g < 5 ? max_g : 5);
+        for (int g = gmax; g >= 1; --g) {
+            if (g == 7) continue;
+            const int threads = g <= 2 ? 256 : 512;
+            const int cta_bytes = layout_cta(threads);
+            if (g * layout_capture(d.max_numffts) + cta_bytes <= limit) {
+                d.G = g;
+                d.threads = threads;
+                d.smem_bytes = g * d.cap_stride + cta_bytes;
+                break;
+            }
         }
     }
     if (d.G == 0) {

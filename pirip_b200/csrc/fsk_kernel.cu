@@ -276,8 +276,10 @@ __device__ void stage_issue(const FskDevCfg &cfg, const FskBatchArgs &args, cons
     cs->stg_valid = 1;
 }
 
+/* G <= 2: 256-thread CTAs, two resident per SM, so the barrier-separated phases of one CTA
+   overlap the other's; G >= 3: one 512-thread CTA per SM */
 template <int G>
-__global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant__ FskDevCfg cfg,
+__global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_kernel(const __grid_constant__ FskDevCfg cfg,
                                                            const __grid_constant__ FskBatchArgs args) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -390,7 +392,8 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
     long long wlast = 0;
 #define WMARK(k)                                         \
     do {                                                 \
-        const long long tnow = clock64();                \
+        tsink += *reinterpret_cast<volatile int *>(&ctl->max_nin); \
+        const long long tnow = clock64() + (tsink & 0);  \
         if (k) wph[k] += tnow - wlast;                   \
         wlast = tnow;                                    \
     } while (0)
@@ -483,35 +486,41 @@ __global__ void __launch_bounds__(512, 1) fsk_demod_kernel(const __grid_constant
         }
         PHASE_MARK(1);
 
-        /* ---- A7: tone frequency estimate --------------------------------------------- */
-        for (int job = warp; job < G * cfg.max_numffts; job += nwarps) {
-            const int g = job / cfg.max_numffts, j = job - g * cfg.max_numffts;
-            const CapPtrs c = cap_ptrs(smem, cfg, g);
-            if (!c.cs->active || j >= c.cs->numffts) continue;
-            const float2 *x = c.xin + j * (Ndft >> 1);
-            float *out = c.mag + (size_t)j * Ndft;
-            switch (cfg.log2_ndft) {
-                case 6: warp_fft_mag<6>(x, fft_slot, out, tw, hann, perm, lane); break;
-                case 7: warp_fft_mag<7>(x, fft_slot, out, tw, hann, perm, lane); break;
-                case 8: warp_fft_mag<8>(x, fft_slot, out, tw, hann, perm, lane); break;
-                case 9: warp_fft_mag<9>(x, fft_slot, out, tw, hann, perm, lane); break;
-                default: warp_fft_mag<10>(x, fft_slot, out, tw, hann, perm, lane); break;
+        /* ---- A7: tone frequency estimate ---------------------------------------------
+           FFT blocks are transformed mag_blocks at a time; the magnitude IIR runs over each batch
+           in block order, so a small magnitude buffer serves any number of blocks */
+        const int MB = cfg.mag_blocks;
+        for (int b0 = 0; b0 < cfg.max_numffts; b0 += MB) {
+            for (int job = warp; job < G * MB; job += nwarps) {
+                const int g = job / MB, jb = job - g * MB, j = b0 + jb;
+                const CapPtrs c = cap_ptrs(smem, cfg, g);
+                if (!c.cs->active || j >= c.cs->numffts) continue;
+                const float2 *x = c.xin + j * (Ndft >> 1);
+                float *out = c.mag + (size_t)jb * Ndft;
+                switch (cfg.log2_ndft) {
+                    case 6: warp_fft_mag<6>(x, fft_slot, out, tw, hann, perm, lane); break;
+                    case 7: warp_fft_mag<7>(x, fft_slot, out, tw, hann, perm, lane); break;
+                    case 8: warp_fft_mag<8>(x, fft_slot, out, tw, hann, perm, lane); break;
+                    case 9: warp_fft_mag<9>(x, fft_slot, out, tw, hann, perm, lane); break;
+                    default: warp_fft_mag<10>(x, fft_slot, out, tw, hann, perm, lane); break;
+                }
             }
+            __syncthreads();
+            const bool last = b0 + MB >= cfg.max_numffts;
+            for (int g = 0; g < G; ++g) {
+                const CapPtrs c = cap_ptrs(smem, cfg, g);
+                if (!c.cs->active) continue;
+                const int jn = c.cs->numffts - b0 < MB ? c.cs->numffts - b0 : MB; /* blocks of this batch */
+                for (int i = tid; i < Ndft; i += nthreads) {
+                    float s = c.Sf[i];
+                    for (int j = 0; j < jn; ++j) s = (s * omtc) + (c.mag[j * Ndft + i] * tc);
+                    c.Sf[i] = s;
+                    if (last) c.mag[i] = s; /* tmpS: scratch copy the peak search blanks */
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
         PHASE_MARK(2);
-        for (int g = 0; g < G; ++g) {
-            const CapPtrs c = cap_ptrs(smem, cfg, g);
-            if (!c.cs->active) continue;
-            const int numffts = c.cs->numffts;
-            for (int i = tid; i < Ndft; i += nthreads) {
-                float s = c.Sf[i];
-                for (int j = 0; j < numffts; ++j) s = (s * omtc) + (c.mag[j * Ndft + i] * tc);
-                c.Sf[i] = s;
-                c.mag[i] = s; /* tmpS: scratch copy the peak search blanks */
-            }
-        }
-        __syncthreads();
         for (int g = warp; g < G; g += nwarps) {
             const CapPtrs c = cap_ptrs(smem, cfg, g);
             if (!c.cs->active) continue;
