@@ -12,6 +12,7 @@ from ._lib import (  # noqa: F401
     FRAME_STATS_DTYPE,
     FskCfg,
     FskPlan,
+    FskStream,
     PiripError,
     kernel_launches,
     lib,

@@ -145,3 +145,79 @@ class FskPlan:
                                              d_llr, d_rx_filt, d_stats, d_nframes, max_frames, stream)
         if rc != 0:
             raise _err("pirip_fsk_demod_batch_dev", rc)
+
+
+# ---- codec2 `struct FSK` API (include/pirip_fsk.h layer 1) -------------------------------------
+
+class COMP(C.Structure):
+    _fields_ = [("real", C.c_float), ("imag", C.c_float)]
+
+
+class FSK(C.Structure):
+    """struct FSK as declared in include/pirip_fsk.h (codec2 fsk.h field names)."""
+    _fields_ = [
+        ("Ndft", C.c_int), ("Fs", C.c_int), ("N", C.c_int), ("Rs", C.c_int), ("Ts", C.c_int), ("Nmem", C.c_int),
+        ("P", C.c_int), ("Nsym", C.c_int), ("Nbits", C.c_int), ("f1_tx", C.c_int), ("tone_spacing", C.c_int),
+        ("mode", C.c_int), ("tc", C.c_float), ("est_min", C.c_int), ("est_max", C.c_int), ("est_space", C.c_int),
+        ("hann_table", C.POINTER(C.c_float)), ("Sf", C.POINTER(C.c_float)), ("phi_c", COMP * 4),
+        ("f_dc", C.c_void_p), ("fft_cfg", C.c_void_p), ("norm_rx_timing", C.c_float), ("tx_phase_c", COMP),
+        ("EbNodB", C.c_float), ("f_est", C.c_float * 4), ("f2_est", C.c_float * 4), ("freq_est_type", C.c_int),
+        ("ppm", C.c_float), ("SNRest", C.c_float), ("v_est", C.c_float), ("rx_sig_pow", C.c_float),
+        ("rx_nse_pow", C.c_float), ("nin", C.c_int), ("burst_mode", C.c_int), ("lock_nin", C.c_int),
+        ("stats", C.c_void_p), ("normalise_eye", C.c_int), ("dev", C.c_void_p)]
+
+
+class FskStream:
+    """Per-stream demodulator through codec2's own entry points: fsk_create_hbr / fsk_nin /
+    fsk_demod / fsk_demod_sd / fsk_destroy, exactly as fsk_demod.c and rtl_fsk call them."""
+
+    def __init__(self, Fs, Rs, M, P=8, Nsym=50, f1_tx=1200, tone_spacing=400, limits=None, mask=False):
+        L = lib()
+        L.fsk_create_hbr.restype = C.POINTER(FSK)
+        L.fsk_create_hbr.argtypes = [C.c_int] * 7
+        L.fsk_destroy.argtypes = [C.POINTER(FSK)]
+        L.fsk_nin.restype = C.c_uint32
+        L.fsk_nin.argtypes = [C.POINTER(FSK)]
+        L.fsk_demod.argtypes = [C.POINTER(FSK), C.c_void_p, C.c_void_p]
+        L.fsk_demod_sd.argtypes = [C.POINTER(FSK), C.c_void_p, C.c_void_p]
+        L.fsk_set_freq_est_limits.argtypes = [C.POINTER(FSK), C.c_int, C.c_int]
+        L.fsk_set_freq_est_alg.argtypes = [C.POINTER(FSK), C.c_int]
+        self.L = L
+        self.fsk = L.fsk_create_hbr(Fs, Rs, M, P, Nsym, f1_tx, tone_spacing)
+        if limits:
+            L.fsk_set_freq_est_limits(self.fsk, limits[0], limits[1])
+        if mask:
+            L.fsk_set_freq_est_alg(self.fsk, 1)
+
+    @property
+    def s(self):
+        return self.fsk.contents
+
+    def nin(self):
+        return int(self.L.fsk_nin(self.fsk))
+
+    def demod(self, samples):
+        """samples: complex64[nin] -> uint8[Nbits]"""
+        samples = np.ascontiguousarray(samples, np.complex64)
+        assert samples.size == self.nin()
+        bits = np.zeros(self.s.Nbits, np.uint8)
+        self.L.fsk_demod(self.fsk, _ptr(bits), _ptr(samples))
+        return bits
+
+    def demod_sd(self, samples):
+        samples = np.ascontiguousarray(samples, np.complex64)
+        assert samples.size == self.nin()
+        filt = np.zeros(self.s.mode * self.s.Nsym, np.float32)
+        self.L.fsk_demod_sd(self.fsk, _ptr(filt), _ptr(samples))
+        return filt
+
+    def close(self):
+        if self.fsk:
+            self.L.fsk_destroy(self.fsk)
+            self.fsk = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
