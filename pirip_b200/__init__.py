@@ -13,6 +13,7 @@ from ._lib import (  # noqa: F401
     FskCfg,
     FskPlan,
     FskStream,
+    DecimPlan,
     PiripError,
     kernel_launches,
     lib,

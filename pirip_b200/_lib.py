@@ -221,3 +221,65 @@ class FskStream:
             self.close()
         except Exception:
             pass
+
+
+# ---- csdr stage (include/pirip_csdr.h) ------------------------------------------------------------
+
+class DecimPlan:
+    """`csdr convert_u8_f | csdr fir_decimate_cc D [transition_bw] | csdr convert_f_s16` as one
+    fused GPU kernel over a batch of u8 IQ streams ([R README.md:109])."""
+
+    def __init__(self, decimation, transition_bw=0.05, device=0):
+        L = lib()
+        L.firdes_filter_len.restype = C.c_int
+        L.firdes_filter_len.argtypes = [C.c_float]
+        L.firdes_lowpass_f.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
+        L.pirip_decim_plan_create.restype = C.c_void_p
+        L.pirip_decim_plan_create.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int]
+        L.pirip_decim_plan_destroy.argtypes = [C.c_void_p]
+        L.pirip_decim_out_count.restype = C.c_size_t
+        L.pirip_decim_out_count.argtypes = [C.c_void_p, C.c_size_t]
+        L.pirip_decim_u8_batch.restype = C.c_int
+        L.pirip_decim_u8_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.pirip_decim_u8_batch_dev.restype = C.c_int
+        L.pirip_decim_u8_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p,
+                                               C.c_void_p, C.c_size_t, C.c_void_p]
+        self.decimation = decimation
+        n = L.firdes_filter_len(transition_bw)
+        self.taps = np.zeros(n, np.float32)
+        L.firdes_lowpass_f(_ptr(self.taps), n, np.float32(0.5 / np.float32(decimation)), 0)
+        self._h = L.pirip_decim_plan_create(decimation, _ptr(self.taps), n, device)
+        if not self._h:
+            raise _err("pirip_decim_plan_create")
+
+    def out_count(self, n):
+        return int(lib().pirip_decim_out_count(self._h, n))
+
+    def run(self, iq_u8, want_f32=True, want_s16=True):
+        iq_u8 = np.ascontiguousarray(iq_u8, np.uint8)
+        assert iq_u8.ndim == 2
+        ns, n = iq_u8.shape[0], iq_u8.shape[1] // 2
+        nout = self.out_count(n)
+        f = np.zeros((ns, nout), np.complex64) if want_f32 else None
+        s = np.zeros((ns, 2 * nout), np.int16) if want_s16 else None
+        rc = lib().pirip_decim_u8_batch(self._h, _ptr(iq_u8), ns, n, _ptr(f), _ptr(s))
+        if rc != 0:
+            raise _err("pirip_decim_u8_batch", rc)
+        return f, s
+
+    def run_dev(self, d_in, n_streams, n, in_stride_bytes, d_out_f32, d_out_s16, out_stride, stream=None):
+        rc = lib().pirip_decim_u8_batch_dev(self._h, d_in, n_streams, n, in_stride_bytes, d_out_f32, d_out_s16, out_stride,
+                                            stream)
+        if rc != 0:
+            raise _err("pirip_decim_u8_batch_dev", rc)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().pirip_decim_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -33,6 +33,8 @@ int current_device() {
     return dev;
 }
 
+const char *last_error() { return g_last_error.c_str(); }
+
 }  // namespace pirip
 
 extern "C" uint64_t pirip_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -15,6 +15,7 @@ int fail(int code, const std::string &msg);
 bool cuda_ok(cudaError_t e, const char *what);
 void count_launch(unsigned n = 1);
 int current_device();
+const char *last_error();
 
 }  // namespace pirip
 
