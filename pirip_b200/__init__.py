@@ -14,6 +14,10 @@ from ._lib import (  # noqa: F401
     FskPlan,
     FskStream,
     DecimPlan,
+    FskLdpcModem,
+    LdpcPlan,
+    ldpc_code,
+    ldpc_encode,
     PiripError,
     kernel_launches,
     lib,

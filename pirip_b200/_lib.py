@@ -283,3 +283,164 @@ class DecimPlan:
             self.close()
         except Exception:
             pass
+
+
+# ---- FEC / framing stage (include/pirip_ldpc.h) ---------------------------------------------------
+
+class LDPC(C.Structure):
+    """struct LDPC (codec2 mpdecode_core.h layout)"""
+    _fields_ = [("name", C.c_char * 32), ("max_iter", C.c_int), ("dec_type", C.c_int), ("q_scale_factor", C.c_float),
+                ("r_scale_factor", C.c_float), ("CodeLength", C.c_int), ("NumberParityBits", C.c_int),
+                ("NumberRowsHcols", C.c_int), ("max_row_weight", C.c_int), ("max_col_weight", C.c_int),
+                ("H_rows", C.POINTER(C.c_uint16)), ("H_cols", C.POINTER(C.c_uint16)),
+                ("ldpc_data_bits_per_frame", C.c_int), ("ldpc_coded_bits_per_frame", C.c_int),
+                ("protection_mode", C.c_int), ("data_bits_per_frame", C.c_int), ("coded_bits_per_frame", C.c_int)]
+
+
+class FreedvAdvanced(C.Structure):
+    _fields_ = [("interleave_frames", C.c_int), ("M", C.c_int), ("Rs", C.c_int), ("Fs", C.c_int),
+                ("first_tone", C.c_int), ("tone_spacing", C.c_int), ("codename", C.c_char_p)]
+
+
+FREEDV_MODE_FSK_LDPC = 9
+RX_TRIAL_SYNC, RX_SYNC, RX_BITS, RX_BIT_ERRORS = 1, 2, 4, 8
+
+
+def _ldpc_protos():
+    L = lib()
+    if getattr(L, "_ldpc_ready", False):
+        return L
+    L.ldpc_codes_find.restype = C.c_int
+    L.ldpc_codes_find.argtypes = [C.c_char_p]
+    L.ldpc_codes_setup.argtypes = [C.POINTER(LDPC), C.c_char_p]
+    L.ldpc_codes_num.restype = C.c_int
+    L.ldpc_encode_frame.argtypes = [C.POINTER(LDPC), C.c_void_p, C.c_void_p]
+    L.run_ldpc_decoder.restype = C.c_int
+    L.run_ldpc_decoder.argtypes = [C.POINTER(LDPC), C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]
+    L.fsk_rx_filt_to_llrs.argtypes = [C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int]
+    L.pirip_ldpc_plan_create.restype = C.c_void_p
+    L.pirip_ldpc_plan_create.argtypes = [C.POINTER(LDPC), C.c_int]
+    L.pirip_ldpc_plan_destroy.argtypes = [C.c_void_p]
+    L.pirip_ldpc_decode_batch.restype = C.c_int
+    L.pirip_ldpc_decode_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.pirip_ldpc_decode_batch_dev.restype = C.c_int
+    L.pirip_ldpc_decode_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p]
+    L.freedv_open_advanced.restype = C.c_void_p
+    L.freedv_open_advanced.argtypes = [C.c_int, C.POINTER(FreedvAdvanced)]
+    L.freedv_close.argtypes = [C.c_void_p]
+    L.freedv_get_bits_per_modem_frame.restype = C.c_int
+    L.freedv_get_bits_per_modem_frame.argtypes = [C.c_void_p]
+    L.freedv_tx_fsk_ldpc_bits_per_frame.restype = C.c_int
+    L.freedv_tx_fsk_ldpc_bits_per_frame.argtypes = [C.c_void_p]
+    L.freedv_tx_fsk_ldpc_framer.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.freedv_gen_crc16.restype = C.c_ushort
+    L.freedv_gen_crc16.argtypes = [C.c_void_p, C.c_int]
+    L.freedv_pack.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.freedv_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    L.freedv_check_crc16_unpacked.restype = C.c_int
+    L.freedv_check_crc16_unpacked.argtypes = [C.c_void_p, C.c_int]
+    L.ofdm_generate_payload_data_bits.argtypes = [C.c_void_p, C.c_int]
+    L.freedv_fsk_ldpc_rx_llrs.restype = C.c_int
+    L.freedv_fsk_ldpc_rx_llrs.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.freedv_fsk_ldpc_rx_info.argtypes = [C.c_void_p, C.c_void_p]
+    L._ldpc_ready = True
+    return L
+
+
+def ldpc_code(name):
+    """ldpc_codes_setup(): returns (struct LDPC, dict view of the tables for the tests)."""
+    L = _ldpc_protos()
+    if L.ldpc_codes_find(name.encode()) < 0:
+        raise PiripError("unknown LDPC code " + name)
+    l = LDPC()
+    L.ldpc_codes_setup(C.byref(l), name.encode())
+    nr = l.NumberParityBits * l.max_row_weight
+    nc = l.NumberRowsHcols * l.max_col_weight
+    view = dict(CodeLength=l.CodeLength, NumberParityBits=l.NumberParityBits, NumberRowsHcols=l.NumberRowsHcols,
+                max_row_weight=l.max_row_weight, max_col_weight=l.max_col_weight,
+                H_rows=np.ctypeslib.as_array(l.H_rows, (nr,)).copy(), H_cols=np.ctypeslib.as_array(l.H_cols, (nc,)).copy())
+    return l, view
+
+
+def ldpc_encode(l, ibits):
+    L = _ldpc_protos()
+    ibits = np.ascontiguousarray(ibits, np.uint8)
+    p = np.zeros(l.NumberParityBits, np.uint8)
+    L.ldpc_encode_frame(C.byref(l), _ptr(ibits), _ptr(p))
+    return p
+
+
+class LdpcPlan:
+    def __init__(self, l, device=0):
+        self.L = _ldpc_protos()
+        self.N = l.CodeLength
+        self._h = self.L.pirip_ldpc_plan_create(C.byref(l), device)
+        if not self._h:
+            raise _err("pirip_ldpc_plan_create")
+
+    def decode(self, llr):
+        llr = np.ascontiguousarray(llr, np.float32).reshape(-1, self.N)
+        n = llr.shape[0]
+        bits = np.zeros((n, self.N), np.uint8)
+        it = np.zeros(n, np.int32)
+        pcc = np.zeros(n, np.int32)
+        rc = self.L.pirip_ldpc_decode_batch(self._h, _ptr(llr), n, _ptr(bits), _ptr(it), _ptr(pcc))
+        if rc != 0:
+            raise _err("pirip_ldpc_decode_batch", rc)
+        return bits, it, pcc
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.pirip_ldpc_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class FskLdpcModem:
+    """freedv_open_advanced(FREEDV_MODE_FSK_LDPC) handle: framer ([R tx/rpitx_fsk.cpp:395]) and the
+    receive-side deframer fed with LLRs."""
+
+    def __init__(self, codename, M=2, Rs=10000, Fs=80000):
+        self.L = _ldpc_protos()
+        self._name = codename.encode()
+        adv = FreedvAdvanced(0, M, Rs, Fs, 0, 0, self._name)
+        self._h = self.L.freedv_open_advanced(FREEDV_MODE_FSK_LDPC, C.byref(adv))
+        if not self._h:
+            raise PiripError("freedv_open_advanced failed for code " + codename)
+        self.data_bits = self.L.freedv_get_bits_per_modem_frame(self._h)
+        self.bits_per_frame = self.L.freedv_tx_fsk_ldpc_bits_per_frame(self._h)
+
+    def frame(self, payload_bits):
+        payload_bits = np.ascontiguousarray(payload_bits, np.uint8)
+        assert payload_bits.size == self.data_bits
+        out = np.zeros(self.bits_per_frame, np.uint8)
+        self.L.freedv_tx_fsk_ldpc_framer(self._h, _ptr(out), _ptr(payload_bits))
+        return out
+
+    def rx(self, llr):
+        llr = np.ascontiguousarray(llr, np.float32)
+        out = np.zeros(self.data_bits, np.uint8)
+        st = self.L.freedv_fsk_ldpc_rx_llrs(self._h, _ptr(llr), llr.size, _ptr(out))
+        return st, out
+
+    def info(self):
+        a = np.zeros(6, np.int32)
+        self.L.freedv_fsk_ldpc_rx_info(self._h, _ptr(a))
+        return dict(state=int(a[0]), uw_loc=int(a[1]), uw_err=int(a[2]), iter=int(a[3]), pcc=int(a[4]), nbits=int(a[5]))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.freedv_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

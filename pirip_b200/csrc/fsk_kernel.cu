@@ -34,6 +34,7 @@
 
 #include "exact_math.h"
 #include "fsk_dev.h"
+#include "llr_dev.h"
 
 namespace {
 
@@ -152,31 +153,6 @@ __device__ __forceinline__ void warp_fft_mag(const float2 *x, float2 *buf, float
         out[i] = sqrtf((X.x * X.x) + (X.y * X.y));
     }
     __syncwarp();
-}
-
-/* log I0(x), Numerical Recipes polynomial in the log domain ([U mpdecode_core.c::bessi0]) */
-__device__ float logbessi0(float x) {
-    const float ax = fabsf(x);
-    double y, ans;
-    if ((double)ax < 3.75) {
-        y = (double)x / 3.75;
-        y *= y;
-        ans = 1.0 + y * (3.5156229 + y * (3.0899424 + y * (1.2067492 + y * (0.2659732 + y * (0.360768e-1 + y * 0.45813e-2)))));
-        return (float)em_log(ans);
-    }
-    y = 3.75 / (double)ax;
-    ans = 0.39894228 + y * (0.1328592e-1 + y * (0.225319e-2 + y * (-0.157565e-2 + y * (0.916281e-2 + y * (-0.2057706e-1 + y * (0.2635537e-1 + y * (-0.1647633e-1 + y * 0.392377e-2)))))));
-    return (float)(((double)ax - 0.5 * em_log((double)ax)) + em_log(ans));
-}
-
-/* linear-log-MAP max* ([U mpdecode_core.c::max_star0]) */
-__device__ float max_star0(float delta1, float delta2) {
-    const double AJIAN = -0.24904163195436, TJIAN = 2.50681740420944;
-    const float diff = delta2 - delta1;
-    if ((double)diff > TJIAN) return delta2;
-    if ((double)diff < -TJIAN) return delta1;
-    if (diff > 0) return (float)((double)delta2 + AJIAN * ((double)diff - TJIAN));
-    return (float)((double)delta1 - AJIAN * ((double)diff + TJIAN));
 }
 
 /* u8 -> float exactly as ((float)b - 127.0)/128.0 */
@@ -981,23 +957,10 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
                 FskCapShared *cs = c.cs;
                 if (!cs->active || cs->nan_flag) continue;
                 const float *rfl = c.mag + Ndft + 3 * Nsym;
-                const float v_est = cs->v_est, scale = 2.0f * cs->SNRest;
-                float num[2] = { -1000000.0f, -1000000.0f }, den[2] = { -1000000.0f, -1000000.0f };
-                for (int m = 0; m < M; ++m) {
-                    const float yr = rfl[m * Nsym + i];
-                    const float env = (float)sqrt((double)(yr * yr / (v_est * v_est)));
-                    const float metric = logbessi0(scale * env);
-                    int mask = 1 << (bps - 1);
-                    for (int k = 0; k < bps; ++k) {
-                        if (mask & m)
-                            num[k] = max_star0(num[k], metric);
-                        else
-                            den[k] = max_star0(den[k], metric);
-                        mask >>= 1;
-                    }
-                }
+                float l2[2];
+                symbol_llrs(rfl + i, Nsym, M, cs->v_est, cs->SNRest, l2);
                 float *lo = args.llr + ((cap0 + g) * args.max_frames + (size_t)cs->frame) * (size_t)Nbits;
-                for (int k = 0; k < bps; ++k) lo[bps * i + k] = -(num[k] - den[k]);
+                for (int k = 0; k < bps; ++k) lo[bps * i + k] = l2[k];
             }
             __syncthreads();
         }

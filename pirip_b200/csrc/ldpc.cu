@@ -1,0 +1,651 @@
+/*
+ * ldpc.cu — LDPC sum-product decoder and soft-decision map on sm_100a, plus the host side of
+ * FSK_LDPC framing (code tables, RA encoder, CRC16, pack/unpack, UW framer/deframer).
+ * Contract: include/pirip_ldpc.h.
+ *
+ * Decoder ([U codec2 mpdecode_core.c::run_ldpc_decoder / init_c_v_nodes / SumProduct / phi0],
+ * on pirip's path through `rtl_fsk --code H_256_512_4` [R README.md:184]):
+ * flooding schedule, check update r = +-phi0(sum phi - phi_self) with the sign parity, variable
+ * update Q = llr + sum r, extrinsic q = Q - r, stop as soon as every check is satisfied.
+ *
+ * Mapping: one CTA per codeword; messages live in shared memory indexed by edge (edges numbered
+ * check by check).  A thread owns whole check nodes in the check phase and whole variable nodes
+ * in the variable phase, and walks their edges in table order, so every float sum is formed in
+ * the same order as the scalar algorithm and the decoded bits, iteration count and parity-check
+ * count are bit-identical to it.  phi0 uses exact_math.h (double exp/log, IEEE order).
+ */
+#include <assert.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/pirip_ldpc.h"
+#include "exact_math.h"
+#include "host_util.h"
+#include "llr_dev.h"
+
+namespace {
+
+/* ------------------------------------------------------------------ device side */
+
+struct LdpcGraph {
+    int N, NPB, E, max_iter;
+    const uint16_t *c_off;  /* [NPB+1] first edge of every check */
+    const uint16_t *v_off;  /* [N+1] first entry of every variable in v_edge */
+    const uint16_t *v_edge; /* [E] edge ids of every variable, in the variable's table order */
+};
+
+/* [U mpdecode_core.c::phi0] CML closed form with the coarse steps above 5 */
+__device__ __forceinline__ float phi0(float x) {
+    if (x > 10.0f) return 0.0f;
+    if ((double)x < 9.08e-5) return 10.0f;
+    if (x > 9.0f) return (float)1.6881e-4;
+    if (x > 8.0f) return (float)4.5887e-4;
+    if (x > 7.0f) return (float)1.2473e-3;
+    if (x > 6.0f) return (float)3.3906e-3;
+    if (x > 5.0f) return (float)9.2168e-3;
+    const float z = (float)em_exp((double)x);
+    return (float)em_log((double)((z + 1.0f) / (z - 1.0f)));
+}
+
+constexpr int kLdpcThreads = 128;
+
+__global__ void __launch_bounds__(kLdpcThreads) ldpc_decode_kernel(const __grid_constant__ LdpcGraph g, const float *llr_in,
+                                                                   unsigned char *bits_out, int *iter_out, int *pcc_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *llr = reinterpret_cast<float *>(smem_raw);
+    float *q_msg = llr + g.N;
+    float *r_msg = q_msg + g.E;
+    uint16_t *c_off = reinterpret_cast<uint16_t *>(r_msg + g.E);
+    uint16_t *v_off = c_off + (g.NPB + 1);
+    uint16_t *v_edge = v_off + (g.N + 1);
+    unsigned char *q_sign = reinterpret_cast<unsigned char *>(v_edge + g.E);
+    unsigned char *dec = q_sign + g.E;
+    __shared__ int ssum;
+    const int tid = threadIdx.x;
+    const size_t cw = blockIdx.x;
+
+    for (int i = tid; i <= g.NPB; i += kLdpcThreads) c_off[i] = g.c_off[i];
+    for (int i = tid; i <= g.N; i += kLdpcThreads) v_off[i] = g.v_off[i];
+    for (int i = tid; i < g.E; i += kLdpcThreads) v_edge[i] = g.v_edge[i];
+    for (int i = tid; i < g.N; i += kLdpcThreads) llr[i] = llr_in[cw * g.N + i];
+    __syncthreads();
+    /* initial variable-to-check messages: the channel LLR on every edge */
+    for (int v = tid; v < g.N; v += kLdpcThreads) {
+        const float x = llr[v];
+        const float ph = phi0(fabsf(x));
+        const unsigned char sg = x < 0.0f ? 1 : 0;
+        for (int j = v_off[v]; j < v_off[v + 1]; ++j) {
+            q_msg[v_edge[j]] = ph;
+            q_sign[v_edge[j]] = sg;
+        }
+        dec[v] = 0;
+    }
+    int result = g.max_iter, pcc = 0;
+    for (int iter = 0; iter < g.max_iter; ++iter) {
+        if (tid == 0) ssum = 0;
+        __syncthreads();
+        /* check-node update */
+        int local = 0;
+        for (int c = tid; c < g.NPB; c += kLdpcThreads) {
+            const int e0 = c_off[c], e1 = c_off[c + 1];
+            int sign = q_sign[e0];
+            float phi_sum = q_msg[e0];
+            for (int e = e0 + 1; e < e1; ++e) {
+                phi_sum += q_msg[e];
+                sign ^= q_sign[e];
+            }
+            if (sign == 0) local++;
+            for (int e = e0; e < e1; ++e) {
+                const float r = phi0(phi_sum - q_msg[e]);
+                r_msg[e] = (sign ^ q_sign[e]) ? -r : r;
+            }
+        }
+        if (local) atomicAdd(&ssum, local);
+        __syncthreads();
+        /* variable-node update */
+        for (int v = tid; v < g.N; v += kLdpcThreads) {
+            float Qi = llr[v];
+            for (int j = v_off[v]; j < v_off[v + 1]; ++j) Qi += r_msg[v_edge[j]];
+            dec[v] = Qi < 0.0f ? 1 : 0;
+            for (int j = v_off[v]; j < v_off[v + 1]; ++j) {
+                const int e = v_edge[j];
+                const float t = Qi - r_msg[e];
+                q_msg[e] = phi0(fabsf(t));
+                q_sign[e] = t > 0.0f ? 0 : 1;
+            }
+        }
+        pcc = ssum;
+        __syncthreads();
+        if (pcc == g.NPB) {
+            result = iter + 1;
+            break;
+        }
+    }
+    for (int v = tid; v < g.N; v += kLdpcThreads) bits_out[cw * g.N + v] = dec[v];
+    if (tid == 0) {
+        if (iter_out) iter_out[cw] = result;
+        if (pcc_out) pcc_out[cw] = pcc;
+    }
+}
+
+__global__ void llr_kernel(const float *rx_filt, float *llr, float v_est, float SNRest, int M, int nsyms) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nsyms) return;
+    float l2[2];
+    symbol_llrs(rx_filt + i, nsyms, M, v_est, SNRest, l2);
+    const int bps = M == 2 ? 1 : 2;
+    for (int k = 0; k < bps; ++k) llr[bps * i + k] = l2[k];
+}
+
+/* ------------------------------------------------------------------ code tables */
+
+struct builtin_code {
+    const char *name;
+    int max_iter, CodeLength, NumberParityBits, NumberRowsHcols, max_row_weight, max_col_weight;
+    const uint16_t *H_rows, *H_cols;
+};
+#include "ldpc_tables.inc"
+
+struct CodeEntry {
+    std::string name;
+    int max_iter, CodeLength, NumberParityBits, NumberRowsHcols, max_row_weight, max_col_weight;
+    std::vector<uint16_t> H_rows, H_cols;
+};
+
+std::mutex g_codes_mu;
+std::vector<CodeEntry> &codes() {
+    static std::vector<CodeEntry> v = [] {
+        std::vector<CodeEntry> w;
+        for (const builtin_code &b : builtin_codes) {
+            CodeEntry e;
+            e.name = b.name;
+            e.max_iter = b.max_iter;
+            e.CodeLength = b.CodeLength;
+            e.NumberParityBits = b.NumberParityBits;
+            e.NumberRowsHcols = b.NumberRowsHcols;
+            e.max_row_weight = b.max_row_weight;
+            e.max_col_weight = b.max_col_weight;
+            e.H_rows.assign(b.H_rows, b.H_rows + (size_t)b.NumberParityBits * b.max_row_weight);
+            e.H_cols.assign(b.H_cols, b.H_cols + (size_t)b.NumberRowsHcols * b.max_col_weight);
+            w.push_back(std::move(e));
+        }
+        return w;
+    }();
+    return v;
+}
+
+/* Tanner graph in edge-list form; node-local edge order = table order (see file header) */
+bool build_graph(const struct LDPC *l, std::vector<uint16_t> &c_off, std::vector<uint16_t> &v_off, std::vector<uint16_t> &v_edge,
+                 std::string &why) {
+    const int N = l->CodeLength, NPB = l->NumberParityBits, K = N - NPB;
+    const bool H1 = l->NumberRowsHcols != N;
+    if (N <= 0 || NPB <= 0 || K <= 0 || N > 60000) {
+        why = "bad code dimensions";
+        return false;
+    }
+    std::vector<std::vector<int>> cvars((size_t)NPB);
+    for (int p = 0; p < NPB; ++p) {
+        for (int j = 0; j < l->max_row_weight; ++j) {
+            const int ind = l->H_rows[p + j * NPB];
+            if (ind > 0) cvars[(size_t)p].push_back(ind - 1);
+        }
+        if (H1) {
+            if (p > 0) cvars[(size_t)p].push_back(K + p - 1);
+            cvars[(size_t)p].push_back(K + p);
+        }
+    }
+    c_off.assign((size_t)NPB + 1, 0);
+    size_t E = 0;
+    for (int p = 0; p < NPB; ++p) {
+        c_off[(size_t)p] = (uint16_t)E;
+        E += cvars[(size_t)p].size();
+    }
+    if (E > 65535) {
+        why = "too many edges";
+        return false;
+    }
+    c_off[(size_t)NPB] = (uint16_t)E;
+    v_off.assign((size_t)N + 1, 0);
+    v_edge.clear();
+    for (int v = 0; v < N; ++v) {
+        v_off[(size_t)v] = (uint16_t)v_edge.size();
+        std::vector<int> checks;
+        if (H1 && v >= K) {
+            checks.push_back(v - K);
+            if (v != N - 1) checks.push_back(v - K + 1);
+        } else {
+            for (int j = 0; j < l->max_col_weight; ++j) {
+                const int ind = l->H_cols[v + j * l->NumberRowsHcols];
+                if (ind > 0) checks.push_back(ind - 1);
+            }
+        }
+        for (int c : checks) {
+            if (c < 0 || c >= NPB) {
+                why = "H_cols refers to a check that does not exist";
+                return false;
+            }
+            int pos = -1;
+            for (size_t i = 0; i < cvars[(size_t)c].size(); ++i)
+                if (cvars[(size_t)c][i] == v) {
+                    pos = (int)i;
+                    break;
+                }
+            if (pos < 0) {
+                why = "H_rows and H_cols disagree";
+                return false;
+            }
+            v_edge.push_back((uint16_t)(c_off[(size_t)c] + pos));
+        }
+    }
+    v_off[(size_t)N] = (uint16_t)v_edge.size();
+    if (v_edge.size() != E) {
+        why = "H_rows and H_cols disagree (edge counts)";
+        return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+/* ------------------------------------------------------------------ batched decoder plan */
+
+struct pirip_ldpc_plan {
+    LdpcGraph g;
+    int device, smem;
+    uint16_t *d_c_off = nullptr, *d_v_off = nullptr, *d_v_edge = nullptr;
+    float *d_llr = nullptr;
+    unsigned char *d_bits = nullptr;
+    int *d_iter = nullptr, *d_pcc = nullptr;
+    size_t cap = 0;
+};
+
+extern "C" pirip_ldpc_plan *pirip_ldpc_plan_create(const struct LDPC *l, int device) {
+    if (!l || !l->H_rows || !l->H_cols) {
+        pirip::set_error("LDPC tables missing");
+        return nullptr;
+    }
+    std::vector<uint16_t> c_off, v_off, v_edge;
+    std::string why;
+    if (!build_graph(l, c_off, v_off, v_edge, why)) {
+        pirip::set_error("LDPC code rejected: " + why);
+        return nullptr;
+    }
+    pirip_ldpc_plan *p = new pirip_ldpc_plan();
+    p->device = device;
+    p->g.N = l->CodeLength;
+    p->g.NPB = l->NumberParityBits;
+    p->g.E = (int)v_edge.size();
+    p->g.max_iter = l->max_iter > 0 ? l->max_iter : 15;
+    p->smem = (p->g.N + 2 * p->g.E) * 4 + ((p->g.NPB + 1) + (p->g.N + 1) + p->g.E) * 2 + p->g.E + p->g.N + 16;
+    p->smem = (p->smem + 15) / 16 * 16;
+    if (p->smem > 227 * 1024) {
+        pirip::set_error("code too large for one CTA's shared memory");
+        delete p;
+        return nullptr;
+    }
+    if (!pirip::cuda_ok(cudaSetDevice(device), "cudaSetDevice") ||
+        !pirip::cuda_ok(cudaMalloc(&p->d_c_off, 2 * c_off.size()), "cudaMalloc") ||
+        !pirip::cuda_ok(cudaMalloc(&p->d_v_off, 2 * v_off.size()), "cudaMalloc") ||
+        !pirip::cuda_ok(cudaMalloc(&p->d_v_edge, 2 * v_edge.size()), "cudaMalloc") ||
+        !pirip::cuda_ok(cudaMemcpy(p->d_c_off, c_off.data(), 2 * c_off.size(), cudaMemcpyHostToDevice), "copy") ||
+        !pirip::cuda_ok(cudaMemcpy(p->d_v_off, v_off.data(), 2 * v_off.size(), cudaMemcpyHostToDevice), "copy") ||
+        !pirip::cuda_ok(cudaMemcpy(p->d_v_edge, v_edge.data(), 2 * v_edge.size(), cudaMemcpyHostToDevice), "copy") ||
+        !pirip::cuda_ok(cudaFuncSetAttribute(ldpc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem), "smem attr")) {
+        pirip_ldpc_plan_destroy(p);
+        return nullptr;
+    }
+    p->g.c_off = p->d_c_off;
+    p->g.v_off = p->d_v_off;
+    p->g.v_edge = p->d_v_edge;
+    return p;
+}
+
+extern "C" void pirip_ldpc_plan_destroy(pirip_ldpc_plan *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    cudaFree(p->d_c_off);
+    cudaFree(p->d_v_off);
+    cudaFree(p->d_v_edge);
+    cudaFree(p->d_llr);
+    cudaFree(p->d_bits);
+    cudaFree(p->d_iter);
+    cudaFree(p->d_pcc);
+    delete p;
+}
+
+extern "C" int pirip_ldpc_decode_batch_dev(pirip_ldpc_plan *p, const float *d_llr, size_t n, uint8_t *d_bits, int32_t *d_iter,
+                                           int32_t *d_pcc, void *stream) {
+    if (!p) return pirip::fail(-1, "plan is NULL");
+    if (n == 0) return 0;
+    if (!d_llr || !d_bits) return pirip::fail(-2, "NULL buffer");
+    if (!pirip::cuda_ok(cudaSetDevice(p->device), "cudaSetDevice")) return -10;
+    ldpc_decode_kernel<<<(unsigned)n, kLdpcThreads, p->smem, (cudaStream_t)stream>>>(p->g, d_llr, d_bits, d_iter, d_pcc);
+    pirip::count_launch();
+    return pirip::cuda_ok(cudaGetLastError(), "ldpc_decode_kernel launch") ? 0 : -11;
+}
+
+extern "C" int pirip_ldpc_decode_batch(pirip_ldpc_plan *p, const float *llr, size_t n, uint8_t *bits, int32_t *iter, int32_t *pcc) {
+    if (!p) return pirip::fail(-1, "plan is NULL");
+    if (n == 0) return 0;
+    if (!pirip::cuda_ok(cudaSetDevice(p->device), "cudaSetDevice")) return -10;
+    if (n > p->cap) {
+        cudaFree(p->d_llr);
+        cudaFree(p->d_bits);
+        cudaFree(p->d_iter);
+        cudaFree(p->d_pcc);
+        p->d_llr = nullptr;
+        p->d_bits = nullptr;
+        p->d_iter = p->d_pcc = nullptr;
+        p->cap = 0;
+        if (!pirip::cuda_ok(cudaMalloc(&p->d_llr, sizeof(float) * n * p->g.N), "cudaMalloc") ||
+            !pirip::cuda_ok(cudaMalloc(&p->d_bits, n * p->g.N), "cudaMalloc") ||
+            !pirip::cuda_ok(cudaMalloc(&p->d_iter, sizeof(int) * n), "cudaMalloc") ||
+            !pirip::cuda_ok(cudaMalloc(&p->d_pcc, sizeof(int) * n), "cudaMalloc"))
+            return -12;
+        p->cap = n;
+    }
+    if (!pirip::cuda_ok(cudaMemcpy(p->d_llr, llr, sizeof(float) * n * p->g.N, cudaMemcpyHostToDevice), "H2D")) return -12;
+    const int rc = pirip_ldpc_decode_batch_dev(p, p->d_llr, n, p->d_bits, p->d_iter, p->d_pcc, nullptr);
+    if (rc) return rc;
+    if (!pirip::cuda_ok(cudaMemcpy(bits, p->d_bits, n * p->g.N, cudaMemcpyDeviceToHost), "ldpc_decode_kernel")) return -13;
+    if (iter && !pirip::cuda_ok(cudaMemcpy(iter, p->d_iter, sizeof(int) * n, cudaMemcpyDeviceToHost), "D2H")) return -13;
+    if (pcc && !pirip::cuda_ok(cudaMemcpy(pcc, p->d_pcc, sizeof(int) * n, cudaMemcpyDeviceToHost), "D2H")) return -13;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ codec2-named entry points */
+
+extern "C" int ldpc_codes_num(void) {
+    std::lock_guard<std::mutex> lk(g_codes_mu);
+    return (int)codes().size();
+}
+
+extern "C" void ldpc_codes_list(void) {
+    std::lock_guard<std::mutex> lk(g_codes_mu);
+    fprintf(stderr, "\n");
+    for (const CodeEntry &e : codes()) {
+        const int K = e.CodeLength - e.NumberParityBits;
+        fprintf(stderr, "%-20s rate %3.2f (%d,%d) \n", e.name.c_str(), (float)K / e.CodeLength, e.CodeLength, K);
+    }
+    fprintf(stderr, "\n");
+}
+
+extern "C" int ldpc_codes_find(char name[]) {
+    std::lock_guard<std::mutex> lk(g_codes_mu);
+    for (size_t i = 0; i < codes().size(); ++i)
+        if (codes()[i].name == name) return (int)i;
+    return -1;
+}
+
+extern "C" void ldpc_codes_setup(struct LDPC *ldpc, char name[]) {
+    const int idx = ldpc_codes_find(name);
+    assert(idx != -1); /* as upstream: an unknown code name is a programming error */
+    std::lock_guard<std::mutex> lk(g_codes_mu);
+    CodeEntry &e = codes()[(size_t)idx];
+    memset(ldpc, 0, sizeof *ldpc);
+    strncpy(ldpc->name, e.name.c_str(), sizeof(ldpc->name) - 1);
+    ldpc->max_iter = e.max_iter;
+    ldpc->dec_type = 0;
+    ldpc->q_scale_factor = 1;
+    ldpc->r_scale_factor = 1;
+    ldpc->CodeLength = e.CodeLength;
+    ldpc->NumberParityBits = e.NumberParityBits;
+    ldpc->NumberRowsHcols = e.NumberRowsHcols;
+    ldpc->max_row_weight = e.max_row_weight;
+    ldpc->max_col_weight = e.max_col_weight;
+    ldpc->H_rows = e.H_rows.data();
+    ldpc->H_cols = e.H_cols.data();
+    ldpc->ldpc_data_bits_per_frame = e.CodeLength - e.NumberParityBits;
+    ldpc->ldpc_coded_bits_per_frame = e.CodeLength;
+    ldpc->protection_mode = 0;
+    ldpc->data_bits_per_frame = ldpc->ldpc_data_bits_per_frame;
+    ldpc->coded_bits_per_frame = ldpc->ldpc_coded_bits_per_frame;
+}
+
+extern "C" int ldpc_codes_add(const char *name, int max_iter, int CodeLength, int NumberParityBits, int NumberRowsHcols,
+                              int max_row_weight, int max_col_weight, const uint16_t *H_rows, const uint16_t *H_cols) {
+    if (!name || !H_rows || !H_cols) return -1;
+    CodeEntry e;
+    e.name = name;
+    e.max_iter = max_iter;
+    e.CodeLength = CodeLength;
+    e.NumberParityBits = NumberParityBits;
+    e.NumberRowsHcols = NumberRowsHcols;
+    e.max_row_weight = max_row_weight;
+    e.max_col_weight = max_col_weight;
+    e.H_rows.assign(H_rows, H_rows + (size_t)NumberParityBits * max_row_weight);
+    e.H_cols.assign(H_cols, H_cols + (size_t)NumberRowsHcols * max_col_weight);
+    std::lock_guard<std::mutex> lk(g_codes_mu);
+    codes().reserve(64); /* keep table pointers handed out by ldpc_codes_setup stable */
+    codes().push_back(std::move(e));
+    return (int)codes().size() - 1;
+}
+
+extern "C" void ldpc_encode_frame(struct LDPC *ldpc, unsigned char ibits[], unsigned char pbits[]) {
+    unsigned prev = 0;
+    const int NPB = ldpc->NumberParityBits;
+    for (int p = 0; p < NPB; ++p) {
+        unsigned par = 0;
+        for (int i = 0; i < ldpc->max_row_weight; ++i) {
+            const int ind = ldpc->H_rows[p + i * NPB];
+            if (ind) par += ibits[ind - 1];
+        }
+        prev = (par + prev) & 1u; /* accumulate along the staircase */
+        pbits[p] = (unsigned char)prev;
+    }
+}
+
+extern "C" int run_ldpc_decoder(struct LDPC *ldpc, uint8_t out_char[], float input[], int *parityCheckCount) {
+    /* one plan per call site would be wasteful: cache the plan for the last table seen */
+    static thread_local pirip_ldpc_plan *cached = nullptr;
+    static thread_local const uint16_t *cached_rows = nullptr;
+    static thread_local int cached_iter = 0;
+    if (!cached || cached_rows != ldpc->H_rows || cached_iter != ldpc->max_iter) {
+        pirip_ldpc_plan_destroy(cached);
+        cached = pirip_ldpc_plan_create(ldpc, pirip::current_device());
+        cached_rows = ldpc->H_rows;
+        cached_iter = ldpc->max_iter;
+        if (!cached) {
+            fprintf(stderr, "libpirip_b200: run_ldpc_decoder: %s\n", pirip::last_error());
+            abort();
+        }
+    }
+    int32_t iter = 0, pcc = 0;
+    if (pirip_ldpc_decode_batch(cached, input, 1, out_char, &iter, &pcc) != 0) {
+        fprintf(stderr, "libpirip_b200: run_ldpc_decoder: %s\n", pirip::last_error());
+        abort();
+    }
+    if (parityCheckCount) *parityCheckCount = pcc;
+    return iter;
+}
+
+extern "C" void fsk_rx_filt_to_llrs(float llr[], float rx_filt[], float v_est, float SNRest, int M, int nsyms) {
+    const int bps = M == 2 ? 1 : 2;
+    float *d_f = nullptr, *d_l = nullptr;
+    bool ok = pirip::cuda_ok(cudaMalloc(&d_f, sizeof(float) * (size_t)(M * nsyms)), "cudaMalloc") &&
+              pirip::cuda_ok(cudaMalloc(&d_l, sizeof(float) * (size_t)(bps * nsyms)), "cudaMalloc") &&
+              pirip::cuda_ok(cudaMemcpy(d_f, rx_filt, sizeof(float) * (size_t)(M * nsyms), cudaMemcpyHostToDevice), "H2D");
+    if (ok) {
+        llr_kernel<<<(nsyms + 127) / 128, 128>>>(d_f, d_l, v_est, SNRest, M, nsyms);
+        pirip::count_launch();
+        ok = pirip::cuda_ok(cudaGetLastError(), "llr_kernel launch") &&
+             pirip::cuda_ok(cudaMemcpy(llr, d_l, sizeof(float) * (size_t)(bps * nsyms), cudaMemcpyDeviceToHost), "llr_kernel");
+    }
+    cudaFree(d_f);
+    cudaFree(d_l);
+    if (!ok) {
+        fprintf(stderr, "libpirip_b200: fsk_rx_filt_to_llrs: %s\n", pirip::last_error());
+        abort();
+    }
+}
+
+/* ------------------------------------------------------------------ framing (host) */
+
+/* CRC-16/CCITT-FALSE, byte-wise form */
+extern "C" unsigned short freedv_gen_crc16(unsigned char *data_p, int length) {
+    unsigned short crc = 0xFFFF;
+    while (length-- > 0) {
+        unsigned char x = (unsigned char)((crc >> 8) ^ *data_p++);
+        x ^= x >> 4;
+        crc = (unsigned short)((crc << 8) ^ ((unsigned short)x << 12) ^ ((unsigned short)x << 5) ^ (unsigned short)x);
+    }
+    return crc;
+}
+
+extern "C" void freedv_pack(unsigned char *bytes, unsigned char *bits, int nbits) {
+    memset(bytes, 0, (size_t)((nbits + 7) / 8));
+    int bit = 7, byte = 0;
+    for (int i = 0; i < nbits; ++i) {
+        bytes[byte] |= (unsigned char)(bits[i] << bit);
+        if (--bit < 0) {
+            bit = 7;
+            byte++;
+        }
+    }
+}
+
+extern "C" void freedv_unpack(unsigned char *bits, unsigned char *bytes, int nbits) {
+    int bit = 7, byte = 0;
+    for (int i = 0; i < nbits; ++i) {
+        bits[i] = (bytes[byte] >> bit) & 0x1;
+        if (--bit < 0) {
+            bit = 7;
+            byte++;
+        }
+    }
+}
+
+extern "C" int freedv_check_crc16_unpacked(unsigned char *bits, int nbits) {
+    assert((nbits % 8) == 0);
+    const int nbytes = nbits / 8;
+    std::vector<unsigned char> bytes((size_t)nbytes);
+    freedv_pack(bytes.data(), bits, nbits);
+    const unsigned short tx = (unsigned short)((bytes[(size_t)nbytes - 2] << 8) | bytes[(size_t)nbytes - 1]);
+    return tx == freedv_gen_crc16(bytes.data(), nbytes - 2);
+}
+
+extern "C" void ofdm_generate_payload_data_bits(uint8_t payload_data_bits[], int n) {
+    /* [U ofdm.c::ofdm_rand] LCG from seed 1, bit = r > 16384 */
+    uint64_t seed = 1;
+    for (int i = 0; i < n; ++i) {
+        seed = (1103515245ull * seed + 12345) % 32768;
+        payload_data_bits[i] = (uint16_t)seed > 16384;
+    }
+}
+
+static const uint8_t fsk_ldpc_uw[32] = { 0, 1, 0, 1, 0, 0, 0, 1, 1, 0, 0, 0, 0, 1, 1, 0,
+                                         1, 1, 1, 1, 1, 1, 1, 0, 0, 0, 0, 1, 0, 1, 0, 1 };
+
+struct freedv {
+    struct LDPC ldpc;
+    int M, Rs, Fs;
+    int bits_per_modem_frame; /* payload bits: K */
+    int bits_per_frame;       /* UW + codeword */
+    /* receive side */
+    std::vector<float> twoframes_llr, frame_llr;
+    std::vector<uint8_t> twoframes_hard;
+    int frame_llr_nbits = 0;
+    int state = 0, best_location = 0, baduw = 0;
+    int thresh1 = 5, thresh2 = 6, baduw_thresh = 1;
+    int last_uw_err = 0, last_iter = 0, last_pcc = 0;
+};
+
+extern "C" struct freedv *freedv_open_advanced(int mode, struct freedv_advanced *adv) {
+    if (mode != FREEDV_MODE_FSK_LDPC || !adv || !adv->codename) return NULL;
+    if (ldpc_codes_find(adv->codename) < 0) return NULL;
+    struct freedv *f = new freedv();
+    ldpc_codes_setup(&f->ldpc, adv->codename);
+    f->M = adv->M;
+    f->Rs = adv->Rs;
+    f->Fs = adv->Fs;
+    f->bits_per_modem_frame = f->ldpc.data_bits_per_frame;
+    f->bits_per_frame = 32 + f->ldpc.coded_bits_per_frame;
+    f->twoframes_llr.assign((size_t)(2 * f->bits_per_frame), 0.0f);
+    f->twoframes_hard.assign((size_t)(2 * f->bits_per_frame), 0);
+    return f;
+}
+
+extern "C" void freedv_close(struct freedv *f) { delete f; }
+extern "C" int freedv_get_bits_per_modem_frame(struct freedv *f) { return f->bits_per_modem_frame; }
+extern "C" int freedv_tx_fsk_ldpc_bits_per_frame(struct freedv *f) { return f->bits_per_frame; }
+
+extern "C" void freedv_tx_fsk_ldpc_framer(struct freedv *f, uint8_t frame[], uint8_t payload_data[]) {
+    memcpy(frame, fsk_ldpc_uw, sizeof fsk_ldpc_uw);
+    memcpy(frame + sizeof fsk_ldpc_uw, payload_data, (size_t)f->bits_per_modem_frame);
+    ldpc_encode_frame(&f->ldpc, frame + sizeof fsk_ldpc_uw, frame + sizeof fsk_ldpc_uw + f->bits_per_modem_frame);
+}
+
+extern "C" int freedv_fsk_ldpc_rx_llrs(struct freedv *f, const float llr[], int nbits, uint8_t payload_bits[]) {
+    const int bpf = f->bits_per_frame;
+    int rx_status = 0;
+    /* queue the modem frame; run the sync state machine once per whole frame of new LLRs */
+    f->frame_llr.insert(f->frame_llr.end(), llr, llr + nbits);
+    f->frame_llr_nbits += nbits;
+    if (f->frame_llr_nbits >= bpf) {
+        memmove(f->twoframes_llr.data(), f->twoframes_llr.data() + bpf, sizeof(float) * (size_t)bpf);
+        memcpy(f->twoframes_llr.data() + bpf, f->frame_llr.data(), sizeof(float) * (size_t)bpf);
+        f->frame_llr.erase(f->frame_llr.begin(), f->frame_llr.begin() + bpf);
+        f->frame_llr_nbits -= bpf;
+        for (int i = 0; i < 2 * bpf; ++i) f->twoframes_hard[(size_t)i] = f->twoframes_llr[(size_t)i] < 0;
+
+        int next_state = f->state, errors = 0;
+        if (f->state == 0) {
+            int best_errors = 32;
+            f->best_location = 0;
+            for (int i = 0; i < bpf; ++i) {
+                errors = 0;
+                for (int u = 0; u < 32; ++u) errors += f->twoframes_hard[(size_t)(i + u)] ^ fsk_ldpc_uw[u];
+                if (errors < best_errors) {
+                    best_errors = errors;
+                    f->best_location = i;
+                }
+            }
+            if (best_errors <= f->thresh1) {
+                errors = best_errors;
+                next_state = 1;
+                f->baduw = 0;
+            }
+        } else {
+            for (int u = 0; u < 32; ++u) errors += f->twoframes_hard[(size_t)(f->best_location + u)] ^ fsk_ldpc_uw[u];
+            if (errors > f->thresh2) {
+                f->baduw++;
+                if (f->baduw >= f->baduw_thresh) next_state = 0;
+            } else {
+                f->baduw = 0;
+            }
+        }
+        f->last_uw_err = errors;
+        f->last_iter = f->last_pcc = 0;
+        if (next_state == 1) {
+            std::vector<uint8_t> decoded((size_t)f->ldpc.CodeLength);
+            int pcc = 0;
+            const int iter = run_ldpc_decoder(&f->ldpc, decoded.data(), &f->twoframes_llr[(size_t)(f->best_location + 32)], &pcc);
+            f->last_iter = iter;
+            f->last_pcc = pcc;
+            if (pcc != f->ldpc.NumberParityBits) rx_status |= FREEDV_RX_BIT_ERRORS;
+            if (freedv_check_crc16_unpacked(decoded.data(), f->bits_per_modem_frame)) {
+                rx_status |= FREEDV_RX_BITS;
+                memcpy(payload_bits, decoded.data(), (size_t)f->bits_per_modem_frame);
+            } else if (f->state == 0) {
+                next_state = 0; /* CRC failed on the first frame after a UW hit: dud UW */
+            }
+        }
+        f->state = next_state;
+    }
+    if (f->state == 1) rx_status |= FREEDV_RX_SYNC;
+    return rx_status;
+}
+
+extern "C" void freedv_fsk_ldpc_rx_info(struct freedv *f, int info[6]) {
+    info[0] = f->state;
+    info[1] = f->best_location;
+    info[2] = f->last_uw_err;
+    info[3] = f->last_iter;
+    info[4] = f->last_pcc;
+    info[5] = f->frame_llr_nbits;
+}
