@@ -324,6 +324,12 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = ncap * nsamp * BYTES_PER_SAMPLE_ALGO / (kernel_ms * 1e-3) / 1e9
+    # DRAM bytes per launch from the committed ncu --set full capture of this same workload
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and ncap == 1250 and nsamp == 240000:
+        t = json.load(open(tpath))
+        traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu:
@@ -338,9 +344,10 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": config, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "kernel": "fsk_demod_kernel<256>",
+                         "traffic": traffic, "algorithmic_bytes": ncap * nsamp * BYTES_PER_SAMPLE_ALGO, "peak_source": peak_src,
+                         "kernel": "fsk_demod_kernel<2> (2 captures per CTA, 2 CTAs per SM)",
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE_ALGO,
-                         "note": "FP32-issue bound, not HBM bound: see DESIGN.md"},
+                         "note": "bound by FP32-add issue and serial-recurrence latency, not HBM: DESIGN.md section 6"},
             "cpu_baseline": cpu_baseline,
             "parity": {"captures_checked": nchk, "bits_and_frames_equal_oracle": bool(ok),
                        "ber_per_capture": [float(b) for b in bers]}}
