@@ -40,21 +40,25 @@ struct FskDevCfg {
     int chunk;           /* samples per pipeline chunk of the streaming phase */
     int fdc_tone_stride; /* float2 elements between the tones of one capture's f_dc */
     int cap_stride;      /* bytes per capture block */
-    int off_fdc, off_xin, off_mag, off_Sf, off_stage, off_scal; /* inside a capture block */
+    int off_fdc, off_xin, off_mag, off_Sf, off_stage, off_phead, off_scal; /* inside a capture block */
     int off_fft, off_tw, off_hann, off_phift, off_perm, off_ctl; /* CTA-wide, after the G capture blocks */
     int stage_bytes;
     int max_numffts;
     int mag_blocks;      /* FFT blocks per batch = capacity of the magnitude buffer */
+    int pipeline;        /* the FFT block count is the same for every nin: estimate one frame ahead */
+    int numffts_const;
     int smem_bytes;
 };
 
 /* per-capture scalars kept in shared memory for the life of the CTA */
 struct FskCapShared {
     float2 phi_c[4];
-    float2 dphi[4];
-    float f_est[4];
-    float f2_est[4];
+    float2 dphi[2][4]; /* estimate slots: frame being demodulated / frame being estimated ahead */
+    float f_est[2][4];
+    float f2_est[2][4];
     int freqi[4];
+    const unsigned char *fsrc; /* raw samples the front stage reads */
+    int fon, fnumffts;
     float norm_rx_timing, ppm, snr_est, EbNodB;
     float fract, one_minus_fract;
     int low, high;

@@ -241,6 +241,17 @@ static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, int
        different banks for the per-tone oscillator lanes; at least 2 spare elements */
     d.fdc_tone_stride = d.Nmem + 2;
     while ((d.fdc_tone_stride & 15) != 2) d.fdc_tone_stride++;
+    {
+        /* frequency estimate one frame ahead (front team inside the CTA): possible when the FFT block
+           count is the same for the three values nin can take.  Measured on B200 it does not pay
+           while two CTAs per SM already overlap each other's phases (13.5 vs 15.0 Gsamples/s), so it
+           is opt-in (PIRIP_FSK_PIPE=1) and covered by the GPU tests. */
+        const int half = d.Ndft / 2;
+        const int n0 = (d.N - d.Ts / 4) / half - 1, n1 = d.N / half - 1, n2 = nin_max / half - 1;
+        const bool fixed_nin = burst_mode || lock_nin;
+        d.numffts_const = n1;
+        d.pipeline = ((fixed_nin || (n0 == n1 && n1 == n2)) && n1 >= 1 && getenv("PIRIP_FSK_PIPE") != nullptr) ? 1 : 0;
+    }
     d.chunk = 128;
     if (const char *e = getenv("PIRIP_FSK_CHUNK")) {
         const int v = atoi(e);
@@ -268,6 +279,8 @@ static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, int
         d.off_stage = off;
         d.stage_bytes = align_up(nin_max * (c.fmt == PIRIP_FMT_U8 ? 2 : (c.fmt == PIRIP_FMT_S16 ? 4 : 8)) + 32, 16);
         off += d.stage_bytes;
+        d.off_phead = off;
+        off += align_up((d.Ts + d.Ts / 4 + 1) * 8, 16);
         d.off_scal = off;
         off += align_up((int)sizeof(FskCapShared), 16);
         /* capture blocks 32 (mod 128) bytes apart: with tones 16 (mod 128) bytes apart the lanes

@@ -89,9 +89,26 @@ __device__ __forceinline__ int fswz(int e) { return e ^ (5 * ((e >> 4) & 3)); }
 /* One warp: Hann-window N = 2^LOGN samples of x, FFT them in the warp's scratch slot with
    kiss_fft's decimation-in-time factor order 4,4,..,(2), write the fft-shifted magnitudes.
    perm[n] is the (swizzled) slot of input n before the first butterfly level. */
+/* u8 -> float exactly as ((float)b - 127.0)/128.0 */
+__device__ __forceinline__ float u8f(unsigned b) { return (float)((int)b - 127) * 0.0078125f; }
+
+/* complex sample i of a raw interleaved stream, converted as the fsk_demod CLI does ([U fsk_demod.c]) */
+__device__ __forceinline__ float2 raw_sample(const unsigned char *src, int fmt, int i) {
+    if (fmt == PIRIP_FMT_U8) {
+        const unsigned w = *reinterpret_cast<const unsigned short *>(src + 2 * i);
+        return make_float2(u8f(w & 0xff), u8f(w >> 8));
+    }
+    if (fmt == PIRIP_FMT_S16) {
+        const short2 v = *reinterpret_cast<const short2 *>(src + 4 * i);
+        return make_float2((float)v.x / 825.0f, (float)v.y / 825.0f); /* FDMDV_SCALE */
+    }
+    return *reinterpret_cast<const float2 *>(src + 8 * (size_t)i);
+}
+
 template <int LOGN>
-__device__ __forceinline__ void warp_fft_mag(const float2 *x, float2 *buf, float *out, const float2 *tw,
-                                             const float *hann, const unsigned short *perm, int lane) {
+__device__ __forceinline__ void warp_fft_mag(const float2 *xs, const unsigned char *src, int fmt, int first, float2 *buf,
+                                             float *out, const float2 *tw, const float *hann, const unsigned short *perm,
+                                             int lane) {
     constexpr int N = 1 << LOGN;
     constexpr int N4 = LOGN / 2;          /* radix-4 levels */
     constexpr bool HAS2 = (LOGN & 1) != 0; /* innermost radix-2 level */
@@ -99,7 +116,7 @@ __device__ __forceinline__ void warp_fft_mag(const float2 *x, float2 *buf, float
     for (int q = 0; q < N / 32; ++q) {
         const int n = lane + (q << 5);
         const float h = hann[n];
-        const float2 v = x[n];
+        const float2 v = xs ? xs[first + n] : raw_sample(src, fmt, first + n);
         buf[perm[n]] = make_float2(h * v.x, h * v.y);
     }
     __syncwarp();
@@ -155,9 +172,6 @@ __device__ __forceinline__ void warp_fft_mag(const float2 *x, float2 *buf, float
     __syncwarp();
 }
 
-/* u8 -> float exactly as ((float)b - 127.0)/128.0 */
-__device__ __forceinline__ float u8f(unsigned b) { return (float)((int)b - 127) * 0.0078125f; }
-
 /* number of integrator outputs whose whole window has been mixed once `j` new samples of
    this frame are in place (window i covers f_dc[i*step, i*step+Ts), new samples start at nold) */
 __device__ __forceinline__ int outputs_ready(int nold, int j, int Ts, int step, int nint) {
@@ -200,6 +214,7 @@ struct CapPtrs {
     float *mag;  /* FFT magnitudes; later tmpS | sig | nse | sqm | rx_filt */
     float *Sf;
     unsigned char *stage; /* TMA landing zone for the next frame's raw samples */
+    float2 *phead;        /* first D timing-line products */
     FskCapShared *cs;
 };
 
@@ -211,16 +226,16 @@ __device__ __forceinline__ CapPtrs cap_ptrs(unsigned char *smem, const FskDevCfg
     p.mag = reinterpret_cast<float *>(cb + cfg.off_mag);
     p.Sf = reinterpret_cast<float *>(cb + cfg.off_Sf);
     p.stage = cb + cfg.off_stage;
+    p.phead = reinterpret_cast<float2 *>(cb + cfg.off_phead);
     p.cs = reinterpret_cast<FskCapShared *>(cb + cfg.off_scal);
     return p;
 }
 
 /* Timing-line product of integrator output e.  Output e becomes ready nold - Ts + 1 samples
    ahead of the input index, so the products live in the consumed part of the input buffer
-   shifted back by D = Ts + Ts/4 + 1 (>= nold_max - Ts + 1); the first D go to the idle
-   magnitude region. */
+   shifted back by D = Ts + Ts/4 + 1 (>= nold_max - Ts + 1); the first D have their own slots. */
 __device__ __forceinline__ float2 *prod_slot(const CapPtrs &c, int e, int D) {
-    return e < D ? reinterpret_cast<float2 *>(c.mag) + e : c.xin + (e - D);
+    return e < D ? c.phead + e : c.xin + (e - D);
 }
 
 __device__ __forceinline__ size_t bytes_per_sample(int fmt) {
@@ -252,6 +267,167 @@ __device__ void stage_issue(const FskDevCfg &cfg, const FskBatchArgs &args, cons
     cs->stg_valid = 1;
 }
 
+
+/* A team of warps that synchronises on its own barrier: the whole CTA (id 0, __syncthreads) or a
+   subset on a named barrier */
+struct Team {
+    int nw, w, lane, bar;
+};
+__device__ __forceinline__ void team_sync(const Team &t) {
+    if (t.bar == 0)
+        __syncthreads();
+    else
+        named_bar_sync(t.bar, t.nw * 32);
+}
+
+struct CtaTables {
+    float2 *fft_slots; /* one Ndft slot per warp of the CTA */
+    const float2 *tw;
+    const float *hann;
+    const unsigned short *perm;
+};
+
+/* A7: tone frequency estimate of one frame for every capture of the CTA, by a team of warps.
+   Reads the raw samples of the frame through cs->fsrc (TMA-staged copy or global memory), leaves
+   f_est / f2_est / dphi in estimate slot `slot` and the updated IIR spectrum in Sf.
+   FFT blocks are transformed mag_blocks at a time; the magnitude IIR runs over each batch in block
+   order, so a small magnitude buffer serves any number of blocks. */
+template <int G, bool FROM_XIN>
+__device__ void front_stage(const FskDevCfg &cfg, unsigned char *smem, const CtaTables &tb, const Team &tm, int slot, int cta_warp) {
+    const int Ndft = cfg.Ndft, M = cfg.M, MB = cfg.mag_blocks;
+    const int lane = tm.lane, tthreads = tm.nw * 32, ttid = tm.w * 32 + lane;
+    const float tc = cfg.tc;
+    const float omtc = 1.0f - tc;
+    float2 *fft_slot = tb.fft_slots + (size_t)cta_warp * Ndft;
+    for (int b0 = 0; b0 < cfg.max_numffts; b0 += MB) {
+        for (int job = tm.w; job < G * MB; job += tm.nw) {
+            const int g = job / MB, jb = job - g * MB, j = b0 + jb;
+            const CapPtrs c = cap_ptrs(smem, cfg, g);
+            if (!c.cs->fon || j >= c.cs->fnumffts) continue;
+            /* the frame already converted into shared memory, or the raw (staged / global) samples */
+            const float2 *xs = FROM_XIN ? c.xin : nullptr;
+            const unsigned char *src = FROM_XIN ? nullptr : c.cs->fsrc;
+            const int fmt = cfg.fmt;
+            float *out = c.mag + (size_t)jb * Ndft;
+            const int first = j * (Ndft >> 1);
+            switch (cfg.log2_ndft) {
+                case 6: warp_fft_mag<6>(xs, src, fmt, first, fft_slot, out, tb.tw, tb.hann, tb.perm, lane); break;
+                case 7: warp_fft_mag<7>(xs, src, fmt, first, fft_slot, out, tb.tw, tb.hann, tb.perm, lane); break;
+                case 8: warp_fft_mag<8>(xs, src, fmt, first, fft_slot, out, tb.tw, tb.hann, tb.perm, lane); break;
+                case 9: warp_fft_mag<9>(xs, src, fmt, first, fft_slot, out, tb.tw, tb.hann, tb.perm, lane); break;
+                default: warp_fft_mag<10>(xs, src, fmt, first, fft_slot, out, tb.tw, tb.hann, tb.perm, lane); break;
+            }
+        }
+        team_sync(tm);
+        const bool last = b0 + MB >= cfg.max_numffts;
+        for (int g = 0; g < G; ++g) {
+            const CapPtrs c = cap_ptrs(smem, cfg, g);
+            if (!c.cs->fon) continue;
+            const int jn = c.cs->fnumffts - b0 < MB ? c.cs->fnumffts - b0 : MB; /* blocks of this batch */
+            for (int i = ttid; i < Ndft; i += tthreads) {
+                float s = c.Sf[i];
+                for (int j = 0; j < jn; ++j) s = (s * omtc) + (c.mag[j * Ndft + i] * tc);
+                c.Sf[i] = s;
+                if (last) c.mag[i] = s; /* tmpS: scratch copy the peak search blanks */
+            }
+        }
+        team_sync(tm);
+    }
+    for (int g = tm.w; g < G; g += tm.nw) {
+        const CapPtrs c = cap_ptrs(smem, cfg, g);
+        if (!c.cs->fon) continue;
+        float *tmpS = c.mag;
+        /* estimator 1: M rounds of argmax (first maximum wins) + blanking */
+        for (int r = 0; r < M; ++r) {
+            float best = 0.0f;
+            int ibest = 0;
+            for (int j = cfg.st + lane; j < cfg.en; j += 32) {
+                const float v = tmpS[j];
+                if (v > best) {
+                    best = v;
+                    ibest = j;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, ibest, off);
+                if (ov > best || (ov == best && oi < ibest)) {
+                    best = ov;
+                    ibest = oi;
+                }
+            }
+            int f_min = ibest - cfg.f_zero;
+            f_min = f_min < 0 ? 0 : f_min;
+            int f_max = ibest + cfg.f_zero;
+            f_max = f_max > Ndft ? Ndft : f_max;
+            for (int j = f_min + lane; j < f_max; j += 32) tmpS[j] = 0.0f;
+            if (lane == 0) c.cs->freqi[r] = ibest - (Ndft >> 1);
+            __syncwarp();
+        }
+        if (lane == 0) {
+            int fi[4];
+            for (int m = 0; m < M; ++m) fi[m] = c.cs->freqi[m];
+            for (int a = 1; a < M; ++a) { /* ascending insertion sort */
+                const int key = fi[a];
+                int b = a - 1;
+                while (b >= 0 && fi[b] > key) {
+                    fi[b + 1] = fi[b];
+                    --b;
+                }
+                fi[b + 1] = key;
+            }
+            for (int m = 0; m < M; ++m) c.cs->f_est[slot][m] = (float)fi[m] * cfg.fs_over_ndft;
+        }
+        /* estimator 2: slide the tone mask over Sf, first maximum wins */
+        {
+            float best = 0.0f;
+            int bbest = 0x7fffffff;
+            for (int b = cfg.st + lane; b < cfg.en - cfg.len_mask; b += 32) {
+                float corr = 0.0f;
+                for (int q = 0; q < cfg.nmask; ++q) corr += c.Sf[b + cfg.mask_pos[q]];
+                if (corr > best) {
+                    best = corr;
+                    bbest = b;
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+                const int oi = __shfl_xor_sync(0xffffffffu, bbest, off);
+                if (ov > best || (ov == best && oi < bbest)) {
+                    best = ov;
+                    bbest = oi;
+                }
+            }
+            if (lane == 0) {
+                const int b_max = (best > 0.0f) ? bbest : cfg.st;
+                const float foff = (float)((b_max - (Ndft >> 1)) * cfg.Fs / Ndft);
+                for (int m = 0; m < M; ++m) c.cs->f2_est[slot][m] = foff + (float)(m * cfg.tone_spacing);
+            }
+        }
+        __syncwarp();
+        if (lane < M) {
+            const float f = cfg.est_type ? c.cs->f2_est[slot][lane] : c.cs->f_est[slot][lane];
+            const float arg = (float)(EM_TWO_PI * (double)(f / (float)cfg.Fs));
+            double sn, csn;
+            em_sincos((double)arg, &sn, &csn);
+            c.cs->dphi[slot][lane] = make_float2((float)csn, (float)sn);
+        }
+    }
+}
+
+/* Raw samples of the frame starting at sample `pos` of capture `cap`: the TMA-staged copy when it
+   covers the range, global memory otherwise */
+__device__ __forceinline__ const unsigned char *frame_src(const FskDevCfg &cfg, const FskBatchArgs &args, const CapPtrs &c,
+                                                          size_t cap, unsigned long long pos, int nsamples) {
+    const size_t bps = bytes_per_sample(cfg.fmt);
+    const size_t a = reinterpret_cast<size_t>(args.iq) + cap * args.capture_stride_bytes + pos * bps;
+    if (c.cs->stg_valid && a >= c.cs->stg_lo && a + (size_t)nsamples * bps <= c.cs->stg_lo + c.cs->stg_bytes)
+        return c.stage + (a - c.cs->stg_lo);
+    return reinterpret_cast<const unsigned char *>(a);
+}
+
 /* G <= 2: 256-thread CTAs, two resident per SM, so the barrier-separated phases of one CTA
    overlap the other's; G >= 3: one 512-thread CTA per SM */
 template <int G>
@@ -265,23 +441,33 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
     const size_t cap0 = (size_t)blockIdx.x * G;
     unsigned char *cta = smem + (size_t)G * cfg.cap_stride;
     FskCtaShared *ctl = reinterpret_cast<FskCtaShared *>(cta + cfg.off_ctl);
-    float2 *fft_slot = reinterpret_cast<float2 *>(cta + cfg.off_fft) + (size_t)warp * Ndft;
     float2 *tw = reinterpret_cast<float2 *>(cta + cfg.off_tw);
     float *hann = reinterpret_cast<float *>(cta + cfg.off_hann);
     float2 *phi_ft = reinterpret_cast<float2 *>(cta + cfg.off_phift);
     unsigned short *perm = reinterpret_cast<unsigned short *>(cta + cfg.off_perm);
-    const float tc = cfg.tc;
-    const float omtc = 1.0f - tc;
     const int D = Ts + Ts / 4 + 1;
     /* Roles of the streaming phase.  Warp w issues on sub-partition w % 4.  The two serial
        warps (oscillators, timing line) share sub-partition 3 and no worker runs there, so the
        latency-bound recurrences never wait for an issue slot; the workers are the warps of
        sub-partitions 0..2. */
     const int osc_warp = nwarps - 1, tim_warp = nwarps - 5;
-    const bool is_worker = (warp & 3) != 3;
-    const int nww = nwarps - nwarps / 4;          /* worker warps */
-    const int nwt = nww * 32;                     /* worker threads */
-    const int wtid = (warp - (warp >> 2)) * 32 + lane; /* dense worker thread index */
+    /* When the frequency estimate of the next frame can run one frame ahead (its FFT block count
+       does not depend on the timing decision and no state is carried out of the launch), the warps
+       of sub-partition 2 and the spare warps of sub-partition 3 form the front team that computes
+       it during the streaming phase; the workers are then the warps of sub-partitions 0 and 1. */
+    const bool pipelined = cfg.pipeline && args.state == nullptr;
+    const bool is_serial = warp == osc_warp || warp == tim_warp;
+    const bool is_worker = pipelined ? (warp & 3) < 2 : (warp & 3) != 3;
+    const bool is_front = pipelined && !is_worker && !is_serial;
+    const int nww = pipelined ? nwarps / 2 : nwarps - nwarps / 4; /* worker warps */
+    const int nwt = nww * 32;                                      /* worker threads */
+    const int wtid = (pipelined ? ((warp >> 2) * 2 + (warp & 3)) : (warp - (warp >> 2))) * 32 + lane; /* dense index */
+    const int nfront = nwarps / 2 - 2; /* front warps: w%4 == 2, and w%4 == 3 except the two serial warps */
+    int front_idx = 0;
+    for (int w = 0; w < warp; ++w)
+        if ((w & 3) >= 2 && w != osc_warp && w != tim_warp) front_idx++;
+    const CtaTables tb = { reinterpret_cast<float2 *>(cta + cfg.off_fft), tw, hann, perm };
+    int slot = 0; /* estimate slot of the frame being demodulated */
     unsigned long long par = 0;        /* phase parity of every per-chunk mbarrier, bit ck */
     unsigned par_in = 0;               /* phase parity of the staging mbarriers, bit g */
 
@@ -334,8 +520,8 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
         }
         if (tid == 0) {
             for (int m = 0; m < 4; ++m) {
-                c.cs->f_est[m] = 0.0f;
-                c.cs->f2_est[m] = 0.0f;
+                c.cs->f_est[0][m] = c.cs->f_est[1][m] = 0.0f;
+                c.cs->f2_est[0][m] = c.cs->f2_est[1][m] = 0.0f;
             }
             c.cs->SNRest = c.cs->v_est = c.cs->rx_sig_pow = c.cs->rx_nse_pow = c.cs->foff = c.cs->rx_timing = 0.0f;
             c.cs->pos = 0;
@@ -343,6 +529,7 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
             c.cs->active = exists ? 1 : 0;
             c.cs->nan_flag = 0;
             c.cs->stg_valid = 0;
+            c.cs->fon = 0;
         }
     }
     __syncthreads();
@@ -351,6 +538,24 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
         if (c.cs->active) stage_issue(cfg, args, c, cap0 + tid, 0, &ctl->bar_in[tid]);
     }
     __syncthreads();
+    if (pipelined) {
+        /* prologue: the whole CTA computes the frequency estimate of frame 0 */
+        if (tid < G) {
+            const CapPtrs c = cap_ptrs(smem, cfg, tid);
+            FskCapShared *cs = c.cs;
+            cs->fon = cs->active && args.max_frames > 0 && (unsigned long long)(cfg.N - Ts / 4) <= args.samples_per_capture;
+            cs->fnumffts = cfg.numffts_const;
+            if (cs->fon) cs->fsrc = frame_src(cfg, args, c, cap0 + tid, 0, cfg.N - Ts / 4);
+        }
+        __syncthreads();
+        for (int g = 0; g < G; ++g) {
+            FskCapShared *cs = cap_ptrs(smem, cfg, g).cs;
+            if (cs->fon && cs->stg_valid) mbar_wait(&ctl->bar_in[g], (par_in >> g) & 1u);
+        }
+        const Team all = { nwarps, warp, lane, 0 };
+        front_stage<G, false>(cfg, smem, tb, all, 0, warp);
+        __syncthreads();
+    }
 
 #ifdef FSK_PHASE_TIMING
     long long tph[10] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
@@ -415,11 +620,7 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
             }
             if (!cs->active) continue;
             const int nin = cs->nin, nold = cs->nold;
-            const size_t bps = bytes_per_sample(cfg.fmt);
-            const size_t a = reinterpret_cast<size_t>(args.iq) + (cap0 + g) * args.capture_stride_bytes + cs->pos * bps;
-            const unsigned char *src = reinterpret_cast<const unsigned char *>(a);
-            if (cs->stg_valid && a >= cs->stg_lo && a + (size_t)nin * bps <= cs->stg_lo + cs->stg_bytes)
-                src = c.stage + (a - cs->stg_lo); /* read the staged copy */
+            const unsigned char *src = frame_src(cfg, args, c, cap0 + g, cs->pos, nin);
             if (cfg.fmt == PIRIP_FMT_U8) {
                 /* 4-byte reads (two samples) over the aligned body, single samples at the ends */
                 const int mis = (int)((reinterpret_cast<size_t>(src) >> 1) & 1);
@@ -452,131 +653,38 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
             }
         }
         __syncthreads();
-        /* the staging buffers are free again: fetch the next frame's samples behind the compute */
-        if (tid < G) {
-            const CapPtrs c = cap_ptrs(smem, cfg, tid);
-            if (c.cs->active)
-                stage_issue(cfg, args, c, cap0 + tid, c.cs->pos + (unsigned long long)c.cs->nin, &ctl->bar_in[tid]);
-            else
-                c.cs->stg_valid = 0;
-        }
         PHASE_MARK(1);
 
-        /* ---- A7: tone frequency estimate ---------------------------------------------
-           FFT blocks are transformed mag_blocks at a time; the magnitude IIR runs over each batch
-           in block order, so a small magnitude buffer serves any number of blocks */
-        const int MB = cfg.mag_blocks;
-        for (int b0 = 0; b0 < cfg.max_numffts; b0 += MB) {
-            for (int job = warp; job < G * MB; job += nwarps) {
-                const int g = job / MB, jb = job - g * MB, j = b0 + jb;
-                const CapPtrs c = cap_ptrs(smem, cfg, g);
-                if (!c.cs->active || j >= c.cs->numffts) continue;
-                const float2 *x = c.xin + j * (Ndft >> 1);
-                float *out = c.mag + (size_t)jb * Ndft;
-                switch (cfg.log2_ndft) {
-                    case 6: warp_fft_mag<6>(x, fft_slot, out, tw, hann, perm, lane); break;
-                    case 7: warp_fft_mag<7>(x, fft_slot, out, tw, hann, perm, lane); break;
-                    case 8: warp_fft_mag<8>(x, fft_slot, out, tw, hann, perm, lane); break;
-                    case 9: warp_fft_mag<9>(x, fft_slot, out, tw, hann, perm, lane); break;
-                    default: warp_fft_mag<10>(x, fft_slot, out, tw, hann, perm, lane); break;
-                }
+        /* ---- A7 for this frame when the front stage is not running one frame ahead ------------- */
+        if (!pipelined) {
+            if (tid < G) {
+                const CapPtrs c = cap_ptrs(smem, cfg, tid);
+                c.cs->fon = c.cs->active;
+                c.cs->fnumffts = c.cs->numffts;
             }
             __syncthreads();
-            const bool last = b0 + MB >= cfg.max_numffts;
-            for (int g = 0; g < G; ++g) {
-                const CapPtrs c = cap_ptrs(smem, cfg, g);
-                if (!c.cs->active) continue;
-                const int jn = c.cs->numffts - b0 < MB ? c.cs->numffts - b0 : MB; /* blocks of this batch */
-                for (int i = tid; i < Ndft; i += nthreads) {
-                    float s = c.Sf[i];
-                    for (int j = 0; j < jn; ++j) s = (s * omtc) + (c.mag[j * Ndft + i] * tc);
-                    c.Sf[i] = s;
-                    if (last) c.mag[i] = s; /* tmpS: scratch copy the peak search blanks */
-                }
-            }
+            const Team all = { nwarps, warp, lane, 0 };
+            front_stage<G, true>(cfg, smem, tb, all, slot, warp);
             __syncthreads();
         }
         PHASE_MARK(2);
-        for (int g = warp; g < G; g += nwarps) {
-            const CapPtrs c = cap_ptrs(smem, cfg, g);
-            if (!c.cs->active) continue;
-            float *tmpS = c.mag;
-            /* estimator 1: M rounds of argmax (first maximum wins) + blanking */
-            for (int r = 0; r < M; ++r) {
-                float best = 0.0f;
-                int ibest = 0;
-                for (int j = cfg.st + lane; j < cfg.en; j += 32) {
-                    const float v = tmpS[j];
-                    if (v > best) {
-                        best = v;
-                        ibest = j;
-                    }
+        /* the staging buffers are free again: fetch the next frame's samples behind the compute */
+        if (tid < G) {
+            const CapPtrs c = cap_ptrs(smem, cfg, tid);
+            FskCapShared *cs = c.cs;
+            cs->fon = 0;
+            if (cs->active) {
+                const unsigned long long npos = cs->pos + (unsigned long long)cs->nin;
+                stage_issue(cfg, args, c, cap0 + tid, npos, &ctl->bar_in[tid]);
+                /* the next frame exists for some nin iff its shortest form fits the capture */
+                if (pipelined && (size_t)cs->frame + 1 < args.max_frames &&
+                    npos + (unsigned long long)(cfg.N - Ts / 4) <= args.samples_per_capture) {
+                    cs->fon = 1;
+                    cs->fnumffts = cfg.numffts_const;
+                    cs->fsrc = frame_src(cfg, args, c, cap0 + tid, npos, cfg.N - Ts / 4);
                 }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, best, off);
-                    const int oi = __shfl_xor_sync(0xffffffffu, ibest, off);
-                    if (ov > best || (ov == best && oi < ibest)) {
-                        best = ov;
-                        ibest = oi;
-                    }
-                }
-                int f_min = ibest - cfg.f_zero;
-                f_min = f_min < 0 ? 0 : f_min;
-                int f_max = ibest + cfg.f_zero;
-                f_max = f_max > Ndft ? Ndft : f_max;
-                for (int j = f_min + lane; j < f_max; j += 32) tmpS[j] = 0.0f;
-                if (lane == 0) c.cs->freqi[r] = ibest - (Ndft >> 1);
-                __syncwarp();
-            }
-            if (lane == 0) {
-                int fi[4];
-                for (int m = 0; m < M; ++m) fi[m] = c.cs->freqi[m];
-                for (int a = 1; a < M; ++a) { /* ascending insertion sort */
-                    const int key = fi[a];
-                    int b = a - 1;
-                    while (b >= 0 && fi[b] > key) {
-                        fi[b + 1] = fi[b];
-                        --b;
-                    }
-                    fi[b + 1] = key;
-                }
-                for (int m = 0; m < M; ++m) c.cs->f_est[m] = (float)fi[m] * cfg.fs_over_ndft;
-            }
-            /* estimator 2: slide the tone mask over Sf, first maximum wins */
-            {
-                float best = 0.0f;
-                int bbest = 0x7fffffff;
-                for (int b = cfg.st + lane; b < cfg.en - cfg.len_mask; b += 32) {
-                    float corr = 0.0f;
-                    for (int q = 0; q < cfg.nmask; ++q) corr += c.Sf[b + cfg.mask_pos[q]];
-                    if (corr > best) {
-                        best = corr;
-                        bbest = b;
-                    }
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, best, off);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bbest, off);
-                    if (ov > best || (ov == best && oi < bbest)) {
-                        best = ov;
-                        bbest = oi;
-                    }
-                }
-                if (lane == 0) {
-                    const int b_max = (best > 0.0f) ? bbest : cfg.st;
-                    const float foff = (float)((b_max - (Ndft >> 1)) * cfg.Fs / Ndft);
-                    for (int m = 0; m < M; ++m) c.cs->f2_est[m] = foff + (float)(m * cfg.tone_spacing);
-                }
-            }
-            __syncwarp();
-            if (lane < M) {
-                const float f = cfg.est_type ? c.cs->f2_est[lane] : c.cs->f_est[lane];
-                const float arg = (float)(EM_TWO_PI * (double)(f / (float)cfg.Fs));
-                double sn, csn;
-                em_sincos((double)arg, &sn, &csn);
-                c.cs->dphi[lane] = make_float2((float)csn, (float)sn);
+            } else {
+                cs->stg_valid = 0;
             }
         }
         __syncthreads();
@@ -591,7 +699,7 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
             const bool on = lane < G * M && cap_ptrs(smem, cfg, g < G ? g : 0).cs->active;
             const CapPtrs c = cap_ptrs(smem, cfg, on ? g : 0);
             const int my_nin = on ? c.cs->nin : 0;
-            const float2 d = on ? c.cs->dphi[m] : make_float2(1.0f, 0.0f);
+            const float2 d = on ? c.cs->dphi[slot][m] : make_float2(1.0f, 0.0f);
             float2 ph = on ? c.cs->phi_c[m] : make_float2(1.0f, 0.0f);
             float2 *dst = c.fdc + m * TS + c.cs->nold;
             /* smallest nin over the active lanes: below it no lane needs a bounds check */
@@ -657,7 +765,7 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
                    the sixteen dependent adds so the chain runs at FADD latency, not LDS latency */
                 while (done < avail) {
                     const bool head = done < D;
-                    const float2 *src = head ? reinterpret_cast<const float2 *>(c.mag) + done : c.xin + (done - D);
+                    const float2 *src = head ? c.phead + done : c.xin + (done - D);
                     const int lim = head ? (avail < D ? avail : D) : avail;
                     int n = lim - done;
                     for (; n >= 8; n -= 8, src += 8, done += 8) {
@@ -831,6 +939,14 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
                 if (lane == 0) mbar_arrive(&ctl->bar_int[ck]);
                 WMARK(4);
             }
+        } else if (is_front) {
+            /* front team: frequency estimate of the NEXT frame from its TMA-staged raw samples */
+            for (int g = 0; g < G; ++g) {
+                FskCapShared *cs = cap_ptrs(smem, cfg, g).cs;
+                if (cs->fon && cs->stg_valid) mbar_wait(&ctl->bar_in[g], (par_in >> g) & 1u);
+            }
+            const Team ft = { nfront, front_idx, lane, 2 };
+            front_stage<G, false>(cfg, smem, tb, ft, slot ^ 1, warp);
         }
         par ^= nchunks >= 64 ? ~0ull : ((1ull << nchunks) - 1ull);
         PHASE_MARK(4); /* own role's time in the streaming phase */
@@ -939,7 +1055,7 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
                 const float ratio = (float)((1e-6 + (double)meanebno) / (1e-6 + (double)stdebno));
                 cs->EbNodB = -6.0f + (20.0f * em_log10f(ratio));
                 cs->snr_est = (float)(.5 * (double)cs->snr_est + .5 * (double)cs->EbNodB);
-                const float *fe = cfg.est_type ? cs->f2_est : cs->f_est;
+                const float *fe = cfg.est_type ? cs->f2_est[slot] : cs->f_est[slot];
                 const float fc_avg = (fe[0] + fe[1]) / 2.0f;
                 const float fc_tx = (float)((cfg.f1_tx + cfg.f1_tx + cfg.tone_spacing) / 2);
                 cs->foff = fc_tx - fc_avg;
@@ -972,8 +1088,8 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
                 if (args.stats) {
                     pirip_frame_stats s;
                     for (int m = 0; m < 4; ++m) {
-                        s.f_est[m] = m < M ? cs->f_est[m] : 0.0f;
-                        s.f2_est[m] = m < M ? cs->f2_est[m] : 0.0f;
+                        s.f_est[m] = m < M ? cs->f_est[slot][m] : 0.0f;
+                        s.f2_est[m] = m < M ? cs->f2_est[slot][m] : 0.0f;
                     }
                     s.norm_rx_timing = cs->norm_rx_timing;
                     s.ppm = cs->ppm;
@@ -995,6 +1111,7 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
             }
         }
         __syncthreads();
+        if (pipelined) slot ^= 1;
         PHASE_MARK(8);
     }
 #ifdef FSK_PHASE_TIMING

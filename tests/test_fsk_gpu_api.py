@@ -149,3 +149,22 @@ def test_device_resident_entry_point_with_torch_tensors():
         ref = orc.fsk_demod_stream(ocfg(C1), iq[c])
         assert int(d_nf[c]) == ref["nframes"]
         assert np.array_equal(d_bits[c, :ref["nframes"] * 50].cpu().numpy(), ref["bits"])
+
+
+def test_front_team_pipelined_schedule_is_bit_identical(monkeypatch):
+    """PIRIP_FSK_PIPE=1: the frequency estimate runs one frame ahead on a front team of warps."""
+    import pirip_b200 as pb
+    monkeypatch.setenv("PIRIP_FSK_PIPE", "1")
+    caps = [synth.capture_u8(800 + i, 2500, 2, 240000, 10000, 10000, 10000, ebno_db=[None, 5.0, 9.0][i % 3])[0]
+            for i in range(5)]
+    n = min(len(c) for c in caps)
+    iq = np.stack([c[:n] for c in caps])
+    plan = pb.FskPlan(**C1)
+    out = plan.demod_batch(iq, want_stats=True)
+    for c in range(iq.shape[0]):
+        ref = orc.fsk_demod_stream(ocfg(C1), iq[c])
+        nf = ref["nframes"]
+        assert out["nframes"][c] == nf
+        assert np.array_equal(out["bits"][c, :nf * 50], ref["bits"])
+        assert np.array_equal(out["stats"][c, :nf].view(np.uint8), ref["stats"].view(np.uint8))
+    plan.close()
