@@ -1,0 +1,118 @@
+#!/usr/bin/env python
+"""Secondary measurements (not the headline bench): the fused csdr stage and the LDPC decoder.
+
+  decim : config-2 front end, u8 IQ at 1.8 MS/s -> convert + 79-tap FIR + /45 + s16, streams
+          resident in HBM; algorithmic bytes = 2 B per input sample + 4 B per output
+  ldpc  : H_256_512_4-sized codewords at a mix of SNRs, LLRs resident in HBM;
+          algorithmic bytes = 4*N in + N out per codeword (compute-bound, reported for completeness)
+Prints one JSON object per workload.  CUDA events on torch's current stream, inputs >> L2.
+"""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+import pirip_b200 as pb  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return (json.load(open(p))["hbm_gbs"], "measured") if os.path.exists(p) else (6650.0, "fallback")
+
+
+def timed(fn, steps, warmup=3):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+def bench_decim(steps):
+    D, nstreams, n = 45, 256, 1800000  # 256 one-second streams at 1.8 MS/s = 921.6 MB of u8
+    dec = pb.DecimPlan(D)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    iq = torch.randint(0, 256, (nstreams, 2 * n), dtype=torch.uint8, device="cuda", generator=g)
+    nout = dec.out_count(n)
+    out = torch.empty((nstreams, 2 * nout), dtype=torch.int16, device="cuda")
+    s = torch.cuda.current_stream()
+    fn = lambda: dec.run_dev(iq.data_ptr(), nstreams, n, iq.stride(0), None, out.data_ptr(), nout,
+                             stream=ctypes.c_void_p(s.cuda_stream))
+    ms = timed(fn, steps)
+    # parity spot check against the oracle on one stream prefix
+    import orc
+    ref_f, ref_s = orc.csdr_decimate_stream(iq[3, :2 * 100000].cpu().numpy(), D)
+    ok = bool(np.array_equal(out[3, :ref_s.size].cpu().numpy(), ref_s))
+    algo = nstreams * (2.0 * n + 4.0 * nout)
+    pk, src = peak()
+    ach = algo / (ms * 1e-3) / 1e9
+    return {"workload": "decim: %d x %.1f Msample u8 IQ streams, fir_decimate_cc %d (%d taps), s16 out" % (nstreams, n / 1e6, D, dec.taps.size),
+            "metric": "input IQ Msamples/s", "value": nstreams * n / (ms * 1e-3) / 1e6, "ms_per_step": ms,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "peak_source": src,
+                         "algorithmic_bytes": algo, "kernel": "fir_decimate_kernel<true>"},
+            "parity_vs_oracle": ok}
+
+
+def bench_ldpc(steps):
+    import orc
+    l, v = pb.ldpc_code("H_256_512_4")
+    N, K = 512, 256
+    ncw = 65536
+    g = np.random.default_rng(7)
+    base = []
+    for eb in (6.0, 3.0, 2.0, 1.0):
+        ib = g.integers(0, 2, K, dtype=np.uint8)
+        cw = np.concatenate([ib, pb.ldpc_encode(l, ib)]).astype(np.float64)
+        sigma2 = 1.0 / (2 * 0.5 * 10 ** (eb / 10))
+        y = (1 - 2 * cw) + g.standard_normal((ncw // 4, N)) * np.sqrt(sigma2)
+        base.append((2 * y / sigma2).astype(np.float32))
+    llr = torch.from_numpy(np.concatenate(base)).cuda()
+    bits = torch.empty((ncw, N), dtype=torch.uint8, device="cuda")
+    it = torch.empty(ncw, dtype=torch.int32, device="cuda")
+    pcc = torch.empty(ncw, dtype=torch.int32, device="cuda")
+    plan = pb.LdpcPlan(l)
+    s = torch.cuda.current_stream()
+    L = pb.lib()
+    fn = lambda: L.pirip_ldpc_decode_batch_dev(plan._h, ctypes.c_void_p(llr.data_ptr()), ncw, ctypes.c_void_p(bits.data_ptr()),
+                                               ctypes.c_void_p(it.data_ptr()), ctypes.c_void_p(pcc.data_ptr()),
+                                               ctypes.c_void_p(s.cuda_stream))
+    ms = timed(fn, steps)
+    idx = [0, ncw // 4 + 1, ncw // 2 + 2, 3 * ncw // 4 + 3]
+    ok = True
+    for i in idx:
+        rb, rit, rpcc = orc.ldpc_decode(v, llr[i].cpu().numpy())
+        ok = ok and np.array_equal(bits[i].cpu().numpy(), rb) and int(it[i]) == rit and int(pcc[i]) == rpcc
+    algo = ncw * (4.0 * N + N)
+    pk, src = peak()
+    ach = algo / (ms * 1e-3) / 1e9
+    return {"workload": "ldpc: %d codewords (512,256), Eb/N0 mix 6/3/2/1 dB, max 15 iterations" % ncw,
+            "metric": "codewords/s", "value": ncw / (ms * 1e-3), "ms_per_step": ms, "mean_iterations": float(it.float().mean()),
+            "coded_Mbit_per_s": ncw * N / (ms * 1e-3) / 1e6,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "peak_source": src,
+                         "algorithmic_bytes": algo, "kernel": "ldpc_decode_kernel",
+                         "note": "compute-bound: ~2*E phi0 evaluations (double exp/log) per iteration"},
+            "parity_vs_oracle": bool(ok)}
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--only", default="")
+    a = ap.parse_args()
+    if a.only in ("", "decim"):
+        print(json.dumps(bench_decim(a.steps)))
+    if a.only in ("", "ldpc"):
+        print(json.dumps(bench_ldpc(a.steps)))
