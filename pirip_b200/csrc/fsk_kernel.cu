@@ -106,7 +106,7 @@ __device__ __forceinline__ float2 raw_sample(const unsigned char *src, int fmt, 
 }
 
 template <int LOGN>
-__device__ __forceinline__ void warp_fft_mag(const float2 *xs, const unsigned char *src, int fmt, int first, float2 *buf,
+__device__ __noinline__ void warp_fft_mag(const float2 *xs, const unsigned char *src, int fmt, int first, float2 *buf,
                                              float *out, const float2 *tw, const float *hann, const unsigned short *perm,
                                              int lane) {
     constexpr int N = 1 << LOGN;
@@ -139,25 +139,47 @@ __device__ __forceinline__ void warp_fft_mag(const float2 *xs, const unsigned ch
         const int lm = (HAS2 ? 1 : 0) + 2 * (N4 - 1 - L); /* log2 m */
         const int m = 1 << lm;
         const int fs = N >> (lm + 2); /* fstride */
+        constexpr int NB = N / 128 > 0 ? N / 128 : 1; /* butterflies per lane at this level */
+        constexpr int PB = NB >= 2 ? 2 : 1;           /* processed two at a time: loads, math, stores */
 #pragma unroll
-        for (int q = 0; q < (N / 128 > 0 ? N / 128 : 1); ++q) {
-            const int b = lane + (q << 5);
-            if (N / 4 >= 32 || b < N / 4) {
+        for (int q0 = 0; q0 < NB; q0 += PB) {
+            int ix[PB][4];
+            float2 F[PB][4], T[PB][3];
+            bool ok[PB];
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                const int b = lane + ((q0 + u) << 5);
+                ok[u] = N / 4 >= 32 || b < N / 4;
                 const int blk = b >> lm, k = b & (m - 1);
                 const int base = (blk << (lm + 2)) + k;
-                const int i0 = fswz(base), i1 = fswz(base + m), i2 = fswz(base + 2 * m), i3 = fswz(base + 3 * m);
-                float2 F0 = buf[i0];
-                const float2 s0 = cmul(buf[i1], tw[k * fs]);
-                const float2 s1 = cmul(buf[i2], tw[2 * k * fs]);
-                const float2 s2 = cmul(buf[i3], tw[3 * k * fs]);
-                const float2 s5 = csub(F0, s1);
-                F0 = cadd(F0, s1);
-                const float2 s3 = cadd(s0, s2);
-                const float2 s4 = csub(s0, s2);
-                buf[i2] = csub(F0, s3);
-                buf[i0] = cadd(F0, s3);
-                buf[i1] = make_float2(s5.x + s4.y, s5.y - s4.x);
-                buf[i3] = make_float2(s5.x - s4.y, s5.y + s4.x);
+                ix[u][0] = fswz(base);
+                ix[u][1] = fswz(base + m);
+                ix[u][2] = fswz(base + 2 * m);
+                ix[u][3] = fswz(base + 3 * m);
+                if (ok[u]) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) F[u][r] = buf[ix[u][r]];
+                    T[u][0] = tw[k * fs];
+                    T[u][1] = tw[2 * k * fs];
+                    T[u][2] = tw[3 * k * fs];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                if (ok[u]) {
+                    float2 F0 = F[u][0];
+                    const float2 s0 = cmul(F[u][1], T[u][0]);
+                    const float2 s1 = cmul(F[u][2], T[u][1]);
+                    const float2 s2 = cmul(F[u][3], T[u][2]);
+                    const float2 s5 = csub(F0, s1);
+                    F0 = cadd(F0, s1);
+                    const float2 s3 = cadd(s0, s2);
+                    const float2 s4 = csub(s0, s2);
+                    buf[ix[u][2]] = csub(F0, s3);
+                    buf[ix[u][0]] = cadd(F0, s3);
+                    buf[ix[u][1]] = make_float2(s5.x + s4.y, s5.y - s4.x);
+                    buf[ix[u][3]] = make_float2(s5.x - s4.y, s5.y + s4.x);
+                }
             }
         }
         __syncwarp();
@@ -443,7 +465,7 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
     FskCtaShared *ctl = reinterpret_cast<FskCtaShared *>(cta + cfg.off_ctl);
     float2 *tw = reinterpret_cast<float2 *>(cta + cfg.off_tw);
     float *hann = reinterpret_cast<float *>(cta + cfg.off_hann);
-    float2 *phi_ft = reinterpret_cast<float2 *>(cta + cfg.off_phift);
+    const float2 *phi_ft = cfg.phi_ft; /* global (L2-resident); loads are issued ahead of their use */
     unsigned short *perm = reinterpret_cast<unsigned short *>(cta + cfg.off_perm);
     const int D = Ts + Ts / 4 + 1;
     /* Roles of the streaming phase.  Warp w issues on sub-partition w % 4.  The two serial
@@ -477,7 +499,6 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
         hann[i] = cfg.hann[i];
         perm[i] = cfg.perm[i];
     }
-    for (int i = tid; i < nint; i += nthreads) phi_ft[i] = cfg.phi_ft[i];
     if (tid == 0) {
         for (int i = 0; i < FSK_MAX_CHUNKS; ++i) {
             mbar_init(&ctl->bar_osc[i], 1);
@@ -582,28 +603,34 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
 #define PHASE_MARK(k)
 #define WMARK(k)
 #endif
-    for (;;) {
-        /* ---- frame bookkeeping: which captures still have a whole frame to read ------- */
-        if (tid == 0) {
-            int any = 0, mx = 0;
-            for (int g = 0; g < G; ++g) {
-                FskCapShared *cs = cap_ptrs(smem, cfg, g).cs;
-                int act = cs->active;
-                if (act && ((size_t)cs->frame >= args.max_frames ||
-                            cs->pos + (unsigned long long)cs->nin > args.samples_per_capture))
-                    act = 0; /* short read ends the loop */
-                cs->active = act;
-                cs->nold = Nmem - cs->nin;
-                cs->numffts = cs->nin / (Ndft >> 1) - 1;
-                if (act) {
-                    any = 1;
-                    mx = cs->nin > mx ? cs->nin : mx;
-                }
+    /* frame bookkeeping: which captures still have a whole frame to read.  Done by one thread
+       before the first frame and at the end of every frame, under that frame's last barrier. */
+    auto bookkeeping = [&]() {
+        int any = 0, mx = 0;
+        for (int g = 0; g < G; ++g) {
+            FskCapShared *cs = cap_ptrs(smem, cfg, g).cs;
+            int act = cs->active;
+            if (act && ((size_t)cs->frame >= args.max_frames ||
+                        cs->pos + (unsigned long long)cs->nin > args.samples_per_capture))
+                act = 0; /* short read ends the loop */
+            cs->active = act;
+            cs->nold = Nmem - cs->nin;
+            cs->numffts = cs->nin / (Ndft >> 1) - 1;
+            if (!pipelined) {
+                cs->fon = act;
+                cs->fnumffts = cs->numffts;
             }
-            ctl->any_active = any;
-            ctl->max_nin = mx;
+            if (act) {
+                any = 1;
+                mx = cs->nin > mx ? cs->nin : mx;
+            }
         }
-        __syncthreads();
+        ctl->any_active = any;
+        ctl->max_nin = mx;
+    };
+    if (tid == 0) bookkeeping();
+    __syncthreads();
+    for (;;) {
         if (!ctl->any_active) break;
         const int max_nin = ctl->max_nin;
         PHASE_MARK(0);
@@ -655,21 +682,20 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
         __syncthreads();
         PHASE_MARK(1);
 
-        /* ---- A7 for this frame when the front stage is not running one frame ahead ------------- */
         if (!pipelined) {
+            /* the staging buffers are free again (the frame now lives in xin): fetch the next frame's
+               samples behind the compute, then A7 for this frame by the whole CTA */
             if (tid < G) {
                 const CapPtrs c = cap_ptrs(smem, cfg, tid);
-                c.cs->fon = c.cs->active;
-                c.cs->fnumffts = c.cs->numffts;
+                if (c.cs->active)
+                    stage_issue(cfg, args, c, cap0 + tid, c.cs->pos + (unsigned long long)c.cs->nin, &ctl->bar_in[tid]);
+                else
+                    c.cs->stg_valid = 0;
             }
-            __syncthreads();
             const Team all = { nwarps, warp, lane, 0 };
             front_stage<G, true>(cfg, smem, tb, all, slot, warp);
-            __syncthreads();
-        }
-        PHASE_MARK(2);
-        /* the staging buffers are free again: fetch the next frame's samples behind the compute */
-        if (tid < G) {
+        } else if (tid < G) {
+            /* front team mode: fetch the next frame and tell the team where its raw samples are */
             const CapPtrs c = cap_ptrs(smem, cfg, tid);
             FskCapShared *cs = c.cs;
             cs->fon = 0;
@@ -677,7 +703,7 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
                 const unsigned long long npos = cs->pos + (unsigned long long)cs->nin;
                 stage_issue(cfg, args, c, cap0 + tid, npos, &ctl->bar_in[tid]);
                 /* the next frame exists for some nin iff its shortest form fits the capture */
-                if (pipelined && (size_t)cs->frame + 1 < args.max_frames &&
+                if ((size_t)cs->frame + 1 < args.max_frames &&
                     npos + (unsigned long long)(cfg.N - Ts / 4) <= args.samples_per_capture) {
                     cs->fon = 1;
                     cs->fnumffts = cfg.numffts_const;
@@ -859,6 +885,11 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
                        still accumulated in ascending sample order from zero */
                     for (int e = (lo & ~1) + 4 * slot; __any_sync(0xffffffffu, e < hi); e += 4 * nslots) {
                         float en[4] = { 0.0f, 0.0f, 0.0f, 0.0f };
+                        float2 phv[4];
+                        if (m == 0 && e < hi) {
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) phv[k] = e + k < nint ? __ldg(phi_ft + e + k) : make_float2(0.0f, 0.0f);
+                        }
                         if (e < hi) {
                             const float2 *s2 = ftone + e;
                             float2 a0 = make_float2(0.0f, 0.0f), a1 = a0, a2 = a0, a3 = a0;
@@ -913,26 +944,22 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
                                 const int o = e + k;
-                                if (o >= lo && o < hi) {
-                                    const float2 ph = phi_ft[o];
-                                    *prod_slot(c, o, D) = make_float2(ft[k] * ph.x, ft[k] * ph.y);
-                                }
+                                if (o >= lo && o < hi) *prod_slot(c, o, D) = make_float2(ft[k] * phv[k].x, ft[k] * phv[k].y);
                             }
                         }
                     }
                 } else {
                     for (int i = lo + slot; __any_sync(0xffffffffu, i < hi); i += nslots) {
                         float en = 0.0f;
+                        float2 ph = make_float2(0.0f, 0.0f);
+                        if (m == 0 && i < hi) ph = __ldg(phi_ft + i);
                         if (i < hi) {
                             const float2 a = window_sum(ftone + i * step, Ts);
                             en = (a.x * a.x) + (a.y * a.y);
                         }
                         float ft = 0.0f;
                         for (int mm = 0; mm < M; ++mm) ft += __shfl_sync(0xffffffffu, en, lane_base + mm);
-                        if (m == 0 && i < hi) {
-                            const float2 ph = phi_ft[i];
-                            *prod_slot(c, i, D) = make_float2(ft * ph.x, ft * ph.y);
-                        }
+                        if (m == 0 && i < hi) *prod_slot(c, i, D) = make_float2(ft * ph.x, ft * ph.y);
                     }
                 }
                 __syncwarp();
@@ -1081,34 +1108,36 @@ __global__ void __launch_bounds__(G <= 2 ? 256 : 512, G <= 2 ? 2 : 1) fsk_demod_
             __syncthreads();
         }
 
-        /* ---- per-frame record, advance ------------------------------------------------- */
-        if (tid < G) {
-            FskCapShared *cs = cap_ptrs(smem, cfg, tid).cs;
-            if (cs->active) {
+        /* ---- per-frame record, advance, next frame's bookkeeping ---------------------------- */
+        if (tid == 0) {
+            for (int g = 0; g < G; ++g) {
+                FskCapShared *cs = cap_ptrs(smem, cfg, g).cs;
+                if (!cs->active) continue;
                 if (args.stats) {
-                    pirip_frame_stats s;
+                    pirip_frame_stats st;
                     for (int m = 0; m < 4; ++m) {
-                        s.f_est[m] = m < M ? cs->f_est[slot][m] : 0.0f;
-                        s.f2_est[m] = m < M ? cs->f2_est[slot][m] : 0.0f;
+                        st.f_est[m] = m < M ? cs->f_est[slot][m] : 0.0f;
+                        st.f2_est[m] = m < M ? cs->f2_est[slot][m] : 0.0f;
                     }
-                    s.norm_rx_timing = cs->norm_rx_timing;
-                    s.ppm = cs->ppm;
-                    s.SNRest = cs->SNRest;
-                    s.v_est = cs->v_est;
-                    s.rx_sig_pow = cs->rx_sig_pow;
-                    s.rx_nse_pow = cs->rx_nse_pow;
-                    s.EbNodB = cs->EbNodB;
-                    s.snr_est = cs->snr_est;
-                    s.foff = cs->foff;
-                    s.rx_timing = cs->rx_timing;
-                    s.nin_next = cs->nin_next;
-                    s.sample_offset = (int32_t)cs->pos;
-                    args.stats[(cap0 + tid) * args.max_frames + (size_t)cs->frame] = s;
+                    st.norm_rx_timing = cs->norm_rx_timing;
+                    st.ppm = cs->ppm;
+                    st.SNRest = cs->SNRest;
+                    st.v_est = cs->v_est;
+                    st.rx_sig_pow = cs->rx_sig_pow;
+                    st.rx_nse_pow = cs->rx_nse_pow;
+                    st.EbNodB = cs->EbNodB;
+                    st.snr_est = cs->snr_est;
+                    st.foff = cs->foff;
+                    st.rx_timing = cs->rx_timing;
+                    st.nin_next = cs->nin_next;
+                    st.sample_offset = (int32_t)cs->pos;
+                    args.stats[(cap0 + g) * args.max_frames + (size_t)cs->frame] = st;
                 }
                 cs->pos += (unsigned long long)cs->nin;
                 cs->nin = cs->nin_next;
                 cs->frame += 1;
             }
+            bookkeeping();
         }
         __syncthreads();
         if (pipelined) slot ^= 1;
