@@ -48,6 +48,26 @@ struct FskDevCfg {
     int pipeline;        /* the FFT block count is the same for every nin: estimate one frame ahead */
     int numffts_const;
     int smem_bytes;
+    /* ---- geometry of the batch kernel (fsk_kernel2.cu): one persistent CTA per SM ---- */
+    struct K2 {
+        int ok;            /* configuration supported by the batch kernel */
+        int gmax;          /* captures demodulated in lockstep by one CTA */
+        int threads;       /* threads per CTA */
+        int chunk;         /* samples per pipeline chunk of the streaming phase */
+        int ring;          /* f_dc ring: elements per tone (power of two, 4 chunks) */
+        int ering;         /* window-energy ring: floats per tone (power of two) */
+        int ckpt_every;    /* oscillator phase checkpoint spacing (samples) */
+        int nckpt;         /* checkpoints per tone */
+        int tail;          /* f_dc samples kept from the end of the previous frame, per tone */
+        int stage_bytes;   /* one staging buffer (two per capture) */
+        int numffts;       /* FFT blocks per frame (independent of nin) */
+        int fast_ts;       /* 1: the 16-window integrator path applies (P == Ts, Ts instantiated) */
+        int cap_stride;    /* bytes per capture block */
+        int off_stage, off_ring, off_tail, off_ckpt, off_ering, off_Sf, off_scal; /* inside a capture block */
+        int off_fft, off_tw, off_hann, off_perm, off_ctl;                        /* CTA-wide, after the capture blocks */
+        int smem_bytes;
+        int num_sms;
+    } k2;
 };
 
 /* per-capture scalars kept in shared memory for the life of the CTA */
@@ -113,6 +133,49 @@ struct FskBatchArgs {
 static inline size_t fsk_state_floats(int Ndft, int M, int Nmem) {
     return sizeof(FskDevStateHdr) / sizeof(float) + (size_t)Ndft + 2u * (size_t)M * (size_t)Nmem;
 }
+
+/* per-capture scalars of the batch kernel (fsk_kernel2.cu) */
+struct Fsk2CapShared {
+    float2 phi_c[4];
+    float2 dphi[2][4]; /* estimate slots by frame parity */
+    float f_est[2][4];
+    float f2_est[2][4];
+    int freqi[4];
+    float norm_rx_timing, ppm, snr_est, EbNodB;
+    float fract, one_minus_fract;
+    int low, high;
+    int nin, nin_next, nold;
+    int nan_flag, active, fon;
+    float SNRest, v_est, rx_sig_pow, rx_nse_pow, foff, rx_timing;
+    float sums[4];
+    unsigned long long pos;
+    unsigned long long stg_lo[2]; /* global address each staged window starts at */
+    unsigned stg_bytes[2];
+    int stg_valid[2];
+    int stg_fills[2]; /* TMA copies issued into each buffer so far: phase parity of its mbarrier */
+    int fast;         /* this frame takes the 16-window integrator path */
+    int frame;
+    int cap; /* capture index in the batch */
+    int pad;
+};
+
+#define FSK2_MAX_CHUNKS 32
+#define FSK2_MAX_G 16
+struct Fsk2CtaShared {
+    unsigned long long bar_osc[FSK2_MAX_CHUNKS]; /* oscillator warp wrote the phases of chunk c */
+    unsigned long long bar_mix[FSK2_MAX_CHUNKS]; /* every worker warp mixed its share of chunk c */
+    unsigned long long bar_int[FSK2_MAX_CHUNKS]; /* every worker warp integrated its share of chunk c */
+    unsigned long long bar_tim[FSK2_MAX_CHUNKS]; /* timing warp consumed the window energies of chunk c */
+    unsigned long long bar_in[FSK2_MAX_G][2];    /* TMA copy into staging buffer b of capture g landed */
+    int any_active;
+    int max_nin;
+    int G;
+    int any_generic; /* some active capture takes the generic integrator path this frame */
+};
+
+/* defined in fsk_kernel2.cu */
+cudaError_t fsk2_launch_demod(const FskDevCfg &cfg, const FskBatchArgs &args, size_t n_captures, cudaStream_t stream);
+cudaError_t fsk2_kernel_prepare(const FskDevCfg &cfg);
 
 /* defined in fsk_kernel.cu */
 cudaError_t fsk_launch_demod(const FskDevCfg &cfg, const FskBatchArgs &args, size_t n_captures, cudaStream_t stream);

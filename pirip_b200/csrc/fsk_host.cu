@@ -148,6 +148,82 @@ static bool cfg_valid(const pirip_fsk_cfg &c, std::string &why) {
     return true;
 }
 
+/* Geometry of the batch kernel (fsk_kernel2.cu): one persistent CTA of 768 threads per SM, as many
+   captures in lockstep as fit 227 KB.  Supported when the FFT block count does not depend on nin
+   (the next frame's frequency estimate then runs one frame ahead); otherwise, or with
+   PIRIP_FSK_K2=0, the batch entry points use fsk_kernel.cu. */
+static void derive_k2(const pirip_fsk_cfg &c, FskDevCfg &d) {
+    FskDevCfg::K2 &k = d.k2;
+    memset(&k, 0, sizeof k);
+    if (const char *e = getenv("PIRIP_FSK_K2"))
+        if (atoi(e) == 0) return;
+    const int half = d.Ndft / 2, nin_max = d.N + d.Ts / 4, nin_min = d.N - d.Ts / 4;
+    const bool fixed_nin = d.burst_mode || d.lock_nin;
+    const int n0 = nin_min / half - 1, n1 = d.N / half - 1, n2 = nin_max / half - 1;
+    if (n1 < 1 || (!fixed_nin && !(n0 == n1 && n1 == n2))) return;
+    if ((n1 + 1) * half > nin_min) return; /* the blocks must lie inside the shortest frame */
+    k.numffts = n1;
+    k.threads = 768;
+    k.chunk = 128;
+    while ((nin_max + k.chunk - 1) / k.chunk > FSK2_MAX_CHUNKS) k.chunk *= 2;
+    if (k.chunk < d.Ts + 16) return;       /* the 4-chunk ring must cover a task's history */
+    k.ring = 4 * k.chunk;
+    k.ering = 4 * k.chunk;
+    k.ckpt_every = 16;
+    k.nckpt = nin_max / k.ckpt_every + 2;
+    k.tail = align_up(2 * d.Ts + d.Ts / 4 + 2, 8);
+    const int bps = c.fmt == PIRIP_FMT_U8 ? 2 : (c.fmt == PIRIP_FMT_S16 ? 4 : 8);
+    k.stage_bytes = align_up(nin_max * bps + 32, 16);
+    const int step = d.Ts / c.P;
+    k.fast_ts = (step == 1 && (d.Ts == 24 || d.Ts == 20 || d.Ts == 40)) ? 1 : 0;
+    if ((3 + c.M) * c.Nsym > c.M * k.ering) return; /* decision scratch lives in the energy ring */
+    int off = 0;
+    k.off_stage = off;
+    off += 2 * k.stage_bytes;
+    k.off_ring = off;
+    off += align_up(c.M * (k.ring + 2) * 8, 16);
+    k.off_tail = off;
+    off += align_up(c.M * k.tail * 8, 16);
+    k.off_ckpt = off;
+    off += align_up(c.M * k.nckpt * 8, 16);
+    k.off_ering = off;
+    off += align_up(c.M * k.ering * 4, 16);
+    k.off_Sf = off;
+    off += align_up(2 * d.Ndft * 4, 16);
+    k.off_scal = off;
+    off += align_up((int)sizeof(Fsk2CapShared), 16);
+    while ((off & 127) != 32) off += 16; /* capture blocks 32 (mod 128) bytes apart: spreads the per-capture lanes over banks */
+    k.cap_stride = off;
+    k.num_sms = 148; /* plan_build replaces it with the device's SM count */
+    const int limit = 227 * 1024;
+    int gcap = k.threads / 32 - 2 - 4; /* at least four worker warps */
+    if (gcap > FSK2_MAX_G) gcap = FSK2_MAX_G;
+    if (gcap * c.M > 32) gcap = 32 / c.M; /* oscillator lanes (g, m) of one warp */
+    if (const char *e = getenv("PIRIP_FSK_K2_G")) {
+        const int v = atoi(e);
+        if (v >= 1 && v < gcap) gcap = v;
+    }
+    for (int g = gcap; g >= 1; --g) {
+        int o = 0;
+        k.off_fft = o;
+        o += align_up(g * d.Ndft * 8, 16);
+        k.off_tw = o;
+        o += align_up(d.Ndft * 8, 16);
+        k.off_hann = o;
+        o += align_up(d.Ndft * 4, 16);
+        k.off_perm = o;
+        o += align_up(d.Ndft * 2, 16);
+        k.off_ctl = o;
+        o += align_up((int)sizeof(Fsk2CtaShared) + g * 2 * (int)sizeof(void *), 16);
+        if (g * k.cap_stride + o <= limit) {
+            k.gmax = g;
+            k.smem_bytes = g * k.cap_stride + o;
+            k.ok = 1;
+            return;
+        }
+    }
+}
+
 /* fill every derived field of FskDevCfg except the device pointers */
 static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, int max_g, FskDevCfg &d, std::string &why) {
     memset(&d, 0, sizeof d);
@@ -345,6 +421,7 @@ static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, int
         why = "configuration needs more than 227 KB of shared memory per capture";
         return false;
     }
+    derive_k2(c, d);
     return true;
 }
 
@@ -380,6 +457,10 @@ static pirip_fsk_plan *plan_build(const pirip_fsk_cfg &cfg, int device, int burs
         delete p;
         return nullptr;
     }
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) p->dev.k2.num_sms = sms;
+    }
     p->h_hann = make_hann(p->dev.Ndft);
     const std::vector<float2> tw = make_twiddles(p->dev.Ndft);
     const std::vector<float2> pf = make_phi_ft(cfg.Rs, cfg.P, p->dev.nint);
@@ -393,7 +474,8 @@ static pirip_fsk_plan *plan_build(const pirip_fsk_cfg &cfg, int device, int burs
         !pirip::cuda_ok(cudaMemcpy(p->d_phi_ft, pf.data(), sizeof(float2) * pf.size(), cudaMemcpyHostToDevice), "copy phi_ft") ||
         !pirip::cuda_ok(cudaMalloc(&p->d_perm, sizeof(unsigned short) * pm.size()), "cudaMalloc perm") ||
         !pirip::cuda_ok(cudaMemcpy(p->d_perm, pm.data(), sizeof(unsigned short) * pm.size(), cudaMemcpyHostToDevice), "copy perm") ||
-        !pirip::cuda_ok(fsk_kernel_prepare(p->dev), "cudaFuncSetAttribute")) {
+        !pirip::cuda_ok(fsk_kernel_prepare(p->dev), "cudaFuncSetAttribute") ||
+        (p->dev.k2.ok && !pirip::cuda_ok(fsk2_kernel_prepare(p->dev), "cudaFuncSetAttribute (batch kernel)"))) {
         plan_free(p);
         return nullptr;
     }
@@ -450,7 +532,9 @@ extern "C" int pirip_fsk_demod_batch_dev(pirip_fsk_plan *plan, const void *d_iq,
     a.nframes = d_nframes;
     a.n_captures = n_captures;
     a.tma_ok = (reinterpret_cast<size_t>(d_iq) & 15) == 0 && getenv("PIRIP_FSK_NO_TMA") == nullptr;
-    if (!pirip::cuda_ok(fsk_launch_demod(plan->dev, a, n_captures, (cudaStream_t)stream), "fsk_demod_kernel launch"))
+    if (plan->dev.k2.ok) {
+        if (!pirip::cuda_ok(fsk2_launch_demod(plan->dev, a, n_captures, (cudaStream_t)stream), "fsk2_kernel launch")) return -11;
+    } else if (!pirip::cuda_ok(fsk_launch_demod(plan->dev, a, n_captures, (cudaStream_t)stream), "fsk_demod_kernel launch"))
         return -11;
     pirip::count_launch();
     return 0;
