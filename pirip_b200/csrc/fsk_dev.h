@@ -62,9 +62,11 @@ struct FskDevCfg {
         int stage_bytes;   /* one staging buffer (two per capture) */
         int numffts;       /* FFT blocks per frame (independent of nin) */
         int fast_ts;       /* 1: the 16-window integrator path applies (P == Ts, Ts instantiated) */
+        int fft_warps;     /* warps that take FFT tasks */
+        int ering_fft_off; /* float offset of the FFT scratch borrowed from a capture's energy ring */
         int cap_stride;    /* bytes per capture block */
         int off_stage, off_ring, off_tail, off_ckpt, off_ering, off_Sf, off_scal; /* inside a capture block */
-        int off_fft, off_tw, off_hann, off_perm, off_ctl;                        /* CTA-wide, after the capture blocks */
+        int off_fft, off_tw, off_hann, off_perm, off_phift, off_ctl;             /* CTA-wide, after the capture blocks */
         int smem_bytes;
         int num_sms;
     } k2;
@@ -154,16 +156,17 @@ struct Fsk2CapShared {
     int stg_valid[2];
     int stg_fills[2]; /* TMA copies issued into each buffer so far: phase parity of its mbarrier */
     int fast;         /* this frame takes the 16-window integrator path */
+    int sf_turn;      /* FFT block whose magnitudes the IIR spectrum takes next */
     int frame;
     int cap; /* capture index in the batch */
-    int pad;
 };
 
 #define FSK2_MAX_CHUNKS 32
+/* FFT scratch slot of one FFT warp, in float2 elements: Ndft, plus the bank skew of the 256-point exchange */
+#define FSK2_FFT_SLOT_ELEMS(ndft) ((ndft) + 16)
+#define FSK2_CKPT_EVERY 16 /* oscillator phase checkpoint spacing (samples) */
 #define FSK2_MAX_G 16
 struct Fsk2CtaShared {
-    unsigned long long bar_osc[FSK2_MAX_CHUNKS]; /* oscillator warp wrote the phases of chunk c */
-    unsigned long long bar_mix[FSK2_MAX_CHUNKS]; /* every worker warp mixed its share of chunk c */
     unsigned long long bar_int[FSK2_MAX_CHUNKS]; /* every worker warp integrated its share of chunk c */
     unsigned long long bar_tim[FSK2_MAX_CHUNKS]; /* timing warp consumed the window energies of chunk c */
     unsigned long long bar_in[FSK2_MAX_G][2];    /* TMA copy into staging buffer b of capture g landed */
@@ -171,6 +174,8 @@ struct Fsk2CtaShared {
     int max_nin;
     int G;
     int any_generic; /* some active capture takes the generic integrator path this frame */
+    int task_ctr[FSK2_MAX_CHUNKS + 1]; /* worker task counter of every pipeline iteration */
+    int pad2[3];
 };
 
 /* defined in fsk_kernel2.cu */

@@ -163,13 +163,17 @@ static void derive_k2(const pirip_fsk_cfg &c, FskDevCfg &d) {
     if (n1 < 1 || (!fixed_nin && !(n0 == n1 && n1 == n2))) return;
     if ((n1 + 1) * half > nin_min) return; /* the blocks must lie inside the shortest frame */
     k.numffts = n1;
-    k.threads = 768;
+    k.threads = 512; /* 16 warps (14 workers, timing, oscillator), 128 registers per thread */
+    if (const char *e = getenv("PIRIP_FSK_K2_NW")) {
+        const int v = atoi(e);
+        if (v == 16 || v == 20 || v == 24) k.threads = 32 * v;
+    }
     k.chunk = 128;
     while ((nin_max + k.chunk - 1) / k.chunk > FSK2_MAX_CHUNKS) k.chunk *= 2;
     if (k.chunk < d.Ts + 16) return;       /* the 4-chunk ring must cover a task's history */
     k.ring = 4 * k.chunk;
     k.ering = 4 * k.chunk;
-    k.ckpt_every = 16;
+    k.ckpt_every = FSK2_CKPT_EVERY;
     k.nckpt = nin_max / k.ckpt_every + 2;
     k.tail = align_up(2 * d.Ts + d.Ts / 4 + 2, 8);
     const int bps = c.fmt == PIRIP_FMT_U8 ? 2 : (c.fmt == PIRIP_FMT_S16 ? 4 : 8);
@@ -196,8 +200,7 @@ static void derive_k2(const pirip_fsk_cfg &c, FskDevCfg &d) {
     k.cap_stride = off;
     k.num_sms = 148; /* plan_build replaces it with the device's SM count */
     const int limit = 227 * 1024;
-    int gcap = k.threads / 32 - 2 - 4; /* at least four worker warps */
-    if (gcap > FSK2_MAX_G) gcap = FSK2_MAX_G;
+    int gcap = FSK2_MAX_G;
     if (gcap * c.M > 32) gcap = 32 / c.M; /* oscillator lanes (g, m) of one warp */
     if (const char *e = getenv("PIRIP_FSK_K2_G")) {
         const int v = atoi(e);
@@ -206,19 +209,27 @@ static void derive_k2(const pirip_fsk_cfg &c, FskDevCfg &d) {
     for (int g = gcap; g >= 1; --g) {
         int o = 0;
         k.off_fft = o;
-        o += align_up(g * d.Ndft * 8, 16);
+        o += align_up((k.threads / 64) * FSK2_FFT_SLOT_ELEMS(d.Ndft) * 8, 16); /* a dedicated FFT scratch slot for half the warps */
         k.off_tw = o;
         o += align_up(d.Ndft * 8, 16);
         k.off_hann = o;
         o += align_up(d.Ndft * 4, 16);
         k.off_perm = o;
         o += align_up(d.Ndft * 2, 16);
+        k.off_phift = o;
+        o += align_up(d.nint * 8, 16);
         k.off_ctl = o;
         o += align_up((int)sizeof(Fsk2CtaShared) + g * 2 * (int)sizeof(void *), 16);
         if (g * k.cap_stride + o <= limit) {
             k.gmax = g;
             k.smem_bytes = g * k.cap_stride + o;
             k.ok = 1;
+            /* the other half of the warps borrow FFT scratch from the energy rings of captures 0 .. NW/2-1, above the
+               decision scratch, when there are enough capture blocks and room */
+            const int nw = k.threads / 32;
+            k.ering_fft_off = align_up((3 + c.M) * c.Nsym, 64);
+            const bool room = k.ering_fft_off + 2 * FSK2_FFT_SLOT_ELEMS(d.Ndft) <= c.M * k.ering && g >= nw / 2;
+            k.fft_warps = room ? nw : nw / 2;
             return;
         }
     }

@@ -26,10 +26,10 @@
  *                       ascending order; 20 16-byte loads per 384 adds), window energies to a
  *                       small ring;
  *      timing warp      lane g: serial timing-line sum of capture g right behind the workers;
- *      FFT warps        warp g: the frequency estimate of the NEXT frame of capture g (its
- *                       position is already known and the TMA copy was issued one frame
- *                       ahead), Hann + radix-4/2 FFT blocks, magnitude IIR held in registers,
- *                       peak pick / mask, dphi.
+ *      FFT warps        the frequency estimate of the NEXT frame of every capture (its position is
+ *                       already known and its TMA copy was issued a frame ahead) as a pool of
+ *                       (capture, block) tasks: Hann + radix-4/2 FFT, magnitudes applied to the IIR
+ *                       spectrum in block order, peak pick / mask, dphi.
  *  - Decision phase: lane (g, symbol) re-sums both tones' windows, interpolates, decides;
  *    then the four serial per-frame sums, SNR / EbNo, optional LLRs, stats record.
  *  - The f_dc ring is XOR-swizzled in 16-byte units by the 128-byte row index, so the
@@ -87,17 +87,32 @@ __device__ __forceinline__ void mbar_arrive(u64 *bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
+/* Wait for the phase with the given parity.  try_wait returns after a short system-dependent time when the
+   phase is still pending (measured on B200: a spinning loop of try_wait was 42% of all issued instructions),
+   so a pending wait backs off with nanosleep and leaves the issue slots to the warps that have work. */
+__device__ __forceinline__ bool mbar_try(u64 *bar, unsigned parity) {
+    unsigned ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "WAIT_LOOP:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
-        "@p bra DONE;\n\t"
-        "bra WAIT_LOOP;\n\t"
-        "DONE:\n\t}" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
+    return ok != 0;
 }
+__device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
+    if (mbar_try(bar, parity)) return;
+    unsigned ns = 32;
+    while (!mbar_try(bar, parity)) {
+        __nanosleep(ns);
+        ns = ns < 256 ? ns * 2 : 256;
+    }
+}
+/* hardware named barriers: a warp blocked in bar.sync costs no issue slots (unlike a polled mbarrier) */
+__device__ __forceinline__ void nbar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void nbar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
 __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, unsigned bytes, u64 *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
@@ -213,26 +228,252 @@ __device__ __forceinline__ void warp_fft_mag(const unsigned char *src, int fmt, 
     __syncwarp();
 }
 
-/* numffts Hann-windowed half-overlapped FFT blocks of one frame; the single-pole magnitude IIR runs
-   over the blocks in order with the spectrum held in registers ([U fsk.c::fsk_demod_freq_est]) */
+/* ---- frequency estimator ([U fsk.c::fsk_demod_freq_est]) as a pool of FFT tasks --------------------------------
+   Task (g, j) = FFT block j of the frame being estimated for capture g.  The FFT warps take tasks round-robin, so
+   the blocks of one capture are transformed concurrently by different warps; the single-pole magnitude IIR must run
+   over the blocks in order, so each task applies its magnitudes (held in registers) to the spectrum when its turn
+   comes (cs->sf_turn), and the task of the last block picks the tones. */
+
+/* tone picking of one capture from its updated spectrum Sf (peak estimator with blanking, mask estimator, dphi) */
+__device__ __noinline__ void pick_tones(const FskDevCfg &cfg, Fsk2CapShared *cs, const float *Sf, float *tmpS, int fb, int M, int lane) {
+    const int Ndft = cfg.Ndft;
+    for (int i = lane; i < Ndft; i += 32) tmpS[i] = Sf[i];
+    __syncwarp();
+    /* estimator 1: M rounds of argmax (first maximum wins) + blanking, on the scratch copy */
+    for (int r = 0; r < M; ++r) {
+        float best = 0.0f;
+        int ibest = 0;
+        for (int j = cfg.st + lane; j < cfg.en; j += 32) {
+            const float v = tmpS[j];
+            if (v > best) {
+                best = v;
+                ibest = j;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, ibest, off);
+            if (ov > best || (ov == best && oi < ibest)) {
+                best = ov;
+                ibest = oi;
+            }
+        }
+        int f_min = ibest - cfg.f_zero;
+        f_min = f_min < 0 ? 0 : f_min;
+        int f_max = ibest + cfg.f_zero;
+        f_max = f_max > Ndft ? Ndft : f_max;
+        for (int j = f_min + lane; j < f_max; j += 32) tmpS[j] = 0.0f;
+        if (lane == 0) cs->freqi[r] = ibest - (Ndft >> 1);
+        __syncwarp();
+    }
+    if (lane == 0) {
+        int fi[4];
+        for (int m = 0; m < M; ++m) fi[m] = cs->freqi[m];
+        for (int a = 1; a < M; ++a) { /* ascending insertion sort */
+            const int key = fi[a];
+            int b = a - 1;
+            while (b >= 0 && fi[b] > key) {
+                fi[b + 1] = fi[b];
+                --b;
+            }
+            fi[b + 1] = key;
+        }
+        for (int m = 0; m < M; ++m) cs->f_est[fb][m] = (float)fi[m] * cfg.fs_over_ndft;
+    }
+    /* estimator 2: slide the tone mask over Sf, first maximum wins */
+    {
+        float best = 0.0f;
+        int bbest = 0x7fffffff;
+        for (int b = cfg.st + lane; b < cfg.en - cfg.len_mask; b += 32) {
+            float corr = 0.0f;
+            for (int q = 0; q < cfg.nmask; ++q) corr += Sf[b + cfg.mask_pos[q]];
+            if (corr > best) {
+                best = corr;
+                bbest = b;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bbest, off);
+            if (ov > best || (ov == best && oi < bbest)) {
+                best = ov;
+                bbest = oi;
+            }
+        }
+        if (lane == 0) {
+            const int b_max = (best > 0.0f) ? bbest : cfg.st;
+            const float foff = (float)((b_max - (Ndft >> 1)) * cfg.Fs / Ndft);
+            for (int m = 0; m < M; ++m) cs->f2_est[fb][m] = foff + (float)(m * cfg.tone_spacing);
+        }
+    }
+    __syncwarp();
+    if (lane < M) {
+        const float f = cfg.est_type ? cs->f2_est[fb][lane] : cs->f_est[fb][lane];
+        const float arg = (float)(EM_TWO_PI * (double)(f / (float)cfg.Fs));
+        double sn, csn;
+        em_sincos((double)arg, &sn, &csn);
+        cs->dphi[fb][lane] = make_float2((float)csn, (float)sn);
+    }
+    __syncwarp();
+}
+
+/* one FFT task: block j of capture cs for the frame of parity fb; src = that frame's raw samples */
 template <int LOGN>
-__device__ __noinline__ void frame_spectrum(const unsigned char *src, int fmt, int numffts, float2 *buf, const float *Sf_in,
-                                            float *Sf_out, const float2 *tw, const float *hann, const unsigned short *perm, float tc,
-                                            int lane) {
+__device__ __noinline__ void fft_task(const FskDevCfg &cfg, Fsk2CapShared *cs, float *Sf2, const unsigned char *src, float2 *buf,
+                                      const float2 *tw, const float *hann, const unsigned short *perm, int j, int nb, int fb, int M,
+                                      int lane) {
     constexpr int N = 1 << LOGN, Q = N / 32;
-    const float omtc = 1.0f - tc;
-    float s[Q];
+    float mg[Q];
+    warp_fft_mag<LOGN>(src, cfg.fmt, j * (N >> 1), buf, mg, tw, hann, perm, lane);
+    /* ordered IIR: wait for block j - 1 of this capture */
+    volatile int *turn = &cs->sf_turn;
+    {
+        int tries = 0;
+        while (*turn != j) {
+            if (++tries > 64) __nanosleep(100);
+        }
+    }
+    __threadfence_block();
+    const float tc = cfg.tc, omtc = 1.0f - tc;
+    const float *Sf_in = j == 0 ? Sf2 + (size_t)(fb ^ 1) * N : Sf2 + (size_t)fb * N;
+    float *Sf_out = Sf2 + (size_t)fb * N;
 #pragma unroll
-    for (int q = 0; q < Q; ++q) s[q] = Sf_in[lane + (q << 5)];
-    for (int j = 0; j < numffts; ++j) {
-        float mg[Q];
-        warp_fft_mag<LOGN>(src, fmt, j * (N >> 1), buf, mg, tw, hann, perm, lane);
+    for (int q = 0; q < Q; ++q) {
+        const int i = lane + (q << 5);
+        Sf_out[i] = (Sf_in[i] * omtc) + (mg[q] * tc);
+    }
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) *turn = j + 1 < nb ? j + 1 : 0; /* the tones are picked in the next phase (pick_tones) */
+}
+
+/* ---- 256-point fast path: two FFT blocks per warp, two radix-4 levels per register pass ----------------------
+   Same butterflies, twiddles and operation order as kiss_fft's 4x4x4x4 decimation in time (and as warp_fft_mag),
+   so the same floats; only the data movement differs.  Lanes 0-15 transform block j0, lanes 16-31 block j0 + 1.
+   Pass A: lane L holds the 16 (digit-reversed) positions 16 L + i and runs levels m = 1 and m = 4 in registers.
+   Exchange through shared memory (real parts, then imaginary parts: 2 KB of scratch serve both blocks).
+   Pass B: lane L holds positions 16 h + L and runs levels m = 16 and m = 64; position = frequency bin.
+   The twiddle of every level-1 butterfly is tw[0] = (1, -0): multiplying by it changes at most the sign of a zero,
+   which the magnitudes cannot see, so level 1 skips the multiplications. */
+__device__ __forceinline__ void bfly4(float2 &F0, float2 &F1, float2 &F2, float2 &F3, float2 T0, float2 T1, float2 T2) {
+    const float2 s0 = cmul(F1, T0), s1 = cmul(F2, T1), s2 = cmul(F3, T2);
+    const float2 s5 = csub(F0, s1);
+    const float2 G0 = cadd(F0, s1);
+    const float2 s3 = cadd(s0, s2), s4 = csub(s0, s2);
+    F2 = csub(G0, s3);
+    F0 = cadd(G0, s3);
+    F1 = make_float2(s5.x + s4.y, s5.y - s4.x);
+    F3 = make_float2(s5.x - s4.y, s5.y + s4.x);
+}
+__device__ __forceinline__ void bfly4_unit(float2 &F0, float2 &F1, float2 &F2, float2 &F3) {
+    const float2 s0 = F1, s1 = F2, s2 = F3;
+    const float2 s5 = csub(F0, s1);
+    const float2 G0 = cadd(F0, s1);
+    const float2 s3 = cadd(s0, s2), s4 = csub(s0, s2);
+    F2 = csub(G0, s3);
+    F0 = cadd(G0, s3);
+    F1 = make_float2(s5.x + s4.y, s5.y - s4.x);
+    F3 = make_float2(s5.x - s4.y, s5.y + s4.x);
+}
+
+#define FSK2_XCHG_HALF (17 * 16) /* floats per block in the exchange scratch (16 rows of 17): the blocks end up 16 banks apart */
+
+/* magnitudes of bins 16 h + L (L = lane & 15) of block j0 (lanes 0-15) / j0 + 1 (lanes 16-31) in mg[h] */
+__device__ __forceinline__ void fft256_pair(const unsigned char *src, int fmt, int first0, bool two, float *xbuf, const float2 *tw,
+                                            const float *hann, float (&mg)[16], int lane) {
+    const int half = lane >> 4, L = lane & 15;
+    const int first = first0 + ((two && half) ? 128 : 0); /* an absent second block repeats the first (discarded) */
+    float2 x[16];
+    {
+        const int c = (L & 3) * 4 + (L >> 2);
 #pragma unroll
-        for (int q = 0; q < Q; ++q) s[q] = (s[q] * omtc) + (mg[q] * tc);
+        for (int i = 0; i < 16; ++i) {
+            const int n = (i & 3) * 64 + (i >> 2) * 16 + c; /* input index whose digit-reversed position is 16 L + i */
+            const float h = hann[n];
+            const float2 v = raw_sample(src, fmt, first + n);
+            x[i] = make_float2(h * v.x, h * v.y);
+        }
+    }
+    /* level m = 1: positions 4 q + {0,1,2,3} */
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bfly4_unit(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+    /* level m = 4: positions k + {0,4,8,12}, twiddles tw[16 k], tw[32 k], tw[48 k] */
+#pragma unroll
+    for (int k = 0; k < 4; ++k) bfly4(x[k], x[k + 4], x[k + 8], x[k + 12], tw[16 * k], tw[32 * k], tw[48 * k]);
+    /* exchange: position 16 L + i -> lane i; rows padded to 17 words and the two blocks 16 banks apart, so the 32
+       lanes hit 32 distinct banks both ways and every access is base + immediate */
+    float *xw = xbuf + half * FSK2_XCHG_HALF + 17 * L; /* writer view: position 16 L + i at word 17 L + i */
+    const float *xr = xbuf + half * FSK2_XCHG_HALF + L; /* reader view: position 16 h + L at word 17 h + L */
+    float2 y[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) xw[i] = x[i].x;
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 16; ++h) y[h].x = xr[17 * h];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) xw[i] = x[i].y;
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 16; ++h) y[h].y = xr[17 * h];
+    __syncwarp();
+    /* level m = 16: positions 64 b + L + 16 r, twiddles tw[4 L], tw[8 L], tw[12 L] */
+    {
+        const float2 T0 = tw[4 * L], T1 = tw[8 * L], T2 = tw[12 * L];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bfly4(y[4 * b], y[4 * b + 1], y[4 * b + 2], y[4 * b + 3], T0, T1, T2);
+    }
+    /* level m = 64: positions k + 64 r with k = 16 c + L */
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const int k = 16 * c + L;
+        bfly4(y[c], y[c + 4], y[c + 8], y[c + 12], tw[k], tw[2 * k], tw[3 * k]);
     }
 #pragma unroll
-    for (int q = 0; q < Q; ++q) Sf_out[lane + (q << 5)] = s[q];
+    for (int h = 0; h < 16; ++h) mg[h] = sqrtf((y[h].x * y[h].x) + (y[h].y * y[h].y));
+}
+
+/* FFT task pair: blocks j0 and j0 + 1 (if it exists) of capture cs for the frame of parity fb */
+__device__ __noinline__ void fft256_task(const FskDevCfg &cfg, Fsk2CapShared *cs, float *Sf2, const unsigned char *src, float2 *buf,
+                                         const float2 *tw, const float *hann, int j0, int nb, int fb, int M, int lane) {
+    constexpr int N = 256;
+    const bool two = j0 + 1 < nb;
+    float mg[16];
+    fft256_pair(src, cfg.fmt, j0 * (N >> 1), two, reinterpret_cast<float *>(buf), tw, hann, mg, lane);
+    /* ordered IIR: wait for the blocks before j0 of this capture (short spin, then back off) */
+    volatile int *turn = &cs->sf_turn;
+    {
+        int tries = 0;
+        while (*turn != j0) {
+            if (++tries > 64) __nanosleep(100);
+        }
+    }
+    __threadfence_block();
+    const int half = lane >> 4, L = lane & 15;
+    const float tc = cfg.tc, omtc = 1.0f - tc;
+    const float *Sf_in = j0 == 0 ? Sf2 + (size_t)(fb ^ 1) * N : Sf2 + (size_t)fb * N;
+    float *Sf_out = Sf2 + (size_t)fb * N;
+    if (half == 0) {
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+            const int i = (16 * h + L + (N >> 1)) & (N - 1); /* fft shift: DC at bin N/2 */
+            Sf_out[i] = (Sf_in[i] * omtc) + (mg[h] * tc);
+        }
+    }
     __syncwarp();
+    if (half == 1 && two) {
+#pragma unroll
+        for (int h = 0; h < 16; ++h) {
+            const int i = (16 * h + L + (N >> 1)) & (N - 1);
+            Sf_out[i] = (Sf_out[i] * omtc) + (mg[h] * tc);
+        }
+    }
+    __threadfence_block();
+    __syncwarp();
+    const int jn = j0 + (two ? 2 : 1);
+    if (lane == 0) *turn = jn < nb ? jn : 0; /* the tones are picked in the next phase (pick_tones) */
 }
 
 struct Cap2 {
@@ -335,34 +576,31 @@ __device__ __forceinline__ int windows_after_chunk(const FrameView &v, int c, in
     return outputs_ready(v.nold, jc, Ts, step, nint);
 }
 
-/* 16 adjacent integrator windows of one tone: window k sums ring samples s0 + k .. s0 + k + TS - 1 in
-   ascending order from zero; |sum|^2 of window k to dst[k].  s0 even. */
-template <int TS>
-__device__ __forceinline__ void integrate16(const float2 *ring_m, unsigned s0, unsigned umask, float *dst) {
-    u64 acc[16];
+/* NWIN adjacent integrator windows of one tone: window k sums ring samples s0 + k .. s0 + k + TS - 1 in ascending order
+   from zero (packed f32x2 adds: real and imaginary part together); |sum|^2 of window k in en[k].  s0 even. */
+template <int TS, int NWIN>
+__device__ __forceinline__ void integrate_windows(const float2 *ring_m, unsigned s0, unsigned umask, float (&en)[NWIN]) {
+    u64 acc[NWIN];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = 0ull;
+    for (int k = 0; k < NWIN; ++k) acc[k] = 0ull;
     const unsigned u0 = s0 >> 1;
-    constexpr int NU = (16 + TS) / 2;
+    constexpr int NU = (NWIN + TS) / 2;
 #pragma unroll
     for (int r = 0; r < NU; ++r) {
         const unsigned u = (u0 + r) & umask;
         const unsigned pu = u ^ ((u >> 3) & 7u);
         const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(ring_m + 2 * pu);
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < NWIN; ++k) {
             if (2 * r >= k && 2 * r < k + TS) acc[k] = add2(acc[k], v.x);
             if (2 * r + 1 >= k && 2 * r + 1 < k + TS) acc[k] = add2(acc[k], v.y);
         }
     }
-    float en[16];
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < NWIN; ++k) {
         const float2 a = upk(acc[k]);
         en[k] = (a.x * a.x) + (a.y * a.y);
     }
-#pragma unroll
-    for (int k = 0; k < 16; k += 4) *reinterpret_cast<float4 *>(dst + k) = make_float4(en[k], en[k + 1], en[k + 2], en[k + 3]);
 }
 
 /* one window, any Ts / alignment */
@@ -374,14 +612,19 @@ __device__ __forceinline__ float window_energy(const float2 *ring_m, unsigned s0
 }
 
 #ifdef FSK2_TIMING
-#define TMARK(var)                      \
-    do {                                \
-        const long long tn_ = clock64(); \
-        var += tn_ - tl_;               \
-        tl_ = tn_;                      \
+/* Debug trace (build with EXTRA=-DFSK2_TIMING): lane 0 of every warp of block 0 stores (code, clock64) pairs for a
+   couple of steady-state frames; read back with pirip_debug_trace().  Global stores only: nothing waits on them. */
+#define FSK2_TRACE_N 512
+__device__ long long g_trace[32][FSK2_TRACE_N];
+#define TR(code)                                                                                                   \
+    do {                                                                                                           \
+        if (tr_on && tr_n < FSK2_TRACE_N) { /* a barrier only blocks at the next access to protected state: touch it first */ \
+            const int sink_ = *reinterpret_cast<volatile int *>(&ctl->G);                                           \
+            g_trace[warp][tr_n++] = ((long long)(code) << 48) | ((clock64() + (sink_ & 0)) & 0xffffffffffffll);     \
+        }                                                                                                          \
     } while (0)
 #else
-#define TMARK(var)
+#define TR(code)
 #endif
 
 template <int M, int NW>
@@ -389,48 +632,53 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int nthreads = NW * 32;
+    /* streaming phase: workers [0, W), timing warp, oscillator warp.  The frequency estimate of the next frame is a
+       phase of its own run by all NF = NW warps (FFT, streaming and decision code each fit the instruction cache;
+       run concurrently they thrashed it: "no instruction" was the top stall reason) */
+    constexpr int W = NW - 2, nwt = W * 32;
+    const int NF = cfg.k2.fft_warps; /* warps of the FFT phase: NW / 2 with a dedicated scratch slot, the rest borrow the
+                                        idle upper part of a capture's energy ring */
+    constexpr int osc_warp = NW - 1, tim_warp = NW - 2;
+    constexpr int CKE = FSK2_CKPT_EVERY;
     const int Ndft = cfg.Ndft, nint = cfg.nint, Nsym = cfg.Nsym, P = cfg.P, Ts = cfg.Ts, Nmem = cfg.Nmem, Nbits = cfg.Nbits;
     const int step = Ts / P;
-    const int CH = cfg.k2.chunk, R = cfg.k2.ring, ER = cfg.k2.ering, CKE = cfg.k2.ckpt_every, NCK = cfg.k2.nckpt, TAILN = cfg.k2.tail;
+    const int CH = cfg.k2.chunk, R = cfg.k2.ring, ER = cfg.k2.ering, NCK = cfg.k2.nckpt, TAILN = cfg.k2.tail;
     const unsigned rmask = (unsigned)R - 1u, umask = ((unsigned)R >> 1) - 1u;
     const int RT = R + 2; /* tone stride of the ring: 16 bytes of skew between tones */
     const int fmt = cfg.fmt;
+    const int nb = cfg.k2.numffts;
     unsigned char *cta = smem + (size_t)cfg.k2.gmax * cfg.k2.cap_stride;
     Fsk2CtaShared *ctl = reinterpret_cast<Fsk2CtaShared *>(cta + cfg.k2.off_ctl);
     float2 *tw = reinterpret_cast<float2 *>(cta + cfg.k2.off_tw);
     float *hann = reinterpret_cast<float *>(cta + cfg.k2.off_hann);
     unsigned short *perm = reinterpret_cast<unsigned short *>(cta + cfg.k2.off_perm);
     float2 *fft_slots = reinterpret_cast<float2 *>(cta + cfg.k2.off_fft);
-    const float2 *phi_ft = cfg.phi_ft;
-    constexpr int osc_warp = NW - 1, tim_warp = NW - 2;
+    float2 *phi_ft = reinterpret_cast<float2 *>(cta + cfg.k2.off_phift); /* timing-line oscillator, [nint] */
+    const unsigned char **srcp = reinterpret_cast<const unsigned char **>(ctl + 1); /* [gmax][2] raw-sample pointer per staging buffer */
+    const bool is_worker = warp < W;
+    const int wtid = warp * 32 + lane;
 
     for (int i = tid; i < Ndft; i += nthreads) {
         tw[i] = cfg.twiddle[i];
         hann[i] = cfg.hann[i];
         perm[i] = cfg.perm[i];
     }
+    for (int i = tid; i < nint; i += nthreads) phi_ft[i] = cfg.phi_ft[i];
 
     const size_t ncap = args.n_captures;
     const int grid = (int)gridDim.x;
     const int ncap_cta = ncap > blockIdx.x ? (int)((ncap - blockIdx.x + grid - 1) / grid) : 0;
 #ifdef FSK2_TIMING
-    long long t_osc = 0, t_oscw = 0, t_wosc = 0, t_mix = 0, t_wmix = 0, t_int = 0, t_wtim = 0, t_tim = 0, t_timw = 0, t_fft = 0,
-              t_fftw = 0, t_stream = 0, t_dec = 0, t_sum = 0, t_llr = 0, t_adv = 0, t_pre = 0;
-    long long tl_ = clock64();
+    bool tr_on = false;
+    int tr_n = 0;
 #endif
 
     for (int k0 = 0; k0 < ncap_cta; k0 += cfg.k2.gmax) {
         const int G = ncap_cta - k0 < cfg.k2.gmax ? ncap_cta - k0 : cfg.k2.gmax;
-        const int W = NW - 2 - G;     /* worker warps: G .. NW-3 */
-        const int nwt = W * 32;
-        const int wtid = (warp - G) * 32 + lane;
-        const bool is_fft = warp < G, is_worker = warp >= G && warp < NW - 2;
         __syncthreads();
         /* ---- barriers and initial state of the group ---- */
         if (tid == 0) {
             for (int i = 0; i < FSK2_MAX_CHUNKS; ++i) {
-                mbar_init(&ctl->bar_osc[i], 1);
-                mbar_init(&ctl->bar_mix[i], W);
                 mbar_init(&ctl->bar_int[i], W);
                 mbar_init(&ctl->bar_tim[i], 1);
             }
@@ -462,6 +710,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                 cs->pos = 0;
                 cs->frame = 0;
                 cs->nan_flag = 0;
+                cs->sf_turn = 0;
                 cs->cap = (int)(blockIdx.x + (size_t)(k0 + g) * grid);
                 cs->stg_valid[0] = cs->stg_valid[1] = 0;
                 cs->stg_fills[0] = cs->stg_fills[1] = 0;
@@ -472,175 +721,125 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
             }
         }
         __syncthreads();
-        const unsigned char *src_cur = nullptr, *src_nxt = nullptr; /* meaningful in threads tid < G */
         if (tid < G) {
             const Cap2 c = cap2(smem, cfg, tid);
-            if (c.cs->fon) stage_issue(cfg, args, c, 0, 0, &ctl->bar_in[tid][0], &src_cur);
+            const unsigned char *s0 = nullptr;
+            if (c.cs->fon) stage_issue(cfg, args, c, 0, 0, &ctl->bar_in[tid][0], &s0);
+            srcp[2 * tid + 0] = s0;
         }
-        /* the raw-sample pointers of the two staging buffers live in shared memory for all roles */
-        const unsigned char **srcp = reinterpret_cast<const unsigned char **>(ctl + 1); /* [gmax][2], after the control block */
-        if (tid < G) srcp[2 * tid + 0] = src_cur;
         __syncthreads();
 
-        /* ---- prologue: frequency estimate of frame 0 ---- */
-        auto freq_estimate = [&](int g, int fb) {
-            /* FFT warp of capture g: estimate for the frame whose parity is fb, from staging buffer fb */
-            const Cap2 c = cap2(smem, cfg, g);
-            Fsk2CapShared *cs = c.cs;
-            if (cs->stg_valid[fb]) mbar_wait(&ctl->bar_in[g][fb], (unsigned)(cs->stg_fills[fb] - 1) & 1u);
-            const unsigned char *src = srcp[2 * g + fb];
-            float2 *buf = fft_slots + (size_t)g * Ndft;
-            const float *Sf_in = c.Sf + (size_t)(fb ^ 1) * Ndft;
-            float *Sf_out = c.Sf + (size_t)fb * Ndft;
-            switch (cfg.log2_ndft) {
-                case 6: frame_spectrum<6>(src, fmt, cfg.k2.numffts, buf, Sf_in, Sf_out, tw, hann, perm, cfg.tc, lane); break;
-                case 7: frame_spectrum<7>(src, fmt, cfg.k2.numffts, buf, Sf_in, Sf_out, tw, hann, perm, cfg.tc, lane); break;
-                case 8: frame_spectrum<8>(src, fmt, cfg.k2.numffts, buf, Sf_in, Sf_out, tw, hann, perm, cfg.tc, lane); break;
-                case 9: frame_spectrum<9>(src, fmt, cfg.k2.numffts, buf, Sf_in, Sf_out, tw, hann, perm, cfg.tc, lane); break;
-                default: frame_spectrum<10>(src, fmt, cfg.k2.numffts, buf, Sf_in, Sf_out, tw, hann, perm, cfg.tc, lane); break;
+        /* the FFT tasks of this warp for the frame of parity fbt (staging buffer fbt) */
+        auto fft_tasks = [&](int fbt) {
+            if (warp >= NF) return;
+            float2 *buf = warp < NW / 2 ? fft_slots + (size_t)warp * FSK2_FFT_SLOT_ELEMS(Ndft)
+                                        : reinterpret_cast<float2 *>(cap2(smem, cfg, warp - NW / 2).ering + cfg.k2.ering_fft_off);
+            const bool pairs = cfg.log2_ndft == 8;        /* 256-point fast path: two blocks per task */
+            const int tpc = pairs ? (nb + 1) >> 1 : nb;   /* tasks per capture */
+            for (int t = warp; t < G * tpc; t += NF) {
+                const int g = t / tpc, j = (t - g * tpc) * (pairs ? 2 : 1);
+                const Cap2 c = cap2(smem, cfg, g);
+                Fsk2CapShared *cs = c.cs;
+                if (!cs->fon) continue;
+                if (cs->stg_valid[fbt]) mbar_wait(&ctl->bar_in[g][fbt], (unsigned)(cs->stg_fills[fbt] - 1) & 1u);
+                const unsigned char *src = srcp[2 * g + fbt];
+                TR(52);
+                switch (cfg.log2_ndft) {
+                    case 6: fft_task<6>(cfg, cs, c.Sf, src, buf, tw, hann, perm, j, nb, fbt, M, lane); break;
+                    case 7: fft_task<7>(cfg, cs, c.Sf, src, buf, tw, hann, perm, j, nb, fbt, M, lane); break;
+                    case 8: fft256_task(cfg, cs, c.Sf, src, buf, tw, hann, j, nb, fbt, M, lane); break;
+                    case 9: fft_task<9>(cfg, cs, c.Sf, src, buf, tw, hann, perm, j, nb, fbt, M, lane); break;
+                    default: fft_task<10>(cfg, cs, c.Sf, src, buf, tw, hann, perm, j, nb, fbt, M, lane); break;
+                }
+                TR(53);
             }
-            /* estimator 1: M rounds of argmax (first maximum wins) + blanking, on a scratch copy */
-            float *tmpS = reinterpret_cast<float *>(buf);
-            for (int i = lane; i < Ndft; i += 32) tmpS[i] = Sf_out[i];
-            __syncwarp();
-            for (int r = 0; r < M; ++r) {
-                float best = 0.0f;
-                int ibest = 0;
-                for (int j = cfg.st + lane; j < cfg.en; j += 32) {
-                    const float v = tmpS[j];
-                    if (v > best) {
-                        best = v;
-                        ibest = j;
-                    }
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, best, off);
-                    const int oi = __shfl_xor_sync(0xffffffffu, ibest, off);
-                    if (ov > best || (ov == best && oi < ibest)) {
-                        best = ov;
-                        ibest = oi;
-                    }
-                }
-                int f_min = ibest - cfg.f_zero;
-                f_min = f_min < 0 ? 0 : f_min;
-                int f_max = ibest + cfg.f_zero;
-                f_max = f_max > Ndft ? Ndft : f_max;
-                for (int j = f_min + lane; j < f_max; j += 32) tmpS[j] = 0.0f;
-                if (lane == 0) cs->freqi[r] = ibest - (Ndft >> 1);
-                __syncwarp();
-            }
-            if (lane == 0) {
-                int fi[4];
-                for (int m = 0; m < M; ++m) fi[m] = cs->freqi[m];
-                for (int a = 1; a < M; ++a) {
-                    const int key = fi[a];
-                    int b = a - 1;
-                    while (b >= 0 && fi[b] > key) {
-                        fi[b + 1] = fi[b];
-                        --b;
-                    }
-                    fi[b + 1] = key;
-                }
-                for (int m = 0; m < M; ++m) cs->f_est[fb][m] = (float)fi[m] * cfg.fs_over_ndft;
-            }
-            /* estimator 2: slide the tone mask over Sf, first maximum wins */
-            {
-                float best = 0.0f;
-                int bbest = 0x7fffffff;
-                for (int b = cfg.st + lane; b < cfg.en - cfg.len_mask; b += 32) {
-                    float corr = 0.0f;
-                    for (int q = 0; q < cfg.nmask; ++q) corr += Sf_out[b + cfg.mask_pos[q]];
-                    if (corr > best) {
-                        best = corr;
-                        bbest = b;
-                    }
-                }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, best, off);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bbest, off);
-                    if (ov > best || (ov == best && oi < bbest)) {
-                        best = ov;
-                        bbest = oi;
-                    }
-                }
-                if (lane == 0) {
-                    const int b_max = (best > 0.0f) ? bbest : cfg.st;
-                    const float foff = (float)((b_max - (Ndft >> 1)) * cfg.Fs / Ndft);
-                    for (int m = 0; m < M; ++m) cs->f2_est[fb][m] = foff + (float)(m * cfg.tone_spacing);
-                }
-            }
-            __syncwarp();
-            if (lane < M) {
-                const float f = cfg.est_type ? cs->f2_est[fb][lane] : cs->f_est[fb][lane];
-                const float arg = (float)(EM_TWO_PI * (double)(f / (float)cfg.Fs));
-                double sn, csn;
-                em_sincos((double)arg, &sn, &csn);
-                cs->dphi[fb][lane] = make_float2((float)csn, (float)sn);
-            }
-            __syncwarp();
         };
-        if (is_fft && cap2(smem, cfg, warp).cs->fon) freq_estimate(warp, 0);
-
-        /* frame bookkeeping by one thread: which captures have a whole frame left */
-        auto bookkeeping = [&]() {
-            int any = 0, mx = 0, gen = 0;
-            for (int g = 0; g < G; ++g) {
-                Fsk2CapShared *cs = cap2(smem, cfg, g).cs;
-                int act = cs->active;
-                if (act && ((size_t)cs->frame >= args.max_frames || cs->pos + (unsigned long long)cs->nin > args.samples_per_capture))
+        /* tone picking for the frame of parity fbt: one warp per capture, highest warps first (the low ones do the
+           per-frame sums of the same phase) */
+        auto pick_phase = [&](int fbt) {
+            if (warp >= NF) return;
+            float *tmpS = reinterpret_cast<float *>(warp < NW / 2 ? fft_slots + (size_t)warp * FSK2_FFT_SLOT_ELEMS(Ndft)
+                                                                   : reinterpret_cast<float2 *>(cap2(smem, cfg, warp - NW / 2).ering + cfg.k2.ering_fft_off));
+            for (int g = NF - 1 - warp; g < G; g += NF) {
+                const Cap2 c = cap2(smem, cfg, g);
+                if (c.cs->fon) pick_tones(cfg, c.cs, c.Sf + (size_t)fbt * Ndft, tmpS, fbt, M, lane);
+            }
+        };
+        /* per-capture end-of-frame bookkeeping by lane g of warp 0: does capture g have a whole frame left; which
+           integrator path it takes; fetch the frame after it.  The CTA-wide flags come from a warp reduction. */
+        auto bookkeeping = [&](int f_next) {
+            /* warp 0 only */
+            const bool mine = lane < G;
+            const Cap2 c = cap2(smem, cfg, mine ? lane : 0);
+            Fsk2CapShared *cs = c.cs;
+            int act = 0, nin = 0, gen = 0;
+            if (mine) {
+                act = cs->active;
+                if (act && ((size_t)f_next >= args.max_frames || cs->pos + (unsigned long long)cs->nin > args.samples_per_capture))
                     act = 0; /* short read ends the loop */
                 cs->active = act;
                 cs->nold = Nmem - cs->nin;
                 /* the 16-window integrator needs 16-byte aligned window starts: f_dc index 0 at an even position */
                 cs->fast = cfg.k2.fast_ts && step == 1 && ((((unsigned)cs->pos - (unsigned)cs->nold) & 1u) == 0);
+                nin = act ? cs->nin : 0;
+                gen = act && !cs->fast;
+                /* plan and fetch frame f_next + 1 into the staging buffer frame f_next - 1 used */
+                cs->fon = 0;
                 if (act) {
-                    any = 1;
-                    mx = cs->nin > mx ? cs->nin : mx;
-                    if (!cs->fast) gen = 1;
+                    const unsigned long long npos = cs->pos + (unsigned long long)cs->nin;
+                    if ((size_t)f_next + 1 < args.max_frames && npos + (unsigned long long)(cfg.N - Ts / 4) <= args.samples_per_capture) {
+                        const int bn = (f_next + 1) & 1;
+                        const unsigned char *s1 = nullptr;
+                        stage_issue(cfg, args, c, bn, npos, &ctl->bar_in[lane][bn], &s1);
+                        srcp[2 * lane + bn] = s1;
+                        cs->fon = 1;
+                    }
                 }
             }
-            ctl->any_active = any;
-            ctl->max_nin = mx;
-            ctl->any_generic = gen;
+            const unsigned any = __ballot_sync(0xffffffffu, act != 0);
+            const unsigned anyg = __ballot_sync(0xffffffffu, gen != 0);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const int o = __shfl_xor_sync(0xffffffffu, nin, off);
+                nin = o > nin ? o : nin;
+            }
+            if (lane == 0) {
+                ctl->any_active = any != 0;
+                ctl->max_nin = nin;
+                ctl->any_generic = anyg != 0;
+            }
+            for (int i = lane; i <= FSK2_MAX_CHUNKS; i += 32) ctl->task_ctr[i] = 0; /* task counters of the next streaming phase */
         };
+
+        /* ---- prologue: frequency estimate of frame 0, then plan frame 0 / fetch frame 1 ---- */
+        fft_tasks(0);
         __syncthreads();
-        if (tid == 0) bookkeeping();
+        pick_phase(0);
         __syncthreads();
-        TMARK(t_pre);
+        if (warp == 0) bookkeeping(0);
+        __syncthreads();
+        TR(1);
 
         unsigned par = 0; /* phase parity of the per-chunk mbarriers, bit c */
         for (int f = 0;; ++f) {
             if (!ctl->any_active) break;
             const int fb = f & 1;
+#ifdef FSK2_TIMING
+            tr_on = blockIdx.x == 0 && lane == 0 && f >= 100 && f < 102;
+            TR(3);
+#endif
             const int max_nin = ctl->max_nin;
             const int nchunks = (max_nin + CH - 1) / CH;
-            /* ---- visibility of frame f's staged samples; plan and fetch frame f + 1 ---- */
+            /* visibility of frame f's staged samples (the copy was issued a frame ago) */
             for (int g = 0; g < G; ++g) {
                 Fsk2CapShared *cs = cap2(smem, cfg, g).cs;
                 if (cs->active && cs->stg_valid[fb]) mbar_wait(&ctl->bar_in[g][fb], (unsigned)(cs->stg_fills[fb] - 1) & 1u);
             }
-            if (tid < G) {
-                const Cap2 c = cap2(smem, cfg, tid);
-                Fsk2CapShared *cs = c.cs;
-                cs->fon = 0;
-                if (cs->active) {
-                    const unsigned long long npos = cs->pos + (unsigned long long)cs->nin;
-                    if ((size_t)f + 1 < args.max_frames && npos + (unsigned long long)(cfg.N - Ts / 4) <= args.samples_per_capture) {
-                        const unsigned char *s = nullptr;
-                        stage_issue(cfg, args, c, fb ^ 1, npos, &ctl->bar_in[tid][fb ^ 1], &s);
-                        srcp[2 * tid + (fb ^ 1)] = s;
-                        cs->fon = 1;
-                    }
-                }
-            }
-            __syncthreads();
-            TMARK(t_adv);
+            TR(2);
 
             /* ================= streaming phase ================= */
             if (warp == osc_warp) {
-                /* A8: oscillator recursion, lane (g, m) */
+                /* A8: oscillator recursion, lane (g, m); two steps per 16-byte store */
                 const int g = lane / M, m = lane - g * M;
                 const bool in_range = lane < G * M;
                 const Cap2 c = cap2(smem, cfg, in_range ? g : 0);
@@ -658,32 +857,32 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                     const int o = __shfl_xor_sync(0xffffffffu, lo, off);
                     lo = o < lo ? o : lo;
                 }
+                const bool vec_ok = __all_sync(0xffffffffu, !on || (p0 & 1u) == 0);
                 for (int ck = 0; ck < nchunks; ++ck) {
-                    if (ck >= 3) {
-                        TMARK(t_osc);
-                        mbar_wait(&ctl->bar_int[ck - 3], (par >> (ck - 3)) & 1u);
-                        TMARK(t_oscw);
-                    }
+                    if (ck >= 3) mbar_wait(&ctl->bar_int[ck - 3], (par >> (ck - 3)) & 1u); /* ring slots free again */
+                    TR(20);
                     const int j0 = ck * CH;
                     const int jend = j0 + CH < max_nin ? j0 + CH : max_nin;
-                    if (jend <= lo && (CKE & 7) == 0) {
+                    if (jend <= lo && vec_ok) {
                         if (on) {
-                            for (int j = j0; j < jend; j += 8) {
-                                const int nb = jend - j < 8 ? jend - j : 8;
-                                if (nb == 8) {
+                            unsigned u = ((p0 + (unsigned)j0) & rmask) >> 1; /* 16-byte unit of the ring */
+                            int j = j0;
+                            for (; j + 16 <= jend; j += 16) {
 #pragma unroll
-                                    for (int q = 0; q < 8; ++q) {
-                                        ph = cmul(ph, d);
-                                        ring_m[rsw(p0 + (unsigned)(j + q), rmask)] = ph;
-                                    }
-                                    if (((j + 8) & (CKE - 1)) == 0) ck_m[(j + 8) / CKE] = ph;
-                                } else {
-                                    for (int q = 0; q < nb; ++q) {
-                                        ph = cmul(ph, d);
-                                        ring_m[rsw(p0 + (unsigned)(j + q), rmask)] = ph;
-                                        if (((j + q + 1) & (CKE - 1)) == 0) ck_m[(j + q + 1) / CKE] = ph;
-                                    }
+                                for (int q = 0; q < 8; ++q) {
+                                    const float2 p1 = cmul(ph, d);
+                                    ph = cmul(p1, d);
+                                    const unsigned uu = (u + q) & umask;
+                                    const unsigned pu = uu ^ ((uu >> 3) & 7u);
+                                    *reinterpret_cast<float4 *>(ring_m + 2 * pu) = make_float4(p1.x, p1.y, ph.x, ph.y);
                                 }
+                                u = (u + 8) & umask;
+                                ck_m[(j + 16) / CKE] = ph;
+                            }
+                            for (; j < jend; ++j) {
+                                ph = cmul(ph, d);
+                                ring_m[rsw(p0 + (unsigned)j, rmask)] = ph;
+                                if (((j + 1) & (CKE - 1)) == 0) ck_m[(j + 1) / CKE] = ph;
                             }
                         }
                     } else {
@@ -695,14 +894,15 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                             }
                         }
                     }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&ctl->bar_osc[ck]);
+                    TR(22);
+                    /* hand the chunk to the workers: named barriers 1..4 in rotation (the oscillator is never more
+                       than three chunks ahead of the integrators) */
+                    nbar_arrive(1 + (ck & 3), 32 * (W + 1));
                 }
                 if (on) {
                     const float av = sqrtf((ph.x * ph.x) + (ph.y * ph.y));
                     c.cs->phi_c[m] = make_float2(ph.x / av, ph.y / av);
                 }
-                TMARK(t_osc);
             } else if (warp == tim_warp) {
                 /* A10: serial timing-line sum, lane g */
                 const int g = lane;
@@ -714,44 +914,32 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                 int done = 0;
                 const float *er = c.ering;
                 for (int ck = 0; ck < nchunks; ++ck) {
-                    TMARK(t_tim);
+                    TR(30);
                     mbar_wait(&ctl->bar_int[ck], (par >> ck) & 1u);
-                    TMARK(t_timw);
+                    TR(31);
                     const int avail = on ? windows_after_chunk(v, ck, CH, Ts, step, nint) : 0;
-                    /* four windows at a time while aligned: 16-byte energy loads, the products are off the chain */
-                    while (done < avail) {
-                        if ((done & 3) == 0 && done + 4 <= avail) {
-                            const int e = done & (ER - 1);
-                            float ft[4];
-                            {
-                                const float4 e0 = *reinterpret_cast<const float4 *>(er + e);
-                                ft[0] = e0.x, ft[1] = e0.y, ft[2] = e0.z, ft[3] = e0.w;
-                            }
-#pragma unroll
-                            for (int m = 1; m < M; ++m) {
-                                const float4 em = *reinterpret_cast<const float4 *>(er + m * ER + e);
-                                ft[0] += em.x, ft[1] += em.y, ft[2] += em.z, ft[3] += em.w;
-                            }
-                            const float4 pa = __ldg(reinterpret_cast<const float4 *>(phi_ft + done));
-                            const float4 pb = __ldg(reinterpret_cast<const float4 *>(phi_ft + done + 2));
-                            const float r0 = ft[0] * pa.x, i0 = ft[0] * pa.y, r1 = ft[1] * pa.z, i1 = ft[1] * pa.w;
-                            const float r2 = ft[2] * pb.x, i2 = ft[2] * pb.y, r3 = ft[3] * pb.z, i3 = ft[3] * pb.w;
-                            tre += r0, tim += i0;
-                            tre += r1, tim += i1;
-                            tre += r2, tim += i2;
-                            tre += r3, tim += i3;
-                            done += 4;
-                        } else {
-                            const int e = done & (ER - 1);
-                            float ft = er[e];
-#pragma unroll
-                            for (int m = 1; m < M; ++m) ft += er[m * ER + e];
-                            const float2 ph = __ldg(phi_ft + done);
-                            tre += ft * ph.x;
-                            tim += ft * ph.y;
-                            done += 1;
-                        }
+                    /* the workers left the timing-line products e_i * phi_ft[i]; eight per iteration while aligned */
+                    const float2 *pr = reinterpret_cast<const float2 *>(er);
+                    while ((done & 7) == 0 && done + 8 <= avail) {
+                        const float4 *src4 = reinterpret_cast<const float4 *>(pr + (done & (ER - 1)));
+                        const float4 a0 = src4[0], a1 = src4[1], a2 = src4[2], a3 = src4[3];
+                        tre += a0.x, tim += a0.y;
+                        tre += a0.z, tim += a0.w;
+                        tre += a1.x, tim += a1.y;
+                        tre += a1.z, tim += a1.w;
+                        tre += a2.x, tim += a2.y;
+                        tre += a2.z, tim += a2.w;
+                        tre += a3.x, tim += a3.y;
+                        tre += a3.z, tim += a3.w;
+                        done += 8;
                     }
+                    while (done < avail) {
+                        const float2 v2 = pr[done & (ER - 1)];
+                        tre += v2.x;
+                        tim += v2.y;
+                        done += 1;
+                    }
+                    TR(32);
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&ctl->bar_tim[ck]);
                 }
@@ -788,88 +976,119 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                         cs->rx_timing = rx_timing;
                     }
                 }
-                TMARK(t_tim);
             } else if (is_worker) {
-                const int chshift = 31 - __clz(CH);
-                for (int ck = 0; ck < nchunks; ++ck) {
-                    const int j0 = ck * CH;
-                    TMARK(t_int);
-                    mbar_wait(&ctl->bar_osc[ck], (par >> ck) & 1u);
-                    TMARK(t_wosc);
-                    /* A8 mix: f_dc = in * conj(phi) in place over the oscillator values, one sample (all tones) per lane */
-                    for (int t = wtid; t < (G << chshift); t += nwt) {
-                        const int g = t >> chshift, j = j0 + (t & (CH - 1));
-                        const Cap2 c = cap2(smem, cfg, g);
-                        if (!c.cs->active || j >= c.cs->nin) continue;
-                        const float2 x = raw_sample(srcp[2 * g + fb], fmt, j);
-                        const unsigned sl = rsw((unsigned)c.cs->pos + (unsigned)j, rmask);
-#pragma unroll
-                        for (int m = 0; m < M; ++m) {
-                            float2 *p = c.ring + m * RT + sl;
-                            *p = mixc(x, *p);
-                        }
-                    }
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&ctl->bar_mix[ck]);
-                    TMARK(t_mix);
-                    mbar_wait(&ctl->bar_mix[ck], (par >> ck) & 1u);
-                    if (ck >= 3) mbar_wait(&ctl->bar_tim[ck - 3], (par >> (ck - 3)) & 1u);
-                    TMARK(t_wmix);
-                    /* A9 integrate + |.|^2 per tone for every window completed by this chunk */
-                    if (cfg.k2.fast_ts && step == 1) {
-                        for (int t = wtid; t < G * M * 8; t += nwt) {
-                            const int q = t & 7, gm = t >> 3;
-                            const int g = gm / M, m = gm - g * M;
-                            const Cap2 c = cap2(smem, cfg, g);
-                            const FrameView v = load_view(c.cs, true);
-                            if (!v.active || !v.fast) continue;
-                            const int w_lo = windows_after_chunk(v, ck - 1, CH, Ts, step, nint);
-                            const int w_hi = windows_after_chunk(v, ck, CH, Ts, step, nint);
+                /* Workers, software-pipelined one chunk deep: iteration `it` mixes chunk it (A8) and integrates the windows
+                   completed by chunk it - 1 (A9), as one pool of warp-sized tasks handed out by an atomic counter
+                   (integrator tasks first: they are the long ones); one barrier per iteration. */
+                const int ppc = CH >> 5;                          /* mix passes (32 samples) per capture and chunk */
+                const int nm_all = G * ppc;
+                const int ni_all = (cfg.k2.fast_ts && step == 1) ? G : 0; /* one integrator task per capture */
+                for (int it = 0; it <= nchunks; ++it) {
+                    TR(40);
+                    if (it < nchunks) nbar_sync(1 + (it & 3), 32 * (W + 1)); /* the oscillator values of chunk `it` are in the ring */
+                    if (it >= 4) mbar_wait(&ctl->bar_tim[it - 4], (par >> (it - 4)) & 1u); /* energy ring slots free again */
+                    TR(41);
+                    const int ck = it - 1; /* chunk whose windows are integrated */
+                    const int NI = it >= 1 ? ni_all : 0, NM = it < nchunks ? nm_all : 0;
+                    const int j0 = it * CH;
+                    for (;;) {
+                        int t = 0;
+                        if (lane == 0) t = atomicAdd(&ctl->task_ctr[it], 1);
+                        t = __shfl_sync(0xffffffffu, t, 0);
+                        if (t >= NI + NM) break;
+                        if (t < NI) {
+                            /* NWIN windows of one tone per lane: lanes (m, q) of capture g = task, so the M tones of a window group
+                               sit QPC lanes apart; the tone energies are summed in tone order across those lanes and each lane turns
+                               NWIN / M of the sums into timing-line products */
+                            constexpr int NWIN = 4 * M, QPC = 32 / M; /* one warp task = one capture: lanes (m, q) */
+                            const int g = t, m = lane / QPC, q = lane & (QPC - 1);
+                            const Cap2 c = cap2(smem, cfg, g < G ? g : 0);
+                            const FrameView v = load_view(c.cs, g < G);
+                            const bool on = v.active && v.fast;
+                            const int w_lo = on ? windows_after_chunk(v, ck - 1, CH, Ts, step, nint) : 0;
+                            const int w_hi = on ? windows_after_chunk(v, ck, CH, Ts, step, nint) : 0;
                             const float2 *ring_m = c.ring + m * RT;
-                            float *er = c.ering + m * ER;
-                            for (int e0 = w_lo + 16 * q; e0 < w_hi; e0 += 128) {
-                                float *dst = er + (e0 & (ER - 1));
-                                const unsigned s0 = v.B + (unsigned)e0;
-                                switch (Ts) {
-                                    case 24: integrate16<24>(ring_m, s0, umask, dst); break;
-                                    case 20: integrate16<20>(ring_m, s0, umask, dst); break;
-                                    default: integrate16<40>(ring_m, s0, umask, dst); break;
+                            float2 *prod = reinterpret_cast<float2 *>(c.ering);
+                            const int lane0 = lane - QPC * m; /* lane of tone 0 of this window group */
+                            for (int e0 = w_lo + NWIN * q; __any_sync(0xffffffffu, e0 < w_hi); e0 += 128) {
+                                float en[NWIN];
+#pragma unroll
+                                for (int k = 0; k < NWIN; ++k) en[k] = 0.0f;
+                                if (e0 < w_hi) {
+                                    const unsigned s0 = v.B + (unsigned)e0;
+                                    switch (Ts) {
+                                        case 24: integrate_windows<24, NWIN>(ring_m, s0, umask, en); break;
+                                        case 20: integrate_windows<20, NWIN>(ring_m, s0, umask, en); break;
+                                        default: integrate_windows<40, NWIN>(ring_m, s0, umask, en); break;
+                                    }
+                                }
+                                constexpr int WPL = NWIN / M; /* windows whose products this lane forms */
+                                float ft[WPL];
+#pragma unroll
+                                for (int k = 0; k < WPL; ++k) ft[k] = 0.0f;
+#pragma unroll
+                                for (int mm = 0; mm < M; ++mm) {
+#pragma unroll
+                                    for (int k = 0; k < NWIN; ++k) {
+                                        const float o = __shfl_sync(0xffffffffu, en[k], lane0 + QPC * mm);
+                                        if (k / WPL == m) ft[k % WPL] += o;
+                                    }
+                                }
+                                if (e0 < w_hi) {
+#pragma unroll
+                                    for (int k = 0; k < WPL; k += 2) {
+                                        const int e = e0 + m * WPL + k;
+                                        const float4 ph = *reinterpret_cast<const float4 *>(phi_ft + e);
+                                        *reinterpret_cast<float4 *>(prod + (e & (ER - 1))) =
+                                            make_float4(ft[k] * ph.x, ft[k] * ph.y, ft[k + 1] * ph.z, ft[k + 1] * ph.w);
+                                    }
+                                }
+                            }
+                        } else {
+                            /* mix 32 consecutive samples of one capture: f_dc = in * conj(phi), in place over the oscillator values */
+                            const int p = t - NI;
+                            const int g = p / ppc, j = j0 + ((p - g * ppc) << 5) + lane;
+                            const Cap2 c = cap2(smem, cfg, g);
+                            if (c.cs->active && j < c.cs->nin) {
+                                const float2 x = raw_sample(srcp[2 * g + fb], fmt, j);
+                                const unsigned sl = rsw((unsigned)c.cs->pos + (unsigned)j, rmask);
+#pragma unroll
+                                for (int m = 0; m < M; ++m) {
+                                    float2 *pp = c.ring + m * RT + sl;
+                                    *pp = mixc(x, *pp);
                                 }
                             }
                         }
                     }
-                    if (ctl->any_generic) {
-                        /* generic windows: captures the fast path does not take */
-                        const int wpc = CH / step + 2; /* upper bound of windows completed per chunk and capture */
-                        for (int t = wtid; t < G * M * wpc; t += nwt) {
-                            const int gm = t / wpc, k = t - gm * wpc;
-                            const int g = gm / M, m = gm - g * M;
+                    if (it >= 1 && ctl->any_generic) {
+                        /* generic windows: captures (or configurations) the 16-window path does not take; one window, all tones, per lane */
+                        const int wpc = CH / step + 2;
+                        for (int t = wtid; t < G * wpc; t += nwt) {
+                            const int g = t / wpc, k = t - g * wpc;
                             const Cap2 c = cap2(smem, cfg, g);
                             const FrameView v = load_view(c.cs, true);
                             if (!v.active || v.fast) continue;
                             const int w_lo = windows_after_chunk(v, ck - 1, CH, Ts, step, nint);
                             const int w_hi = windows_after_chunk(v, ck, CH, Ts, step, nint);
-                            for (int i = w_lo + k; i < w_hi; i += wpc)
-                                c.ering[m * ER + (i & (ER - 1))] = window_energy(c.ring + m * RT, v.B + (unsigned)(i * step), rmask, Ts);
+                            float2 *prod = reinterpret_cast<float2 *>(c.ering);
+                            for (int i = w_lo + k; i < w_hi; i += wpc) {
+                                float ft = 0.0f;
+#pragma unroll
+                                for (int m = 0; m < M; ++m) ft += window_energy(c.ring + m * RT, v.B + (unsigned)(i * step), rmask, Ts);
+                                const float2 ph = phi_ft[i];
+                                prod[i & (ER - 1)] = make_float2(ft * ph.x, ft * ph.y);
+                            }
                         }
                     }
+                    TR(44);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&ctl->bar_int[ck]);
+                    if (it >= 1 && lane == 0) mbar_arrive(&ctl->bar_int[ck]);
+                    if (it < nchunks) nbar_sync(5, nwt); /* chunk `it` is mixed before anyone integrates it */
                 }
-                TMARK(t_int);
-            } else if (is_fft) {
-                /* A7 for frame f + 1 of capture `warp`, from the staging buffer fetched this iteration */
-                if (cap2(smem, cfg, warp).cs->fon) freq_estimate(warp, fb ^ 1);
-                TMARK(t_fft);
             }
             par ^= nchunks >= 32 ? ~0u : ((1u << nchunks) - 1u);
             __syncthreads();
-#ifdef FSK2_TIMING
-            if (warp == osc_warp) TMARK(t_oscw);
-            else if (warp == tim_warp) TMARK(t_timw);
-            else if (is_worker) TMARK(t_wosc);
-            else TMARK(t_fftw);
-#endif
+            TR(10);
 
             /* ---- A11: re-sum the two integrator outputs around the timing instant of every symbol, interpolate,
                         decide.  Lane (g, symbol), all tones. ---- */
@@ -905,19 +1124,23 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                         d[m] = cs->dphi[fb][m];
                     }
                     const unsigned char *src = srcp[2 * g + fb];
-                    for (int jj = cq * CKE; jj < last - nold; ++jj) {
+                    int jj = cq * CKE;
+                    for (; jj < jf; ++jj) { /* lead-in: phases only */
 #pragma unroll
                         for (int m = 0; m < M; ++m) ph[m] = cmul(ph[m], d[m]);
-                        if (jj >= jf) {
-                            const float2 x = raw_sample(src, fmt, jj);
-                            const int id = jj + nold;
+                    }
+                    const int jl = last - nold;
+#pragma unroll 4
+                    for (; jj < jl; ++jj) {
+                        const float2 x = raw_sample(src, fmt, jj);
+                        const int id = jj + nold;
 #pragma unroll
-                            for (int m = 0; m < M; ++m) {
-                                const float2 fv = mixc(x, ph[m]);
-                                const u64 v = pk(fv.x, fv.y);
-                                if (id < olo + Ts) a[m] = add2(a[m], v);
-                                if (id >= ohi) b[m] = add2(b[m], v);
-                            }
+                        for (int m = 0; m < M; ++m) {
+                            ph[m] = cmul(ph[m], d[m]);
+                            const float2 fv = mixc(x, ph[m]);
+                            const u64 v = pk(fv.x, fv.y);
+                            if (id < olo + Ts) a[m] = add2(a[m], v);
+                            if (id >= ohi) b[m] = add2(b[m], v);
                         }
                     }
                 }
@@ -968,8 +1191,21 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                     for (int i = tid; i < Nbits; i += nthreads) bo[i] = f ? bo[i - Nbits] : 0;
                 }
             }
+            TR(14);
+            /* A7 for frame f + 1 (all warps), from the staging buffer whose copy was issued at the end of the last
+               frame: touches nothing the decisions of frame f use */
+            fft_tasks(fb ^ 1);
             __syncthreads();
-            TMARK(t_dec);
+            TR(11);
+            /* f_dc tail of this frame for the next frame's decisions (the ring keeps it until then) */
+            for (int t = tid; t < G * M * TAILN; t += nthreads) {
+                const int gm = t / TAILN, k = t - gm * TAILN;
+                const int g = gm / M, m = gm - g * M;
+                const Cap2 c = cap2(smem, cfg, g);
+                if (!c.cs->active) continue;
+                const unsigned pend = (unsigned)c.cs->pos + (unsigned)c.cs->nin;
+                c.tail[m * TAILN + k] = c.ring[m * RT + rsw(pend - (unsigned)TAILN + (unsigned)k, rmask)];
+            }
             if (warp < G) {
                 /* four serial sums over the symbols of capture `warp`, lanes 0..3 */
                 const Cap2 c = cap2(smem, cfg, warp);
@@ -1008,17 +1244,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                     cs->foff = fc_tx - fc_avg;
                 }
             }
-            /* f_dc tail of this frame for the next frame's decisions (the ring keeps it until then) */
-            for (int t = tid; t < G * M * TAILN; t += nthreads) {
-                const int gm = t / TAILN, k = t - gm * TAILN;
-                const int g = gm / M, m = gm - g * M;
-                const Cap2 c = cap2(smem, cfg, g);
-                if (!c.cs->active) continue;
-                const unsigned pend = (unsigned)c.cs->pos + (unsigned)c.cs->nin;
-                c.tail[m * TAILN + k] = c.ring[m * RT + rsw(pend - (unsigned)TAILN + (unsigned)k, rmask)];
-            }
+            pick_phase(fb ^ 1); /* tones of frame f + 1 from the spectrum the FFT tasks just updated */
             __syncthreads();
-            TMARK(t_sum);
+            TR(12);
 
             /* ---- A12: soft decisions ([U mpdecode_core.c::fsk_rx_filt_to_llrs]) ---- */
             if (args.llr) {
@@ -1036,41 +1264,41 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                 }
                 __syncthreads();
             }
-            TMARK(t_llr);
+            TR(13);
 
-            /* ---- per-frame record, advance, next frame's bookkeeping ---- */
-            if (tid == 0) {
-                for (int g = 0; g < G; ++g) {
-                    Fsk2CapShared *cs = cap2(smem, cfg, g).cs;
-                    if (!cs->active) continue;
-                    if (args.stats) {
-                        pirip_frame_stats st;
-                        for (int m = 0; m < 4; ++m) {
-                            st.f_est[m] = m < M ? cs->f_est[fb][m] : 0.0f;
-                            st.f2_est[m] = m < M ? cs->f2_est[fb][m] : 0.0f;
+            /* ---- per-frame record, advance, next frame's bookkeeping: lane g of warp 0 ---- */
+            if (warp == 0) {
+                if (lane < G) {
+                    Fsk2CapShared *cs = cap2(smem, cfg, lane).cs;
+                    if (cs->active) {
+                        if (args.stats) {
+                            pirip_frame_stats *st = &args.stats[(size_t)cs->cap * args.max_frames + (size_t)f];
+                            for (int m = 0; m < 4; ++m) {
+                                st->f_est[m] = m < M ? cs->f_est[fb][m] : 0.0f;
+                                st->f2_est[m] = m < M ? cs->f2_est[fb][m] : 0.0f;
+                            }
+                            st->norm_rx_timing = cs->norm_rx_timing;
+                            st->ppm = cs->ppm;
+                            st->SNRest = cs->SNRest;
+                            st->v_est = cs->v_est;
+                            st->rx_sig_pow = cs->rx_sig_pow;
+                            st->rx_nse_pow = cs->rx_nse_pow;
+                            st->EbNodB = cs->EbNodB;
+                            st->snr_est = cs->snr_est;
+                            st->foff = cs->foff;
+                            st->rx_timing = cs->rx_timing;
+                            st->nin_next = cs->nin_next;
+                            st->sample_offset = (int32_t)cs->pos;
                         }
-                        st.norm_rx_timing = cs->norm_rx_timing;
-                        st.ppm = cs->ppm;
-                        st.SNRest = cs->SNRest;
-                        st.v_est = cs->v_est;
-                        st.rx_sig_pow = cs->rx_sig_pow;
-                        st.rx_nse_pow = cs->rx_nse_pow;
-                        st.EbNodB = cs->EbNodB;
-                        st.snr_est = cs->snr_est;
-                        st.foff = cs->foff;
-                        st.rx_timing = cs->rx_timing;
-                        st.nin_next = cs->nin_next;
-                        st.sample_offset = (int32_t)cs->pos;
-                        args.stats[(size_t)cs->cap * args.max_frames + (size_t)f] = st;
+                        cs->pos += (unsigned long long)cs->nin;
+                        cs->nin = cs->nin_next;
+                        cs->frame += 1;
                     }
-                    cs->pos += (unsigned long long)cs->nin;
-                    cs->nin = cs->nin_next;
-                    cs->frame += 1;
                 }
-                bookkeeping();
+                __syncwarp();
+                bookkeeping(f + 1);
             }
             __syncthreads();
-            TMARK(t_adv);
         }
 
         /* ---- results of the group ---- */
@@ -1085,14 +1313,6 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
             }
         }
     }
-#ifdef FSK2_TIMING
-    if (blockIdx.x == 0 && lane == 0 && (warp == 0 || warp == NW - 3 || warp == tim_warp || warp == osc_warp))
-        printf("w%02d pre %lld adv %lld | osc %lld oscwait %lld | tim %lld timwait %lld | w-osc %lld mix %lld w-mix %lld int %lld | fft %lld "
-               "fftwait %lld | dec %lld sum %lld llr %lld\n",
-               warp, t_pre, t_adv, t_osc, t_oscw, t_tim, t_timw, t_wosc, t_mix, t_wmix, t_int, t_fft, t_fftw, t_dec, t_sum, t_llr);
-    (void)t_wtim;
-    (void)t_stream;
-#endif
 }
 
 template <int M, int NW>
@@ -1106,9 +1326,17 @@ cudaError_t launch_mn(const FskDevCfg &cfg, const FskBatchArgs &args, size_t n_c
 }
 
 cudaError_t dispatch(const FskDevCfg &cfg, const FskBatchArgs &args, size_t n, cudaStream_t stream, bool prep) {
-    if (cfg.k2.threads != 768) return cudaErrorInvalidValue;
-    if (cfg.M == 2) return launch_mn<2, 24>(cfg, args, n, stream, prep);
-    return launch_mn<4, 24>(cfg, args, n, stream, prep);
+    const int nw = cfg.k2.threads / 32;
+    if (cfg.M == 2) {
+        if (nw == 16) return launch_mn<2, 16>(cfg, args, n, stream, prep);
+        if (nw == 20) return launch_mn<2, 20>(cfg, args, n, stream, prep);
+        if (nw == 24) return launch_mn<2, 24>(cfg, args, n, stream, prep);
+    } else {
+        if (nw == 16) return launch_mn<4, 16>(cfg, args, n, stream, prep);
+        if (nw == 20) return launch_mn<4, 20>(cfg, args, n, stream, prep);
+        if (nw == 24) return launch_mn<4, 24>(cfg, args, n, stream, prep);
+    }
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace
@@ -1122,3 +1350,10 @@ cudaError_t fsk2_launch_demod(const FskDevCfg &cfg, const FskBatchArgs &args, si
     if (n_captures == 0) return cudaSuccess;
     return dispatch(cfg, args, n_captures, stream, false);
 }
+
+#ifdef FSK2_TIMING
+extern "C" int pirip_debug_trace(long long *out, size_t n) {
+    if (n > 32u * FSK2_TRACE_N) n = 32u * FSK2_TRACE_N;
+    return (int)cudaMemcpyFromSymbol(out, g_trace, n * sizeof(long long));
+}
+#endif
