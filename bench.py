@@ -324,6 +324,10 @@ def main():
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     achieved = ncap * nsamp * BYTES_PER_SAMPLE_ALGO / (kernel_ms * 1e-3) / 1e9
+    Lk = pb.lib()
+    Lk.pirip_fsk_plan_kernel.restype = ctypes.c_char_p
+    Lk.pirip_fsk_plan_kernel.argtypes = [ctypes.c_void_p]
+    kernel_name = Lk.pirip_fsk_plan_kernel(plan._h).decode()
     # DRAM bytes per launch from the committed ncu --set full capture of this same workload
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
@@ -345,9 +349,9 @@ def main():
             "config": config, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes": ncap * nsamp * BYTES_PER_SAMPLE_ALGO, "peak_source": peak_src,
-                         "kernel": "fsk_demod_kernel<2> (2 captures per CTA, 2 CTAs per SM)",
+                         "kernel": kernel_name,
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE_ALGO,
-                         "note": "bound by FP32-add issue and serial-recurrence latency, not HBM: DESIGN.md section 6"},
+                         "note": "bound by instruction issue and the latency of the exact-order recurrences, not HBM: DESIGN.md section 6"},
             "cpu_baseline": cpu_baseline,
             "parity": {"captures_checked": nchk, "bits_and_frames_equal_oracle": bool(ok),
                        "ber_per_capture": [float(b) for b in bers]}}

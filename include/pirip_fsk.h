@@ -211,6 +211,10 @@ int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_t n_capture
                           size_t samples_per_capture, uint8_t *bits, float *llr, float *rx_filt,
                           struct pirip_frame_stats *stats, int32_t *nframes, size_t max_frames);
 
+/* one-line description of the kernel and launch geometry the batch entry points use for this plan
+   (static storage inside the plan; valid until the plan is destroyed) */
+const char *pirip_fsk_plan_kernel(const pirip_fsk_plan *plan);
+
 /* number of kernel launches issued by this library so far (bench.py gpu_launches) */
 uint64_t pirip_kernel_launches(void);
 /* last error message of the calling thread ("" if none) */

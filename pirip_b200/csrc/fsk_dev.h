@@ -130,6 +130,8 @@ struct FskBatchArgs {
     size_t state_stride_floats;
     float *Sf_out;                    /* optional [ncap][Ndft] copy of Sf after the last frame */
     int tma_ok;                       /* iq is 16-byte aligned: stage frames with TMA bulk copies */
+    const unsigned long long *landed; /* optional (batch kernel): samples of every capture already in device memory; the
+                                         host raises it while it streams the captures in, the kernel never reads ahead */
 };
 
 static inline size_t fsk_state_floats(int Ndft, int M, int Nmem) {

@@ -523,6 +523,15 @@ __device__ __forceinline__ FrameView load_view(const Fsk2CapShared *cs, bool exi
     return v;
 }
 
+/* Streamed ingest: the host copies the captures to the device in time slices while the kernel runs and publishes how many
+   samples of every capture have landed; a frame is fetched only once all of it is there. */
+__device__ __forceinline__ void wait_landed(const FskBatchArgs &args, unsigned long long need) {
+    if (!args.landed) return;
+    if (need > args.samples_per_capture) need = args.samples_per_capture;
+    const volatile unsigned long long *p = args.landed;
+    while (*p < need) __nanosleep(400);
+}
+
 /* Issue the TMA bulk copy of raw samples [pos, pos + nin_max) of capture cs->cap into staging buffer b
    (16-byte aligned superset, clipped to the batch allocation) and record where the frame's samples
    will be read from: the staged copy when it covers nin_max samples, global memory otherwise. */
@@ -584,16 +593,28 @@ __device__ __forceinline__ void integrate_windows(const float2 *ring_m, unsigned
 #pragma unroll
     for (int k = 0; k < NWIN; ++k) acc[k] = 0ull;
     const unsigned u0 = s0 >> 1;
-    constexpr int NU = (NWIN + TS) / 2;
+    constexpr int NU = (NWIN + TS) / 2, NB = 8; /* 16-byte units, loaded NB at a time ahead of the adds that use them */
 #pragma unroll
-    for (int r = 0; r < NU; ++r) {
-        const unsigned u = (u0 + r) & umask;
-        const unsigned pu = u ^ ((u >> 3) & 7u);
-        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(ring_m + 2 * pu);
+    for (int r0 = 0; r0 < NU; r0 += NB) {
+        ulonglong2 v[NB];
 #pragma unroll
-        for (int k = 0; k < NWIN; ++k) {
-            if (2 * r >= k && 2 * r < k + TS) acc[k] = add2(acc[k], v.x);
-            if (2 * r + 1 >= k && 2 * r + 1 < k + TS) acc[k] = add2(acc[k], v.y);
+        for (int b = 0; b < NB; ++b) {
+            if (r0 + b < NU) {
+                const unsigned u = (u0 + r0 + b) & umask;
+                const unsigned pu = u ^ ((u >> 3) & 7u);
+                v[b] = *reinterpret_cast<const ulonglong2 *>(ring_m + 2 * pu);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const int r = r0 + b;
+            if (r < NU) {
+#pragma unroll
+                for (int k = 0; k < NWIN; ++k) {
+                    if (2 * r >= k && 2 * r < k + TS) acc[k] = add2(acc[k], v[b].x);
+                    if (2 * r + 1 >= k && 2 * r + 1 < k + TS) acc[k] = add2(acc[k], v[b].y);
+                }
+            }
         }
     }
 #pragma unroll
@@ -724,7 +745,10 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
         if (tid < G) {
             const Cap2 c = cap2(smem, cfg, tid);
             const unsigned char *s0 = nullptr;
-            if (c.cs->fon) stage_issue(cfg, args, c, 0, 0, &ctl->bar_in[tid][0], &s0);
+            if (c.cs->fon) {
+                wait_landed(args, (unsigned long long)(cfg.N + Ts / 4 + 8));
+                stage_issue(cfg, args, c, 0, 0, &ctl->bar_in[tid][0], &s0);
+            }
             srcp[2 * tid + 0] = s0;
         }
         __syncthreads();
@@ -790,6 +814,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                     if ((size_t)f_next + 1 < args.max_frames && npos + (unsigned long long)(cfg.N - Ts / 4) <= args.samples_per_capture) {
                         const int bn = (f_next + 1) & 1;
                         const unsigned char *s1 = nullptr;
+                        wait_landed(args, npos + (unsigned long long)(cfg.N + Ts / 4 + 8));
                         stage_issue(cfg, args, c, bn, npos, &ctl->bar_in[lane][bn], &s1);
                         srcp[2 * lane + bn] = s1;
                         cs->fon = 1;
@@ -977,39 +1002,70 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                     }
                 }
             } else if (is_worker) {
-                /* Workers, software-pipelined one chunk deep: iteration `it` mixes chunk it (A8) and integrates the windows
-                   completed by chunk it - 1 (A9), as one pool of warp-sized tasks handed out by an atomic counter
-                   (integrator tasks first: they are the long ones); one barrier per iteration. */
-                const int ppc = CH >> 5;                          /* mix passes (32 samples) per capture and chunk */
-                const int nm_all = G * ppc;
-                const int ni_all = (cfg.k2.fast_ts && step == 1) ? G : 0; /* one integrator task per capture */
-                for (int it = 0; it <= nchunks; ++it) {
+                /* Workers: warp w owns capture w (and w + W, ...): per chunk it mixes the capture's samples (A8) and integrates
+                   the windows they complete (A9), so mixing and integration of a capture need no cross-warp barrier; the
+                   only hand-offs are oscillator -> workers (named barrier) and workers -> timing warp (mbarrier). */
+                for (int ck = 0; ck < nchunks; ++ck) {
+                    const int j0 = ck * CH;
                     TR(40);
-                    if (it < nchunks) nbar_sync(1 + (it & 3), 32 * (W + 1)); /* the oscillator values of chunk `it` are in the ring */
-                    if (it >= 4) mbar_wait(&ctl->bar_tim[it - 4], (par >> (it - 4)) & 1u); /* energy ring slots free again */
+                    /* the raw samples do not depend on the oscillator: fetch this warp's first 128 of the chunk before waiting */
+                    float2 xpre[4];
+                    {
+                        const int g = warp;
+                        const bool have = g < G && cap2(smem, cfg, g < G ? g : 0).cs->active;
+                        const unsigned char *src = have ? srcp[2 * g + fb] : nullptr;
+                        const int nin_g = have ? cap2(smem, cfg, g).cs->nin : 0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            const int j = j0 + lane + 32 * q;
+                            xpre[q] = j < nin_g ? raw_sample(src, fmt, j) : make_float2(0.0f, 0.0f);
+                        }
+                    }
+                    nbar_sync(1 + (ck & 3), 32 * (W + 1)); /* the oscillator values of chunk ck are in the ring */
                     TR(41);
-                    const int ck = it - 1; /* chunk whose windows are integrated */
-                    const int NI = it >= 1 ? ni_all : 0, NM = it < nchunks ? nm_all : 0;
-                    const int j0 = it * CH;
-                    for (;;) {
-                        int t = 0;
-                        if (lane == 0) t = atomicAdd(&ctl->task_ctr[it], 1);
-                        t = __shfl_sync(0xffffffffu, t, 0);
-                        if (t >= NI + NM) break;
-                        if (t < NI) {
-                            /* NWIN windows of one tone per lane: lanes (m, q) of capture g = task, so the M tones of a window group
-                               sit QPC lanes apart; the tone energies are summed in tone order across those lanes and each lane turns
-                               NWIN / M of the sums into timing-line products */
-                            constexpr int NWIN = 4 * M, QPC = 32 / M; /* one warp task = one capture: lanes (m, q) */
-                            const int g = t, m = lane / QPC, q = lane & (QPC - 1);
-                            const Cap2 c = cap2(smem, cfg, g < G ? g : 0);
-                            const FrameView v = load_view(c.cs, g < G);
-                            const bool on = v.active && v.fast;
-                            const int w_lo = on ? windows_after_chunk(v, ck - 1, CH, Ts, step, nint) : 0;
-                            const int w_hi = on ? windows_after_chunk(v, ck, CH, Ts, step, nint) : 0;
+                    for (int g = warp; g < G; g += W) {
+                        const Cap2 c = cap2(smem, cfg, g);
+                        const FrameView v = load_view(c.cs, true);
+                        if (!v.active) continue;
+                        /* A8 mix: f_dc = in * conj(phi) in place over the oscillator values; four samples per lane, loads first */
+                        const unsigned char *src = srcp[2 * g + fb];
+                        for (int q0 = 0; q0 < CH; q0 += 128) {
+                            float2 x[4], o[4][M];
+                            unsigned sl[4];
+                            bool ok[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int j = j0 + q0 + lane + 32 * q;
+                                ok[q] = j < v.nin;
+                                sl[q] = rsw(v.p0 + (unsigned)j, rmask);
+                                if (g == warp && q0 == 0)
+                                    x[q] = xpre[q];
+                                else
+                                    x[q] = ok[q] ? raw_sample(src, fmt, j) : make_float2(0.0f, 0.0f);
+#pragma unroll
+                                for (int m = 0; m < M; ++m) o[q][m] = c.ring[m * RT + sl[q]];
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                if (ok[q]) {
+#pragma unroll
+                                    for (int m = 0; m < M; ++m) c.ring[m * RT + sl[q]] = mixc(x[q], o[q][m]);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        TR(42);
+                        if (ck >= 3) mbar_wait(&ctl->bar_tim[ck - 3], (par >> (ck - 3)) & 1u); /* product ring slots free again */
+                        const int w_lo = windows_after_chunk(v, ck - 1, CH, Ts, step, nint);
+                        const int w_hi = windows_after_chunk(v, ck, CH, Ts, step, nint);
+                        float2 *prod = reinterpret_cast<float2 *>(c.ering);
+                        if (v.fast) {
+                            /* A9, NWIN windows of one tone per lane: lanes (m, q), so the M tones of a window group sit QPC lanes
+                               apart; the tone energies are summed in tone order across those lanes and each lane turns NWIN / M
+                               of the sums into timing-line products */
+                            constexpr int NWIN = 4 * M, QPC = 32 / M;
+                            const int m = lane / QPC, q = lane & (QPC - 1);
                             const float2 *ring_m = c.ring + m * RT;
-                            float2 *prod = reinterpret_cast<float2 *>(c.ering);
-                            const int lane0 = lane - QPC * m; /* lane of tone 0 of this window group */
                             for (int e0 = w_lo + NWIN * q; __any_sync(0xffffffffu, e0 < w_hi); e0 += 128) {
                                 float en[NWIN];
 #pragma unroll
@@ -1030,8 +1086,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                                 for (int mm = 0; mm < M; ++mm) {
 #pragma unroll
                                     for (int k = 0; k < NWIN; ++k) {
-                                        const float o = __shfl_sync(0xffffffffu, en[k], lane0 + QPC * mm);
-                                        if (k / WPL == m) ft[k % WPL] += o;
+                                        const float oe = __shfl_sync(0xffffffffu, en[k], q + QPC * mm);
+                                        if (k / WPL == m) ft[k % WPL] += oe;
                                     }
                                 }
                                 if (e0 < w_hi) {
@@ -1045,33 +1101,8 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                                 }
                             }
                         } else {
-                            /* mix 32 consecutive samples of one capture: f_dc = in * conj(phi), in place over the oscillator values */
-                            const int p = t - NI;
-                            const int g = p / ppc, j = j0 + ((p - g * ppc) << 5) + lane;
-                            const Cap2 c = cap2(smem, cfg, g);
-                            if (c.cs->active && j < c.cs->nin) {
-                                const float2 x = raw_sample(srcp[2 * g + fb], fmt, j);
-                                const unsigned sl = rsw((unsigned)c.cs->pos + (unsigned)j, rmask);
-#pragma unroll
-                                for (int m = 0; m < M; ++m) {
-                                    float2 *pp = c.ring + m * RT + sl;
-                                    *pp = mixc(x, *pp);
-                                }
-                            }
-                        }
-                    }
-                    if (it >= 1 && ctl->any_generic) {
-                        /* generic windows: captures (or configurations) the 16-window path does not take; one window, all tones, per lane */
-                        const int wpc = CH / step + 2;
-                        for (int t = wtid; t < G * wpc; t += nwt) {
-                            const int g = t / wpc, k = t - g * wpc;
-                            const Cap2 c = cap2(smem, cfg, g);
-                            const FrameView v = load_view(c.cs, true);
-                            if (!v.active || v.fast) continue;
-                            const int w_lo = windows_after_chunk(v, ck - 1, CH, Ts, step, nint);
-                            const int w_hi = windows_after_chunk(v, ck, CH, Ts, step, nint);
-                            float2 *prod = reinterpret_cast<float2 *>(c.ering);
-                            for (int i = w_lo + k; i < w_hi; i += wpc) {
+                            /* generic windows (any P, Ts, alignment): one window, all tones, per lane */
+                            for (int i = w_lo + lane; i < w_hi; i += 32) {
                                 float ft = 0.0f;
 #pragma unroll
                                 for (int m = 0; m < M; ++m) ft += window_energy(c.ring + m * RT, v.B + (unsigned)(i * step), rmask, Ts);
@@ -1082,8 +1113,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                     }
                     TR(44);
                     __syncwarp();
-                    if (it >= 1 && lane == 0) mbar_arrive(&ctl->bar_int[ck]);
-                    if (it < nchunks) nbar_sync(5, nwt); /* chunk `it` is mixed before anyone integrates it */
+                    if (lane == 0) mbar_arrive(&ctl->bar_int[ck]);
                 }
             }
             par ^= nchunks >= 32 ? ~0u : ((1u << nchunks) - 1u);

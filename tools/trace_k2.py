@@ -29,14 +29,14 @@ clk = buf & ((1 << 48) - 1)
 t0 = clk[clk > 0].min()
 names = {1: "pre", 2: "adv/top-done", 3: "frame-top", 10: "stream-sync-done", 14: "decide-lanes-done", 11: "decide+fft-done", 12: "sums-done", 13: "llr-done",
          20: "osc-chunk-start", 22: "osc-chunk-end", 30: "tim-wait", 31: "tim-go", 32: "tim-chunk-done", 40: "w-loop", 41: "w-osc-passed",
-         42: "w-mix-done", 43: "w-mixbar-passed", 44: "w-int-done", 50: "fft-end", 51: "fft-start", 52: "task", 53: "task-end"}
+         42: "w-mix-done", 43: "w-mixbar-passed", 44: "w-int-done", 50: "fft-end", 51: "fft-start", 52: "task", 53: "task-end", 45: "INT", 46: "mix"}
 NW = int(os.environ.get('PIRIP_FSK_K2_NW', '16'))
 for w in (NW - 1, NW - 2, NW // 2, NW - 3, 0, NW // 2 - 1):
     ev = [(int(clk[w, i] - t0), int(code[w, i])) for i in range(N) if buf[w, i] != 0]
     print("warp", w, "events", len(ev))
     prev = None
     out = []
-    for t, c in ev[:64]:
+    for t, c in ev[:int(os.environ.get('TRN','64'))]:
         out.append("%s@%d(+%d)" % (names.get(c, str(c)), t, 0 if prev is None else t - prev))
         prev = t
     print("  " + " ".join(out))
