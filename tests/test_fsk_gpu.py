@@ -89,3 +89,45 @@ def test_batch_matches_oracle(name):
     out = plan.demod_batch(iq, want_llr=pk.get("soft", False), want_rx_filt=True, want_stats=True)
     compare(plan, pk, iq, out)
     plan.close()
+
+
+def test_many_captures_per_sm_lockstep():
+    """The batch kernel (fsk_kernel2.cu) demodulates several captures per CTA in lockstep: captures with
+    different noise, timing and clock offsets (so their nin decisions differ inside one CTA) must come out exactly
+    as the per-capture kernel (fsk_kernel.cu, PIRIP_FSK_K2=0) and the oracle produce them."""
+    import os
+    import torch
+    import pirip_b200 as pb
+    pk, gk = CONFIGS["c1_2fsk_240k_10k_p24_limits"]
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    ncap = 3 * sms + 7  # 3..4 captures per CTA, uneven
+    base = [synth.capture_u8(7000 + c, 2500, 2, pk["Fs"], pk["Rs"], gk["f1"], gk["spacing"],
+                             ebno_db=[None, 12.0, 9.0, 6.0, 3.0][c % 5])[0] for c in range(24)]
+    n = min(len(x) for x in base)
+    base = np.stack([x[:n] for x in base])
+    # distinct streams per capture: rotate the 24 base captures by a capture-dependent number of samples
+    iq = np.stack([np.roll(base[c % 24], -2 * ((7 * c) % 977)) for c in range(ncap)])
+    old = os.environ.get("PIRIP_FSK_K2")
+    try:
+        os.environ["PIRIP_FSK_K2"] = "0"
+        p_ref = pb.FskPlan(**pk)
+        ref = p_ref.demod_batch(iq, want_rx_filt=True, want_stats=True)
+        p_ref.close()
+        os.environ["PIRIP_FSK_K2"] = "1"
+        plan = pb.FskPlan(**pk)
+        out = plan.demod_batch(iq, want_rx_filt=True, want_stats=True)
+    finally:
+        if old is None:
+            os.environ.pop("PIRIP_FSK_K2", None)
+        else:
+            os.environ["PIRIP_FSK_K2"] = old
+    assert np.array_equal(out["nframes"], ref["nframes"])
+    assert np.array_equal(out["bits"], ref["bits"])
+    assert out["stats"].tobytes() == ref["stats"].tobytes(), "per-frame floats differ from the per-capture kernel"
+    assert out["rx_filt"].tobytes() == ref["rx_filt"].tobytes()
+    # some captures must have slipped (nin != N) for the test to mean anything
+    nin = out["stats"]["nin_next"]
+    assert (nin[out["stats"]["sample_offset"] > 0] != 1200).any()
+    sub = list(range(0, ncap, max(1, ncap // 10)))
+    compare(plan, pk, iq[sub], {k: (v[sub] if isinstance(v, np.ndarray) else v) for k, v in out.items()})
+    plan.close()
