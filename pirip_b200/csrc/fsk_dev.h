@@ -176,8 +176,6 @@ struct Fsk2CtaShared {
     int max_nin;
     int G;
     int any_generic; /* some active capture takes the generic integrator path this frame */
-    int task_ctr[FSK2_MAX_CHUNKS + 1]; /* worker task counter of every pipeline iteration */
-    int pad2[3];
 };
 
 /* defined in fsk_kernel2.cu */

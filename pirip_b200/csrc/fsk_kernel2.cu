@@ -656,7 +656,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
     /* streaming phase: workers [0, W), timing warp, oscillator warp.  The frequency estimate of the next frame is a
        phase of its own run by all NF = NW warps (FFT, streaming and decision code each fit the instruction cache;
        run concurrently they thrashed it: "no instruction" was the top stall reason) */
-    constexpr int W = NW - 2, nwt = W * 32;
+    constexpr int W = NW - 2;
     const int NF = cfg.k2.fft_warps; /* warps of the FFT phase: NW / 2 with a dedicated scratch slot, the rest borrow the
                                         idle upper part of a capture's energy ring */
     constexpr int osc_warp = NW - 1, tim_warp = NW - 2;
@@ -677,7 +677,6 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
     float2 *phi_ft = reinterpret_cast<float2 *>(cta + cfg.k2.off_phift); /* timing-line oscillator, [nint] */
     const unsigned char **srcp = reinterpret_cast<const unsigned char **>(ctl + 1); /* [gmax][2] raw-sample pointer per staging buffer */
     const bool is_worker = warp < W;
-    const int wtid = warp * 32 + lane;
 
     for (int i = tid; i < Ndft; i += nthreads) {
         tw[i] = cfg.twiddle[i];
@@ -696,11 +695,12 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
 
     for (int k0 = 0; k0 < ncap_cta; k0 += cfg.k2.gmax) {
         const int G = ncap_cta - k0 < cfg.k2.gmax ? ncap_cta - k0 : cfg.k2.gmax;
+        constexpr int osc_cnt = 32 * (W + 1), int_cnt = W;
         __syncthreads();
         /* ---- barriers and initial state of the group ---- */
         if (tid == 0) {
             for (int i = 0; i < FSK2_MAX_CHUNKS; ++i) {
-                mbar_init(&ctl->bar_int[i], W);
+                mbar_init(&ctl->bar_int[i], int_cnt);
                 mbar_init(&ctl->bar_tim[i], 1);
             }
             for (int g = 0; g < FSK2_MAX_G; ++g) {
@@ -833,7 +833,6 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                 ctl->max_nin = nin;
                 ctl->any_generic = anyg != 0;
             }
-            for (int i = lane; i <= FSK2_MAX_CHUNKS; i += 32) ctl->task_ctr[i] = 0; /* task counters of the next streaming phase */
         };
 
         /* ---- prologue: frequency estimate of frame 0, then plan frame 0 / fetch frame 1 ---- */
@@ -856,9 +855,24 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
             const int max_nin = ctl->max_nin;
             const int nchunks = (max_nin + CH - 1) / CH;
             /* visibility of frame f's staged samples (the copy was issued a frame ago) */
-            for (int g = 0; g < G; ++g) {
-                Fsk2CapShared *cs = cap2(smem, cfg, g).cs;
-                if (cs->active && cs->stg_valid[fb]) mbar_wait(&ctl->bar_in[g][fb], (unsigned)(cs->stg_fills[fb] - 1) & 1u);
+            {
+                /* gather what to wait for first (independent loads), then wait: the copies landed long ago */
+                unsigned waitm = 0, parm = 0;
+#pragma unroll
+                for (int g = 0; g < FSK2_MAX_G; ++g) {
+                    if (g < G) {
+                        const Fsk2CapShared *cs = cap2(smem, cfg, g).cs;
+                        if (cs->active && cs->stg_valid[fb]) {
+                            waitm |= 1u << g;
+                            parm |= ((unsigned)(cs->stg_fills[fb] - 1) & 1u) << g;
+                        }
+                    }
+                }
+                while (waitm) {
+                    const int g = __ffs(waitm) - 1;
+                    waitm &= waitm - 1;
+                    mbar_wait(&ctl->bar_in[g][fb], (parm >> g) & 1u);
+                }
             }
             TR(2);
 
@@ -922,7 +936,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                     TR(22);
                     /* hand the chunk to the workers: named barriers 1..4 in rotation (the oscillator is never more
                        than three chunks ahead of the integrators) */
-                    nbar_arrive(1 + (ck & 3), 32 * (W + 1));
+                    nbar_arrive(1 + (ck & 3), osc_cnt);
                 }
                 if (on) {
                     const float av = sqrtf((ph.x * ph.x) + (ph.y * ph.y));
@@ -1002,118 +1016,116 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                     }
                 }
             } else if (is_worker) {
-                /* Workers: warp w owns capture w (and w + W, ...): per chunk it mixes the capture's samples (A8) and integrates
-                   the windows they complete (A9), so mixing and integration of a capture need no cross-warp barrier; the
-                   only hand-offs are oscillator -> workers (named barrier) and workers -> timing warp (mbarrier). */
-                for (int ck = 0; ck < nchunks; ++ck) {
+                /* A8 mix of chunk ck of capture g by one warp: f_dc = in * conj(phi) in place over the oscillator values;
+                   four samples per lane, all loads first */
+                auto mix_chunk = [&](int g, int ck) {
+                    const Cap2 c = cap2(smem, cfg, g);
+                    const FrameView v = load_view(c.cs, true);
+                    const unsigned char *src = srcp[2 * g + fb];
                     const int j0 = ck * CH;
-                    TR(40);
-                    /* the raw samples do not depend on the oscillator: fetch this warp's first 128 of the chunk before waiting */
-                    float2 xpre[4];
-                    {
-                        const int g = warp;
-                        const bool have = g < G && cap2(smem, cfg, g < G ? g : 0).cs->active;
-                        const unsigned char *src = have ? srcp[2 * g + fb] : nullptr;
-                        const int nin_g = have ? cap2(smem, cfg, g).cs->nin : 0;
+                    for (int q0 = 0; q0 < CH; q0 += 128) {
+                        float2 x[4], o[4][M];
+                        unsigned sl[4];
+                        bool ok[4];
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {
-                            const int j = j0 + lane + 32 * q;
-                            xpre[q] = j < nin_g ? raw_sample(src, fmt, j) : make_float2(0.0f, 0.0f);
+                            const int j = j0 + q0 + lane + 32 * q;
+                            ok[q] = j < v.nin;
+                            sl[q] = rsw(v.p0 + (unsigned)j, rmask);
+                            x[q] = ok[q] ? raw_sample(src, fmt, j) : make_float2(0.0f, 0.0f);
+#pragma unroll
+                            for (int m = 0; m < M; ++m) o[q][m] = c.ring[m * RT + sl[q]];
                         }
-                    }
-                    nbar_sync(1 + (ck & 3), 32 * (W + 1)); /* the oscillator values of chunk ck are in the ring */
-                    TR(41);
-                    for (int g = warp; g < G; g += W) {
-                        const Cap2 c = cap2(smem, cfg, g);
-                        const FrameView v = load_view(c.cs, true);
-                        if (!v.active) continue;
-                        /* A8 mix: f_dc = in * conj(phi) in place over the oscillator values; four samples per lane, loads first */
-                        const unsigned char *src = srcp[2 * g + fb];
-                        for (int q0 = 0; q0 < CH; q0 += 128) {
-                            float2 x[4], o[4][M];
-                            unsigned sl[4];
-                            bool ok[4];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int j = j0 + q0 + lane + 32 * q;
-                                ok[q] = j < v.nin;
-                                sl[q] = rsw(v.p0 + (unsigned)j, rmask);
-                                if (g == warp && q0 == 0)
-                                    x[q] = xpre[q];
-                                else
-                                    x[q] = ok[q] ? raw_sample(src, fmt, j) : make_float2(0.0f, 0.0f);
+                        for (int q = 0; q < 4; ++q) {
+                            if (ok[q]) {
 #pragma unroll
-                                for (int m = 0; m < M; ++m) o[q][m] = c.ring[m * RT + sl[q]];
-                            }
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                if (ok[q]) {
-#pragma unroll
-                                    for (int m = 0; m < M; ++m) c.ring[m * RT + sl[q]] = mixc(x[q], o[q][m]);
-                                }
-                            }
-                        }
-                        __syncwarp();
-                        TR(42);
-                        if (ck >= 3) mbar_wait(&ctl->bar_tim[ck - 3], (par >> (ck - 3)) & 1u); /* product ring slots free again */
-                        const int w_lo = windows_after_chunk(v, ck - 1, CH, Ts, step, nint);
-                        const int w_hi = windows_after_chunk(v, ck, CH, Ts, step, nint);
-                        float2 *prod = reinterpret_cast<float2 *>(c.ering);
-                        if (v.fast) {
-                            /* A9, NWIN windows of one tone per lane: lanes (m, q), so the M tones of a window group sit QPC lanes
-                               apart; the tone energies are summed in tone order across those lanes and each lane turns NWIN / M
-                               of the sums into timing-line products */
-                            constexpr int NWIN = 4 * M, QPC = 32 / M;
-                            const int m = lane / QPC, q = lane & (QPC - 1);
-                            const float2 *ring_m = c.ring + m * RT;
-                            for (int e0 = w_lo + NWIN * q; __any_sync(0xffffffffu, e0 < w_hi); e0 += 128) {
-                                float en[NWIN];
-#pragma unroll
-                                for (int k = 0; k < NWIN; ++k) en[k] = 0.0f;
-                                if (e0 < w_hi) {
-                                    const unsigned s0 = v.B + (unsigned)e0;
-                                    switch (Ts) {
-                                        case 24: integrate_windows<24, NWIN>(ring_m, s0, umask, en); break;
-                                        case 20: integrate_windows<20, NWIN>(ring_m, s0, umask, en); break;
-                                        default: integrate_windows<40, NWIN>(ring_m, s0, umask, en); break;
-                                    }
-                                }
-                                constexpr int WPL = NWIN / M; /* windows whose products this lane forms */
-                                float ft[WPL];
-#pragma unroll
-                                for (int k = 0; k < WPL; ++k) ft[k] = 0.0f;
-#pragma unroll
-                                for (int mm = 0; mm < M; ++mm) {
-#pragma unroll
-                                    for (int k = 0; k < NWIN; ++k) {
-                                        const float oe = __shfl_sync(0xffffffffu, en[k], q + QPC * mm);
-                                        if (k / WPL == m) ft[k % WPL] += oe;
-                                    }
-                                }
-                                if (e0 < w_hi) {
-#pragma unroll
-                                    for (int k = 0; k < WPL; k += 2) {
-                                        const int e = e0 + m * WPL + k;
-                                        const float4 ph = *reinterpret_cast<const float4 *>(phi_ft + e);
-                                        *reinterpret_cast<float4 *>(prod + (e & (ER - 1))) =
-                                            make_float4(ft[k] * ph.x, ft[k] * ph.y, ft[k + 1] * ph.z, ft[k + 1] * ph.w);
-                                    }
-                                }
-                            }
-                        } else {
-                            /* generic windows (any P, Ts, alignment): one window, all tones, per lane */
-                            for (int i = w_lo + lane; i < w_hi; i += 32) {
-                                float ft = 0.0f;
-#pragma unroll
-                                for (int m = 0; m < M; ++m) ft += window_energy(c.ring + m * RT, v.B + (unsigned)(i * step), rmask, Ts);
-                                const float2 ph = phi_ft[i];
-                                prod[i & (ER - 1)] = make_float2(ft * ph.x, ft * ph.y);
+                                for (int m = 0; m < M; ++m) c.ring[m * RT + sl[q]] = mixc(x[q], o[q][m]);
                             }
                         }
                     }
-                    TR(44);
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&ctl->bar_int[ck]);
+                };
+                /* A9 for the windows of capture g completed by chunk ck, by one warp: integrate, |.|^2, sum over the tones,
+                   multiply by the timing oscillator */
+                auto integrate_chunk = [&](int g, int ck) {
+                    const Cap2 c = cap2(smem, cfg, g);
+                    const FrameView v = load_view(c.cs, true);
+                    const int w_lo = windows_after_chunk(v, ck - 1, CH, Ts, step, nint);
+                    const int w_hi = windows_after_chunk(v, ck, CH, Ts, step, nint);
+                    float2 *prod = reinterpret_cast<float2 *>(c.ering);
+                    if (v.fast) {
+                        /* NWIN windows of one tone per lane: lanes (m, q), so the M tones of a window group sit QPC lanes apart;
+                           the tone energies are summed in tone order across those lanes and each lane turns NWIN / M of the
+                           sums into timing-line products */
+                        constexpr int NWIN = 4 * M, QPC = 32 / M;
+                        const int m = lane / QPC, q = lane & (QPC - 1);
+                        const float2 *ring_m = c.ring + m * RT;
+                        for (int e0 = w_lo + NWIN * q; __any_sync(0xffffffffu, e0 < w_hi); e0 += 128) {
+                            float en[NWIN];
+#pragma unroll
+                            for (int k = 0; k < NWIN; ++k) en[k] = 0.0f;
+                            if (e0 < w_hi) {
+                                const unsigned s0 = v.B + (unsigned)e0;
+                                switch (Ts) {
+                                    case 24: integrate_windows<24, NWIN>(ring_m, s0, umask, en); break;
+                                    case 20: integrate_windows<20, NWIN>(ring_m, s0, umask, en); break;
+                                    default: integrate_windows<40, NWIN>(ring_m, s0, umask, en); break;
+                                }
+                            }
+                            constexpr int WPL = NWIN / M; /* windows whose products this lane forms */
+                            float ft[WPL];
+#pragma unroll
+                            for (int k = 0; k < WPL; ++k) ft[k] = 0.0f;
+#pragma unroll
+                            for (int mm = 0; mm < M; ++mm) {
+#pragma unroll
+                                for (int k = 0; k < NWIN; ++k) {
+                                    const float oe = __shfl_sync(0xffffffffu, en[k], q + QPC * mm);
+                                    if (k / WPL == m) ft[k % WPL] += oe;
+                                }
+                            }
+                            if (e0 < w_hi) {
+#pragma unroll
+                                for (int k = 0; k < WPL; k += 2) {
+                                    const int e = e0 + m * WPL + k;
+                                    const float4 ph = *reinterpret_cast<const float4 *>(phi_ft + e);
+                                    *reinterpret_cast<float4 *>(prod + (e & (ER - 1))) =
+                                        make_float4(ft[k] * ph.x, ft[k] * ph.y, ft[k + 1] * ph.z, ft[k + 1] * ph.w);
+                                }
+                            }
+                        }
+                    } else {
+                        /* generic windows (any P, Ts, alignment): one window, all tones, per lane */
+                        for (int i = w_lo + lane; i < w_hi; i += 32) {
+                            float ft = 0.0f;
+#pragma unroll
+                            for (int m = 0; m < M; ++m) ft += window_energy(c.ring + m * RT, v.B + (unsigned)(i * step), rmask, Ts);
+                            const float2 ph = phi_ft[i];
+                            prod[i & (ER - 1)] = make_float2(ft * ph.x, ft * ph.y);
+                        }
+                    }
+                };
+                {
+                    /* every worker warp w owns captures w, w + W, ...: per chunk it mixes the capture's samples and integrates
+                       the windows they complete, so a capture needs no cross-warp barrier between the two (measured: splitting the
+                       workers into mixing helpers and integrating owners, 13.3 ms, lost to this, 10.8 ms); the only hand-offs are
+                       oscillator -> workers (named barrier) and workers -> timing warp (mbarrier) */
+                    for (int ck = 0; ck < nchunks; ++ck) {
+                        TR(40);
+                        nbar_sync(1 + (ck & 3), osc_cnt);
+                        TR(41);
+                        for (int g = warp; g < G; g += W) {
+                            if (!cap2(smem, cfg, g).cs->active) continue;
+                            mix_chunk(g, ck);
+                            TR(42);
+                            if (ck >= 3) mbar_wait(&ctl->bar_tim[ck - 3], (par >> (ck - 3)) & 1u);
+                            integrate_chunk(g, ck);
+                        }
+                        TR(44);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&ctl->bar_int[ck]);
+                    }
                 }
             }
             par ^= nchunks >= 32 ? ~0u : ((1u << nchunks) - 1u);
