@@ -855,24 +855,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
             const int max_nin = ctl->max_nin;
             const int nchunks = (max_nin + CH - 1) / CH;
             /* visibility of frame f's staged samples (the copy was issued a frame ago) */
-            {
-                /* gather what to wait for first (independent loads), then wait: the copies landed long ago */
-                unsigned waitm = 0, parm = 0;
-#pragma unroll
-                for (int g = 0; g < FSK2_MAX_G; ++g) {
-                    if (g < G) {
-                        const Fsk2CapShared *cs = cap2(smem, cfg, g).cs;
-                        if (cs->active && cs->stg_valid[fb]) {
-                            waitm |= 1u << g;
-                            parm |= ((unsigned)(cs->stg_fills[fb] - 1) & 1u) << g;
-                        }
-                    }
-                }
-                while (waitm) {
-                    const int g = __ffs(waitm) - 1;
-                    waitm &= waitm - 1;
-                    mbar_wait(&ctl->bar_in[g][fb], (parm >> g) & 1u);
-                }
+            for (int g = 0; g < G; ++g) {
+                Fsk2CapShared *cs = cap2(smem, cfg, g).cs;
+                if (cs->active && cs->stg_valid[fb]) mbar_wait(&ctl->bar_in[g][fb], (unsigned)(cs->stg_fills[fb] - 1) & 1u);
             }
             TR(2);
 
