@@ -1,0 +1,151 @@
+"""the rtl_fsk-shaped receiver tool on the GPU library.
+
+N1  `rtl_fsk --code H_256_512_4 -b` writes the record stream (1 rx_status byte + K/8 payload bytes per modem frame)
+    that pirip's own tx/frame_repeater.c consumes ([R tx/frame_repeater.c:55-106], [R script/frame_repeater:36-38]).
+    The REAL reference frame_repeater, compiled from /root/reference by oracle/Makefile into oracle/_ref/, is put
+    behind the tool and must re-emit the bursts with its burst-control bytes 1 / 0 / 2 ([R tx/rpitx_fsk.cpp:433-497]).
+N2  `-s 1800000 -a 40000`: the csdr decimator in front of the modem, one process instead of four ([R README.md:109,172]).
+N3  `-u host`: one JSON line per second of signal with the keys script/dash.py reads ([R script/dash.py:26-46]).
+"""
+import json
+import os
+import socket
+import subprocess
+
+import numpy as np
+import pytest
+
+import orc
+import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "tools", "bin")
+REPEATER = os.path.join(ROOT, "oracle", "_ref", "frame_repeater")
+
+
+def build_tools():
+    subprocess.check_call(["make", "-C", os.path.join(ROOT, "tools"), "-s"], stdout=subprocess.DEVNULL)
+
+
+def coded_bursts(Fs, Rs, name, nbursts, frames_per_burst, ebno_db, seed):
+    """IQ of `nbursts` bursts as rpitx_fsk sends them: preamble, frames [UW | data + CRC | parity], silence between
+    ([R tx/rpitx_fsk.cpp:313-336,369-423]); returns (u8 IQ, list of payload byte strings per burst)."""
+    import pirip_b200 as pb
+    m = pb.FskLdpcModem(name, M=2, Rs=Rs, Fs=Fs)
+    g = synth.rng(seed)
+    preamble = np.array([0, 1] * 25, np.uint8)
+    segs, silent, sent = [], [], []
+    for b in range(nbursts):
+        segs.append(g.integers(0, 2, 700, dtype=np.uint8)); silent.append(True)
+        segs.append(preamble); silent.append(False)
+        burst = []
+        for f in range(frames_per_burst):
+            payload = orc.payload_data_bits(m.data_bits).copy()
+            payload[0:8] = [0, 0, 0, 0, 0, 0, 0, 1]                     # source address 0x01 ([R tx/rpitx_fsk.cpp:382-386])
+            payload[8:16] = [(10 * b + f + 1) >> (7 - i) & 1 for i in range(8)]  # sequence number
+            payload = orc.insert_crc(payload)
+            burst.append(np.packbits(payload).tobytes())
+            segs.append(m.frame(payload)); silent.append(False)
+        sent.append(burst)
+    segs.append(g.integers(0, 2, 1500, dtype=np.uint8)); silent.append(True)
+    x = synth.fsk_mod(np.concatenate(segs), 2, Fs, Rs, Rs, Rs, timing_offset=3.3, phase0=0.7)
+    Ts, pos = Fs // Rs, 0
+    for s, quiet in zip(segs, silent):
+        if quiet:
+            x[pos:pos + s.size * Ts] = 0
+        pos += s.size * Ts
+    x = synth.add_awgn(x, ebno_db, Ts, 2, g)
+    m.close()
+    return synth.to_u8(x, amp=45.0), sent
+
+
+def test_burst_records_drive_the_reference_frame_repeater(tmp_path):
+    if not os.path.exists(REPEATER):
+        pytest.skip("oracle/_ref/frame_repeater not built (needs /root/reference at build time)")
+    build_tools()
+    Fs, Rs, name = 80000, 10000, "H_256_512_4"
+    iq, sent = coded_bursts(Fs, Rs, name, nbursts=2, frames_per_burst=3, ebno_db=9.0, seed=314)
+    f = tmp_path / "iq.u8"
+    iq.tofile(f)
+    rx = subprocess.run([os.path.join(BIN, "rtl_fsk"), "-i", str(f), "-s", str(Fs), "-a", str(Fs), "-r", str(Rs), "-m", "2",
+                         "--code", name, "-b", "-q", "-"], capture_output=True, check=True)
+    rec = np.frombuffer(rx.stdout, np.uint8).reshape(-1, 33)           # status byte + 256/8 payload bytes per modem frame
+    assert rec.shape[0] == (iq.size // 2) // 400                       # one record per modem frame (N = 50 symbols * Ts 8)
+    got = [r[1:].tobytes() for r in rec if r[0] & 0x4]                 # FREEDV_RX_BITS
+    assert got == [p for burst in sent for p in burst]                 # every frame of both bursts, in order, CRC clean
+    assert all(not r[1:].any() for r in rec if not r[0] & 0x4)         # zeros when there is no frame
+    # pirip's own state machine behind it: rtl_fsk -b | frame_repeater 256 0x2
+    rep = subprocess.run([REPEATER, "256", "0x2"], input=rx.stdout, capture_output=True, check=True, timeout=60)
+    out = np.frombuffer(rep.stdout, np.uint8).reshape(-1, 33)
+    want_ctl, want_data = [], []
+    for burst in sent:
+        for k, p in enumerate(burst):
+            want_ctl.append(1 if k == 0 else 0)
+            want_data.append(bytes([0x02]) + p[1:])                    # source address rewritten to ours
+        want_ctl.append(2)
+        want_data.append(bytes(32))
+    assert out[:, 0].tolist() == want_ctl
+    assert [r[1:].tobytes() for r in out] == want_data
+
+
+def test_source_address_filter_and_payload_stream(tmp_path):
+    build_tools()
+    Fs, Rs, name = 80000, 10000, "H_256_512_4"
+    iq, sent = coded_bursts(Fs, Rs, name, nbursts=1, frames_per_burst=3, ebno_db=10.0, seed=27)
+    f = tmp_path / "iq.u8"
+    iq.tofile(f)
+    base = [os.path.join(BIN, "rtl_fsk"), "-i", str(f), "-a", str(Fs), "-r", str(Rs), "-m", "2", "--code", name, "-q"]
+    plain = subprocess.run(base + ["-"], capture_output=True, check=True).stdout
+    assert plain == b"".join(sent[0])                                  # packed payload bytes only [R README.md:297]
+    filtered = subprocess.run(base + ["--filter", "0x1", "-"], capture_output=True, check=True).stdout
+    assert filtered == b""                                             # frames from address 0x01 are dropped [R README.md:303]
+
+
+def test_uncoded_decimating_front_end_matches_the_csdr_pipeline(tmp_path):
+    """rtl_fsk -s 1800000 -a 40000 -r 1000 == csdr convert_u8_f | fir_decimate_cc 45 -> fsk_demod (float samples), and the
+    100-bit test packets arrive ([R README.md:109,114])."""
+    build_tools()
+    Fs_in, Fs, Rs = 1800000, 40000, 1000
+    bits = synth.test_bits(1200)
+    x = synth.fsk_mod(bits, 2, Fs_in, Rs, 1000, 1000, timing_offset=333.0, phase0=0.3)
+    x = synth.add_awgn(x, 12.0, Fs_in // Rs, 2, synth.rng(77))
+    iq = synth.to_u8(x, amp=80.0)
+    f = tmp_path / "iq.u8"
+    iq.tofile(f)
+    rx = subprocess.run([os.path.join(BIN, "rtl_fsk"), "-i", str(f), "-s", str(Fs_in), "-a", str(Fs), "-r", str(Rs), "-m", "2",
+                         "--fsk_lower", "500", "-q", "-"], capture_output=True, check=True)
+    got = np.frombuffer(rx.stdout, np.uint8)
+    # oracle: csdr stage in floats, then the demodulator on complex float input
+    dec, _ = orc.csdr_decimate_stream(iq, 45)
+    ref = orc.fsk_demod_stream(orc.demod_cfg(Fs, Rs, 2, P=8, limits=(500, Fs // 2), fmt=orc.FMT_F32), dec)
+    assert np.array_equal(got, ref["bits"][:got.size]) and got.size >= ref["bits"].size - 50
+    put = subprocess.run([os.path.join(BIN, "fsk_put_test_bits"), "-q", "-p", "8", "-"], input=rx.stdout, capture_output=True)
+    assert put.returncode == 0, put.stderr.decode()
+
+
+def test_dashboard_telemetry_has_the_fields_dash_py_reads(tmp_path):
+    build_tools()
+    Fs, Rs = 240000, 10000
+    bits = synth.test_bits(25000)                                       # 2.5 s of signal: two telemetry lines
+    x = synth.fsk_mod(bits, 2, Fs, Rs, 10000, 10000, timing_offset=5.0)
+    iq = synth.to_u8(synth.add_awgn(x, 10.0, Fs // Rs, 2, synth.rng(3)), amp=70.0)
+    f = tmp_path / "iq.u8"
+    iq.tofile(f)
+    sock = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    sock.bind(("127.0.0.1", 8001))
+    sock.settimeout(30)
+    try:
+        subprocess.run([os.path.join(BIN, "rtl_fsk"), "-i", str(f), "-a", str(Fs), "-r", str(Rs), "-m", "2", "-p", "24",
+                        "--fsk_lower", "500", "--fsk_upper", "25000", "-u", "127.0.0.1", "-q", os.devnull], check=True)
+        lines = [sock.recv(65536) for _ in range(2)]
+    finally:
+        sock.close()
+    for raw in lines:
+        d = json.loads(raw)
+        assert set(d) >= {"SfdB", "f_est_Hz", "fsk_lower_Hz", "fsk_upper_Hz", "SNRest_lin", "norm_rx_timing", "Fs_Hz"}
+        assert len(d["SfdB"]) == 256 and d["Fs_Hz"] == Fs and (d["fsk_lower_Hz"], d["fsk_upper_Hz"]) == (500, 25000)
+        assert sorted(round(v / 1000) for v in d["f_est_Hz"]) == [10, 20]   # tones at +10 / +20 kHz
+        assert len(d["norm_rx_timing"]) >= 190 and all(-0.5 <= t <= 0.5 for t in d["norm_rx_timing"])
+        assert d["SNRest_lin"] > 3

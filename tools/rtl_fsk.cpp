@@ -1,0 +1,272 @@
+/*
+ * rtl_fsk — file-source build of the integrated receiver pirip runs everywhere ([R README.md:114,172,184,292],
+ * [R test/loopback_rtl_fsk.sh:10], [R script/frame_repeater:36], [R script/ping:47]): u8 IQ in -> optional csdr
+ * decimation (-s -> -a) -> fsk_demod, or with --code the FSK_LDPC receive side (fsk_demod_sd -> LLRs -> unique-word
+ * sync -> LDPC -> CRC) -> stdout.  The USB tuner of drowe67/librtlsdr's rtl_fsk (out of scope) is
+ * replaced by `-i file` ("-" = stdin, the byte stream `rtl_sdr` writes); everything downstream of the samples keeps
+ * rtl_fsk's command line and output formats, so `rtl_fsk ... -b | frame_repeater 256 0x2` and
+ * `rtl_fsk ... | fsk_put_test_bits -` run as in pirip's scripts:
+ *
+ *   rtl_fsk [-i iqfile] [-s rtlFs] [-a modemFs] -r Rs -m M [-p P] [--code NAME] [--mask spacing]
+ *           [--fsk_lower Hz] [--fsk_upper Hz] [--filter addr] [--testframes] [-b] [-q] [-v] [-u host] [-f Hz] [-g gain] [-L] out
+ *
+ *   uncoded          Nbits bytes per modem frame, one bit per byte                       [R README.md:114]
+ *   --code NAME      packed payload bytes of every frame whose CRC checks                [R README.md:184,297]
+ *   -b               records of 1 rx_status byte + K/8 payload bytes at EVERY modem frame, zeros when there is no
+ *                    frame — the clock of tx/frame_repeater.c                            [R tx/frame_repeater.c:55-62]
+ *   --filter addr    drop frames whose first payload byte (source address) equals addr   [R README.md:303-304]
+ *   -v               per-frame log line with the fields of                               [R README.md:200-208]
+ *   -u host          once per second of signal one JSON line over UDP to host:8001 with the keys script/dash.py reads
+ *                    (SfdB, f_est_Hz, fsk_lower_Hz, fsk_upper_Hz, SNRest_lin, norm_rx_timing, Fs_Hz) [R script/dash.py:26-46]
+ *
+ * All arithmetic runs in libpirip_b200.so (GPU); there is no CPU fallback.
+ */
+#include <arpa/inet.h>
+#include <getopt.h>
+#include <math.h>
+#include <netdb.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/socket.h>
+#include <unistd.h>
+
+#include <string>
+#include <vector>
+
+#include "../include/pirip_csdr.h"
+#include "../include/pirip_fsk.h"
+#include "../include/pirip_ldpc.h"
+
+static void usage(const char *p) {
+    fprintf(stderr,
+            "usage: %s [-i iqfile] [-s rtlFs] [-a modemFs] -r Rs -m M [-p P] [--code NAME] [--mask spacing] [--fsk_lower Hz]\n"
+            "          [--fsk_upper Hz] [--filter addr] [--testframes] [-b] [-q] [-v] [-u host] [-f Hz] [-g gain] [-L] OutputFile\n",
+            p);
+    exit(1);
+}
+
+int main(int argc, char *argv[]) {
+    int Fs_rtl = 0, Fs = 0, Rs = 10000, M = 2, P = 0, lower = -1, upper = -1, mask = 0, filter_addr = -1;
+    int burst_records = 0, quiet = 0, verbose = 0, testframes = 0;
+    const char *code = nullptr, *inname = "-", *dash_host = nullptr;
+    static struct option lo[] = { { "code", required_argument, 0, 'c' },      { "mask", required_argument, 0, 'k' },
+                                  { "fsk_lower", required_argument, 0, 'l' }, { "fsk_upper", required_argument, 0, 'U' },
+                                  { "filter", required_argument, 0, 'F' },    { "testframes", no_argument, 0, 't' },
+                                  { "help", no_argument, 0, 'h' },            { 0, 0, 0, 0 } };
+    int o;
+    while ((o = getopt_long(argc, argv, "i:s:a:r:m:p:f:g:u:bqvLh", lo, NULL)) != -1) {
+        switch (o) {
+            case 'i': inname = optarg; break;
+            case 's': Fs_rtl = atoi(optarg); break;
+            case 'a': Fs = atoi(optarg); break;
+            case 'r': Rs = atoi(optarg); break;
+            case 'm': M = atoi(optarg); break;
+            case 'p': P = atoi(optarg); break;
+            case 'c': code = optarg; break;
+            case 'k': mask = atoi(optarg); break;
+            case 'l': lower = atoi(optarg); break;
+            case 'U': upper = atoi(optarg); break;
+            case 'F': filter_addr = (int)strtol(optarg, NULL, 0); break;
+            case 't': testframes = 1; break;
+            case 'b': burst_records = 1; break;
+            case 'q': quiet = 1; break;
+            case 'v': verbose = 1; break;
+            case 'u': dash_host = optarg; break;
+            case 'f': case 'g': case 'L': break; /* tuner frequency / gain / logging: nothing to tune in a file */
+            default: usage(argv[0]);
+        }
+    }
+    if (argc - optind < 1) usage(argv[0]);
+    const char *outname = argv[optind];
+    if (Fs_rtl == 0 && Fs == 0) Fs = Fs_rtl = 240000;
+    if (Fs == 0) Fs = Fs_rtl;
+    if (Fs_rtl == 0) Fs_rtl = Fs;
+    if ((M != 2 && M != 4) || Rs <= 0 || Fs % Rs || Fs_rtl % Fs) usage(argv[0]);
+    const int D = Fs_rtl / Fs; /* csdr decimation ratio, e.g. 1.8M -> 40k = 45 [R README.md:109], 2.4M -> 80k = 30 [R README.md:172] */
+    if (P == 0) P = FSK_DEFAULT_P;
+    if ((Fs / Rs) % P || P < 4) {
+        fprintf(stderr, "rtl_fsk: Ts/P must be an integer and P >= 4\n");
+        return 1;
+    }
+    FILE *fin = strcmp(inname, "-") == 0 ? stdin : fopen(inname, "rb");
+    FILE *fout = strcmp(outname, "-") == 0 ? stdout : fopen(outname, "wb");
+    if (!fin || !fout) {
+        fprintf(stderr, "rtl_fsk: couldn't open files\n");
+        return 1;
+    }
+
+    struct FSK *fsk = fsk_create_hbr(Fs, Rs, M, P, FSK_DEFAULT_NSYM, 1200, mask ? mask : 400);
+    /* coded mode follows the FSK_LDPC modem's estimator window (0 .. Fs/2, [U freedv_fsk.c]) unless told otherwise */
+    if (lower >= 0 || upper >= 0 || code) {
+        if (lower < 0) lower = 0;
+        if (upper < 0) upper = Fs / 2;
+        fsk_set_freq_est_limits(fsk, lower, upper);
+    }
+    if (mask) fsk_set_freq_est_alg(fsk, 1);
+
+    struct freedv *fdv = nullptr;
+    int K = 0;
+    if (code) {
+        struct freedv_advanced adv;
+        memset(&adv, 0, sizeof adv);
+        adv.codename = (char *)code;
+        adv.Rs = Rs;
+        adv.Fs = Fs;
+        adv.M = M;
+        fdv = freedv_open_advanced(FREEDV_MODE_FSK_LDPC, &adv);
+        if (!fdv) {
+            fprintf(stderr, "rtl_fsk: unknown LDPC code %s\n", code);
+            return 1;
+        }
+        K = freedv_get_bits_per_modem_frame(fdv);
+    }
+    std::vector<uint8_t> test_payload((size_t)(K > 0 ? K : 1));
+    if (testframes && K) ofdm_generate_payload_data_bits(test_payload.data(), K);
+
+    /* csdr front end: convert_u8_f + fir_decimate_cc D with the CLI's default taps (transition 0.05, Hamming) */
+    std::vector<float> taps;
+    if (D > 1) {
+        taps.resize((size_t)firdes_filter_len(0.05f));
+        firdes_lowpass_f(taps.data(), (int)taps.size(), 0.5f / (float)D, 1 /* WINDOW_HAMMING */);
+    }
+    const int L = (int)taps.size();
+
+    int sock = -1;
+    struct sockaddr_in dash;
+    memset(&dash, 0, sizeof dash);
+    if (dash_host) {
+        struct hostent *he = gethostbyname(dash_host);
+        sock = socket(AF_INET, SOCK_DGRAM, 0);
+        if (he && sock >= 0) {
+            dash.sin_family = AF_INET;
+            dash.sin_port = htons(8001);
+            memcpy(&dash.sin_addr, he->h_addr_list[0], (size_t)he->h_length);
+        } else {
+            fprintf(stderr, "rtl_fsk: can't reach dashboard host %s\n", dash_host);
+            sock = -1;
+        }
+    }
+
+    const int nmax = fsk->N + fsk->Ts * 2;
+    std::vector<COMP> mod((size_t)nmax);
+    std::vector<uint8_t> bits((size_t)fsk->Nbits), payload((size_t)(K > 0 ? K : 1)), packed((size_t)(K > 0 ? K / 8 : 1));
+    std::vector<float> filt((size_t)(fsk->mode * fsk->Nsym)), llrs((size_t)fsk->Nbits);
+    std::vector<unsigned char> raw;       /* undecimated u8 samples not yet consumed */
+    std::vector<float> fbuf;              /* their float form (csdr convention) */
+    std::vector<complexf> dec((size_t)nmax);
+    std::vector<float> timing_1s;
+    long frames = 0, packets = 0, test_errs = 0, test_bits_n = 0;
+    double since_dash = 0.0;
+
+    for (;;) {
+        const int nin = (int)fsk_nin(fsk);
+        if (D == 1) {
+            raw.resize((size_t)nin * 2);
+            if (fread(raw.data(), 2, (size_t)nin, fin) != (size_t)nin) break; /* short read ends the loop */
+            for (int i = 0; i < nin; ++i) { /* the fsk_demod -d convention [U fsk_demod.c] */
+                mod[(size_t)i].real = ((float)raw[2 * (size_t)i] - 127.0) / 128.0;
+                mod[(size_t)i].imag = ((float)raw[2 * (size_t)i + 1] - 127.0) / 128.0;
+            }
+        } else {
+            /* one causal FIR over the continuous stream, phase anchored at stream sample 0 (csdr main loop):
+               nin outputs need D*(nin-1)+L inputs; D*nin of them are consumed */
+            const size_t need = (size_t)D * (size_t)(nin - 1) + (size_t)L;
+            const size_t have = raw.size() / 2;
+            if (have < need) {
+                const size_t want = need - have;
+                raw.resize((have + want) * 2);
+                if (fread(raw.data() + have * 2, 2, want, fin) != want) break;
+            }
+            fbuf.resize(need * 2);
+            convert_u8_f(raw.data(), fbuf.data(), (int)(need * 2));
+            const int got = fir_decimate_cc((complexf *)fbuf.data(), dec.data(), (int)need, D, taps.data(), L);
+            if (got < nin) break;
+            for (int i = 0; i < nin; ++i) {
+                mod[(size_t)i].real = dec[(size_t)i].i;
+                mod[(size_t)i].imag = dec[(size_t)i].q;
+            }
+            raw.erase(raw.begin(), raw.begin() + (std::ptrdiff_t)((size_t)D * (size_t)nin * 2));
+        }
+
+        if (!code) {
+            fsk_demod(fsk, bits.data(), mod.data());
+            fwrite(bits.data(), 1, (size_t)fsk->Nbits, fout);
+        } else {
+            fsk_demod_sd(fsk, filt.data(), mod.data());
+            fsk_rx_filt_to_llrs(llrs.data(), filt.data(), fsk->v_est, fsk->SNRest, fsk->mode, fsk->Nsym);
+            int st = freedv_fsk_ldpc_rx_llrs(fdv, llrs.data(), fsk->Nbits, payload.data());
+            bool deliver = (st & FREEDV_RX_BITS) != 0;
+            if (deliver) freedv_pack(packed.data(), payload.data(), K);
+            if (deliver && filter_addr >= 0 && packed[0] == (uint8_t)filter_addr) { /* our own repeater talking */
+                deliver = false;
+                st &= ~FREEDV_RX_BITS;
+            }
+            if (deliver) {
+                packets++;
+                if (testframes) {
+                    for (int i = 0; i < K - 16; ++i) test_errs += payload[(size_t)i] != test_payload[(size_t)i];
+                    test_bits_n += K - 16;
+                }
+            }
+            if (verbose && (st & (FREEDV_RX_BITS | FREEDV_RX_BIT_ERRORS))) {
+                int info[6];
+                freedv_fsk_ldpc_rx_info(fdv, info);
+                fprintf(stderr, "%3d nbits: %3d state: %d uw_loc: %3d uw_err: %2d snrdB: %4.1f iter: %2d pcc: %3d rxst: %c%c%c%c\n",
+                        (int)packets, info[5], info[0], info[1], info[2], 10.0 * log10((double)fsk->SNRest + 1.0), info[3], info[4],
+                        st & FREEDV_RX_BIT_ERRORS ? 'E' : '-', st & FREEDV_RX_BITS ? 'B' : '-', st & FREEDV_RX_SYNC ? 'S' : '-',
+                        st & FREEDV_RX_TRIAL_SYNC ? 'T' : '-');
+            }
+            if (burst_records) {
+                const uint8_t sb = (uint8_t)st;
+                if (!deliver) memset(packed.data(), 0, packed.size());
+                fwrite(&sb, 1, 1, fout);
+                fwrite(packed.data(), 1, (size_t)K / 8, fout);
+            } else if (deliver) {
+                fwrite(packed.data(), 1, (size_t)K / 8, fout);
+            }
+        }
+        if (fin == stdin || fout == stdout) fflush(fout);
+        frames++;
+
+        /* dashboard telemetry, once per second of signal */
+        timing_1s.push_back(fsk->norm_rx_timing);
+        since_dash += (double)nin / (double)Fs;
+        if (sock >= 0 && since_dash >= 1.0) {
+            std::string js = "{\"SfdB\":[";
+            char num[256];
+            for (int i = 0; i < fsk->Ndft; ++i) {
+                snprintf(num, sizeof num, "%s%.1f", i ? "," : "", 20.0 * log10((double)fsk->Sf[i] + 1e-9));
+                js += num;
+            }
+            js += "],\"f_est_Hz\":[";
+            for (int m = 0; m < M; ++m) {
+                snprintf(num, sizeof num, "%s%.0f", m ? "," : "", (double)(fsk->freq_est_type ? fsk->f2_est[m] : fsk->f_est[m]));
+                js += num;
+            }
+            snprintf(num, sizeof num, "],\"fsk_lower_Hz\":%d,\"fsk_upper_Hz\":%d,\"Fs_Hz\":%d,\"SNRest_lin\":%.3f,\"norm_rx_timing\":[",
+                     fsk->est_min, fsk->est_max, Fs, (double)fsk->SNRest);
+            js += num;
+            for (size_t i = 0; i < timing_1s.size(); ++i) {
+                snprintf(num, sizeof num, "%s%.3f", i ? "," : "", (double)timing_1s[i]);
+                js += num;
+            }
+            js += "]}\n";
+            sendto(sock, js.data(), js.size(), 0, (struct sockaddr *)&dash, sizeof dash);
+            timing_1s.clear();
+            since_dash = 0.0;
+        }
+    }
+    if (!quiet) {
+        fprintf(stderr, "rtl_fsk: %ld modem frames", frames);
+        if (code) fprintf(stderr, ", %ld packets", packets);
+        if (testframes && test_bits_n) fprintf(stderr, ", test frame BER %.4f (%ld/%ld)", (double)test_errs / (double)test_bits_n, test_errs, test_bits_n);
+        fprintf(stderr, "\n");
+    }
+    if (fdv) freedv_close(fdv);
+    fsk_destroy(fsk);
+    fclose(fout);
+    if (sock >= 0) close(sock);
+    return 0;
+}
