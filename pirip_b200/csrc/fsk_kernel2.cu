@@ -109,6 +109,16 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
         ns = ns < 256 ? ns * 2 : 256;
     }
 }
+/* release / acquire accesses to a shared-memory flag (CTA scope): the ordered hand-off of the IIR spectrum between FFT warps */
+__device__ __forceinline__ void st_release_shared(int *p, int v) {
+    asm volatile("st.release.cta.shared.s32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_shared(const int *p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared.s32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+
 /* hardware named barriers: a warp blocked in bar.sync costs no issue slots (unlike a polled mbarrier) */
 __device__ __forceinline__ void nbar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void nbar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -263,6 +273,7 @@ __device__ __noinline__ void pick_tones(const FskDevCfg &cfg, Fsk2CapShared *cs,
         f_min = f_min < 0 ? 0 : f_min;
         int f_max = ibest + cfg.f_zero;
         f_max = f_max > Ndft ? Ndft : f_max;
+        __syncwarp(); /* every lane has read its part of tmpS before anyone blanks */
         for (int j = f_min + lane; j < f_max; j += 32) tmpS[j] = 0.0f;
         if (lane == 0) cs->freqi[r] = ibest - (Ndft >> 1);
         __syncwarp();
@@ -328,14 +339,13 @@ __device__ __noinline__ void fft_task(const FskDevCfg &cfg, Fsk2CapShared *cs, f
     float mg[Q];
     warp_fft_mag<LOGN>(src, cfg.fmt, j * (N >> 1), buf, mg, tw, hann, perm, lane);
     /* ordered IIR: wait for block j - 1 of this capture */
-    volatile int *turn = &cs->sf_turn;
+    int *turn = &cs->sf_turn;
     {
         int tries = 0;
-        while (*turn != j) {
+        while (ld_acquire_shared(turn) != j) {
             if (++tries > 64) __nanosleep(100);
         }
     }
-    __threadfence_block();
     const float tc = cfg.tc, omtc = 1.0f - tc;
     const float *Sf_in = j == 0 ? Sf2 + (size_t)(fb ^ 1) * N : Sf2 + (size_t)fb * N;
     float *Sf_out = Sf2 + (size_t)fb * N;
@@ -344,9 +354,8 @@ __device__ __noinline__ void fft_task(const FskDevCfg &cfg, Fsk2CapShared *cs, f
         const int i = lane + (q << 5);
         Sf_out[i] = (Sf_in[i] * omtc) + (mg[q] * tc);
     }
-    __threadfence_block();
     __syncwarp();
-    if (lane == 0) *turn = j + 1 < nb ? j + 1 : 0; /* the tones are picked in the next phase (pick_tones) */
+    if (lane == 0) st_release_shared(turn, j + 1 < nb ? j + 1 : 0); /* the tones are picked in the next phase (pick_tones) */
 }
 
 /* ---- 256-point fast path: two FFT blocks per warp, two radix-4 levels per register pass ----------------------
@@ -443,14 +452,13 @@ __device__ __noinline__ void fft256_task(const FskDevCfg &cfg, Fsk2CapShared *cs
     float mg[16];
     fft256_pair(src, cfg.fmt, j0 * (N >> 1), two, reinterpret_cast<float *>(buf), tw, hann, mg, lane);
     /* ordered IIR: wait for the blocks before j0 of this capture (short spin, then back off) */
-    volatile int *turn = &cs->sf_turn;
+    int *turn = &cs->sf_turn;
     {
         int tries = 0;
-        while (*turn != j0) {
+        while (ld_acquire_shared(turn) != j0) {
             if (++tries > 64) __nanosleep(100);
         }
     }
-    __threadfence_block();
     const int half = lane >> 4, L = lane & 15;
     const float tc = cfg.tc, omtc = 1.0f - tc;
     const float *Sf_in = j0 == 0 ? Sf2 + (size_t)(fb ^ 1) * N : Sf2 + (size_t)fb * N;
@@ -470,10 +478,9 @@ __device__ __noinline__ void fft256_task(const FskDevCfg &cfg, Fsk2CapShared *cs
             Sf_out[i] = (Sf_out[i] * omtc) + (mg[h] * tc);
         }
     }
-    __threadfence_block();
     __syncwarp();
     const int jn = j0 + (two ? 2 : 1);
-    if (lane == 0) *turn = jn < nb ? jn : 0; /* the tones are picked in the next phase (pick_tones) */
+    if (lane == 0) st_release_shared(turn, jn < nb ? jn : 0); /* the tones are picked in the next phase (pick_tones) */
 }
 
 struct Cap2 {
