@@ -149,3 +149,51 @@ def test_dashboard_telemetry_has_the_fields_dash_py_reads(tmp_path):
         assert sorted(round(v / 1000) for v in d["f_est_Hz"]) == [10, 20]   # tones at +10 / +20 kHz
         assert len(d["norm_rx_timing"]) >= 190 and all(-0.5 <= t <= 0.5 for t in d["norm_rx_timing"])
         assert d["SNRest_lin"] > 3
+
+
+def test_frame_repeater_loopback_in_files(tmp_path):
+    """`script/frame_repeater start_loopback` with files for the radios ([R script/frame_repeater:47-64]): pirip's transmitter
+    command line (tools/rpitx_fsk: IQ-file build, N4) sends two bursts of three test frames from source 0x01; the GPU
+    receiver feeds the reference's own frame_repeater; its output goes through the transmitter again (--packed, burst-control
+    bytes) and the receiver gets the same frames back from source 0x02 — and drops them when told to filter 0x2."""
+    if not os.path.exists(REPEATER):
+        pytest.skip("oracle/_ref/frame_repeater not built (needs /root/reference at build time)")
+    build_tools()
+    code, Rs, Fs = "H_256_512_4", 10000, 80000
+    tx = [os.path.join(BIN, "rpitx_fsk")]
+    rx = [os.path.join(BIN, "rtl_fsk"), "-a", str(Fs), "-r", str(Rs), "-m", "2", "--code", code, "-q"]
+    a, b = tmp_path / "a.u8", tmp_path / "b.u8"
+    subprocess.run(tx + ["/dev/zero", "--code", code, "-r", str(Rs), "-s", str(Rs), "--testframes", "3", "--bursts", "2", "--seq",
+                         "--source", "0x1", "--fs", str(Fs), "--ebno", "10", "-o", str(a)], check=True, capture_output=True)
+    rec = subprocess.run(rx + ["-i", str(a), "--filter", "0x2", "-b", "-"], check=True, capture_output=True).stdout
+    first = [r[1:] for r in np.frombuffer(rec, np.uint8).reshape(-1, 33) if r[0] & 0x4]
+    assert len(first) == 6 and all(r[0] == 0x01 for r in first) and [int(r[1]) for r in first] == [1, 2, 3, 1, 2, 3]
+    rep = subprocess.run([REPEATER, "256", "0x2"], input=rec, check=True, capture_output=True, timeout=60).stdout
+    subprocess.run(tx + ["-", "--code", code, "-r", str(Rs), "-s", str(Rs), "--packed", "--fs", str(Fs), "--ebno", "10", "--seed", "5",
+                         "-o", str(b)], input=rep, check=True, capture_output=True)
+    back = subprocess.run(rx + ["-i", str(b), "-"], check=True, capture_output=True).stdout
+    back = np.frombuffer(back, np.uint8).reshape(-1, 32)
+    assert back.shape[0] == 6
+    for got, sent in zip(back, first):
+        assert got[0] == 0x02 and np.array_equal(got[1:30], sent[1:30])     # same frame, new source address (and new CRC)
+    assert subprocess.run(rx + ["-i", str(b), "--filter", "0x2", "-"], check=True, capture_output=True).stdout == b""
+
+
+def test_transmitter_test_modes(tmp_path):
+    """[R README.md:191,196]: --testframes counted by the receiver's own --testframes; [R README.md:101]: uncoded test bits."""
+    build_tools()
+    code = "H_256_512_4"
+    a = tmp_path / "a.u8"
+    subprocess.run([os.path.join(BIN, "rpitx_fsk"), "/dev/zero", "--code", code, "-r", "10000", "-s", "10000", "--testframes", "4",
+                    "--fs", "80000", "--ebno", "9", "-o", str(a)], check=True, capture_output=True)
+    r = subprocess.run([os.path.join(BIN, "rtl_fsk"), "-i", str(a), "-a", "80000", "-r", "10000", "-m", "2", "--code", code,
+                        "--testframes", os.devnull], check=True, capture_output=True)
+    assert b"4 packets" in r.stderr and b"BER 0.0000" in r.stderr, r.stderr
+    bits = subprocess.run([os.path.join(BIN, "fsk_get_test_bits"), "-", "3000"], capture_output=True, check=True).stdout
+    t = tmp_path / "t.u8"
+    subprocess.run([os.path.join(BIN, "rpitx_fsk"), "-", "-r", "10000", "-s", "10000", "--fs", "240000", "--ebno", "11", "-o", str(t)],
+                   input=bits, check=True, capture_output=True)
+    dem = subprocess.run([os.path.join(BIN, "rtl_fsk"), "-i", str(t), "-a", "240000", "-r", "10000", "-m", "2", "-p", "24", "-q", "-"],
+                         check=True, capture_output=True).stdout
+    put = subprocess.run([os.path.join(BIN, "fsk_put_test_bits"), "-q", "-p", "25", "-"], input=dem, capture_output=True)
+    assert put.returncode == 0, put.stderr.decode()
