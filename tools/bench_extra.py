@@ -66,6 +66,53 @@ def bench_decim(steps):
             "parity_vs_oracle": ok}
 
 
+def bench_chain_c2(steps):
+    """Config 2 end to end on the device: 1.8 MS/s u8 IQ -> fused csdr stage (/45, s16 as in [R README.md:109]) ->
+    fsk_demod -c 2 40000 1000 --fsk_lower 500 -> bits; rate quoted per INPUT sample.  Two launches per step."""
+    import orc
+    import synth
+    D, nstreams, nbits = 45, 592, 1500  # 1.5 s streams: 2.7 Msamples each, 3.2 GB of u8 in total
+    base = []
+    for c in range(8):
+        x = synth.fsk_mod(synth.test_bits(nbits), 2, 1800000, 1000, 1000, 1000, timing_offset=37.0 * c, phase0=0.3 * c)
+        x = synth.add_awgn(x, [None, 12.0, 9.0, 6.0][c % 4], 1800, 2, synth.rng(40 + c))
+        base.append(synth.to_u8(x, amp=70.0))
+    n = min(b.size for b in base) // 2
+    base_t = torch.from_numpy(np.stack([b[:2 * n] for b in base])).cuda()
+    iq = base_t[torch.arange(nstreams, device="cuda") % 8].contiguous()
+    dec = pb.DecimPlan(D)
+    nout = dec.out_count(n)
+    mid = torch.empty((nstreams, 2 * nout), dtype=torch.int16, device="cuda")
+    plan = pb.FskPlan(Fs=40000, Rs=1000, M=2, P=8, limits=(500, 20000), fmt=pb.FMT_S16)
+    mf = plan.max_frames(nout)
+    bits = torch.zeros((nstreams, mf * plan.nbits), dtype=torch.uint8, device="cuda")
+    nf = torch.zeros(nstreams, dtype=torch.int32, device="cuda")
+    s = torch.cuda.current_stream()
+    sp = ctypes.c_void_p(s.cuda_stream)
+
+    def fn():
+        dec.run_dev(iq.data_ptr(), nstreams, n, iq.stride(0), None, mid.data_ptr(), nout, stream=sp)
+        plan.demod_batch_dev(mid.data_ptr(), nstreams, nout, mid.stride(0) * 2, bits.data_ptr(), nf.data_ptr(), mf, stream=sp)
+
+    ms = timed(fn, steps)
+    _, ref_s = orc.csdr_decimate_stream(iq[5].cpu().numpy(), D)
+    ref = orc.fsk_demod_stream(orc.demod_cfg(40000, 1000, 2, P=8, limits=(500, 20000), fmt=orc.FMT_S16), ref_s)
+    k = int(nf[5])
+    ok = k == ref["nframes"] and bool(np.array_equal(bits[5, :k * plan.nbits].cpu().numpy(), ref["bits"]))
+    algo = nstreams * (2.0 * n + float(k * plan.nbits))
+    pk, src = peak()
+    ach = algo / (ms * 1e-3) / 1e9
+    L = pb.lib()
+    L.pirip_fsk_plan_kernel.restype = ctypes.c_char_p
+    L.pirip_fsk_plan_kernel.argtypes = [ctypes.c_void_p]
+    return {"workload": "chain C2: %d x %.2f Msample u8 IQ streams at 1.8 MS/s -> /45 (79 taps, s16) -> 2FSK Fs=40k Rs=1k --fsk_lower 500 -> bits"
+                        % (nstreams, n / 1e6),
+            "metric": "input IQ Msamples/s", "value": nstreams * n / (ms * 1e-3) / 1e6, "ms_per_step": ms, "launches_per_step": 2,
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "peak_source": src,
+                         "algorithmic_bytes": algo, "kernel": "fir_decimate_kernel<true> + " + L.pirip_fsk_plan_kernel(plan._h).decode()},
+            "parity_vs_oracle": ok}
+
+
 def bench_ldpc(steps):
     import orc
     l, v = pb.ldpc_code("H_256_512_4")
@@ -114,5 +161,7 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.only in ("", "decim"):
         print(json.dumps(bench_decim(a.steps)))
+    if a.only in ("", "chain"):
+        print(json.dumps(bench_chain_c2(a.steps)))
     if a.only in ("", "ldpc"):
         print(json.dumps(bench_ldpc(a.steps)))
