@@ -100,6 +100,234 @@ __global__ void __launch_bounds__(kTile) fir_decimate_kernel(const __grid_consta
     }
 }
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Fast path for u8 input and the decimator shapes of pirip's pipelines (D = 45 / 30 with the default 79 taps,
+ * [R README.md:109,172], [R script/frame_repeater:36]): the stage is HBM-class work (2 B in per sample, 7 flops),
+ * so the kernel is built around instruction count and shared-memory bandwidth, not around a staged float tile.
+ *
+ *  - One thread owns NBLK consecutive outputs of one stream and walks its D*NBLK (+ halo) input samples ONCE, in
+ *    order: sample r of input block j is tap r of output j, tap D + r of output j - 1, ... so every sample is
+ *    loaded and converted once and feeds ceil(L / D) rotating accumulators (the generic kernel reads every staged
+ *    sample L / D = 1.76 times from shared memory).  Each output still accumulates its products in tap order from
+ *    zero with separate multiply and add, so the floats are those of the scalar loop.
+ *  - Raw bytes come straight from global memory into registers (4-byte loads; a thread's words are contiguous, so
+ *    every 32-byte sector is fetched from HBM once and re-hit in L1); there is no staged copy of the samples at all.
+ *  - convert_u8_f is a table lookup.  The table holds the 256 exact values in 32 lane-private columns (row stride
+ *    256 B, table aligned to 64 KB in the shared window), so a lookup is conflict-free for any data and its address
+ *    is ONE byte-permute: {table base | lane column} with the sample byte dropped into address bits 8-15.
+ *  - Taps are kernel parameters: with the block loop unrolled every tap is an immediate constant-bank operand.
+ *  Per input sample: 0.5 LDG + 2 PRMT + 2 LDS + 7.0 FMUL/FADD, nothing else.
+ */
+constexpr int kFastThreads = 512;
+constexpr int kFastMaxTaps = 96;
+constexpr unsigned kFastSmem = 2 * 65536 - 1024; /* room for a 64 KB table on a 64 KB boundary of the shared window */
+
+struct DecimFastArgs {
+    const unsigned char *in;
+    size_t in_stride_bytes;
+    size_t n_out;      /* outputs per stream */
+    size_t n_streams;
+    const float *lut;  /* device, 256 exact convert_u8_f values */
+    float2 *out_f32;
+    short2 *out_s16;
+    size_t out_stride;
+    unsigned dyn_smem;
+    float taps[kFastMaxTaps];
+};
+
+__device__ __forceinline__ unsigned smem_addr(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+/* table address of byte K of word w for this lane: bytes {base.0, w.K, base.2, base.3} */
+template <int K>
+__device__ __forceinline__ unsigned lut_addr(unsigned lane_base, unsigned w) {
+    unsigned r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(lane_base), "r"(w), "n"(0x3200 | ((4 + K) << 4)));
+    return r;
+}
+
+template <bool F32, bool S16>
+__device__ __forceinline__ void emit_output(const DecimFastArgs &a, size_t o, float2 acc) {
+    if (F32) a.out_f32[o] = acc;
+    /* convert_f_s16: (short)(in * SHRT_MAX), C truncation toward zero */
+    if (S16) a.out_s16[o] = make_short2((short)__float2int_rz(acc.x * 32767.0f), (short)__float2int_rz(acc.y * 32767.0f));
+}
+
+/* accumulate input sample (xi, xq) = sample r of block jb (relative to the group) into the outputs it is a tap of;
+   outputs outside [lo, NBLK) are not accumulated when CLIP (halo blocks) */
+template <int D, int L, int NA, int NBLK, bool HALO>
+__device__ __forceinline__ void fir_feed(const DecimFastArgs &a, float2 (&acc)[NA], int jbm, int r, float xi, float xq) {
+    /* jbm = block index modulo NA (accumulator role); for halo blocks jbm also encodes e = block - NBLK via HALO path */
+#pragma unroll
+    for (int aa = 0; aa < NA; ++aa) {
+        const int t = aa * D + r;
+        if (t < L) {
+            const int ai = (jbm - aa + 4 * NA) % NA;
+            acc[ai].x += xi * a.taps[t];
+            acc[ai].y += xq * a.taps[t];
+        }
+    }
+}
+
+template <int D, int L, int NBLK, bool F32, bool S16>
+__global__ void __launch_bounds__(kFastThreads, 1) fir_decimate_u8_fast(const __grid_constant__ DecimFastArgs a) {
+    constexpr int NA = (L + D - 1) / D; /* outputs a sample contributes to = live accumulators */
+    /* blocks per unrolled body: a whole number of 16-byte chunks (8 samples) and of accumulator rotations */
+    constexpr int PB16 = (D % 8 == 0) ? 1 : (D % 4 == 0) ? 2 : (D % 2 == 0) ? 4 : 8;
+    constexpr int U = (PB16 % NA == 0) ? PB16 : PB16 * NA;
+    constexpr int CB = U * D / 8; /* 16-byte chunks per body */
+    constexpr int SUBC = (CB % 9 == 0) ? 9 : (CB % 5 == 0) ? 5 : (CB % 3 == 0) ? 3 : 1; /* chunks per pipeline step */
+    constexpr int NSUB = CB / SUBC;
+    constexpr int HS = L - D; /* halo samples after the group */
+    static_assert(NBLK % U == 0, "group must be whole bodies");
+    static_assert(L <= kFastMaxTaps && L > D, "tap count");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const unsigned sbase = smem_addr(smem_raw);
+    const unsigned lut0 = (sbase + 65535u) & ~65535u;
+    if (lut0 + 65536u > sbase + a.dyn_smem) __trap();
+    for (int i = tid; i < 256 * 32; i += kFastThreads) {
+        const float v = a.lut[i >> 5];
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut0 + ((unsigned)(i >> 5) << 8) + ((unsigned)(i & 31) << 2)), "f"(v) : "memory");
+    }
+    __syncthreads();
+    const unsigned lb = lut0 + 4u * (unsigned)lane;
+
+    const size_t gps = a.n_out / NBLK; /* whole groups per stream */
+    const size_t total = gps * a.n_streams;
+    for (size_t gid = (size_t)blockIdx.x * kFastThreads + tid; gid < total; gid += (size_t)gridDim.x * kFastThreads) {
+        const size_t stream = gid / gps, grp = gid - stream * gps;
+        const size_t k0 = grp * NBLK;
+        const uint4 *src = reinterpret_cast<const uint4 *>(a.in + stream * a.in_stride_bytes + 2 * (size_t)D * k0);
+        const size_t obase = stream * a.out_stride + k0;
+        float2 acc[NA];
+#pragma unroll
+        for (int i = 0; i < NA; ++i) acc[i] = make_float2(0.0f, 0.0f);
+        unsigned cur[4 * SUBC], nxt[4 * SUBC];
+#pragma unroll
+        for (int c = 0; c < SUBC; ++c) {
+            const uint4 v = __ldg(src + c);
+            cur[4 * c] = v.x, cur[4 * c + 1] = v.y, cur[4 * c + 2] = v.z, cur[4 * c + 3] = v.w;
+        }
+#pragma unroll 1
+        for (int j = 0; j < NBLK; j += U) {
+#pragma unroll
+            for (int sub = 0; sub < NSUB; ++sub) {
+                /* the next step's chunks are in flight while this step's samples are consumed */
+                if (sub + 1 < NSUB || j + U < NBLK) {
+#pragma unroll
+                    for (int c = 0; c < SUBC; ++c) {
+                        const uint4 v = __ldg(src + (sub + 1) * SUBC + c);
+                        nxt[4 * c] = v.x, nxt[4 * c + 1] = v.y, nxt[4 * c + 2] = v.z, nxt[4 * c + 3] = v.w;
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 8 * SUBC; ++i) {
+                    const int s = sub * 8 * SUBC + i; /* sample of the body */
+                    const int u = s / D, r = s - u * D;
+                    const unsigned ww = cur[i >> 1];
+                    const float xi = lds_f32((i & 1) ? lut_addr<2>(lb, ww) : lut_addr<0>(lb, ww));
+                    const float xq = lds_f32((i & 1) ? lut_addr<3>(lb, ww) : lut_addr<1>(lb, ww));
+                    fir_feed<D, L, NA, NBLK, false>(a, acc, u % NA, r, xi, xq);
+                    if (r == D - 1) {
+                        /* the output whose last taps were in this block: NA - 1 blocks back */
+                        const int done = (u + 1) % NA;
+                        const int o = j + u - (NA - 1);
+                        if (o >= 0) emit_output<F32, S16>(a, obase + (size_t)o, acc[done]);
+                        acc[done] = make_float2(0.0f, 0.0f);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 4 * SUBC; ++c) cur[c] = nxt[c];
+            }
+            src += CB;
+        }
+        /* halo: the L - D samples after the group finish its last NA - 1 outputs; loaded without touching a byte
+           beyond the last sample the stream is known to hold */
+        {
+            constexpr int HW = (HS + 1) / 2; /* words */
+            unsigned w[HW];
+            const unsigned *s32 = reinterpret_cast<const unsigned *>(src);
+#pragma unroll
+            for (int c = 0; c < HW / 4; ++c) {
+                const uint4 v = __ldg(src + c);
+                w[4 * c] = v.x, w[4 * c + 1] = v.y, w[4 * c + 2] = v.z, w[4 * c + 3] = v.w;
+            }
+#pragma unroll
+            for (int i = (HW / 4) * 4; i < HW; ++i) {
+                if (i == HW - 1 && (HS & 1))
+                    w[i] = *reinterpret_cast<const unsigned short *>(s32 + i);
+                else
+                    w[i] = __ldg(s32 + i);
+            }
+#pragma unroll
+            for (int sI = 0; sI < HS; ++sI) {
+                const int e = sI / D, r = sI - e * D;
+                const unsigned ww = w[sI >> 1];
+                const float xi = lds_f32((sI & 1) ? lut_addr<2>(lb, ww) : lut_addr<0>(lb, ww));
+                const float xq = lds_f32((sI & 1) ? lut_addr<3>(lb, ww) : lut_addr<1>(lb, ww));
+#pragma unroll
+                for (int aa = e + 1; aa < NA; ++aa) {
+                    const int t = aa * D + r;
+                    if (t < L) {
+                        const int ai = ((NBLK + e) - aa + 4 * NA) % NA;
+                        acc[ai].x += xi * a.taps[t];
+                        acc[ai].y += xq * a.taps[t];
+                    }
+                }
+                if (r == D - 1 || sI == HS - 1) emit_output<F32, S16>(a, obase + (size_t)(NBLK + e - (NA - 1)), acc[((NBLK + e) + 1) % NA]);
+            }
+        }
+    }
+    /* the n_out % NBLK outputs at the end of every stream: plain tap loop, one output per thread */
+    const size_t rem = a.n_out - gps * NBLK;
+    for (size_t i = (size_t)blockIdx.x * kFastThreads + tid; i < rem * a.n_streams; i += (size_t)gridDim.x * kFastThreads) {
+        const size_t stream = i / rem, k = gps * NBLK + (i - stream * rem);
+        const unsigned short *x = reinterpret_cast<const unsigned short *>(a.in + stream * a.in_stride_bytes) + k * (size_t)D;
+        float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+        for (int t = 0; t < L; ++t) {
+            const unsigned ww = x[t];
+            const float h = a.taps[t];
+            acc.x += lds_f32(lut_addr<0>(lb, ww)) * h;
+            acc.y += lds_f32(lut_addr<1>(lb, ww)) * h;
+        }
+        emit_output<F32, S16>(a, stream * a.out_stride + k, acc);
+    }
+}
+
+template <int D, int L, int NBLK>
+cudaError_t fast_launch(const DecimFastArgs &a, bool prepare_only, int sms, cudaStream_t stream) {
+    const bool f = a.out_f32 != nullptr, s = a.out_s16 != nullptr;
+#define PIRIP_FAST_CASE(F, S)                                                                                              \
+    do {                                                                                                                   \
+        if (prepare_only) {                                                                                                \
+            cudaError_t e = cudaFuncSetAttribute(fir_decimate_u8_fast<D, L, NBLK, F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.dyn_smem); \
+            if (e != cudaSuccess) return e;                                                                                \
+        } else if (f == F && s == S) {                                                                                     \
+            fir_decimate_u8_fast<D, L, NBLK, F, S><<<sms, kFastThreads, a.dyn_smem, stream>>>(a);                            \
+            return cudaGetLastError();                                                                                     \
+        }                                                                                                                  \
+    } while (0)
+    PIRIP_FAST_CASE(true, true);
+    PIRIP_FAST_CASE(true, false);
+    PIRIP_FAST_CASE(false, true);
+#undef PIRIP_FAST_CASE
+    return cudaSuccess;
+}
+
+/* which (D, L) shapes have a fast instantiation; NBLK outputs per thread */
+cudaError_t fast_dispatch(int D, int L, const DecimFastArgs &a, bool prepare_only, int sms, cudaStream_t stream, bool *handled) {
+    *handled = true;
+    if (D == 45 && L == 79) return fast_launch<45, 79, 16>(a, prepare_only, sms, stream);
+    if (D == 30 && L == 79) return fast_launch<30, 79, 12>(a, prepare_only, sms, stream);
+    *handled = false;
+    return cudaSuccess;
+}
+
 size_t out_count(size_t n, int D, int L) { return n >= (size_t)L ? (n - (size_t)L) / (size_t)D + 1 : 0; }
 
 }  // namespace
@@ -108,6 +336,9 @@ struct pirip_decim_plan {
     int D, L, device;
     float *d_taps = nullptr, *d_lut = nullptr;
     int smem_u8 = 0, smem_f32 = 0;
+    bool fast = false; /* a fir_decimate_u8_fast instantiation exists for (D, L) */
+    int sms = 0;
+    std::vector<float> taps;
     /* reusable buffers of the host-buffer entry point */
     unsigned char *d_in = nullptr;
     float2 *d_out = nullptr;
@@ -131,6 +362,27 @@ static cudaError_t decim_launch(pirip_decim_plan *p, bool u8in, const void *d_in
     a.out_s16 = (short2 *)d_out_s16;
     a.out_stride = out_stride;
     if (a.n_out == 0 || n_streams == 0) return cudaSuccess;
+    /* u8 streams on 16-byte boundaries take the register-streaming kernel */
+    if (u8in && p->fast && (reinterpret_cast<size_t>(d_in) & 15) == 0 && (in_stride_bytes & 15) == 0 && !getenv("PIRIP_DECIM_GENERIC")) {
+        DecimFastArgs f;
+        f.in = a.in;
+        f.in_stride_bytes = in_stride_bytes;
+        f.n_out = a.n_out;
+        f.n_streams = n_streams;
+        f.lut = p->d_lut;
+        f.out_f32 = a.out_f32;
+        f.out_s16 = a.out_s16;
+        f.out_stride = out_stride;
+        f.dyn_smem = kFastSmem;
+        memset(f.taps, 0, sizeof(f.taps));
+        memcpy(f.taps, p->taps.data(), sizeof(float) * p->taps.size());
+        bool handled = false;
+        cudaError_t e = fast_dispatch(p->D, p->L, f, false, p->sms, stream, &handled);
+        if (handled) {
+            pirip::count_launch();
+            return e;
+        }
+    }
     dim3 grid((unsigned)((a.n_out + kTile - 1) / kTile), (unsigned)n_streams);
     if (u8in)
         fir_decimate_kernel<true><<<grid, kTile, p->smem_u8, stream>>>(a);
@@ -159,6 +411,7 @@ extern "C" pirip_decim_plan *pirip_decim_plan_create(int decimation, const float
     }
     float lut[256];
     for (int b = 0; b < 256; ++b) lut[b] = ((float)b) / (UCHAR_MAX / 2.0) - 1.0; /* convert_u8_f */
+    p->taps.assign(taps, taps + taps_length);
     if (!pirip::cuda_ok(cudaSetDevice(device), "cudaSetDevice") ||
         !pirip::cuda_ok(cudaMalloc(&p->d_taps, sizeof(float) * (size_t)taps_length), "cudaMalloc taps") ||
         !pirip::cuda_ok(cudaMalloc(&p->d_lut, sizeof(lut)), "cudaMalloc lut") ||
@@ -168,6 +421,20 @@ extern "C" pirip_decim_plan *pirip_decim_plan_create(int decimation, const float
         !pirip::cuda_ok(cudaFuncSetAttribute(fir_decimate_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem_f32), "smem attr")) {
         pirip_decim_plan_destroy(p);
         return nullptr;
+    }
+    {
+        DecimFastArgs f;
+        memset(&f, 0, sizeof(f));
+        f.dyn_smem = kFastSmem;
+        bool handled = false;
+        cudaDeviceProp prop;
+        if (!pirip::cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties") ||
+            !pirip::cuda_ok(fast_dispatch(p->D, p->L, f, true, 0, nullptr, &handled), "smem attr (fast decimator)")) {
+            pirip_decim_plan_destroy(p);
+            return nullptr;
+        }
+        p->fast = handled;
+        p->sms = prop.multiProcessorCount;
     }
     return p;
 }

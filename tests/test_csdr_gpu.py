@@ -82,3 +82,32 @@ def test_config2_chain_decimate_then_demod():
                               ref["stats"]["norm_rx_timing"].view(np.uint32))
         ber, n = synth.ber_vs_stream(out["bits"][c, :nf * 50])
         assert ber < 0.06  # few hundred bits at 10 dB through the aliasing-prone csdr default filter
+
+
+@pytest.mark.parametrize("D,n,rows", [(45, 45 * 16 * 40 + 79, 5), (45, 45 * 16 * 3 + 78 + 45 * 15, 2), (30, 30 * 15 * 7 + 79 + 30 * 4, 4),
+                                      (30, 30 * 15 * 2 + 79, 1), (45, 45 * 15 + 79, 3)])
+def test_register_streaming_kernel_vs_generic_kernel_and_oracle(D, n, rows):
+    """fir_decimate_u8_fast (D = 45 / 30, 79 taps: whole groups of 16 / 15 outputs per thread, halo blocks, the
+    per-stream remainder loop) against the generic staged kernel (PIRIP_DECIM_GENERIC=1) and the oracle."""
+    import os
+
+    import pirip_b200 as pb
+    g = synth.rng(D * 7 + n % 1013)
+    iq = g.integers(0, 256, (rows, 2 * n), dtype=np.uint8)
+    p = pb.DecimPlan(D)
+    f, s = p.run(iq)
+    os.environ["PIRIP_DECIM_GENERIC"] = "1"
+    try:
+        fg, sg = p.run(iq)
+    finally:
+        del os.environ["PIRIP_DECIM_GENERIC"]
+    assert np.array_equal(f.view(np.uint32), fg.view(np.uint32)) and np.array_equal(s, sg)
+    for r in range(rows):
+        yf, ys = orc.csdr_decimate_stream(iq[r], D)
+        assert np.array_equal(f[r].view(np.uint32), yf.view(np.uint32)) and np.array_equal(s[r], ys)
+    # extreme byte values: the table rows at both ends
+    iq2 = np.where(g.integers(0, 2, iq.shape, dtype=np.uint8) == 1, 255, 0).astype(np.uint8)
+    f2, s2 = p.run(iq2)
+    yf, ys = orc.csdr_decimate_stream(iq2[0], D)
+    assert np.array_equal(f2[0].view(np.uint32), yf.view(np.uint32)) and np.array_equal(s2[0], ys)
+    p.close()
