@@ -63,6 +63,7 @@ struct FskDevCfg {
         int numffts;       /* FFT blocks per frame (independent of nin) */
         int fast_ts;       /* 1: the 16-window integrator path applies (P == Ts, Ts instantiated) */
         int fft_warps;     /* warps that take FFT tasks */
+        int fft_early;     /* FFT tasks of the next frame a capture-less worker warp runs during the streaming phase */
         int ering_fft_off; /* float offset of the FFT scratch borrowed from a capture's energy ring */
         int cap_stride;    /* bytes per capture block */
         int off_stage, off_ring, off_tail, off_ckpt, off_ering, off_Sf, off_scal; /* inside a capture block */

@@ -234,6 +234,10 @@ static void derive_k2(const pirip_fsk_cfg &c, FskDevCfg &d) {
             k.ering_fft_off = align_up((3 + c.M) * c.Nsym, 64);
             const bool room = k.ering_fft_off + 2 * FSK2_FFT_SLOT_ELEMS(d.Ndft) <= c.M * k.ering && g >= nw / 2;
             k.fft_warps = room ? nw : nw / 2;
+            /* opt-in: measured SLOWER on B200 (1250 x 1 s captures: 0 -> 10.82 ms, 5 -> 11.17 ms, 7 -> 12.32 ms, 9 -> 11.93 ms):
+               FFT code running beside the streaming code slows the worker chain more than the shorter FFT phase saves */
+            k.fft_early = 0;
+            if (const char *e = getenv("PIRIP_FSK_K2_FFT_EARLY")) k.fft_early = atoi(e) < 0 ? 0 : atoi(e);
             return;
         }
     }

@@ -683,7 +683,6 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
     float2 *fft_slots = reinterpret_cast<float2 *>(cta + cfg.k2.off_fft);
     float2 *phi_ft = reinterpret_cast<float2 *>(cta + cfg.k2.off_phift); /* timing-line oscillator, [nint] */
     const unsigned char **srcp = reinterpret_cast<const unsigned char **>(ctl + 1); /* [gmax][2] raw-sample pointer per staging buffer */
-    const bool is_worker = warp < W;
 
     for (int i = tid; i < Ndft; i += nthreads) {
         tw[i] = cfg.twiddle[i];
@@ -702,7 +701,10 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
 
     for (int k0 = 0; k0 < ncap_cta; k0 += cfg.k2.gmax) {
         const int G = ncap_cta - k0 < cfg.k2.gmax ? ncap_cta - k0 : cfg.k2.gmax;
-        constexpr int osc_cnt = 32 * (W + 1), int_cnt = W;
+        /* worker warps with a capture; the others have no part in the streaming hand-offs and run FFT tasks of the next
+           frame during the streaming phase instead */
+        const int nwork = G < W ? G : W;
+        const int osc_cnt = 32 * (nwork + 1), int_cnt = nwork;
         __syncthreads();
         /* ---- barriers and initial state of the group ---- */
         if (tid == 0) {
@@ -761,13 +763,16 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
         __syncthreads();
 
         /* the FFT tasks of this warp for the frame of parity fbt (staging buffer fbt) */
-        auto fft_tasks = [&](int fbt) {
-            if (warp >= NF) return;
-            float2 *buf = warp < NW / 2 ? fft_slots + (size_t)warp * FSK2_FFT_SLOT_ELEMS(Ndft)
-                                        : reinterpret_cast<float2 *>(cap2(smem, cfg, warp - NW / 2).ering + cfg.k2.ering_fft_off);
-            const bool pairs = cfg.log2_ndft == 8;        /* 256-point fast path: two blocks per task */
-            const int tpc = pairs ? (nb + 1) >> 1 : nb;   /* tasks per capture */
-            for (int t = warp; t < G * tpc; t += NF) {
+        const bool pairs = cfg.log2_ndft == 8;        /* 256-point fast path: two blocks per task */
+        const int tpc = pairs ? (nb + 1) >> 1 : nb;   /* tasks per capture */
+        /* tasks [0, t_early) are run during the streaming phase by the worker warps without a capture (dedicated scratch
+           slots only), the rest after the decisions by all FFT warps */
+        const int early_pool = (W - nwork) < NW / 2 ? (W - nwork) : NW / 2;
+        const int t_early = early_pool * cfg.k2.fft_early < G * tpc ? early_pool * cfg.k2.fft_early : G * tpc;
+        auto fft_tasks = [&](int fbt, int t_first, int t_end, int idx, int stride, int slot) {
+            float2 *buf = slot < NW / 2 ? fft_slots + (size_t)slot * FSK2_FFT_SLOT_ELEMS(Ndft)
+                                        : reinterpret_cast<float2 *>(cap2(smem, cfg, slot - NW / 2).ering + cfg.k2.ering_fft_off);
+            for (int t = t_first + idx; t < t_end; t += stride) {
                 const int g = t / tpc, j = (t - g * tpc) * (pairs ? 2 : 1);
                 const Cap2 c = cap2(smem, cfg, g);
                 Fsk2CapShared *cs = c.cs;
@@ -843,7 +848,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
         };
 
         /* ---- prologue: frequency estimate of frame 0, then plan frame 0 / fetch frame 1 ---- */
-        fft_tasks(0);
+        if (warp < NF) fft_tasks(0, 0, G * tpc, warp, NF, warp);
         __syncthreads();
         pick_phase(0);
         __syncthreads();
@@ -1007,7 +1012,10 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                         cs->rx_timing = rx_timing;
                     }
                 }
-            } else if (is_worker) {
+            } else if (warp >= nwork) {
+                /* A7 for frame f + 1, first part: its samples were fetched a frame ahead and its position is known */
+                if (warp - nwork < early_pool) fft_tasks(fb ^ 1, 0, t_early, warp - nwork, early_pool, warp - nwork);
+            } else {
                 /* A8 mix of chunk ck of capture g by one warp: f_dc = in * conj(phi) in place over the oscillator values;
                    four samples per lane, all loads first */
                 auto mix_chunk = [&](int g, int ck) {
@@ -1228,7 +1236,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
             TR(14);
             /* A7 for frame f + 1 (all warps), from the staging buffer whose copy was issued at the end of the last
                frame: touches nothing the decisions of frame f use */
-            fft_tasks(fb ^ 1);
+            if (warp < NF) fft_tasks(fb ^ 1, t_early, G * tpc, warp, NF, warp);
             __syncthreads();
             TR(11);
             /* f_dc tail of this frame for the next frame's decisions (the ring keeps it until then) */
