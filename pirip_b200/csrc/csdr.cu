@@ -14,6 +14,7 @@
  * then runs the L-tap loop for one output out of shared memory.  HBM traffic is therefore the
  * algorithmic 2 B per input sample (+ L-D samples of halo per tile) and 8/D B of output.
  */
+#include <cuda.h>
 #include <limits.h>
 #include <math.h>
 #include <stdio.h>
@@ -132,6 +133,7 @@ struct DecimFastArgs {
     short2 *out_s16;
     size_t out_stride;
     unsigned dyn_smem;
+    int lockstep; /* TMA kernel: CTA-wide barrier before every pipeline step */
     float taps[kFastMaxTaps];
 };
 
@@ -172,6 +174,98 @@ __device__ __forceinline__ void fir_feed(const DecimFastArgs &a, float2 (&acc)[N
     }
 }
 
+/* the 8 * SUBC samples of pipeline step `sub` of a body that starts at block j of the group */
+template <int D, int L, int NA, int SUBC, bool F32, bool S16>
+__device__ __forceinline__ void fir_substep(const DecimFastArgs &a, float2 (&acc)[NA], const unsigned (&cur)[4 * SUBC], const int sub,
+                                            const int j, const size_t obase, const unsigned lb, const bool valid) {
+#pragma unroll
+    for (int i = 0; i < 8 * SUBC; ++i) {
+        const int s = sub * 8 * SUBC + i; /* sample of the body */
+        const int u = s / D, r = s - u * D;
+        const unsigned ww = cur[i >> 1];
+        const float xi = lds_f32((i & 1) ? lut_addr<2>(lb, ww) : lut_addr<0>(lb, ww));
+        const float xq = lds_f32((i & 1) ? lut_addr<3>(lb, ww) : lut_addr<1>(lb, ww));
+        fir_feed<D, L, NA, 0, false>(a, acc, u % NA, r, xi, xq);
+        if (r == D - 1) {
+            /* the output whose last taps were in this block: NA - 1 blocks back */
+            const int done = (u + 1) % NA;
+            const int o = j + u - (NA - 1);
+            if (o >= 0 && valid) emit_output<F32, S16>(a, obase + (size_t)o, acc[done]);
+            acc[done] = make_float2(0.0f, 0.0f);
+        }
+    }
+}
+
+/* the L - D samples after a group finish its last NA - 1 outputs; loaded without touching a byte beyond the last
+   sample the stream is known to hold */
+template <int D, int L, int NA, int NBLK, bool F32, bool S16>
+__device__ __forceinline__ void fir_halo(const DecimFastArgs &a, float2 (&acc)[NA], const uint4 *src, const size_t obase, const unsigned lb) {
+    constexpr int HS = L - D;
+    constexpr int HW = (HS + 1) / 2; /* words */
+    unsigned w[HW];
+    const unsigned *s32 = reinterpret_cast<const unsigned *>(src);
+#pragma unroll
+    for (int c = 0; c < HW / 4; ++c) {
+        const uint4 v = __ldg(src + c);
+        w[4 * c] = v.x, w[4 * c + 1] = v.y, w[4 * c + 2] = v.z, w[4 * c + 3] = v.w;
+    }
+#pragma unroll
+    for (int i = (HW / 4) * 4; i < HW; ++i) {
+        if (i == HW - 1 && (HS & 1))
+            w[i] = *reinterpret_cast<const unsigned short *>(s32 + i);
+        else
+            w[i] = __ldg(s32 + i);
+    }
+#pragma unroll
+    for (int sI = 0; sI < HS; ++sI) {
+        const int e = sI / D, r = sI - e * D;
+        const unsigned ww = w[sI >> 1];
+        const float xi = lds_f32((sI & 1) ? lut_addr<2>(lb, ww) : lut_addr<0>(lb, ww));
+        const float xq = lds_f32((sI & 1) ? lut_addr<3>(lb, ww) : lut_addr<1>(lb, ww));
+#pragma unroll
+        for (int aa = e + 1; aa < NA; ++aa) {
+            const int t = aa * D + r;
+            if (t < L) {
+                const int ai = ((NBLK + e) - aa + 4 * NA) % NA;
+                acc[ai].x += xi * a.taps[t];
+                acc[ai].y += xq * a.taps[t];
+            }
+        }
+        if (r == D - 1 || sI == HS - 1) emit_output<F32, S16>(a, obase + (size_t)(NBLK + e - (NA - 1)), acc[((NBLK + e) + 1) % NA]);
+    }
+}
+
+/* the n_out % NBLK outputs at the end of every stream: plain tap loop, one output per thread */
+template <int D, int L, int NBLK, bool F32, bool S16>
+__device__ __forceinline__ void fir_remainder(const DecimFastArgs &a, const unsigned lb, const size_t gps, const size_t tid_global,
+                                              const size_t nthreads_global) {
+    const size_t rem = a.n_out - gps * NBLK;
+    for (size_t i = tid_global; i < rem * a.n_streams; i += nthreads_global) {
+        const size_t stream = i / rem, k = gps * NBLK + (i - stream * rem);
+        const unsigned short *x = reinterpret_cast<const unsigned short *>(a.in + stream * a.in_stride_bytes) + k * (size_t)D;
+        float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+        for (int t = 0; t < L; ++t) {
+            const unsigned ww = x[t];
+            const float h = a.taps[t];
+            acc.x += lds_f32(lut_addr<0>(lb, ww)) * h;
+            acc.y += lds_f32(lut_addr<1>(lb, ww)) * h;
+        }
+        emit_output<F32, S16>(a, stream * a.out_stride + k, acc);
+    }
+}
+
+/* fill the lane-private conversion table; returns this lane's column base */
+__device__ __forceinline__ unsigned fir_lut_setup(const DecimFastArgs &a, const unsigned sbase, const int tid, const int nthreads) {
+    const unsigned lut0 = (sbase + 65535u) & ~65535u;
+    if (lut0 + 65536u > sbase + a.dyn_smem) __trap();
+    for (int i = tid; i < 256 * 32; i += nthreads) {
+        const float v = a.lut[i >> 5];
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut0 + ((unsigned)(i >> 5) << 8) + ((unsigned)(i & 31) << 2)), "f"(v) : "memory");
+    }
+    return lut0;
+}
+
 template <int D, int L, int NBLK, bool F32, bool S16>
 __global__ void __launch_bounds__(kFastThreads, 1) fir_decimate_u8_fast(const __grid_constant__ DecimFastArgs a) {
     constexpr int NA = (L + D - 1) / D; /* outputs a sample contributes to = live accumulators */
@@ -187,12 +281,7 @@ __global__ void __launch_bounds__(kFastThreads, 1) fir_decimate_u8_fast(const __
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31;
     const unsigned sbase = smem_addr(smem_raw);
-    const unsigned lut0 = (sbase + 65535u) & ~65535u;
-    if (lut0 + 65536u > sbase + a.dyn_smem) __trap();
-    for (int i = tid; i < 256 * 32; i += kFastThreads) {
-        const float v = a.lut[i >> 5];
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(lut0 + ((unsigned)(i >> 5) << 8) + ((unsigned)(i & 31) << 2)), "f"(v) : "memory");
-    }
+    const unsigned lut0 = fir_lut_setup(a, sbase, tid, kFastThreads);
     __syncthreads();
     const unsigned lb = lut0 + 4u * (unsigned)lane;
 
@@ -224,91 +313,174 @@ __global__ void __launch_bounds__(kFastThreads, 1) fir_decimate_u8_fast(const __
                         nxt[4 * c] = v.x, nxt[4 * c + 1] = v.y, nxt[4 * c + 2] = v.z, nxt[4 * c + 3] = v.w;
                     }
                 }
-#pragma unroll
-                for (int i = 0; i < 8 * SUBC; ++i) {
-                    const int s = sub * 8 * SUBC + i; /* sample of the body */
-                    const int u = s / D, r = s - u * D;
-                    const unsigned ww = cur[i >> 1];
-                    const float xi = lds_f32((i & 1) ? lut_addr<2>(lb, ww) : lut_addr<0>(lb, ww));
-                    const float xq = lds_f32((i & 1) ? lut_addr<3>(lb, ww) : lut_addr<1>(lb, ww));
-                    fir_feed<D, L, NA, NBLK, false>(a, acc, u % NA, r, xi, xq);
-                    if (r == D - 1) {
-                        /* the output whose last taps were in this block: NA - 1 blocks back */
-                        const int done = (u + 1) % NA;
-                        const int o = j + u - (NA - 1);
-                        if (o >= 0) emit_output<F32, S16>(a, obase + (size_t)o, acc[done]);
-                        acc[done] = make_float2(0.0f, 0.0f);
-                    }
-                }
+                fir_substep<D, L, NA, SUBC, F32, S16>(a, acc, cur, sub, j, obase, lb, true);
 #pragma unroll
                 for (int c = 0; c < 4 * SUBC; ++c) cur[c] = nxt[c];
             }
             src += CB;
         }
-        /* halo: the L - D samples after the group finish its last NA - 1 outputs; loaded without touching a byte
-           beyond the last sample the stream is known to hold */
-        {
-            constexpr int HW = (HS + 1) / 2; /* words */
-            unsigned w[HW];
-            const unsigned *s32 = reinterpret_cast<const unsigned *>(src);
+        fir_halo<D, L, NA, NBLK, F32, S16>(a, acc, src, obase, lb);
+    }
+    fir_remainder<D, L, NBLK, F32, S16>(a, lb, gps, (size_t)blockIdx.x * kFastThreads + tid, (size_t)gridDim.x * kFastThreads);
+}
+
+/* ---- the same arithmetic with the raw bytes staged by TMA ------------------------------------------------------
+   The register-streaming kernel above is bound by L1TEX tag look-ups (ncu: l1tex throughput 89-99 %): the lanes of a warp
+   own runs 1440 B apart, so every 16-byte load touches 32 different lines.  Here a warp owns 32 consecutive runs of one
+   stream and fetches pipeline step s of all of them with ONE 3-D tensor copy (coordinates {byte in run, run, stream},
+   box = 144 B x 32 runs; TMA wants the box to start on a 16-byte boundary of global memory, hence steps of whole
+   16-byte chunks rather than whole 90-byte blocks) into a 4.5 KB buffer of its own, two buffers per warp, completion on
+   an mbarrier: no L1 look-ups.  Lane l reads its 144 B with nine 16-byte shared loads (row pitch 9 chunks, odd:
+   conflict-free per quarter-warp) and feeds the same fir_substep.  Runs beyond the end of a stream are zero-filled by
+   the tensor map and their outputs not written.  With a.lockstep the warps of a CTA meet at a named barrier before
+   every step, so that they walk the 69 KB unrolled body together and share its instruction-cache lines. */
+constexpr int kStepBytes = 144;          /* bytes of one run per pipeline step (9 chunks of 16) */
+constexpr int kTmaBuf = 32 * kStepBytes; /* one staging buffer: 32 runs */
+constexpr int kTmaWarps = kFastThreads / 32;
+/* 64 KB table on a 64 KB boundary of the shared window + 32 buffers on either side of it + mbarriers; with the window's
+   first KB reserved that is 213 248 B, the rest is slack for other bases (the kernel traps if the pieces do not fit) */
+constexpr unsigned kTmaSmem = 220 * 1024;
+
+__device__ __forceinline__ void mbar_init1(unsigned bar) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_expect(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_3d(unsigned dst, const CUtensorMap *map, int c0, int c1, int c2, unsigned bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+                 "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+                 : "memory");
+}
+
+template <int D, int L, int NBLK, bool F32, bool S16>
+__global__ void __launch_bounds__(kFastThreads, 1)
+fir_decimate_u8_tma(const __grid_constant__ DecimFastArgs a, const __grid_constant__ CUtensorMap tmap) {
+    constexpr int NA = (L + D - 1) / D;
+    constexpr int PB16 = (D % 8 == 0) ? 1 : (D % 4 == 0) ? 2 : (D % 2 == 0) ? 4 : 8;
+    constexpr int U = (PB16 % NA == 0) ? PB16 : PB16 * NA;
+    constexpr int CB = U * D / 8;
+    constexpr int SUBC = kStepBytes / 16;
+    constexpr int NSUB = CB / SUBC;
+    constexpr int NSTEPS = (NBLK / U) * NSUB; /* pipeline steps per run */
+    static_assert(CB % SUBC == 0 && NBLK % U == 0 && NSTEPS >= 2, "a run must be whole pipeline steps");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned sbase = smem_addr(smem_raw);
+    const unsigned lut0 = fir_lut_setup(a, sbase, tid, kFastThreads);
+    const unsigned lb = lut0 + 4u * (unsigned)lane;
+    /* staging buffers: below the table as far as they fit, the rest above it; mbarriers in the last 256 bytes */
+    const unsigned bars = sbase + a.dyn_smem - 256u;
+    const unsigned lo0 = (sbase + 127u) & ~127u;
+    const unsigned below = (lut0 - lo0) / kTmaBuf;
+    unsigned buf0, buf1, bar0, bar1;
+    {
+        const unsigned i0 = 2u * (unsigned)warp, i1 = i0 + 1u;
+        buf0 = i0 < below ? lo0 + i0 * kTmaBuf : lut0 + 65536u + (i0 - below) * kTmaBuf;
+        buf1 = i1 < below ? lo0 + i1 * kTmaBuf : lut0 + 65536u + (i1 - below) * kTmaBuf;
+        bar0 = bars + 8u * i0;
+        bar1 = bars + 8u * i1;
+        if (buf0 + kTmaBuf > bars || buf1 + kTmaBuf > bars) __trap();
+        if (lane == 0) {
+            mbar_init1(bar0);
+            mbar_init1(bar1);
+        }
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    unsigned par0 = 0, par1 = 0;
+    const bool lockstep = a.lockstep != 0;
+
+    const size_t gps = a.n_out / NBLK;     /* whole runs (groups of NBLK outputs) per stream */
+    const size_t tps = (gps + 31) / 32;    /* warp tasks per stream */
+    const size_t ntasks = tps * a.n_streams;
+    /* the task loop is uniform over the CTA (a warp without a task only keeps the barriers company) */
+    for (size_t base = (size_t)blockIdx.x * kTmaWarps; base < ntasks; base += (size_t)gridDim.x * kTmaWarps) {
+        const size_t task = base + warp;
+        const bool live = task < ntasks;
+        const size_t stream = live ? task / tps : 0, wt = live ? task - stream * tps : 0;
+        const size_t grp = wt * 32 + (size_t)lane;
+        const bool valid = live && grp < gps;
+        const size_t k0 = grp * NBLK;
+        const size_t obase = stream * a.out_stride + k0;
+        const int row0 = (int)(wt * 32), st = (int)stream;
+        if (live && lane == 0) {
+            mbar_expect(bar0, kTmaBuf);
+            tma_load_3d(buf0, &tmap, 0, row0, st, bar0);
+            mbar_expect(bar1, kTmaBuf);
+            tma_load_3d(buf1, &tmap, kStepBytes, row0, st, bar1);
+        }
+        float2 acc[NA];
 #pragma unroll
-            for (int c = 0; c < HW / 4; ++c) {
-                const uint4 v = __ldg(src + c);
-                w[4 * c] = v.x, w[4 * c + 1] = v.y, w[4 * c + 2] = v.z, w[4 * c + 3] = v.w;
-            }
+        for (int i = 0; i < NA; ++i) acc[i] = make_float2(0.0f, 0.0f);
+#pragma unroll 1
+        for (int j = 0; j < NBLK; j += U) {
 #pragma unroll
-            for (int i = (HW / 4) * 4; i < HW; ++i) {
-                if (i == HW - 1 && (HS & 1))
-                    w[i] = *reinterpret_cast<const unsigned short *>(s32 + i);
-                else
-                    w[i] = __ldg(s32 + i);
-            }
+            for (int sub = 0; sub < NSUB; ++sub) {
+                const int step = (j / U) * NSUB + sub;
+                const bool odd = (step & 1) != 0;
+                if (lockstep) asm volatile("bar.sync 1, %0;" ::"n"(kFastThreads) : "memory");
+                if (live) {
+                    const unsigned bar = odd ? bar1 : bar0, buf = odd ? buf1 : buf0;
+                    if (odd) {
+                        mbar_wait_parity(bar, par1);
+                        par1 ^= 1u;
+                    } else {
+                        mbar_wait_parity(bar, par0);
+                        par0 ^= 1u;
+                    }
+                    unsigned cur[4 * SUBC];
+                    const unsigned mine = buf + (unsigned)lane * kStepBytes;
 #pragma unroll
-            for (int sI = 0; sI < HS; ++sI) {
-                const int e = sI / D, r = sI - e * D;
-                const unsigned ww = w[sI >> 1];
-                const float xi = lds_f32((sI & 1) ? lut_addr<2>(lb, ww) : lut_addr<0>(lb, ww));
-                const float xq = lds_f32((sI & 1) ? lut_addr<3>(lb, ww) : lut_addr<1>(lb, ww));
-#pragma unroll
-                for (int aa = e + 1; aa < NA; ++aa) {
-                    const int t = aa * D + r;
-                    if (t < L) {
-                        const int ai = ((NBLK + e) - aa + 4 * NA) % NA;
-                        acc[ai].x += xi * a.taps[t];
-                        acc[ai].y += xq * a.taps[t];
+                    for (int c = 0; c < SUBC; ++c)
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(cur[4 * c]), "=r"(cur[4 * c + 1]), "=r"(cur[4 * c + 2]), "=r"(cur[4 * c + 3])
+                                     : "r"(mine + 16u * c)
+                                     : "memory");
+                    fir_substep<D, L, NA, SUBC, F32, S16>(a, acc, cur, sub, j, obase, lb, valid);
+                    /* every lane has consumed its words: the buffer can take the step after next */
+                    __syncwarp();
+                    if (lane == 0 && step + 2 < NSTEPS) {
+                        mbar_expect(bar, kTmaBuf);
+                        tma_load_3d(buf, &tmap, kStepBytes * (step + 2), row0, st, bar);
                     }
                 }
-                if (r == D - 1 || sI == HS - 1) emit_output<F32, S16>(a, obase + (size_t)(NBLK + e - (NA - 1)), acc[((NBLK + e) + 1) % NA]);
             }
         }
-    }
-    /* the n_out % NBLK outputs at the end of every stream: plain tap loop, one output per thread */
-    const size_t rem = a.n_out - gps * NBLK;
-    for (size_t i = (size_t)blockIdx.x * kFastThreads + tid; i < rem * a.n_streams; i += (size_t)gridDim.x * kFastThreads) {
-        const size_t stream = i / rem, k = gps * NBLK + (i - stream * rem);
-        const unsigned short *x = reinterpret_cast<const unsigned short *>(a.in + stream * a.in_stride_bytes) + k * (size_t)D;
-        float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll 1
-        for (int t = 0; t < L; ++t) {
-            const unsigned ww = x[t];
-            const float h = a.taps[t];
-            acc.x += lds_f32(lut_addr<0>(lb, ww)) * h;
-            acc.y += lds_f32(lut_addr<1>(lb, ww)) * h;
+        if (valid) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.in + stream * a.in_stride_bytes + 2 * (size_t)D * (k0 + NBLK));
+            fir_halo<D, L, NA, NBLK, F32, S16>(a, acc, src, obase, lb);
         }
-        emit_output<F32, S16>(a, stream * a.out_stride + k, acc);
+        __syncwarp();
     }
+    fir_remainder<D, L, NBLK, F32, S16>(a, lb, gps, (size_t)blockIdx.x * kFastThreads + tid, (size_t)gridDim.x * kFastThreads);
 }
 
 template <int D, int L, int NBLK>
-cudaError_t fast_launch(const DecimFastArgs &a, bool prepare_only, int sms, cudaStream_t stream) {
+cudaError_t fast_launch(const DecimFastArgs &a, const CUtensorMap *tmap, bool prepare_only, int sms, cudaStream_t stream) {
     const bool f = a.out_f32 != nullptr, s = a.out_s16 != nullptr;
 #define PIRIP_FAST_CASE(F, S)                                                                                              \
     do {                                                                                                                   \
         if (prepare_only) {                                                                                                \
-            cudaError_t e = cudaFuncSetAttribute(fir_decimate_u8_fast<D, L, NBLK, F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.dyn_smem); \
+            cudaError_t e = cudaFuncSetAttribute(fir_decimate_u8_fast<D, L, NBLK, F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFastSmem); \
+            if (e != cudaSuccess) return e;                                                                                \
+            e = cudaFuncSetAttribute(fir_decimate_u8_tma<D, L, NBLK, F, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTmaSmem); \
             if (e != cudaSuccess) return e;                                                                                \
         } else if (f == F && s == S) {                                                                                     \
-            fir_decimate_u8_fast<D, L, NBLK, F, S><<<sms, kFastThreads, a.dyn_smem, stream>>>(a);                            \
+            if (tmap)                                                                                                      \
+                fir_decimate_u8_tma<D, L, NBLK, F, S><<<sms, kFastThreads, a.dyn_smem, stream>>>(a, *tmap);                  \
+            else                                                                                                           \
+                fir_decimate_u8_fast<D, L, NBLK, F, S><<<sms, kFastThreads, a.dyn_smem, stream>>>(a);                        \
             return cudaGetLastError();                                                                                     \
         }                                                                                                                  \
     } while (0)
@@ -319,13 +491,50 @@ cudaError_t fast_launch(const DecimFastArgs &a, bool prepare_only, int sms, cuda
     return cudaSuccess;
 }
 
-/* which (D, L) shapes have a fast instantiation; NBLK outputs per thread */
-cudaError_t fast_dispatch(int D, int L, const DecimFastArgs &a, bool prepare_only, int sms, cudaStream_t stream, bool *handled) {
+/* which (D, L) shapes have a fast instantiation; *nblk = outputs per thread (run = 2 D nblk bytes) */
+cudaError_t fast_dispatch(int D, int L, const DecimFastArgs &a, const CUtensorMap *tmap, bool prepare_only, int sms, cudaStream_t stream,
+                          bool *handled, int *nblk) {
     *handled = true;
-    if (D == 45 && L == 79) return fast_launch<45, 79, 16>(a, prepare_only, sms, stream);
-    if (D == 30 && L == 79) return fast_launch<30, 79, 12>(a, prepare_only, sms, stream);
+    if (D == 45 && L == 79) {
+        *nblk = 16;
+        return fast_launch<45, 79, 16>(a, tmap, prepare_only, sms, stream);
+    }
+    if (D == 30 && L == 79) {
+        *nblk = 12;
+        return fast_launch<30, 79, 12>(a, tmap, prepare_only, sms, stream);
+    }
     *handled = false;
+    *nblk = 0;
     return cudaSuccess;
+}
+
+/* cuTensorMapEncodeTiled through the runtime's driver entry point (libcuda is not linked) */
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
+/* tensor view of the batch for the TMA kernel: {byte in run, run, stream}, box = one pipeline step of 32 runs */
+bool make_run_map(CUtensorMap *map, const void *in, size_t in_stride_bytes, size_t n_streams, size_t runs_per_stream, int run_bytes,
+                  int box_bytes) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc || runs_per_stream == 0) return false;
+    if (runs_per_stream > 0xffffffffull || n_streams > 0xffffffffull || in_stride_bytes >= (1ull << 40)) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)run_bytes, (cuuint64_t)runs_per_stream, (cuuint64_t)n_streams};
+    const cuuint64_t strides[2] = {(cuuint64_t)run_bytes, (cuuint64_t)in_stride_bytes};
+    const cuuint32_t box[3] = {(cuuint32_t)box_bytes, 32u, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void *>(in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 size_t out_count(size_t n, int D, int L) { return n >= (size_t)L ? (n - (size_t)L) / (size_t)D + 1 : 0; }
@@ -336,7 +545,8 @@ struct pirip_decim_plan {
     int D, L, device;
     float *d_taps = nullptr, *d_lut = nullptr;
     int smem_u8 = 0, smem_f32 = 0;
-    bool fast = false; /* a fir_decimate_u8_fast instantiation exists for (D, L) */
+    bool fast = false; /* a fir_decimate_u8_fast / _tma instantiation exists for (D, L) */
+    int fast_nblk = 0; /* outputs per thread of that instantiation */
     int sms = 0;
     std::vector<float> taps;
     /* reusable buffers of the host-buffer entry point */
@@ -373,11 +583,17 @@ static cudaError_t decim_launch(pirip_decim_plan *p, bool u8in, const void *d_in
         f.out_f32 = a.out_f32;
         f.out_s16 = a.out_s16;
         f.out_stride = out_stride;
-        f.dyn_smem = kFastSmem;
         memset(f.taps, 0, sizeof(f.taps));
         memcpy(f.taps, p->taps.data(), sizeof(float) * p->taps.size());
+        /* raw bytes staged by TMA when the tensor view can be encoded; register-streaming loads otherwise */
+        CUtensorMap tmap;
+        const bool use_tma = !getenv("PIRIP_DECIM_NO_TMA") &&
+                             make_run_map(&tmap, d_in, in_stride_bytes, n_streams, a.n_out / (size_t)p->fast_nblk, 2 * p->D * p->fast_nblk, kStepBytes);
+        f.dyn_smem = use_tma ? kTmaSmem : kFastSmem;
+        f.lockstep = getenv("PIRIP_DECIM_LOCKSTEP") ? atoi(getenv("PIRIP_DECIM_LOCKSTEP")) : 1; /* measured: 0.323 vs 0.332 ms */
         bool handled = false;
-        cudaError_t e = fast_dispatch(p->D, p->L, f, false, p->sms, stream, &handled);
+        int nblk = 0;
+        cudaError_t e = fast_dispatch(p->D, p->L, f, use_tma ? &tmap : nullptr, false, p->sms, stream, &handled, &nblk);
         if (handled) {
             pirip::count_launch();
             return e;
@@ -429,7 +645,7 @@ extern "C" pirip_decim_plan *pirip_decim_plan_create(int decimation, const float
         bool handled = false;
         cudaDeviceProp prop;
         if (!pirip::cuda_ok(cudaGetDeviceProperties(&prop, device), "cudaGetDeviceProperties") ||
-            !pirip::cuda_ok(fast_dispatch(p->D, p->L, f, true, 0, nullptr, &handled), "smem attr (fast decimator)")) {
+            !pirip::cuda_ok(fast_dispatch(p->D, p->L, f, nullptr, true, 0, nullptr, &handled, &p->fast_nblk), "smem attr (fast decimator)")) {
             pirip_decim_plan_destroy(p);
             return nullptr;
         }

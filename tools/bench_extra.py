@@ -62,7 +62,7 @@ def bench_decim(steps):
     return {"workload": "decim: %d x %.1f Msample u8 IQ streams, fir_decimate_cc %d (%d taps), s16 out" % (nstreams, n / 1e6, D, dec.taps.size),
             "metric": "input IQ Msamples/s", "value": nstreams * n / (ms * 1e-3) / 1e6, "ms_per_step": ms,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "peak_source": src,
-                         "algorithmic_bytes": algo, "kernel": "fir_decimate_kernel<true>"},
+                         "algorithmic_bytes": algo, "kernel": "fir_decimate_u8_tma<45, 79, 16> (PIRIP_DECIM_NO_TMA=1: fir_decimate_u8_fast; PIRIP_DECIM_GENERIC=1: fir_decimate_kernel<true>)"},
             "parity_vs_oracle": ok}
 
 
@@ -109,7 +109,7 @@ def bench_chain_c2(steps):
                         % (nstreams, n / 1e6),
             "metric": "input IQ Msamples/s", "value": nstreams * n / (ms * 1e-3) / 1e6, "ms_per_step": ms, "launches_per_step": 2,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "peak_source": src,
-                         "algorithmic_bytes": algo, "kernel": "fir_decimate_kernel<true> + " + L.pirip_fsk_plan_kernel(plan._h).decode()},
+                         "algorithmic_bytes": algo, "kernel": "fir_decimate_u8_tma<45, 79, 16> + " + L.pirip_fsk_plan_kernel(plan._h).decode()},
             "parity_vs_oracle": ok}
 
 
