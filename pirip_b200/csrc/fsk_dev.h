@@ -64,6 +64,7 @@ struct FskDevCfg {
         int fast_ts;       /* 1: the 16-window integrator path applies (P == Ts, Ts instantiated) */
         int fft_warps;     /* warps that take FFT tasks */
         int fft_early;     /* FFT tasks of the next frame a capture-less worker warp runs during the streaming phase */
+        int task_queue;    /* 1: FFT tasks, per-frame sums and tone picking are handed out from one queue after the decisions */
         int ering_fft_off; /* float offset of the FFT scratch borrowed from a capture's energy ring */
         int cap_stride;    /* bytes per capture block */
         int off_stage, off_ring, off_tail, off_ckpt, off_ering, off_Sf, off_scal; /* inside a capture block */
@@ -160,6 +161,7 @@ struct Fsk2CapShared {
     int stg_fills[2]; /* TMA copies issued into each buffer so far: phase parity of its mbarrier */
     int fast;         /* this frame takes the 16-window integrator path */
     int sf_turn;      /* FFT block whose magnitudes the IIR spectrum takes next */
+    int est_done;     /* 1 + index of the last frame whose spectrum is complete (release / acquire) */
     int frame;
     int cap; /* capture index in the batch */
 };
@@ -169,6 +171,10 @@ struct Fsk2CapShared {
 #define FSK2_FFT_SLOT_ELEMS(ndft) ((ndft) + 16)
 #define FSK2_CKPT_EVERY 16 /* oscillator phase checkpoint spacing (samples) */
 #define FSK2_MAX_G 16
+#define FSK2_MAX_Q 640 /* post-decision queue entries: FFT tasks + 2 per capture */
+#define FSK2_Q_FFT 0
+#define FSK2_Q_SUMS 1
+#define FSK2_Q_PICK 2
 struct Fsk2CtaShared {
     unsigned long long bar_int[FSK2_MAX_CHUNKS]; /* every worker warp integrated its share of chunk c */
     unsigned long long bar_tim[FSK2_MAX_CHUNKS]; /* timing warp consumed the window energies of chunk c */
@@ -177,6 +183,10 @@ struct Fsk2CtaShared {
     int max_nin;
     int G;
     int any_generic; /* some active capture takes the generic integrator path this frame */
+    int task_next;   /* post-decision task queue: next entry to hand out */
+    int decide_done; /* warps that have finished their decision lanes this frame */
+    int q_len;       /* entries of the queue (fixed per capture group) */
+    unsigned short queue[FSK2_MAX_Q]; /* task kind << 12 | FFT task / capture index, in hand-out order */
 };
 
 /* defined in fsk_kernel2.cu */

@@ -237,6 +237,9 @@ static void derive_k2(const pirip_fsk_cfg &c, FskDevCfg &d) {
             /* opt-in: measured SLOWER on B200 (1250 x 1 s captures: 0 -> 10.82 ms, 5 -> 11.17 ms, 7 -> 12.32 ms, 9 -> 11.93 ms):
                FFT code running beside the streaming code slows the worker chain more than the shorter FFT phase saves */
             k.fft_early = 0;
+            /* the queue needs every warp to be able to run an FFT task */
+            k.task_queue = (k.fft_warps == nw && g * (k.numffts + 2) <= FSK2_MAX_Q) ? 1 : 0;
+            if (const char *e = getenv("PIRIP_FSK_K2_QUEUE")) k.task_queue = k.task_queue ? atoi(e) : 0; /* 0 static, 1 queue, 2 mixed order */
             if (const char *e = getenv("PIRIP_FSK_K2_FFT_EARLY")) k.fft_early = atoi(e) < 0 ? 0 : atoi(e);
             return;
         }

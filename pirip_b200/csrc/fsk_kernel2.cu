@@ -333,7 +333,7 @@ __device__ __noinline__ void pick_tones(const FskDevCfg &cfg, Fsk2CapShared *cs,
 /* one FFT task: block j of capture cs for the frame of parity fb; src = that frame's raw samples */
 template <int LOGN>
 __device__ __noinline__ void fft_task(const FskDevCfg &cfg, Fsk2CapShared *cs, float *Sf2, const unsigned char *src, float2 *buf,
-                                      const float2 *tw, const float *hann, const unsigned short *perm, int j, int nb, int fb, int M,
+                                      const float2 *tw, const float *hann, const unsigned short *perm, int j, int nb, int fb, int tag,
                                       int lane) {
     constexpr int N = 1 << LOGN, Q = N / 32;
     float mg[Q];
@@ -355,7 +355,14 @@ __device__ __noinline__ void fft_task(const FskDevCfg &cfg, Fsk2CapShared *cs, f
         Sf_out[i] = (Sf_in[i] * omtc) + (mg[q] * tc);
     }
     __syncwarp();
-    if (lane == 0) st_release_shared(turn, j + 1 < nb ? j + 1 : 0); /* the tones are picked in the next phase (pick_tones) */
+    if (lane == 0) {
+        if (j + 1 < nb) {
+            st_release_shared(turn, j + 1);
+        } else {
+            st_release_shared(turn, 0);
+            st_release_shared(&cs->est_done, tag); /* the spectrum is complete: the tones can be picked (pick_tones) */
+        }
+    }
 }
 
 /* ---- 256-point fast path: two FFT blocks per warp, two radix-4 levels per register pass ----------------------
@@ -446,7 +453,7 @@ __device__ __forceinline__ void fft256_pair(const unsigned char *src, int fmt, i
 
 /* FFT task pair: blocks j0 and j0 + 1 (if it exists) of capture cs for the frame of parity fb */
 __device__ __noinline__ void fft256_task(const FskDevCfg &cfg, Fsk2CapShared *cs, float *Sf2, const unsigned char *src, float2 *buf,
-                                         const float2 *tw, const float *hann, int j0, int nb, int fb, int M, int lane) {
+                                         const float2 *tw, const float *hann, int j0, int nb, int fb, int tag, int lane) {
     constexpr int N = 256;
     const bool two = j0 + 1 < nb;
     float mg[16];
@@ -480,7 +487,14 @@ __device__ __noinline__ void fft256_task(const FskDevCfg &cfg, Fsk2CapShared *cs
     }
     __syncwarp();
     const int jn = j0 + (two ? 2 : 1);
-    if (lane == 0) st_release_shared(turn, jn < nb ? jn : 0); /* the tones are picked in the next phase (pick_tones) */
+    if (lane == 0) {
+        if (jn < nb) {
+            st_release_shared(turn, jn);
+        } else {
+            st_release_shared(turn, 0);
+            st_release_shared(&cs->est_done, tag); /* the spectrum is complete: the tones can be picked (pick_tones) */
+        }
+    }
 }
 
 struct Cap2 {
@@ -718,6 +732,27 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
             }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
             ctl->G = G;
+            /* hand-out order of the post-decision queue: one round of FFT tasks, the per-frame sums (they need only the
+               decisions), the remaining FFT tasks with the tone picking of a capture one round behind its last FFT task
+               (so that it rarely waits), the remaining pickings */
+            {
+                const bool prs = cfg.log2_ndft == 8;
+                const int tpc_ = prs ? (nb + 1) >> 1 : nb;
+                const int nf = G * tpc_;
+                int n = 0, picked = 0;
+                const bool mixed = cfg.k2.task_queue == 2;
+                for (int t = 0; t < nf; ++t) {
+                    ctl->queue[n++] = (unsigned short)((FSK2_Q_FFT << 12) | t);
+                    if (mixed && t == (NW < nf ? NW : nf) - 1)
+                        for (int g = 0; g < G; ++g) ctl->queue[n++] = (unsigned short)((FSK2_Q_SUMS << 12) | g);
+                    while (mixed && picked < G && (picked + 1) * tpc_ - 1 <= t - NW)
+                        ctl->queue[n++] = (unsigned short)((FSK2_Q_PICK << 12) | picked++);
+                }
+                if (!mixed)
+                    for (int g = 0; g < G; ++g) ctl->queue[n++] = (unsigned short)((FSK2_Q_SUMS << 12) | g);
+                while (picked < G) ctl->queue[n++] = (unsigned short)((FSK2_Q_PICK << 12) | picked++);
+                ctl->q_len = n;
+            }
         }
         for (int g = 0; g < G; ++g) {
             const Cap2 c = cap2(smem, cfg, g);
@@ -741,6 +776,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                 cs->frame = 0;
                 cs->nan_flag = 0;
                 cs->sf_turn = 0;
+                cs->est_done = 0;
                 cs->cap = (int)(blockIdx.x + (size_t)(k0 + g) * grid);
                 cs->stg_valid[0] = cs->stg_valid[1] = 0;
                 cs->stg_fills[0] = cs->stg_fills[1] = 0;
@@ -769,7 +805,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
            slots only), the rest after the decisions by all FFT warps */
         const int early_pool = (W - nwork) < NW / 2 ? (W - nwork) : NW / 2;
         const int t_early = early_pool * cfg.k2.fft_early < G * tpc ? early_pool * cfg.k2.fft_early : G * tpc;
-        auto fft_tasks = [&](int fbt, int t_first, int t_end, int idx, int stride, int slot) {
+        auto fft_tasks = [&](int fbt, int t_first, int t_end, int idx, int stride, int slot, int tag) {
             float2 *buf = slot < NW / 2 ? fft_slots + (size_t)slot * FSK2_FFT_SLOT_ELEMS(Ndft)
                                         : reinterpret_cast<float2 *>(cap2(smem, cfg, slot - NW / 2).ering + cfg.k2.ering_fft_off);
             for (int t = t_first + idx; t < t_end; t += stride) {
@@ -781,11 +817,11 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                 const unsigned char *src = srcp[2 * g + fbt];
                 TR(52);
                 switch (cfg.log2_ndft) {
-                    case 6: fft_task<6>(cfg, cs, c.Sf, src, buf, tw, hann, perm, j, nb, fbt, M, lane); break;
-                    case 7: fft_task<7>(cfg, cs, c.Sf, src, buf, tw, hann, perm, j, nb, fbt, M, lane); break;
-                    case 8: fft256_task(cfg, cs, c.Sf, src, buf, tw, hann, j, nb, fbt, M, lane); break;
-                    case 9: fft_task<9>(cfg, cs, c.Sf, src, buf, tw, hann, perm, j, nb, fbt, M, lane); break;
-                    default: fft_task<10>(cfg, cs, c.Sf, src, buf, tw, hann, perm, j, nb, fbt, M, lane); break;
+                    case 6: fft_task<6>(cfg, cs, c.Sf, src, buf, tw, hann, perm, j, nb, fbt, tag, lane); break;
+                    case 7: fft_task<7>(cfg, cs, c.Sf, src, buf, tw, hann, perm, j, nb, fbt, tag, lane); break;
+                    case 8: fft256_task(cfg, cs, c.Sf, src, buf, tw, hann, j, nb, fbt, tag, lane); break;
+                    case 9: fft_task<9>(cfg, cs, c.Sf, src, buf, tw, hann, perm, j, nb, fbt, tag, lane); break;
+                    default: fft_task<10>(cfg, cs, c.Sf, src, buf, tw, hann, perm, j, nb, fbt, tag, lane); break;
                 }
                 TR(53);
             }
@@ -848,7 +884,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
         };
 
         /* ---- prologue: frequency estimate of frame 0, then plan frame 0 / fetch frame 1 ---- */
-        if (warp < NF) fft_tasks(0, 0, G * tpc, warp, NF, warp);
+        if (warp < NF) fft_tasks(0, 0, G * tpc, warp, NF, warp, 0);
         __syncthreads();
         pick_phase(0);
         __syncthreads();
@@ -866,6 +902,10 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
 #endif
             const int max_nin = ctl->max_nin;
             const int nchunks = (max_nin + CH - 1) / CH;
+            if (tid == 0) { /* the queue of this frame opens after the streaming phase's barrier */
+                ctl->task_next = 0;
+                ctl->decide_done = 0;
+            }
             /* visibility of frame f's staged samples (the copy was issued a frame ago) */
             for (int g = 0; g < G; ++g) {
                 Fsk2CapShared *cs = cap2(smem, cfg, g).cs;
@@ -1014,7 +1054,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                 }
             } else if (warp >= nwork) {
                 /* A7 for frame f + 1, first part: its samples were fetched a frame ahead and its position is known */
-                if (warp - nwork < early_pool) fft_tasks(fb ^ 1, 0, t_early, warp - nwork, early_pool, warp - nwork);
+                if (warp - nwork < early_pool) fft_tasks(fb ^ 1, 0, t_early, warp - nwork, early_pool, warp - nwork, f + 1);
             } else {
                 /* A8 mix of chunk ck of capture g by one warp: f_dc = in * conj(phi) in place over the oscillator values;
                    four samples per lane, all loads first */
@@ -1234,23 +1274,9 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                 }
             }
             TR(14);
-            /* A7 for frame f + 1 (all warps), from the staging buffer whose copy was issued at the end of the last
-               frame: touches nothing the decisions of frame f use */
-            if (warp < NF) fft_tasks(fb ^ 1, t_early, G * tpc, warp, NF, warp);
-            __syncthreads();
-            TR(11);
-            /* f_dc tail of this frame for the next frame's decisions (the ring keeps it until then) */
-            for (int t = tid; t < G * M * TAILN; t += nthreads) {
-                const int gm = t / TAILN, k = t - gm * TAILN;
-                const int g = gm / M, m = gm - g * M;
+            /* the four serial per-frame sums of capture g and the estimates derived from them, lanes 0..3 of one warp */
+            auto frame_sums = [&](int g) {
                 const Cap2 c = cap2(smem, cfg, g);
-                if (!c.cs->active) continue;
-                const unsigned pend = (unsigned)c.cs->pos + (unsigned)c.cs->nin;
-                c.tail[m * TAILN + k] = c.ring[m * RT + rsw(pend - (unsigned)TAILN + (unsigned)k, rmask)];
-            }
-            if (warp < G) {
-                /* four serial sums over the symbols of capture `warp`, lanes 0..3 */
-                const Cap2 c = cap2(smem, cfg, warp);
                 Fsk2CapShared *cs = c.cs;
                 const bool on = cs->active && !cs->nan_flag;
                 const int s = lane;
@@ -1285,8 +1311,76 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                     const float fc_tx = (float)((cfg.f1_tx + cfg.f1_tx + cfg.tone_spacing) / 2);
                     cs->foff = fc_tx - fc_avg;
                 }
+                __syncwarp();
+            };
+            /* f_dc tail of this frame for the next frame's decisions (the ring keeps it until then); after every warp's
+               decision lanes, which read the previous tail */
+            auto copy_tail = [&]() {
+                for (int t = tid; t < G * M * TAILN; t += nthreads) {
+                    const int gm = t / TAILN, k = t - gm * TAILN;
+                    const int g = gm / M, m = gm - g * M;
+                    const Cap2 c = cap2(smem, cfg, g);
+                    if (!c.cs->active) continue;
+                    const unsigned pend = (unsigned)c.cs->pos + (unsigned)c.cs->nin;
+                    c.tail[m * TAILN + k] = c.ring[m * RT + rsw(pend - (unsigned)TAILN + (unsigned)k, rmask)];
+                }
+            };
+            /* measured on B200 (1 s captures, ms per launch, static / queue / queue in mixed order): 9 captures per CTA (36 FFT
+               tasks on 16 warps: a ragged third round) 10.9 / 10.35 / 10.9; 8 captures per CTA (two full rounds) 9.66 / 9.89 /
+               10.63.  So the queue is used when the FFT tasks do not fill whole rounds, FFT tasks first: serial tasks running
+               beside FFT tasks only pay off in the ragged round (different code side by side costs instruction-cache misses) */
+            if (cfg.k2.task_queue == 2 || (cfg.k2.task_queue == 1 && (G * tpc) % NF != 0)) {
+                /* One queue for everything between the decisions and the next frame: the FFT tasks of frame f + 1 (its
+                   samples were fetched a frame ahead and touch nothing the decisions use), then the per-frame sums of every
+                   capture, then the tone picking of every capture.  A warp takes the next task whenever it is free, so the
+                   serial tasks (sums: 4 lanes, picking: one warp) run beside the FFT tasks instead of after them.  Tasks are
+                   handed out in order and wait only for lower-numbered ones (IIR turn, est_done) or for the decision lanes. */
+                __syncwarp();
+                if (lane == 0) {
+                    __threadfence_block();
+                    atomicAdd(&ctl->decide_done, 1);
+                }
+                const int n_all = ctl->q_len;
+                float2 *buf = warp < NW / 2 ? fft_slots + (size_t)warp * FSK2_FFT_SLOT_ELEMS(Ndft)
+                                            : reinterpret_cast<float2 *>(cap2(smem, cfg, warp - NW / 2).ering + cfg.k2.ering_fft_off);
+                for (;;) {
+                    int t = 0;
+                    if (lane == 0) t = atomicAdd(&ctl->task_next, 1);
+                    t = __shfl_sync(0xffffffffu, t, 0);
+                    if (t >= n_all) break;
+                    const int code = ctl->queue[t], kind = code >> 12, qi = code & 0xfff;
+                    if (kind == FSK2_Q_FFT) {
+                        if (qi >= t_early) fft_tasks(fb ^ 1, qi, qi + 1, 0, 1, warp, f + 1); /* below t_early: done while streaming */
+                    } else if (kind == FSK2_Q_SUMS) {
+                        int tries = 0;
+                        while (ld_acquire_shared(&ctl->decide_done) < NW) {
+                            if (++tries > 16) __nanosleep(200);
+                        }
+                        frame_sums(qi);
+                    } else {
+                        const Cap2 c = cap2(smem, cfg, qi);
+                        if (c.cs->fon) {
+                            int tries = 0;
+                            while (ld_acquire_shared(&c.cs->est_done) != f + 1) {
+                                if (++tries > 16) __nanosleep(200);
+                            }
+                            pick_tones(cfg, c.cs, c.Sf + (size_t)(fb ^ 1) * Ndft, reinterpret_cast<float *>(buf), fb ^ 1, M, lane);
+                        }
+                    }
+                }
+                __syncthreads();
+                TR(11);
+                copy_tail();
+            } else {
+                /* A7 for frame f + 1 (all warps), from the staging buffer whose copy was issued at the end of the last
+                   frame: touches nothing the decisions of frame f use */
+                if (warp < NF) fft_tasks(fb ^ 1, t_early, G * tpc, warp, NF, warp, f + 1);
+                __syncthreads();
+                TR(11);
+                copy_tail();
+                if (warp < G) frame_sums(warp);
+                pick_phase(fb ^ 1); /* tones of frame f + 1 from the spectrum the FFT tasks just updated */
             }
-            pick_phase(fb ^ 1); /* tones of frame f + 1 from the spectrum the FFT tasks just updated */
             __syncthreads();
             TR(12);
 
