@@ -652,7 +652,12 @@ extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_
     const size_t nin_max = (size_t)(plan->dev.N + plan->dev.Ts / 4);
     size_t nslices = 8;
     while (nslices > 1 && samples_per_capture / nslices < 8 * nin_max) nslices /= 2;
-    const bool streamed = plan->dev.k2.ok && nchunks == 1 && nslices > 1 && getenv("PIRIP_FSK_NO_STREAM_INGEST") == nullptr;
+    /* A kernel that waits for copies issued after its launch needs launches to be asynchronous.  Tools that inject into
+       the CUDA runtime (Nsight Compute's kernel replay, compute-sanitizer: CUDA_INJECTION64_PATH is set for the process)
+       serialise the launch on the host, which would leave the kernel waiting for ever: copy first, then run. */
+    const bool injected = getenv("CUDA_INJECTION64_PATH") != nullptr || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
+                          (getenv("CUDA_LAUNCH_BLOCKING") != nullptr && atoi(getenv("CUDA_LAUNCH_BLOCKING")) != 0);
+    const bool streamed = plan->dev.k2.ok && nchunks == 1 && nslices > 1 && !injected && getenv("PIRIP_FSK_NO_STREAM_INGEST") == nullptr;
     if (rc == 0 && streamed) {
         if (!w.d_landed) CK(cudaMalloc(&w.d_landed, sizeof(unsigned long long)), "cudaMalloc landed");
         if (!w.h_marks) CK(cudaHostAlloc(&w.h_marks, 16 * sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc marks");

@@ -546,11 +546,17 @@ __device__ __forceinline__ FrameView load_view(const Fsk2CapShared *cs, bool exi
 
 /* Streamed ingest: the host copies the captures to the device in time slices while the kernel runs and publishes how many
    samples of every capture have landed; a frame is fetched only once all of it is there. */
-__device__ __forceinline__ void wait_landed(const FskBatchArgs &args, unsigned long long need) {
+__device__ __noinline__ void wait_landed(const FskBatchArgs &args, unsigned long long need) {
     if (!args.landed) return;
     if (need > args.samples_per_capture) need = args.samples_per_capture;
     const volatile unsigned long long *p = args.landed;
-    while (*p < need) __nanosleep(400);
+    /* the copies are issued by the host right after the launch; if they never come (a tool serialised the launch), fail
+       the launch after a few seconds instead of occupying the GPU for ever */
+    unsigned spins = 0;
+    while (*p < need) {
+        __nanosleep(400);
+        if (++spins > 12000000u) __trap();
+    }
 }
 
 /* Issue the TMA bulk copy of raw samples [pos, pos + nin_max) of capture cs->cap into staging buffer b
