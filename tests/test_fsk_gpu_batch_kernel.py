@@ -100,3 +100,21 @@ def test_kernel_description_names_the_batch_kernel():
     L.pirip_fsk_plan_kernel.argtypes = [ctypes.c_void_p]
     assert L.pirip_fsk_plan_kernel(plan._h).decode().startswith("fsk2_kernel")
     plan.close()
+
+
+@pytest.mark.parametrize("per_cta", [9, 8, 3])
+def test_post_decision_schedules_give_identical_output(per_cta):
+    """static split / task queue (FFT tasks, sums, tone picking from one counter) / queue in mixed order, and FFT tasks of
+    the next frame on capture-less worker warps during the streaming phase: same floats, same bits.  9 captures per CTA
+    leaves a ragged FFT round (the queue's default case), 8 fills whole rounds (static by default), 3 leaves idle workers."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    ncap = sms * per_cta if per_cta < 9 else sms * 8 + 37
+    iq = _batch(ncap, 300)
+    ref = _run(iq, {"PIRIP_FSK_K2": "1", "PIRIP_FSK_K2_QUEUE": "0", "PIRIP_FSK_K2_FFT_EARLY": None})
+    for env in ({"PIRIP_FSK_K2_QUEUE": "1"}, {"PIRIP_FSK_K2_QUEUE": "2"}, {"PIRIP_FSK_K2_QUEUE": None},
+                {"PIRIP_FSK_K2_QUEUE": "0", "PIRIP_FSK_K2_FFT_EARLY": "3"}, {"PIRIP_FSK_K2_QUEUE": "2", "PIRIP_FSK_K2_FFT_EARLY": "2"}):
+        e = {"PIRIP_FSK_K2": "1", "PIRIP_FSK_K2_QUEUE": None, "PIRIP_FSK_K2_FFT_EARLY": None}
+        e.update(env)
+        _same(_run(iq, e), ref)
+    _oracle_sample(iq, ref, [0, ncap // 2, ncap - 1])
