@@ -164,6 +164,15 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
+    # stdout carries exactly ONE line, the JSON: libraries that write to file descriptor 1 themselves (NCCL prints its
+    # version banner there when NCCL_DEBUG is set) are sent to stderr, the JSON line goes to the original descriptor
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(line):
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -195,7 +204,7 @@ def main():
                                  "sample": "%d of the %d captures per step, one capture stream per thread; "
                                            "oracle restatement of codec2 fsk_demod (gcc -O2)" % (ncap, args.captures)},
                 "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------ our arm (GPU)
@@ -355,7 +364,7 @@ def main():
             "cpu_baseline": cpu_baseline,
             "parity": {"captures_checked": nchk, "bits_and_frames_equal_oracle": bool(ok),
                        "ber_per_capture": [float(b) for b in bers]}}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
