@@ -41,8 +41,8 @@ def timed(fn, steps, warmup=3):
     return e0.elapsed_time(e1) / steps
 
 
-def bench_decim(steps):
-    D, nstreams, n = 45, 256, 1800000  # 256 one-second streams at 1.8 MS/s = 921.6 MB of u8
+def bench_decim(steps, D=45, n=1800000):
+    nstreams = 256  # 256 one-second streams at 1.8 MS/s (D = 45) or 2.4 MS/s (D = 30): 0.9 / 1.2 GB of u8
     dec = pb.DecimPlan(D)
     g = torch.Generator(device="cuda").manual_seed(1)
     iq = torch.randint(0, 256, (nstreams, 2 * n), dtype=torch.uint8, device="cuda", generator=g)
@@ -62,7 +62,7 @@ def bench_decim(steps):
     return {"workload": "decim: %d x %.1f Msample u8 IQ streams, fir_decimate_cc %d (%d taps), s16 out" % (nstreams, n / 1e6, D, dec.taps.size),
             "metric": "input IQ Msamples/s", "value": nstreams * n / (ms * 1e-3) / 1e6, "ms_per_step": ms,
             "roofline": {"bound": "hbm", "achieved": ach, "peak": pk, "unit": "GB/s", "frac": ach / pk, "peak_source": src,
-                         "algorithmic_bytes": algo, "kernel": "fir_decimate_u8_tma<45, 79, 16> (PIRIP_DECIM_NO_TMA=1: fir_decimate_u8_fast; PIRIP_DECIM_GENERIC=1: fir_decimate_kernel<true>)"},
+                         "algorithmic_bytes": algo, "kernel": "fir_decimate_u8_tma<%d, 79, %d> (PIRIP_DECIM_NO_TMA=1: fir_decimate_u8_fast; PIRIP_DECIM_GENERIC=1: fir_decimate_kernel<true>)" % (D, 16 if D == 45 else 12)},
             "parity_vs_oracle": ok}
 
 
@@ -161,6 +161,8 @@ if __name__ == "__main__":
     a = ap.parse_args()
     if a.only in ("", "decim"):
         print(json.dumps(bench_decim(a.steps)))
+    if a.only in ("", "decim30"):  # rtl_fsk -s 2400000 -a 80000 [R README.md:172]
+        print(json.dumps(bench_decim(a.steps, D=30, n=2400000)))
     if a.only in ("", "chain"):
         print(json.dumps(bench_chain_c2(a.steps)))
     if a.only in ("", "ldpc"):
