@@ -650,8 +650,12 @@ extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_
        a frame.  PCIe and the SMs work at the same time although the batch is a single launch. */
     const size_t bps = bytes_per_sample(plan->dev.fmt);
     const size_t nin_max = (size_t)(plan->dev.N + plan->dev.Ts / 4);
-    size_t nslices = 8;
-    while (nslices > 1 && samples_per_capture / nslices < 8 * nin_max) nslices /= 2;
+    /* the kernel runs about as fast as PCIe delivers (C1: 10.4 ms of kernel, 11 ms of copy for 600 MB), so it trails the copy
+       by one slice: what is left to do when the last byte has landed is one slice of work */
+    size_t nslices = 24; /* measured, C1 batch of 1250 x 1 s: 8 slices 12.63 ms, 16: 12.05, 24: 12.00, 32: 12.01 per call */
+    if (const char *e = getenv("PIRIP_FSK_INGEST_SLICES"))
+        if (atoi(e) >= 1 && atoi(e) <= 64) nslices = (size_t)atoi(e);
+    while (nslices > 1 && samples_per_capture / nslices < 4 * nin_max) nslices /= 2;
     /* A kernel that waits for copies issued after its launch needs launches to be asynchronous.  Tools that inject into
        the CUDA runtime (Nsight Compute's kernel replay, compute-sanitizer: CUDA_INJECTION64_PATH is set for the process)
        serialise the launch on the host, which would leave the kernel waiting for ever: copy first, then run. */
@@ -660,7 +664,7 @@ extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_
     const bool streamed = plan->dev.k2.ok && nchunks == 1 && nslices > 1 && !injected && getenv("PIRIP_FSK_NO_STREAM_INGEST") == nullptr;
     if (rc == 0 && streamed) {
         if (!w.d_landed) CK(cudaMalloc(&w.d_landed, sizeof(unsigned long long)), "cudaMalloc landed");
-        if (!w.h_marks) CK(cudaHostAlloc(&w.h_marks, 16 * sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc marks");
+        if (!w.h_marks) CK(cudaHostAlloc(&w.h_marks, 72 * sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc marks");
         if (!w.ev_reset) CK(cudaEventCreateWithFlags(&w.ev_reset, cudaEventDisableTiming), "cudaEventCreate");
     }
     for (size_t c0 = 0, ci = 0; rc == 0 && c0 < n_captures; c0 += per, ++ci) {

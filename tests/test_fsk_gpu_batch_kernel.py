@@ -74,7 +74,7 @@ def test_more_captures_than_one_launch_keeps_resident():
 
 
 def test_streamed_ingest_equals_copy_then_run():
-    # long enough for eight time slices (>= 8 * 8 * nin_max samples per capture)
+    # long enough for sixteen time slices (>= 4 * nin_max samples per slice)
     iq = _batch(40, 3400)
     assert iq.shape[1] // 2 >= 64 * 1206
     a = _run(iq, {"PIRIP_FSK_K2": "1", "PIRIP_FSK_NO_STREAM_INGEST": None})
