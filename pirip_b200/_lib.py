@@ -13,7 +13,8 @@ class PiripError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libpirip_b200.so")
+    # PIRIP_B200_LIB: another build of the same library (A/B timing of two source versions, tools/ab_k2.py)
+    return os.environ.get("PIRIP_B200_LIB") or os.path.join(_HERE, "libpirip_b200.so")
 
 
 _lib = None
