@@ -8,11 +8,15 @@
  * anchored at stream sample 0, accumulated in tap order in float (no FMA contraction, so the
  * result is bit-identical to the scalar loop).
  *
- * Mapping: one CTA produces TILE consecutive outputs of one stream.  Its D*(TILE-1)+L input
- * samples are read once from HBM (coalesced 4-byte loads), converted through a 256-entry
- * table of the exact convert_u8_f values and staged as float2 in shared memory; every thread
- * then runs the L-tap loop for one output out of shared memory.  HBM traffic is therefore the
- * algorithmic 2 B per input sample (+ L-D samples of halo per tile) and 8/D B of output.
+ * Three kernels, one arithmetic:
+ *  fir_decimate_u8_tma   u8 input, D = 45 / 30 with 79 taps, 16-byte aligned streams: every sample read and converted
+ *                        once (rotating accumulators), lane-private conversion table, taps as constants, raw bytes
+ *                        staged per warp by 3-D TMA tensor copies.  The default for pirip's pipelines.
+ *  fir_decimate_u8_fast  the same compute with the raw bytes loaded straight into registers (no tensor map needed).
+ *  fir_decimate_kernel   generic (any D / L / alignment, f32 input): one CTA produces TILE consecutive outputs of one
+ *                        stream from a float2 tile staged in shared memory, one thread per output.
+ * HBM traffic is the algorithmic 2 B per input sample (+ L - D samples of halo per run / tile) and 8/D (f32) or
+ * 4/D (s16) B of output.
  */
 #include <cuda.h>
 #include <limits.h>
@@ -158,11 +162,10 @@ __device__ __forceinline__ void emit_output(const DecimFastArgs &a, size_t o, fl
     if (S16) a.out_s16[o] = make_short2((short)__float2int_rz(acc.x * 32767.0f), (short)__float2int_rz(acc.y * 32767.0f));
 }
 
-/* accumulate input sample (xi, xq) = sample r of block jb (relative to the group) into the outputs it is a tap of;
-   outputs outside [lo, NBLK) are not accumulated when CLIP (halo blocks) */
-template <int D, int L, int NA, int NBLK, bool HALO>
+/* accumulate input sample (xi, xq) = sample r of an input block into the outputs it is a tap of: tap aa D + r of the
+   output aa blocks back, whose accumulator is (jbm - aa) mod NA with jbm = block index mod NA */
+template <int D, int L, int NA>
 __device__ __forceinline__ void fir_feed(const DecimFastArgs &a, float2 (&acc)[NA], int jbm, int r, float xi, float xq) {
-    /* jbm = block index modulo NA (accumulator role); for halo blocks jbm also encodes e = block - NBLK via HALO path */
 #pragma unroll
     for (int aa = 0; aa < NA; ++aa) {
         const int t = aa * D + r;
@@ -185,7 +188,7 @@ __device__ __forceinline__ void fir_substep(const DecimFastArgs &a, float2 (&acc
         const unsigned ww = cur[i >> 1];
         const float xi = lds_f32((i & 1) ? lut_addr<2>(lb, ww) : lut_addr<0>(lb, ww));
         const float xq = lds_f32((i & 1) ? lut_addr<3>(lb, ww) : lut_addr<1>(lb, ww));
-        fir_feed<D, L, NA, 0, false>(a, acc, u % NA, r, xi, xq);
+        fir_feed<D, L, NA>(a, acc, u % NA, r, xi, xq);
         if (r == D - 1) {
             /* the output whose last taps were in this block: NA - 1 blocks back */
             const int done = (u + 1) % NA;
