@@ -75,3 +75,31 @@ def test_csdr_pipeline_matches_oracle(tmp_path):
     assert np.array_equal(np.frombuffer(dem.stdout, np.uint8), ref["bits"])
     ber, n = synth.ber_vs_stream(np.frombuffer(dem.stdout, np.uint8))
     assert n >= 100 and ber == 0.0
+
+
+@pytest.mark.gpu
+def test_fsk_demod_stats_lines(tmp_path):
+    """fsk_demod -t / --stats: one JSON object per N frames on stderr with upstream's keys; the bit stream is unchanged"""
+    import json
+    build_tools()
+    Fs, Rb = 240000, 10000
+    bits = synth.test_bits(3000)
+    x = synth.add_awgn(synth.fsk_mod(bits, 2, Fs, Rb, 10000, 10000, timing_offset=3.0), 12.0, Fs // Rb, 2, synth.rng(8))
+    iq = synth.to_u8(x, amp=70.0)
+    f = tmp_path / "iq.u8"
+    iq.tofile(f)
+    base = [os.path.join(BIN, "fsk_demod"), "-d", "-p", "24", "--fsk_lower", "500", "--fsk_upper", "25000"]
+    plain = subprocess.run(base + ["2", str(Fs), str(Rb), str(f), "-"], capture_output=True, check=True)
+    st = subprocess.run(base + ["-t4", "2", str(Fs), str(Rb), str(f), "-"], capture_output=True, check=True)
+    assert st.stdout == plain.stdout and plain.stderr == b""
+    lines = [json.loads(ln) for ln in st.stderr.decode().splitlines()]
+    nframes = len(plain.stdout) // 50
+    assert len(lines) == nframes // 4 and nframes >= 40
+    ref = orc.fsk_demod_stream(orc.demod_cfg(Fs, Rb, 2, P=24, limits=(500, 25000)), iq)
+    for k, ln in enumerate(lines):
+        assert set(ln) >= {"secs", "EbNodB", "ppm", "f1_est", "f2_est", "eye_diagram", "samp_fft"}
+        fr = 4 * (k + 1) - 1  # the frame the line was printed after
+        assert abs(ln["f1_est"] - float(ref["stats"]["f_est"][fr][0])) < 0.06 and abs(ln["f2_est"] - float(ref["stats"]["f_est"][fr][1])) < 0.06
+    assert abs(lines[-1]["f1_est"] - 10000) < 1000 and abs(lines[-1]["f2_est"] - 20000) < 1000
+    st8 = subprocess.run(base + ["--stats", "2", str(Fs), str(Rb), str(f), "-"], capture_output=True, check=True)
+    assert len(st8.stderr.decode().splitlines()) == nframes // 8

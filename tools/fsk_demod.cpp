@@ -5,6 +5,9 @@
  *               [--batch] M Fs Rs InputFile OutputFile          ("-" = stdin / stdout)
  *   -d  u8 complex input (rtl_sdr format)      -c  s16 complex input      -f  float complex input
  *   -s  soft decisions: Nbits float32 LLRs per frame instead of Nbits bytes (one bit per byte)
+ *   -t[N] / --stats[=N]  modem statistics as one JSON object per N frames (default 8) on stderr, upstream's keys
+ *       "secs", "EbNodB", "ppm", "f1_est" .. "fM_est" ([U fsk_demod.c]); the eye diagram and input spectrum arrays of
+ *       upstream's line are not produced ("eye_diagram": [], "samp_fft": [])
  * Default mode follows upstream's main loop call for call: fread fsk_nin() samples, convert,
  * fsk_demod()/fsk_demod_sd(), fwrite — the state stays on the GPU between calls.  --batch reads the
  * whole input first and runs it as one capture through the persistent kernel (same output bytes).
@@ -14,6 +17,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <vector>
 
@@ -24,25 +28,28 @@
 
 static void usage(const char *p) {
     fprintf(stderr,
-            "usage: %s [-c|-d|-f] [-p P] [--nsym N] [--fsk_lower Hz] [--fsk_upper Hz] [--mask spacing] [-s] [--batch]\n"
+            "usage: %s [-c|-d|-f] [-p P] [--nsym N] [--fsk_lower Hz] [--fsk_upper Hz] [--mask spacing] [-s] [-t[N]|--stats[=N]] [--batch]\n"
             "          (2|4) SampleRate SymbolRate InputModemRawFile OutputFile\n", p);
     exit(1);
 }
 
 int main(int argc, char *argv[]) {
     int fmt = PIRIP_FMT_S16, real_input = 1, P = 0, nsym = FSK_DEFAULT_NSYM, lower = -1, upper = -1, mask = 0, soft = 0, batch = 0;
+    int stats_every = 0;
     static struct option lo[] = { { "fsk_lower", required_argument, 0, 'b' }, { "fsk_upper", required_argument, 0, 'u' },
                                   { "mask", required_argument, 0, 'm' },      { "nsym", required_argument, 0, 'n' },
                                   { "batch", no_argument, 0, 'B' },           { "help", no_argument, 0, 'h' },
+                                  { "stats", optional_argument, 0, 't' },
                                   { 0, 0, 0, 0 } };
     int o;
-    while ((o = getopt_long(argc, argv, "cdfp:sh", lo, NULL)) != -1) {
+    while ((o = getopt_long(argc, argv, "cdfp:sht::", lo, NULL)) != -1) {
         switch (o) {
             case 'c': fmt = PIRIP_FMT_S16; real_input = 0; break;
             case 'd': fmt = PIRIP_FMT_U8; real_input = 0; break;
             case 'f': fmt = PIRIP_FMT_F32; real_input = 0; break;
             case 'p': P = atoi(optarg); break;
             case 's': soft = 1; break;
+            case 't': stats_every = optarg ? atoi(optarg) : 8; if (stats_every < 1) stats_every = 8; break;
             case 'b': lower = atoi(optarg); break;
             case 'u': upper = atoi(optarg); break;
             case 'm': mask = atoi(optarg); break;
@@ -110,6 +117,7 @@ int main(int argc, char *argv[]) {
     std::vector<COMP> mod((size_t)nmax);
     std::vector<uint8_t> bits((size_t)fsk->Nbits);
     std::vector<float> filt((size_t)(fsk->mode * fsk->Nsym)), llrs((size_t)fsk->Nbits);
+    long frames_seen = 0;
     for (;;) {
         const size_t nin = fsk_nin(fsk);
         if (fread(raw.data(), bps, nin, fin) != nin) break; /* short read ends the loop, as upstream */
@@ -142,6 +150,15 @@ int main(int argc, char *argv[]) {
             fwrite(bits.data(), 1, (size_t)fsk->Nbits, fout);
         }
         if (fin == stdin || fout == stdout) fflush(fout);
+        if (stats_every && ++frames_seen % stats_every == 0) {
+            struct MODEM_STATS st;
+            fsk_get_demod_stats(fsk, &st);
+            fprintf(stderr, "{\"secs\": %ld, \"EbNodB\": %5.1f, \"ppm\": %4d,", (long)time(NULL), st.snr_est, (int)fsk->ppm);
+            const float *fe = fsk->freq_est_type ? fsk->f2_est : fsk->f_est;
+            fprintf(stderr, " \"f1_est\":%.1f, \"f2_est\":%.1f", fe[0], fe[1]);
+            if (fsk->mode == 4) fprintf(stderr, ", \"f3_est\":%.1f, \"f4_est\":%.1f", fe[2], fe[3]);
+            fprintf(stderr, ", \"eye_diagram\":[], \"samp_fft\":[]}\n");
+        }
     }
     fsk_destroy(fsk);
     fclose(fout);
