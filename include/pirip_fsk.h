@@ -211,6 +211,25 @@ int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_t n_capture
                           size_t samples_per_capture, uint8_t *bits, float *llr, float *rx_filt,
                           struct pirip_frame_stats *stats, int32_t *nframes, size_t max_frames);
 
+/* Numerics mode of the batch entry points.
+ *   PIRIP_FSK_MODE_FAST (default where the configuration allows it): the tolerance-mode kernel — tone estimates exact,
+ *     integrators / timing / LLRs within the float tolerance stated in DESIGN.md, every discrete decision guarded by a
+ *     margin; captures with a decision inside the margin are re-run by the exact kernel in the same call, so hard bits,
+ *     nin and frame counts are the scalar algorithm's.
+ *   PIRIP_FSK_MODE_EXACT: the exact-order kernel for every capture (every float bit-identical to the CPU evaluation).
+ * The environment variable PIRIP_FSK_MODE=exact selects the exact mode for plans created afterwards. */
+#define PIRIP_FSK_MODE_EXACT 0
+#define PIRIP_FSK_MODE_FAST 1
+int pirip_fsk_plan_set_mode(pirip_fsk_plan *plan, int mode);
+int pirip_fsk_plan_mode(const pirip_fsk_plan *plan);
+/* after a batch call in fast mode: number of captures the guards sent to the exact kernel (synchronises the device);
+   flags_out (may be NULL) receives the per-capture flag words of the first n captures: 0 = clean, else
+   reason bits (1 symbol margin, 2 nin threshold, 4 ppm threshold, 8 NaN) | (1 + first flagged frame) << 8 */
+long pirip_fsk_plan_flagged(pirip_fsk_plan *plan, int32_t *flags_out, size_t n);
+/* frames the fast kernel replayed exactly inside the kernel since the plan was created (out[0]) and replays it had to
+   give up (out[1]: those captures are flagged and re-run by the exact kernel); synchronises the device */
+int pirip_fsk_plan_replays(pirip_fsk_plan *plan, int32_t out[2]);
+
 /* one-line description of the kernel and launch geometry the batch entry points use for this plan
    (static storage inside the plan; valid until the plan is destroyed) */
 const char *pirip_fsk_plan_kernel(const pirip_fsk_plan *plan);

@@ -6,6 +6,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 FMT_U8, FMT_S16, FMT_F32 = 0, 1, 2
+MODE_EXACT, MODE_FAST = 0, 1
 
 
 class PiripError(RuntimeError):
@@ -60,6 +61,16 @@ def lib():
     L.pirip_fsk_demod_batch.restype = C.c_int
     L.pirip_fsk_demod_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pirip_fsk_plan_set_mode.restype = C.c_int
+    L.pirip_fsk_plan_set_mode.argtypes = [C.c_void_p, C.c_int]
+    L.pirip_fsk_plan_mode.restype = C.c_int
+    L.pirip_fsk_plan_mode.argtypes = [C.c_void_p]
+    L.pirip_fsk_plan_flagged.restype = C.c_long
+    L.pirip_fsk_plan_flagged.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+    L.pirip_fsk_plan_replays.restype = C.c_int
+    L.pirip_fsk_plan_replays.argtypes = [C.c_void_p, C.c_void_p]
+    L.pirip_fsk_plan_kernel.restype = C.c_char_p
+    L.pirip_fsk_plan_kernel.argtypes = [C.c_void_p]
     L.pirip_kernel_launches.restype = C.c_uint64
     L.pirip_last_error.restype = C.c_char_p
     L.pirip_version.restype = C.c_char_p
@@ -107,6 +118,36 @@ class FskPlan:
 
     def max_frames(self, samples_per_capture):
         return int(lib().pirip_fsk_plan_max_frames(self._h, samples_per_capture))
+
+    # ---- numerics mode (include/pirip_fsk.h: PIRIP_FSK_MODE_*) ------------------------------
+    def set_mode(self, mode):
+        """'fast' (tolerance kernel + exact re-run of flagged captures) or 'exact'."""
+        rc = lib().pirip_fsk_plan_set_mode(self._h, {"exact": MODE_EXACT, "fast": MODE_FAST}[mode])
+        if rc != 0:
+            raise _err("pirip_fsk_plan_set_mode", rc)
+
+    @property
+    def mode(self):
+        return "fast" if lib().pirip_fsk_plan_mode(self._h) == 1 else "exact"
+
+    def kernel(self):
+        return lib().pirip_fsk_plan_kernel(self._h).decode()
+
+    def replays(self):
+        """(replayed, failed) exact in-kernel frame replays since the plan was created."""
+        out = np.zeros(2, np.int32)
+        rc = lib().pirip_fsk_plan_replays(self._h, _ptr(out))
+        if rc != 0:
+            raise _err("pirip_fsk_plan_replays", rc)
+        return int(out[0]), int(out[1])
+
+    def flagged(self, n=0):
+        """(count, flags[n]) of the last batch call: captures the guards sent to the exact kernel."""
+        flags = np.zeros(n, np.int32) if n else None
+        cnt = lib().pirip_fsk_plan_flagged(self._h, _ptr(flags), n)
+        if cnt < 0:
+            raise _err("pirip_fsk_plan_flagged", cnt)
+        return int(cnt), flags
 
     def close(self):
         if getattr(self, "_h", None):

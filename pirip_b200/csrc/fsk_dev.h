@@ -134,6 +134,12 @@ struct FskBatchArgs {
     int tma_ok;                       /* iq is 16-byte aligned: stage frames with TMA bulk copies */
     const unsigned long long *landed; /* optional (batch kernel): samples of every capture already in device memory; the
                                          host raises it while it streams the captures in, the kernel never reads ahead */
+    /* optional (batch kernel): demodulate only the captures cap_list[0 .. *cap_count) of the batch (device memory, read
+       when the kernel starts: the re-run of captures the fast kernel flagged); n_captures is then the launch bound and
+       total_captures the size of the batch the buffers are laid out for */
+    const int *cap_list;
+    const int *cap_count;
+    size_t total_captures;
 };
 
 static inline size_t fsk_state_floats(int Ndft, int M, int Nmem) {
@@ -192,6 +198,21 @@ struct Fsk2CtaShared {
 /* defined in fsk_kernel2.cu */
 cudaError_t fsk2_launch_demod(const FskDevCfg &cfg, const FskBatchArgs &args, size_t n_captures, cudaStream_t stream);
 cudaError_t fsk2_kernel_prepare(const FskDevCfg &cfg);
+
+/* defined in fsk_fast.cu: the tolerance-mode batch kernel (exact tone estimates, fast integrators, guarded decisions) */
+struct FskFastPlan;
+#ifdef __cplusplus
+#include <string>
+FskFastPlan *fsk_fast_plan_create(const pirip_fsk_cfg &c, const FskDevCfg &d, const float *h_hann, const float2 *h_phi_ft, int device,
+                                  std::string &why);
+void fsk_fast_plan_destroy(FskFastPlan *p);
+const char *fsk_fast_plan_desc(const FskFastPlan *p);
+cudaError_t fsk_fast_flag_buffers(FskFastPlan *p, size_t n, int **flags, int **list, int **count);
+cudaError_t fsk_fast_launch(FskFastPlan *p, const FskBatchArgs &b, int *d_flags, int *d_list, int *d_count, cudaStream_t stream,
+                            size_t off, size_t total, size_t slot);
+cudaError_t fsk_fast_replay_counts(FskFastPlan *p, int out[8]);
+int fsk_fast_uses_chain(const FskFastPlan *p);
+#endif
 
 /* defined in fsk_kernel.cu */
 cudaError_t fsk_launch_demod(const FskDevCfg &cfg, const FskBatchArgs &args, size_t n_captures, cudaStream_t stream);

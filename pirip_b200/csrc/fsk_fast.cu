@@ -1,0 +1,1776 @@
+/*
+ * fsk_fast.cu — tolerance-mode batch demodulator ("fast path") for the IQ -> bits hot path.
+ *
+ * One CTA of 64 threads demodulates one capture for its whole length (frame loop inside the kernel); nine CTAs
+ * are resident per SM for the benchmark shape, so 1250 captures are one wave.  What it computes per frame is
+ * codec2's fsk_demod_core ([U fsk.c::fsk_demod_freq_est / fsk_demod_core])
+ * on the samples the fsk_demod CLI loop would hand it ([U fsk_demod.c], [R README.md:105,109],
+ * [R test/loopback_rtl_sdr.sh:16]).
+ *
+ * Numerics contract (north_star: "hard-decision bits and frame indices bit-exact, freq/timing estimates and LLRs
+ * within a stated float tolerance"):
+ *   EXACT    - input conversion, Hann window, FFT (kiss_fft's butterflies, operand order and float twiddles, no
+ *              FMA), magnitudes, the IIR spectrum, peak picking / mask correlation: the tone estimates f_est /
+ *              f2_est are the same floats the scalar algorithm produces, for every frame, by construction.
+ *   FAST     - down-conversion with a closed-form oscillator (phase kept as a 32-bit fraction of a turn, amplitude
+ *              drift of the scalar float recursion modelled), sliding-window integrators, parallel timing-line
+ *              sum, FMA everywhere.  Decision variables agree with the scalar algorithm to ~1e-6 relative.
+ *   GUARDED  - every discrete decision taken from a FAST quantity (symbol arg-max, the nin slip thresholds at
+ *              |norm_rx_timing| = 0.25, the ppm update threshold) is checked against a margin; a capture with a
+ *              decision inside the margin is FLAGGED and re-run by the exact kernel (fsk_kernel2.cu) from the
+ *              host side of this file's caller, so hard bits / nin / frame counts stay bit-exact.
+ *
+ * Exact sections use __fmul_rn / __fadd_rn / __fsqrt_rn (never contracted); fast sections call fmaf explicitly.
+ * The translation unit is still built with -fmad=false so that nothing is fused by accident.
+ */
+#include <assert.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "exact_math.h"
+#include "fsk_dev.h"
+#include "host_util.h"
+
+namespace {
+
+typedef unsigned long long u64;
+constexpr int T = 64;          /* threads per CTA (one capture) */
+constexpr int TAILPAD_MIN = 8;
+
+struct OscEntry {
+    float2 dphi;     /* the float pair the scalar algorithm multiplies by every sample */
+    float2 dstride;  /* dphi^(2T) evaluated in double: phase step of a thread between its sample pairs */
+    unsigned step32; /* angle of dphi as a 32-bit fraction of a turn */
+    float lng;       /* ln |dphi| : per-sample amplitude drift of the scalar float recursion */
+    float f;         /* the frequency estimate this entry stands for (Hz) */
+    float pad;
+};
+
+struct FastCfg {
+    int Fs, Rs, P, Nsym, Ts, N, Nmem, Ndft, Nbits, nint, step;
+    int st, en, nb, f_zero, est_type, tone_spacing, f1_tx, fixed_nin, soft;
+    int nmask, len_mask, mask_pos[FSK_MAX_MASK];
+    int log2_ndft, nfac, fac_p[FSK_MAX_FFT_FACTORS], fac_m[FSK_MAX_FFT_FACTORS], fac_fstride[FSK_MAX_FFT_FACTORS];
+    int nin_max, nin_min, tailpad, RO, bps;
+    float fs_over_ndft, in_scale, g_sym, g_tim;
+    float2 tw_l2[9]; /* 256-point FFT: twiddles of the second butterfly level, [k'-1][j-1] = tw[16 k' j] */
+    const float *hannS;     /* [Ndft] Hann window times in_scale */
+    const float2 *twiddle;  /* [Ndft] kiss_fft twiddles */
+    const OscEntry *osc;    /* [Ndft][4] */
+    const float2 *ftideal;  /* [P] e^{j 2 pi k / P} */
+    const float2 *ftcorr;   /* [T] mean of (timing oscillator of the scalar recursion) / ideal over a thread's run of outputs */
+    const float2 *phi_ft;   /* [nint] the timing oscillator exactly as the scalar float recursion produces it (exact replay) */
+    int off_raw, raw_bytes, off_fdc, fdcS, off_Sf, off_hann, off_filt, off_ideal, off_misc, smem_bytes;
+    int fft_blocks_per_round; /* blocks transformed at a time: as many as fit the scratch row */
+    int prune;                /* 256-point FFT: the estimator window lies inside output bins k < 32 */
+    int exit_on_flag;
+};
+
+struct FastArgs {
+    const unsigned char *iq;
+    size_t stride, nsamples, max_frames, n_captures;
+    size_t alloc_end; /* first byte address past the input allocation that bulk copies may touch (16-byte aligned down) */
+    unsigned char *bits;
+    float *llr, *rx_filt;
+    pirip_frame_stats *stats;
+    int32_t *nframes;
+    int *flags;      /* [n_captures] 0 = clean, else reason bits | (first flagged frame << 8) */
+    int *flag_list;  /* compacted indices of flagged captures */
+    int *flag_count;
+    int tma_ok;
+    /* exact-oscillator side chain (fsk_osc_chain_kernel): NULL when it does not run beside this launch */
+    u64 *mbox;          /* [n_captures][max_frames + 1] per-frame mailbox: what the side chain needs to run frame f */
+    float4 *ckpt;       /* [n_captures][2][ckpt_per_frame][4] records {phi.x, phi.y, tag, ~tag}: oscillator state before every 64th
+                           sample, by frame parity; tag = (frame + 1) << 8 | chunk makes a record self-validating (no fences) */
+    int *afin;          /* [n_captures] set by the fast kernel when it has finished a capture */
+    int *replays;       /* [2] counters: frames replayed exactly, replays that failed (side chain not available in time) */
+    int ckpt_per_frame;
+};
+
+enum { FLAG_SYM = 1, FLAG_TIM = 2, FLAG_PPM = 4, FLAG_NAN = 8 };
+
+struct Misc {
+    u64 bar;
+    u64 pos;
+    float2 dphi[4], dstride[4];
+    unsigned step32[4], acc[4];
+    float lng[4], f_est[4], f2_est[4];
+    int freqi[4];
+    int bmax, nin, nin_next, nold, numffts, low, high, roff, cont, pending, frame, flags, use_tma, parity;
+    float fract, omf, norm_rx_timing, ppm, snr_est, rx_timing, SNRest, v_est, rx_sig_pow, rx_nse_pow, EbNodB, foff;
+    float red[2][8];
+    int nflag_sym;
+    /* exact replay */
+    int fflags;         /* flags raised in the current frame */
+    int nin_prev, rp_ok;
+    u64 pos_prev;
+    float2 dphi_prev[4];
+    float2 xtc;         /* exact timing-line sum */
+    int osc_idx[4];
+};
+
+#define MBOX_VALID (1ull << 63)
+#define MBOX_END (1ull << 62)
+#define CKPT_EVERY 128 /* nominal samples per checkpoint chunk: a frame of nin samples has ceil(nin / 128) chunks of nearly equal length */
+
+/* checkpoint chunks of a frame of nin samples: K = ceil(nin / CKPT_EVERY) chunks, the first nin % K one sample longer */
+__host__ __device__ __forceinline__ int ck_chunks(int nin) { return (nin + CKPT_EVERY - 1) / CKPT_EVERY; }
+__host__ __device__ __forceinline__ int ck_start(int nin, int k) {
+    const int K = ck_chunks(nin), base = nin / K, rem = nin - base * K;
+    return k * base + (k < rem ? k : rem);
+}
+__host__ __device__ __forceinline__ int ck_of(int nin, int j) { /* chunk holding sample j */
+    const int K = ck_chunks(nin), base = nin / K, rem = nin - base * K;
+    const int split = rem * (base + 1);
+    return j < split ? j / (base + 1) : rem + (j - split) / base;
+}
+
+/* ------------------------------------------------------------------ small device helpers */
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(u64 *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(u64 *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(u64 *bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity) {
+    if (mbar_try(bar, parity)) return;
+    unsigned ns = 32;
+    while (!mbar_try(bar, parity)) {
+        __nanosleep(ns);
+        ns = ns < 256 ? ns * 2 : 256;
+    }
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, unsigned bytes, u64 *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+/* packed f32x2 add / sub (Blackwell FADD2): bit-identical to two scalar IEEE additions (tools/micro/f32x2_exact.cu), half
+   the issue slots.  Only additions are packed: ptxas would contract a packed multiply feeding a packed add into FFMA2. */
+__device__ __forceinline__ u64 pk(float2 a) {
+    u64 r;
+    asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 upk(u64 r) {
+    float2 a;
+    asm("mov.b64 {%0,%1}, %2;" : "=f"(a.x), "=f"(a.y) : "l"(r));
+    return a;
+}
+__device__ __forceinline__ float2 xadd(float2 a, float2 b) {
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
+    return upk(r);
+}
+__device__ __forceinline__ float2 xsub(float2 a, float2 b) {
+    u64 r;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk(a)), "l"(pk(b)));
+    return upk(r);
+}
+/* exact complex multiply, the operation sequence of kiss_fft's C_MUL (a.x*b.x - a.y*b.y, a.x*b.y + a.y*b.x): four scalar
+   multiplies (never fused), the subtraction written as an addition of the exactly negated product */
+__device__ __forceinline__ float2 xmul(float2 a, float2 b) {
+    return xadd(make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.x, b.y)), make_float2(__fmul_rn(a.y, -b.y), __fmul_rn(a.y, b.x)));
+}
+
+/* [U kiss_fft.c::kf_bfly4], forward transform, one butterfly; s0..s2 are the twiddled inputs */
+__device__ __forceinline__ void bfly4_core(float2 &f0, float2 &f1, float2 &f2, float2 &f3, float2 s0, float2 s1, float2 s2) {
+    const float2 s5 = xsub(f0, s1);
+    f0 = xadd(f0, s1);
+    const float2 s3 = xadd(s0, s2);
+    const float2 s4 = xsub(s0, s2);
+    f2 = xsub(f0, s3);
+    f0 = xadd(f0, s3);
+    f1 = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
+    f3 = make_float2(__fsub_rn(s5.x, s4.y), __fadd_rn(s5.y, s4.x));
+}
+__device__ __forceinline__ void bfly4_tw(float2 &f0, float2 &f1, float2 &f2, float2 &f3, float2 t1, float2 t2, float2 t3) {
+    bfly4_core(f0, f1, f2, f3, xmul(f1, t1), xmul(f2, t2), xmul(f3, t3));
+}
+/* twiddles (1, -0): x*(1,-0) == x for every finite x (up to the sign of a zero), so the products are skipped */
+__device__ __forceinline__ void bfly4_unit(float2 &f0, float2 &f1, float2 &f2, float2 &f3) { bfly4_core(f0, f1, f2, f3, f1, f2, f3); }
+/* the same butterfly when only outputs 0 and 1 (f0, f1) are needed */
+__device__ __forceinline__ void bfly4_tw_01(float2 &f0, float2 &f1, float2 f2, float2 f3, float2 t1, float2 t2, float2 t3) {
+    const float2 s0 = xmul(f1, t1), s1 = xmul(f2, t2), s2 = xmul(f3, t3);
+    const float2 s5 = xsub(f0, s1);
+    f0 = xadd(f0, s1);
+    const float2 s3 = xadd(s0, s2);
+    const float2 s4 = xsub(s0, s2);
+    f0 = xadd(f0, s3);
+    f1 = make_float2(__fadd_rn(s5.x, s4.y), __fsub_rn(s5.y, s4.x));
+}
+/* ... and when only output 0 is needed */
+__device__ __forceinline__ float2 bfly4_tw_0(float2 f0, float2 f1, float2 f2, float2 f3, float2 t1, float2 t2, float2 t3) {
+    const float2 s0 = xmul(f1, t1), s1 = xmul(f2, t2), s2 = xmul(f3, t3);
+    return xadd(xadd(f0, s1), xadd(s0, s2));
+}
+
+/* fast complex helpers (FMA) */
+__device__ __forceinline__ float2 fcmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+/* x * conj(p) */
+__device__ __forceinline__ float2 fmix(float2 x, float2 p) { return make_float2(fmaf(x.x, p.x, x.y * p.y), fmaf(x.y, p.x, -x.x * p.y)); }
+
+/* (float)b - 127 exactly, without the conversion pipe: 0x4B000000 | b is the float 2^23 + b */
+__device__ __forceinline__ float u8m127(unsigned w, unsigned sel) { return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540u | sel)) - 8388735.0f; }
+
+/* complex sample at byte pointer p (shared or global), converted as the fsk_demod CLI does ([U fsk_demod.c]); the u8
+   value is returned WITHOUT its exact power-of-two scale 1/128 (cfg.in_scale), which the callers fold into a table */
+template <int FMT>
+__device__ __forceinline__ float2 raw_cvt(const unsigned char *p) {
+    if (FMT == PIRIP_FMT_U8) {
+        const unsigned w = *reinterpret_cast<const unsigned short *>(p);
+        return make_float2(u8m127(w, 0), u8m127(w, 1));
+    } else if (FMT == PIRIP_FMT_S16) {
+        const short2 s = *reinterpret_cast<const short2 *>(p);
+        return make_float2(__fdiv_rn((float)s.x, 825.0f), __fdiv_rn((float)s.y, 825.0f));
+    } else {
+        return *reinterpret_cast<const float2 *>(p);
+    }
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+/* ------------------------------------------------------------------ exact FFT, 256 points, registers */
+/* One 256-point block by 16 threads: two radix-4 levels per register pass (a 16-point sub-transform), one exchange
+   through shared memory.  The butterflies, their operands and the order of the additions are kiss_fft's
+   ([U kiss_fft.c::kf_work] with factors 4,4,4,4), so the outputs are the floats kiss_fft produces.
+   t16: thread within the block's group; src: first raw sample of the block; xch: the group's exchange buffer
+   (16 x 17 float2); magout: magnitudes of bins [st, en) of this block. */
+template <int FMT>
+__device__ __forceinline__ void fft256_block(const FastCfg &cfg, int t16, const unsigned char *src, const float *hannS, float2 *xch,
+                                             float *magout, const float2 (&t3)[3], const float2 (&t4)[4][3]) {
+    float2 F[16];
+    /* leaf order: F[4 k3 + k4] = x[n + 16 k3 + 64 k4] */
+#pragma unroll
+    for (int k3 = 0; k3 < 4; ++k3)
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4) {
+            const int n = t16 + 16 * k3 + 64 * k4;
+            const float2 x = raw_cvt<FMT>(src + (size_t)n * cfg.bps);
+            const float h = hannS[n];
+            F[4 * k3 + k4] = make_float2(__fmul_rn(h, x.x), __fmul_rn(h, x.y));
+        }
+#pragma unroll
+    for (int k3 = 0; k3 < 4; ++k3) bfly4_unit(F[4 * k3], F[4 * k3 + 1], F[4 * k3 + 2], F[4 * k3 + 3]);
+    bfly4_unit(F[0], F[4], F[8], F[12]);
+#pragma unroll
+    for (int k = 1; k < 4; ++k) bfly4_tw(F[k], F[k + 4], F[k + 8], F[k + 12], cfg.tw_l2[3 * (k - 1)], cfg.tw_l2[3 * (k - 1) + 1], cfg.tw_l2[3 * (k - 1) + 2]);
+    /* exchange: thread n holds Y_n[q]; thread q needs Y_n[q] for all n */
+#pragma unroll
+    for (int q = 0; q < 16; ++q) xch[q * 17 + t16] = F[q];
+    const unsigned gmask = 0xffffu << (threadIdx.x & 16); /* the 16 threads of this block's group */
+    __syncwarp(gmask);
+#pragma unroll
+    for (int n = 0; n < 16; ++n) F[n] = xch[t16 * 17 + n];
+    __syncwarp(gmask);
+    if (cfg.prune) {
+        /* the estimator window lies inside bins k < 32 (l = 0, jj < 2): the butterflies that only feed other bins are skipped;
+           the ones that remain are the same operations on the same operands */
+#pragma unroll
+        for (int kA = 0; kA < 4; ++kA) bfly4_tw_01(F[kA], F[kA + 4], F[kA + 8], F[kA + 12], t3[0], t3[1], t3[2]);
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+            const float2 v = bfly4_tw_0(F[4 * jj], F[4 * jj + 1], F[4 * jj + 2], F[4 * jj + 3], t4[jj][0], t4[jj][1], t4[jj][2]);
+            const int i = t16 + 16 * jj + 128;
+            if (i >= cfg.st && i < cfg.en) magout[i - cfg.st] = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
+        }
+        return;
+    }
+    /* level 3 (m = 16, fstride = 4): per kA over kB, twiddles tw[4q], tw[8q], tw[12q] */
+#pragma unroll
+    for (int kA = 0; kA < 4; ++kA) bfly4_tw(F[kA], F[kA + 4], F[kA + 8], F[kA + 12], t3[0], t3[1], t3[2]);
+    /* level 4 (m = 64, fstride = 1): per r = q + 16 jj over kA, twiddles tw[r], tw[2r], tw[3r] */
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) bfly4_tw(F[4 * jj], F[4 * jj + 1], F[4 * jj + 2], F[4 * jj + 3], t4[jj][0], t4[jj][1], t4[jj][2]);
+    /* F[l + 4 jj] = X[q + 16 jj + 64 l]; fft shift, magnitude of the bins the estimator looks at */
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int k = t16 + 16 * jj + 64 * l;
+            const int i = (k + 128) & 255;
+            if (i >= cfg.st && i < cfg.en) {
+                const float2 v = F[l + 4 * jj];
+                magout[i - cfg.st] = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
+            }
+        }
+}
+
+/* ------------------------------------------------------------------ exact FFT, any power of two, shared memory */
+/* nblk blocks (block j at raw sample a0 + j*Ndft/2 of the frame) transformed in buf (nblk x Ndft float2), all
+   CTA threads; same butterfly sequence as [U kiss_fft.c::kf_work].  Ends with the magnitudes of bins [st, en). */
+template <int FMT>
+__device__ void fft_generic(const FastCfg &cfg, int tid, const unsigned char *frame_raw, int j0, int nblk, const float *hannS, float2 *buf,
+                            float *mag) {
+    const int Ndft = cfg.Ndft, half = Ndft >> 1;
+    for (int e = tid; e < nblk * Ndft; e += T) {
+        const int b = e >> cfg.log2_ndft, pos = e & (Ndft - 1);
+        int n = 0;
+        for (int s = 0; s < cfg.nfac; ++s) n += ((pos / cfg.fac_m[s]) % cfg.fac_p[s]) * cfg.fac_fstride[s];
+        const float2 x = raw_cvt<FMT>(frame_raw + ((size_t)(j0 + b) * half + n) * cfg.bps);
+        const float h = hannS[n];
+        buf[e] = make_float2(__fmul_rn(h, x.x), __fmul_rn(h, x.y));
+    }
+    __syncthreads();
+    for (int s = cfg.nfac - 1; s >= 0; --s) {
+        const int p = cfg.fac_p[s], m = cfg.fac_m[s], fs = cfg.fac_fstride[s];
+        const int per_blk = Ndft / p;
+        for (int e = tid; e < nblk * per_blk; e += T) {
+            const int b = e / per_blk, bi = e - b * per_blk;
+            const int grp = bi / m, k = bi - grp * m;
+            float2 *F = buf + (size_t)b * Ndft + grp * p * m + k;
+            if (p == 4) {
+                float2 f0 = F[0], f1 = F[m], f2 = F[2 * m], f3 = F[3 * m];
+                bfly4_tw(f0, f1, f2, f3, cfg.twiddle[k * fs], cfg.twiddle[2 * k * fs], cfg.twiddle[3 * k * fs]);
+                F[0] = f0;
+                F[m] = f1;
+                F[2 * m] = f2;
+                F[3 * m] = f3;
+            } else { /* [U kiss_fft.c::kf_bfly2] */
+                const float2 t = xmul(F[m], cfg.twiddle[k * fs]);
+                const float2 f0 = F[0];
+                F[m] = xsub(f0, t);
+                F[0] = xadd(f0, t);
+            }
+        }
+        __syncthreads();
+    }
+    for (int e = tid; e < nblk * cfg.nb; e += T) {
+        const int b = e / cfg.nb, i = cfg.st + (e - b * cfg.nb);
+        const float2 v = buf[(size_t)b * Ndft + ((i + half) & (Ndft - 1))];
+        mag[(size_t)b * cfg.nb + (i - cfg.st)] = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
+    }
+    __syncthreads();
+}
+
+/* float log I0(x) ([U mpdecode_core.c::bessi0] polynomial in the log domain), tolerance mode */
+__device__ __forceinline__ float logbessi0_f(float x) {
+    const float ax = fabsf(x);
+    if (ax < 3.75f) {
+        float y = x * (1.0f / 3.75f);
+        y *= y;
+        const float ans = 1.0f + y * (3.5156229f + y * (3.0899424f + y * (1.2067492f + y * (0.2659732f + y * (0.360768e-1f + y * 0.45813e-2f)))));
+        return logf(ans);
+    }
+    const float y = 3.75f / ax;
+    const float ans = 0.39894228f + y * (0.1328592e-1f + y * (0.225319e-2f + y * (-0.157565e-2f + y * (0.916281e-2f + y * (-0.2057706e-1f + y * (0.2635537e-1f + y * (-0.1647633e-1f + y * 0.392377e-2f)))))));
+    return (ax - 0.5f * logf(ax)) + logf(ans);
+}
+__device__ __forceinline__ float max_star0_f(float d1, float d2) {
+    const float AJIAN = -0.24904163195436f, TJIAN = 2.50681740420944f;
+    const float diff = d2 - d1;
+    if (diff > TJIAN) return d2;
+    if (diff < -TJIAN) return d1;
+    if (diff > 0) return d2 + AJIAN * (diff - TJIAN);
+    return d1 - AJIAN * (diff + TJIAN);
+}
+
+/* ------------------------------------------------------------------ exact oscillator side chain */
+/* release / acquire accesses to global memory shared by the two kernels of a launch (gpu scope) */
+__device__ __forceinline__ void st_release_u64(u64 *p, u64 v) { asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ u64 ld_acquire_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) { asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ void st_relaxed_s32(int *p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+/* a checkpoint record, read past L1; valid when its tag words are the expected ones */
+__device__ __forceinline__ bool ld_ckpt(const float4 *p, int tag, float2 *phi) {
+    float4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    *phi = make_float2(v.x, v.y);
+    return __float_as_int(v.z) == tag && __float_as_int(v.w) == ~tag;
+}
+__device__ __forceinline__ void st_release_s32(int *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire_s32(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+/* [U comp_prim.h::cmult] as fsk_demod_core applies it to the oscillator: never fused */
+__device__ __forceinline__ float2 ocmul(float2 a, float2 b) {
+    return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
+}
+
+/* The one computation of the path that cannot be reformulated without changing its floats: the recursive oscillator
+   phi_c[m] *= dphi_m of [U fsk.c::fsk_demod_core] (one rounding per sample, renormalised once per frame).  The fast kernel
+   mixes with a closed-form phase and needs the scalar algorithm's exact phases only when a frame has to be replayed
+   exactly - but then from the capture's first sample on.  This kernel runs beside the fast kernel, ONE LANE PER CAPTURE
+   (32 independent serial chains per warp), follows the frame sequence the fast kernel publishes in `mbox` (frame length and
+   the oscillator table entries chosen by the exact tone estimate) and leaves a checkpoint of phi_c every 64 samples.
+   It never blocks the fast kernel; a lane without a mailbox entry idles, the warp sleeps when no lane has work, and the
+   kernel gives up after ~100 ms without any (a tool serialising the two kernels): the fast kernel then falls back to
+   flagging, i.e. to the exact kernel. */
+template <int M>
+__global__ void fsk_osc_chain_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ FastArgs args) {
+    /* lane = (capture, tone): 32 / M captures per warp, every lane one serial chain of dependent multiply-adds.  The CTAs of
+       this kernel ask for most of an SM's shared memory so that they get SMs of their own: a chain warp that shares its
+       scheduler with the fast kernel's warps falls behind the frames it is meant to shadow. */
+    const int lane = threadIdx.x & 31;
+    const int m = lane % M;
+    const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const size_t cap = gw * (32 / M) + lane / M;
+    bool done = cap >= args.n_captures, have = false;
+    float2 phi = make_float2(1.0f, 0.0f), dphi = make_float2(1.0f, 0.0f);
+    int f = 0, k = 0, K = 0, base = 0, rem = 0;
+    const u64 *box = args.mbox + (done ? 0 : cap * (args.max_frames + 1));
+    float4 *ck = args.ckpt + (done ? 0 : cap * (size_t)(2 * args.ckpt_per_frame * 4)) + m;
+    const int *afin = args.afin + (done ? 0 : cap);
+    unsigned idle = 0;
+    while (true) {
+        if (__all_sync(0xffffffffu, done)) break;
+        /* Poll first, look at the answers last: a lane waiting for its next frame reads its mailbox word, a working lane the
+           capture's "finished" flag; both words are consumed after the steps below, whose operands (dphi, have) they would
+           change - so the loads' latency hides behind a chunk of steps.  The words are self-contained: relaxed loads. */
+        u64 w = 0;
+        int fin = 0;
+        const bool poll_box = !done && !have, poll_fin = !done && have;
+        if (poll_box) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(box + f) : "memory");
+        if (poll_fin) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(fin) : "l"(afin) : "memory");
+        if (__any_sync(0xffffffffu, have)) {
+            idle = 0;
+            if (have) {
+                const int tag = ((f + 1) << 8) | k;
+                ck[((size_t)(f & 1) * args.ckpt_per_frame + k) * 4] = make_float4(phi.x, phi.y, __int_as_float(tag), __int_as_float(~tag));
+            }
+            const int n = have ? base + (k < rem ? 1 : 0) : 0;
+            /* the warp runs the shortest count of its working lanes without any predicate (a lane without work steps a scratch
+               copy), then the one or two steps by which the counts differ with a per-lane select */
+            int nmin = have ? n : 0x7fffffff, nmax = n;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int a = __shfl_xor_sync(0xffffffffu, nmin, o), b = __shfl_xor_sync(0xffffffffu, nmax, o);
+                nmin = a < nmin ? a : nmin;
+                nmax = b > nmax ? b : nmax;
+            }
+            float2 wp = phi;
+#pragma unroll 8
+            for (int it = 0; it < nmin; ++it) wp = ocmul(wp, dphi);
+            for (int it = nmin; it < nmax; ++it) {
+                const float2 r = ocmul(wp, dphi);
+                if (it < n) wp = r;
+            }
+            if (have) {
+                phi = wp;
+                if (++k == K) {
+                    /* [U comp_prim.h::comp_normalize] */
+                    const float av = __fsqrt_rn(__fadd_rn(__fmul_rn(phi.x, phi.x), __fmul_rn(phi.y, phi.y)));
+                    phi = make_float2(__fdiv_rn(phi.x, av), __fdiv_rn(phi.y, av));
+                    ++f;
+                    have = false;
+                }
+            }
+        } else {
+            __nanosleep(500);
+            if (++idle > 200000u) break;
+        }
+        /* the answers.  Tied to the chain's result (never a NaN) so that neither compiler hoists the tests - and with them the
+           wait for the loads - above the steps. */
+        {
+            const int never = (phi.x != phi.x) ? 1 : 0;
+            fin += never;
+            w += (u64)never;
+        }
+        if (poll_fin && fin) done = true, have = false; /* the fast kernel has finished this capture: nobody will ask any more */
+        if (poll_box && (w & MBOX_VALID)) {
+            if (w & MBOX_END)
+                done = true;
+            else {
+                const int code = (int)((w >> 48) & 3);
+                const int nin = code == 0 ? cfg.nin_min : (code == 1 ? cfg.N : cfg.nin_max);
+                K = ck_chunks(nin);
+                base = nin / K;
+                rem = nin - base * K;
+                dphi = cfg.osc[(w >> (12 * m)) & 0xfff].dphi;
+                have = true;
+                k = 0;
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ exact replay of one frame */
+/* Recompute frame `frame` of capture `cap` with the scalar algorithm's own operations ([U fsk.c::fsk_demod_core],
+   SURVEY.md App. A.3): mixing with the recursive oscillator (from the side chain's checkpoints), integrators summed from
+   zero in ascending order, the timing-line sum accumulated serially, atan2 / log10 through exact_math.h.  Given the exact
+   tone estimates (always exact in this kernel) the results are the floats of the CPU evaluation, so the decisions the
+   fast path could not take safely are taken here.  Rare (a few frames per 10^4); all CTA threads take part.
+   On success: bits / rx_filt of the frame rewritten, ms-> timing, nin_next, interpolation and per-frame statistics set
+   from the exact values, `filt` holds the exact magnitudes; the fast baseband memory of the frame's last `tailpad` samples
+   is kept (the next frame continues the FAST oscillator phase).  Returns false when the side chain did not deliver. */
+template <int M, int FMT>
+__device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastArgs &args, unsigned char *smem, size_t cap, int frame,
+                                                int nin, u64 pos) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float2 *fdc = reinterpret_cast<float2 *>(smem + cfg.off_fdc);
+    float *filt = reinterpret_cast<float *>(smem + cfg.off_filt);
+    Misc *ms = reinterpret_cast<Misc *>(smem + cfg.off_misc);
+    const int Ts = cfg.Ts, P = cfg.P, Nsym = cfg.Nsym, Nmem = cfg.Nmem, fdcS = cfg.fdcS, step = cfg.step, nint = cfg.nint, bps = cfg.bps;
+    const int nold = Nmem - nin;
+    const unsigned char *cap_base = args.iq + cap * args.stride;
+
+    /* the checkpoint records this frame needs (its own chunks and the chunks of the previous frame's tail) must have been
+       written by the side chain: every thread polls one record; all or nothing */
+    const float4 *ck = args.ckpt + cap * (size_t)(2 * args.ckpt_per_frame * 4);
+    const int nprev = ms->nin_prev;
+    const int jt0 = nprev - nold;                         /* first tail sample, in the previous frame's numbering */
+    const int ct0 = frame > 0 ? ck_of(nprev, jt0) : 0;    /* its checkpoint chunk */
+    const int nct = frame > 0 ? ck_chunks(nprev) - ct0 : 0;
+    const int ncn = ck_chunks(nin);
+    {
+        int ok = (args.ckpt && Nsym <= T && cfg.tailpad <= 64) ? 1 : 0;
+        const long long t0 = clock64();
+        for (int task = tid; ok && task < M * (nct + ncn); task += T) {
+            const int m = task / (nct + ncn), seg = task - m * (nct + ncn);
+            const bool prev = seg < nct;
+            const int chunk = prev ? ct0 + seg : seg - nct, fr_ = prev ? frame - 1 : frame;
+            const float4 *rec = ck + ((size_t)(fr_ & 1) * args.ckpt_per_frame + chunk) * 4 + m;
+            float2 dummy;
+            while (!ld_ckpt(rec, ((fr_ + 1) << 8) | chunk, &dummy)) {
+                if (clock64() - t0 > 6000000ll) { /* ~3 ms */
+                    ok = 0;
+                    break;
+                }
+                __nanosleep(200);
+            }
+        }
+        if (tid == 0 && args.replays) atomicAdd(args.replays + 3, (int)((clock64() - t0) >> 10));
+        if (!__syncthreads_and(ok)) return false;
+    }
+
+    /* keep the fast baseband memory the next frame's tail is taken from */
+    constexpr int KEEP = (M * 64 + T - 1) / T; /* tailpad <= 64 */
+    float2 keep[KEEP];
+#pragma unroll
+    for (int i = 0; i < KEEP; ++i) {
+        const int e = tid + i * T;
+        const int m = e / cfg.tailpad, k = e - m * cfg.tailpad;
+        keep[i] = (m < M) ? fdc[m * fdcS + Nmem - cfg.tailpad + k] : make_float2(0.0f, 0.0f);
+    }
+    __syncthreads();
+
+    /* exact f_dc: the tail comes from the previous frame's last nold samples (its oscillator), then the nin new samples */
+    {
+        if (frame == 0)
+            for (int i = tid; i < M * nold; i += T) fdc[(i / nold) * fdcS + (i % nold)] = make_float2(0.0f, 0.0f);
+        for (int task = tid; task < M * (nct + ncn); task += T) {
+            const int m = task / (nct + ncn), seg = task - m * (nct + ncn);
+            const bool prev = seg < nct;
+            const int chunk = prev ? ct0 + seg : seg - nct;
+            const int fr_ = prev ? frame - 1 : frame;
+            const int jend = prev ? nprev : nin;
+            const int jc = ck_start(jend, chunk), jhi = ck_start(jend, chunk + 1); /* the chunk's samples */
+            const int jlo = (prev && chunk == ct0) ? jt0 : jc;
+            const float2 d = prev ? ms->dphi_prev[m] : ms->dphi[m];
+            float2 phi;
+            ld_ckpt(ck + ((size_t)(fr_ & 1) * args.ckpt_per_frame + chunk) * 4 + m, 0, &phi); /* validated above */
+            const unsigned char *src = cap_base + ((prev ? ms->pos_prev : pos)) * bps;
+            for (int j = jc; j < jhi; ++j) {
+                phi = ocmul(phi, d);
+                if (j >= jlo) {
+                    float2 x = raw_cvt<FMT>(src + (size_t)j * bps);
+                    x.x = __fmul_rn(x.x, cfg.in_scale); /* exact: power of two (1 for s16 / f32) */
+                    x.y = __fmul_rn(x.y, cfg.in_scale);
+                    /* in * conj(phi) as cmult(in, cconj(phi)) evaluates it */
+                    const float2 y = make_float2(__fadd_rn(__fmul_rn(x.x, phi.x), __fmul_rn(x.y, phi.y)),
+                                                 __fadd_rn(__fmul_rn(x.x, -phi.y), __fmul_rn(x.y, phi.x)));
+                    const int idx = prev ? j - jt0 : nold + j;
+                    fdc[m * fdcS + idx] = y;
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    /* window energies and the timing line, accumulated in the scalar order (warp 0; lane 0 carries the sum) */
+    if (warp == 0) {
+        float2 tc = make_float2(0.0f, 0.0f);
+        for (int i0 = 0; i0 < nint; i0 += 32) {
+            const int i = i0 + lane;
+            float2 prod = make_float2(0.0f, 0.0f);
+            if (i < nint) {
+                float ft1 = 0.0f;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const float2 *f = fdc + m * fdcS + i * step;
+                    float2 a = make_float2(0.0f, 0.0f);
+                    for (int k = 0; k < Ts; ++k) a = xadd(a, f[k]);
+                    ft1 = __fadd_rn(ft1, __fadd_rn(__fmul_rn(a.x, a.x), __fmul_rn(a.y, a.y)));
+                }
+                const float2 w = cfg.phi_ft[i];
+                prod = make_float2(__fmul_rn(ft1, w.x), __fmul_rn(ft1, w.y));
+            }
+            const int n = nint - i0 < 32 ? nint - i0 : 32;
+            for (int l = 0; l < n; ++l) {
+                const float px = __shfl_sync(0xffffffffu, prod.x, l), py = __shfl_sync(0xffffffffu, prod.y, l);
+                tc = xadd(tc, make_float2(px, py));
+            }
+        }
+        if (lane == 0) {
+            ms->xtc = tc;
+            int fl = 0;
+            if (isnan(tc.x) || isnan(tc.y)) fl = FLAG_NAN;
+            const float norm = (float)((double)em_atan2f(tc.y, tc.x) / (2 * EM_PI));
+            const float rx_timing = __fmul_rn(norm, (float)P);
+            const float d = __fsub_rn(norm, ms->red[0][7]); /* red[0][7]: norm_rx_timing of the previous frame */
+            if (fabsf(fabsf(d) - 0.2f) < 4e-6f) fl |= FLAG_PPM;  /* the previous value is a fast one: cannot be settled here */
+            float ppm = ms->red[0][6];
+            if ((double)fabsf(d) < .2) {
+                const float appm = (float)(1e6 * (double)d / (double)(float)Nsym);
+                ppm = (float)(.9 * (double)ppm + .1 * (double)appm);
+            }
+            ms->ppm = ppm;
+            ms->norm_rx_timing = norm;
+            int nn = nin;
+            if (!cfg.fixed_nin) nn = (double)norm > 0.25 ? cfg.N + Ts / 4 : ((double)norm < -0.25 ? cfg.N - Ts / 4 : cfg.N);
+            ms->nin_next = nn;
+            const float lowf = floorf(rx_timing);
+            ms->low = (int)lowf;
+            ms->fract = __fsub_rn(rx_timing, (float)ms->low);
+            ms->high = (int)ceilf(rx_timing);
+            ms->omf = __fsub_rn(1.0f, ms->fract);
+            ms->rx_timing = rx_timing;
+            ms->fflags = fl;
+        }
+    }
+    __syncthreads();
+    if (ms->fflags) {
+        /* not settled (NaN input, ppm threshold): leave the frame flagged */
+#pragma unroll
+        for (int i = 0; i < KEEP; ++i) {
+            const int e = tid + i * T;
+            const int m = e / cfg.tailpad, k = e - m * cfg.tailpad;
+            if (m < M) fdc[m * fdcS + Nmem - cfg.tailpad + k] = keep[i];
+        }
+        __syncthreads();
+        return false;
+    }
+
+    /* exact decisions, one thread per symbol; the per-frame sums in symbol order through the warps */
+    float mx = 0.0f, nse_t = 0.0f, sq = 0.0f;
+    const bool vs = tid < Nsym;
+    if (tid < ((Nsym + 31) & ~31) && Nsym <= T) {
+        if (vs) {
+            const int low = ms->low, high = ms->high;
+            const float fr_w = ms->fract, omf = ms->omf;
+            const int st = (tid + 1) * P;
+            float tmax[M];
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const float2 *fa = fdc + m * fdcS + (st + low) * step, *fb = fdc + m * fdcS + (st + high) * step;
+                float2 a = make_float2(0.0f, 0.0f), b = make_float2(0.0f, 0.0f);
+                for (int k = 0; k < Ts; ++k) {
+                    a = xadd(a, fa[k]);
+                    b = xadd(b, fb[k]);
+                }
+                float2 t = make_float2(__fmul_rn(omf, a.x), __fmul_rn(omf, a.y));
+                t = xadd(t, make_float2(__fmul_rn(fr_w, b.x), __fmul_rn(fr_w, b.y)));
+                tmax[m] = __fadd_rn(__fmul_rn(t.x, t.x), __fmul_rn(t.y, t.y));
+            }
+            mx = tmax[0];
+            int symv = 0;
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+                if (tmax[m] > mx) {
+                    mx = tmax[m];
+                    symv = m;
+                }
+            if (args.bits) {
+                unsigned char *bo = args.bits + (cap * args.max_frames + (size_t)frame) * (size_t)cfg.Nbits;
+                if (M == 2)
+                    bo[tid] = (unsigned char)(symv == 1);
+                else {
+                    bo[2 * tid + 1] = (unsigned char)(symv & 1);
+                    bo[2 * tid] = (unsigned char)((symv & 2) >> 1);
+                }
+            }
+            float sum = 0.0f;
+            float *fo = args.rx_filt ? args.rx_filt + (cap * args.max_frames + (size_t)frame) * (size_t)(M * Nsym) : nullptr;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const float rf = __fsqrt_rn(tmax[m]);
+                filt[m * Nsym + tid] = rf;
+                if (fo) fo[m * Nsym + tid] = rf;
+                sum = __fadd_rn(sum, tmax[m]);
+            }
+            nse_t = __fdiv_rn(__fsub_rn(sum, mx), (float)(M - 1));
+            sq = __fsqrt_rn(mx);
+        }
+    }
+    /* serial sums in symbol order: warp 0 (symbols 0..31), then warp 1 */
+    for (int w = 0; w < T / 32; ++w) {
+        if (warp == w) {
+            float s_sig = w == 0 ? 0.0f : ms->red[1][0], s_nse = w == 0 ? (float)1E-12 : ms->red[1][1];
+            float s_std = w == 0 ? 0.0f : ms->red[1][2], s_mean = w == 0 ? 0.0f : ms->red[1][3];
+            const int n = Nsym - 32 * w < 32 ? Nsym - 32 * w : 32;
+            for (int l = 0; l < n; ++l) {
+                const float a = __shfl_sync(0xffffffffu, mx, l), b = __shfl_sync(0xffffffffu, nse_t, l), c = __shfl_sync(0xffffffffu, sq, l);
+                s_sig = __fadd_rn(s_sig, a);
+                s_nse = __fadd_rn(s_nse, b);
+                s_std = __fadd_rn(s_std, a);
+                s_mean = __fadd_rn(s_mean, c);
+            }
+            if (lane == 0) {
+                ms->red[1][0] = s_sig;
+                ms->red[1][1] = s_nse;
+                ms->red[1][2] = s_std;
+                ms->red[1][3] = s_mean;
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const float nsymf = (float)Nsym;
+        const float sig = __fdiv_rn(ms->red[1][0], nsymf), nse = __fdiv_rn(ms->red[1][1], nsymf);
+        ms->rx_sig_pow = sig;
+        ms->rx_nse_pow = nse;
+        ms->v_est = (float)sqrt((double)__fsub_rn(sig, nse));
+        ms->SNRest = __fdiv_rn(sig, nse);
+        const float meanebno = __fdiv_rn(ms->red[1][3], nsymf);
+        float stdebno = __fsub_rn(__fdiv_rn(ms->red[1][2], nsymf), __fmul_rn(meanebno, meanebno));
+        stdebno = (double)stdebno > 0.0 ? (float)sqrt((double)stdebno) : 0.0f;
+        ms->EbNodB = __fadd_rn(-6.0f, __fmul_rn(20.0f, em_log10f((float)((1e-6 + (double)meanebno) / (1e-6 + (double)stdebno)))));
+        ms->snr_est = (float)(.5 * (double)ms->red[0][5] + .5 * (double)ms->EbNodB); /* red[0][5]: snr_est before this frame */
+        if (args.replays) atomicAdd(args.replays, 1);
+    }
+    /* the fast baseband memory of the frame's end, for the next frame's tail */
+#pragma unroll
+    for (int i = 0; i < KEEP; ++i) {
+        const int e = tid + i * T;
+        const int m = e / cfg.tailpad, k = e - m * cfg.tailpad;
+        if (m < M) fdc[m * fdcS + Nmem - cfg.tailpad + k] = keep[i];
+    }
+    __syncthreads();
+    return true;
+}
+
+/* ------------------------------------------------------------------ the kernel */
+template <int M, int FMT, bool STEP1>
+__global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ FastArgs args) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const size_t cap = blockIdx.x;
+    if (cap >= args.n_captures) return;
+
+    unsigned char *raw = smem + cfg.off_raw;
+    float2 *fdc = reinterpret_cast<float2 *>(smem + cfg.off_fdc);
+    float *Sf = reinterpret_cast<float *>(smem + cfg.off_Sf);
+    float *hannS = reinterpret_cast<float *>(smem + cfg.off_hann);
+    float *filt = reinterpret_cast<float *>(smem + cfg.off_filt);
+    float2 *ideal = reinterpret_cast<float2 *>(smem + cfg.off_ideal);
+    Misc *ms = reinterpret_cast<Misc *>(smem + cfg.off_misc);
+
+    const int Ndft = cfg.Ndft, half = Ndft >> 1, nb = cfg.nb, Ts = cfg.Ts, P = cfg.P, Nsym = cfg.Nsym, Nmem = cfg.Nmem, fdcS = cfg.fdcS;
+    const int step = cfg.step, nint = cfg.nint, bps = cfg.bps;
+    const unsigned char *cap_base = args.iq + cap * args.stride;
+
+    /* per-thread constants: FFT twiddles of the last two levels (256-point path), timing-line correction */
+    float2 t3[3], t4[4][3];
+    if (cfg.log2_ndft == 8) {
+        const int q = tid & 15;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) t3[j] = cfg.twiddle[4 * q * (j + 1)];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) t4[jj][j] = cfg.twiddle[(q + 16 * jj) * (j + 1)];
+    }
+    const float2 ftc = cfg.ftcorr[tid];
+
+    for (int i = tid; i < Ndft; i += T) hannS[i] = cfg.hannS[i];
+    for (int i = tid; i < nb; i += T) Sf[i] = 0.0f;
+    for (int i = tid; i <= P; i += T) ideal[i] = cfg.ftideal[i % P];
+    for (int i = tid; i < M * fdcS; i += T) fdc[i] = make_float2(0.0f, 0.0f);
+    if (tid == 0) {
+        mbar_init(&ms->bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        ms->pos = 0;
+        ms->nin = cfg.N;
+        ms->nin_next = cfg.N;
+        ms->frame = 0;
+        ms->flags = 0;
+        ms->fflags = 0;
+        ms->nin_prev = 0;
+        ms->pos_prev = 0;
+        for (int m = 0; m < 4; ++m) ms->dphi[m] = ms->dphi_prev[m] = make_float2(1.0f, 0.0f);
+        ms->nflag_sym = 0;
+        ms->parity = 0;
+        ms->pending = 0;
+        ms->norm_rx_timing = ms->ppm = ms->snr_est = 0.0f;
+        for (int m = 0; m < 4; ++m) ms->acc[m] = 0u;
+    }
+    __syncthreads();
+
+    /* issue the copy of raw samples [pos, pos + nin_max) (16-byte aligned superset) into `raw`; thread 0 only */
+    auto issue_raw = [&](u64 pos) {
+        const size_t a = reinterpret_cast<size_t>(cap_base) + pos * bps;
+        size_t want_end = a + (size_t)cfg.nin_max * bps;
+        const size_t cap_end = reinterpret_cast<size_t>(cap_base) + args.nsamples * bps;
+        if (want_end > cap_end) want_end = cap_end;
+        const size_t lo = a & ~(size_t)15;
+        const size_t hi = (want_end + 15) & ~(size_t)15;
+        ms->roff = (int)(a - lo);
+        if (args.tma_ok && hi <= args.alloc_end && hi > lo) {
+            const unsigned bytes = (unsigned)(hi - lo);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_arrive_expect_tx(&ms->bar, bytes);
+            tma_load_1d(raw, reinterpret_cast<const void *>(lo), bytes, &ms->bar);
+            ms->use_tma = 1;
+            ms->pending = 1;
+        } else {
+            ms->use_tma = 0;
+            ms->pending = 0;
+        }
+    };
+    if (tid == 0) {
+        ms->cont = (args.max_frames > 0 && (u64)cfg.N <= args.nsamples) ? 1 : 0;
+        if (ms->cont) issue_raw(0);
+    }
+    __syncthreads();
+
+    while (ms->cont) {
+        const int nin = ms->nin, nold = Nmem - nin, frame = ms->frame;
+        const u64 pos = ms->pos;
+        /* ---- raw samples of this frame ---- */
+        if (ms->use_tma) {
+            if (tid == 0) mbar_wait(&ms->bar, (unsigned)ms->parity); /* the others block in the barrier below: no issue slots */
+        } else {
+            /* generic copy (unaligned input, or the superset would cross the end of the allocation) */
+            const unsigned char *g = cap_base + pos * bps;
+            const size_t have = (args.nsamples - pos) * bps;
+            const size_t nbytes = (size_t)cfg.nin_max * bps < have ? (size_t)cfg.nin_max * bps : have;
+            for (size_t i = tid; i < nbytes; i += T) raw[ms->roff + i] = g[i];
+        }
+        __syncthreads();
+        const unsigned char *fr = raw + ms->roff; /* sample 0 of the frame */
+
+        /* ---- A7: tone frequency estimate (exact) ---- */
+        const int numffts = nin / half - 1;
+        {
+            float2 *scratch = fdc + cfg.tailpad;                       /* row 0 beyond the tail */
+            float *mag = reinterpret_cast<float *>(fdc + fdcS + cfg.tailpad); /* row 1 beyond the tail */
+            const float tc = 0.1f, c9 = __fsub_rn(1.0f, tc);
+            if (cfg.log2_ndft == 8) {
+                const int gpr = cfg.fft_blocks_per_round; /* thread groups (blocks) per round: as many as the scratch row holds */
+                for (int j0 = 0; j0 < numffts; j0 += gpr) {
+                    const int j = j0 + (tid >> 4);
+                    if ((tid >> 4) < gpr && j < numffts)
+                        fft256_block<FMT>(cfg, tid & 15, fr + (size_t)j * half * bps, hannS, scratch + (tid >> 4) * 272, mag + (size_t)(tid >> 4) * nb, t3, t4);
+                    __syncthreads();
+                    const int nr = numffts - j0 < gpr ? numffts - j0 : gpr;
+                    for (int b = tid; b < nb; b += T) {
+                        float s = Sf[b];
+                        for (int r = 0; r < nr; ++r) s = __fadd_rn(__fmul_rn(s, c9), __fmul_rn(mag[r * nb + b], tc));
+                        Sf[b] = s;
+                    }
+                    __syncthreads();
+                }
+            } else {
+                const int per = cfg.fft_blocks_per_round;
+                for (int j0 = 0; j0 < numffts; j0 += per) {
+                    const int nr = numffts - j0 < per ? numffts - j0 : per;
+                    fft_generic<FMT>(cfg, tid, fr, j0, nr, hannS, scratch, mag);
+                    for (int b = tid; b < nb; b += T) {
+                        float s = Sf[b];
+                        for (int r = 0; r < nr; ++r) s = __fadd_rn(__fmul_rn(s, c9), __fmul_rn(mag[r * nb + b], tc));
+                        Sf[b] = s;
+                    }
+                    __syncthreads();
+                }
+            }
+            /* peak picking with blanking (warp 0) and the mask correlation (warp 1), on Sf[st, en) */
+            float *tmp = mag; /* scratch copy for the blanking */
+            if (warp == 0) {
+                for (int b = lane; b < nb; b += 32) tmp[b] = Sf[b];
+                __syncwarp();
+                int fq[4];
+                for (int it = 0; it < M; ++it) {
+                    float best = 0.0f;
+                    int bi = 0;
+                    for (int b = lane; b < nb; b += 32) {
+                        const float v = tmp[b];
+                        if (v > best) {
+                            best = v;
+                            bi = cfg.st + b;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                        if (ov > best || (ov == best && ov > 0.0f && oi < bi)) {
+                            best = ov;
+                            bi = oi;
+                        }
+                    }
+                    const int imax = bi;
+                    int lo = imax - cfg.f_zero, hi = imax + cfg.f_zero;
+                    lo = lo < cfg.st ? cfg.st : lo;
+                    hi = hi > cfg.en ? cfg.en : hi;
+                    for (int b = lo + lane; b < hi; b += 32) tmp[b - cfg.st] = 0.0f;
+                    __syncwarp();
+                    fq[it] = imax - half;
+                }
+                if (lane == 0) {
+                    /* ascending sort as upstream writes it */
+                    int i = 1;
+                    while (i < M) {
+                        if (fq[i] >= fq[i - 1])
+                            i++;
+                        else {
+                            const int j = fq[i];
+                            fq[i] = fq[i - 1];
+                            fq[i - 1] = j;
+                            if (i > 1) i--;
+                        }
+                    }
+                    for (int m = 0; m < M; ++m) {
+                        ms->freqi[m] = fq[m];
+                        ms->f_est[m] = __fmul_rn((float)fq[m], cfg.fs_over_ndft);
+                    }
+                }
+            } else if (warp == 1) {
+                float best = 0.0f;
+                int bi = cfg.st;
+                bool found = false;
+                for (int b = cfg.st + lane; b < cfg.en - cfg.len_mask; b += 32) {
+                    float corr = 0.0f;
+                    for (int k = 0; k < cfg.nmask; ++k) corr = __fadd_rn(corr, Sf[b - cfg.st + cfg.mask_pos[k]]);
+                    if (corr > best) {
+                        best = corr;
+                        bi = b;
+                        found = true;
+                    }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    const bool of = __shfl_xor_sync(0xffffffffu, (int)found, o) != 0;
+                    if (of && (!found || ov > best || (ov == best && oi < bi))) {
+                        best = ov;
+                        bi = oi;
+                        found = true;
+                    }
+                }
+                if (lane == 0) {
+                    ms->bmax = found ? bi : cfg.st;
+                    const float foff = (float)((ms->bmax - half) * cfg.Fs / Ndft);
+                    for (int m = 0; m < M; ++m) ms->f2_est[m] = __fadd_rn(foff, (float)(m * cfg.tone_spacing));
+                }
+            }
+            __syncthreads();
+            if (tid < M) {
+                const int m = tid;
+                const int ei = cfg.est_type ? ms->bmax * 4 + m : (ms->freqi[m] + half) * 4;
+                const OscEntry e = cfg.osc[ei];
+                ms->dphi_prev[m] = ms->dphi[m];
+                ms->dphi[m] = e.dphi;
+                ms->dstride[m] = e.dstride;
+                ms->step32[m] = e.step32;
+                ms->lng[m] = e.lng;
+                ms->osc_idx[m] = ei;
+            }
+            __syncthreads();
+            if (tid == 0 && args.mbox) {
+                /* tell the exact-oscillator side chain what this frame is */
+                u64 w = MBOX_VALID | ((u64)(nin == cfg.nin_min ? 0 : (nin == cfg.N ? 1 : 2)) << 48);
+                for (int m = 0; m < M; ++m) w |= (u64)ms->osc_idx[m] << (12 * m);
+                st_relaxed_u64(args.mbox + cap * (args.max_frames + 1) + frame, w); /* self-contained word: no fence */
+            }
+        }
+
+        /* ---- A8: mix the nin new samples down with each tone (fast): pairs of samples, a thread steps 2T samples ---- */
+        {
+            const int par = nold & 1; /* pairs start where nold + j is even: 16-byte stores */
+            const int npairs = (nin + par + 1) >> 1;
+            float2 p0[M], p1[M], D[M];
+            const int j0 = 2 * tid - par;
+#pragma unroll
+            for (int m = 0; m < M; ++m) {
+                const unsigned ph = ms->acc[m] + (unsigned)(j0 + 1) * ms->step32[m];
+                float sn, cs;
+                sincospif((float)(int)ph * 4.656612873077393e-10f, &sn, &cs); /* 2^-31: pi*x = 2 pi * turns */
+                const float amp = cfg.in_scale * fmaf((float)(j0 + 1), ms->lng[m], 1.0f);
+                p0[m] = make_float2(cs * amp, sn * amp);
+                p1[m] = fcmul(p0[m], ms->dphi[m]);
+                D[m] = ms->dstride[m];
+            }
+            const bool al4 = FMT == PIRIP_FMT_U8 && (((ms->roff - 2 * par) & 3) == 0);
+            const unsigned char *p = fr + (ptrdiff_t)j0 * bps;
+            float2 *dst = fdc + nold + j0;
+            for (int q = tid; q < npairs; q += T, p += 2 * T * bps, dst += 2 * T) {
+                const int j = 2 * q - par;
+                float2 x0, x1;
+                if (al4) {
+                    const unsigned w = *reinterpret_cast<const unsigned *>(p);
+                    x0 = make_float2(u8m127(w, 0), u8m127(w, 1));
+                    x1 = make_float2(u8m127(w, 2), u8m127(w, 3));
+                } else {
+                    x0 = j >= 0 ? raw_cvt<FMT>(p) : make_float2(0.0f, 0.0f);
+                    x1 = raw_cvt<FMT>(p + bps);
+                }
+                const bool full = j >= 0 && j + 1 < nin;
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const float2 y0 = fmix(x0, p0[m]), y1 = fmix(x1, p1[m]);
+                    if (full)
+                        *reinterpret_cast<float4 *>(dst + m * fdcS) = make_float4(y0.x, y0.y, y1.x, y1.y);
+                    else if (j >= 0)
+                        dst[m * fdcS] = y0;
+                    else if (j + 1 < nin)
+                        dst[m * fdcS + 1] = y1;
+                    p0[m] = fcmul(p0[m], D[m]);
+                    p1[m] = fcmul(p1[m], D[m]);
+                }
+            }
+        }
+        __syncthreads();
+        /* raw is free: fetch the next frame (its start is known, its length is not: fetch the longest) */
+        if (tid == 0) {
+            const u64 npos = pos + (u64)nin;
+            ms->parity ^= ms->use_tma;
+            if ((size_t)frame + 1 < args.max_frames && npos + (u64)cfg.nin_min <= args.nsamples)
+                issue_raw(npos);
+            else {
+                ms->pending = 0;
+                ms->use_tma = 0;
+            }
+        }
+
+        /* ---- A9/A10: sliding-window integrators, window energies, timing line (fast) ---- */
+        {
+            float tr = 0.0f, ti = 0.0f;
+            const int i0 = tid * cfg.RO;
+            if (i0 < nint) {
+                const int cnt = nint - i0 < cfg.RO ? nint - i0 : cfg.RO;
+                if (STEP1) {
+                    /* step == 1, Ts even, RO even: two outputs per iteration, 16-byte loads (window starts are even) */
+                    const float4 *r4[M];
+                    float2 S[M];
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        r4[m] = reinterpret_cast<const float4 *>(fdc + m * fdcS + i0);
+                        float2 a = make_float2(0.0f, 0.0f), b = make_float2(0.0f, 0.0f);
+                        for (int k = 0; k < (Ts >> 1); ++k) {
+                            const float4 v = r4[m][k];
+                            a = xadd(a, make_float2(v.x, v.y));
+                            b = xadd(b, make_float2(v.z, v.w));
+                        }
+                        S[m] = xadd(a, b);
+                    }
+                    const int hTs = Ts >> 1;
+                    int ip = i0 % P;
+#pragma unroll 2
+                    for (int o = 0; o < cnt; o += 2) {
+                        float e0 = 0.0f, e1 = 0.0f;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) {
+                            const float4 ov = r4[m][o >> 1], nv = r4[m][hTs + (o >> 1)];
+                            e0 += fmaf(S[m].x, S[m].x, S[m].y * S[m].y);
+                            const float2 S1 = xadd(S[m], xsub(make_float2(nv.x, nv.y), make_float2(ov.x, ov.y)));
+                            e1 += fmaf(S1.x, S1.x, S1.y * S1.y);
+                            S[m] = xadd(S1, xsub(make_float2(nv.z, nv.w), make_float2(ov.z, ov.w)));
+                        }
+                        const float2 w0 = ideal[ip], w1 = ideal[ip + 1]; /* the table holds P + 1 entries: no wrap inside a pair */
+                        if (o + 1 >= cnt) e1 = 0.0f;
+                        tr = fmaf(e0, w0.x, tr);
+                        ti = fmaf(e0, w0.y, ti);
+                        tr = fmaf(e1, w1.x, tr);
+                        ti = fmaf(e1, w1.y, ti);
+                        ip += 2;
+                        if (ip >= P) ip -= P;
+                    }
+                } else {
+                    float2 S[M];
+                    const float2 *r[M];
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        r[m] = fdc + m * fdcS + i0 * step;
+                        float2 a = make_float2(0.0f, 0.0f);
+                        for (int k = 0; k < Ts; ++k) a = xadd(a, r[m][k]);
+                        S[m] = a;
+                    }
+                    int ip = i0 % P;
+                    for (int o = 0; o < cnt; ++o) {
+                        float e = 0.0f;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) e += fmaf(S[m].x, S[m].x, S[m].y * S[m].y);
+                        const float2 w = ideal[ip];
+                        tr = fmaf(e, w.x, tr);
+                        ti = fmaf(e, w.y, ti);
+                        ip = ip + 1 == P ? 0 : ip + 1;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) {
+                            for (int k = 0; k < step; ++k) S[m] = xadd(S[m], xsub(r[m][Ts + k], r[m][k]));
+                            r[m] += step;
+                        }
+                    }
+                }
+                /* the scalar recursion's timing oscillator over this run, relative to the ideal one */
+                const float cr = fmaf(tr, ftc.x, -ti * ftc.y), ci = fmaf(tr, ftc.y, ti * ftc.x);
+                tr = cr;
+                ti = ci;
+            }
+            tr = warp_sum(tr);
+            ti = warp_sum(ti);
+            if (lane == 0) {
+                ms->red[warp][0] = tr;
+                ms->red[warp][1] = ti;
+            }
+        }
+        __syncthreads();
+
+        /* ---- A10: timing estimate, nin for the next call, interpolation weights (thread 0) ---- */
+        if (tid == 0) {
+            const float tcr = ms->red[0][0] + ms->red[1][0], tci = ms->red[0][1] + ms->red[1][1];
+            int fl = 0;
+            if (isnan(tcr) || isnan(tci)) fl |= FLAG_NAN;
+            const float norm = atan2f(tci, tcr) * 0.15915494309189535f;
+            const float rx_timing = norm * (float)P;
+            const float d = norm - ms->norm_rx_timing;
+            ms->red[0][7] = ms->norm_rx_timing; /* for an exact replay of this frame */
+            ms->red[0][6] = ms->ppm;
+            ms->norm_rx_timing = norm;
+            if (fabsf(fabsf(d) - 0.2f) < cfg.g_tim) fl |= FLAG_PPM;
+            if (fabsf(d) < 0.2f) ms->ppm = 0.9f * ms->ppm + 0.1f * (1e6f * d / (float)Nsym);
+            int nn = nin;
+            if (!cfg.fixed_nin) {
+                if (fabsf(fabsf(norm) - 0.25f) < cfg.g_tim) fl |= FLAG_TIM;
+                nn = norm > 0.25f ? cfg.N + Ts / 4 : (norm < -0.25f ? cfg.N - Ts / 4 : cfg.N);
+            }
+            ms->nin_next = nn;
+            const float lowf = floorf(rx_timing);
+            ms->low = (int)lowf;
+            ms->high = (int)ceilf(rx_timing);
+            ms->fract = rx_timing - lowf;
+            ms->omf = 1.0f - ms->fract;
+            ms->rx_timing = rx_timing;
+            ms->fflags = fl;
+        }
+        __syncthreads();
+
+        /* ---- A11: resample at the timing instant, decide, per-symbol statistics (fast, guarded) ---- */
+        {
+            const int low = ms->low;
+            const float fr_w = ms->fract, omf = ms->omf;
+            const int L = Ts + step, per = (L + 3) >> 2;
+            float s_sig = 0.0f, s_nse = 0.0f, s_mean = 0.0f;
+            int fl = 0;
+            unsigned char *bo = args.bits ? args.bits + (cap * args.max_frames + (size_t)frame) * (size_t)cfg.Nbits : nullptr;
+            float *fo = args.rx_filt ? args.rx_filt + (cap * args.max_frames + (size_t)frame) * (size_t)(M * Nsym) : nullptr;
+            const int ntask = (Nsym * 4 + 31) & ~31;
+            for (int task = tid; task < ntask; task += T) {
+                const int sym = task >> 2, sub = task & 3;
+                const bool valid = sym < Nsym;
+                const int base = ((sym + 1) * P + low) * step;
+                const int k0 = sub * per, k1 = (k0 + per < L) ? k0 + per : L;
+                float2 t[M];
+#pragma unroll
+                for (int m = 0; m < M; ++m) t[m] = make_float2(0.0f, 0.0f);
+                if (valid) {
+                    /* entries [0, step) leave the window (weight 1 - fract), [Ts, Ts + step) enter it (weight fract) */
+                    int k = k0;
+                    for (; k < k1 && k < step; ++k)
+#pragma unroll
+                        for (int m = 0; m < M; ++m) {
+                            const float2 v = fdc[m * fdcS + base + k];
+                            t[m].x = fmaf(omf, v.x, t[m].x);
+                            t[m].y = fmaf(omf, v.y, t[m].y);
+                        }
+                    const int kmid = k1 < Ts ? k1 : Ts;
+                    for (; k < kmid; ++k)
+#pragma unroll
+                        for (int m = 0; m < M; ++m) t[m] = xadd(t[m], fdc[m * fdcS + base + k]);
+                    for (; k < k1; ++k)
+#pragma unroll
+                        for (int m = 0; m < M; ++m) {
+                            const float2 v = fdc[m * fdcS + base + k];
+                            t[m].x = fmaf(fr_w, v.x, t[m].x);
+                            t[m].y = fmaf(fr_w, v.y, t[m].y);
+                        }
+                }
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    t[m].x += __shfl_xor_sync(0xffffffffu, t[m].x, 1);
+                    t[m].y += __shfl_xor_sync(0xffffffffu, t[m].y, 1);
+                    t[m].x += __shfl_xor_sync(0xffffffffu, t[m].x, 2);
+                    t[m].y += __shfl_xor_sync(0xffffffffu, t[m].y, 2);
+                }
+                if (valid && sub == 0) {
+                    float e[M];
+                    float mx = 0.0f, sum = 0.0f, second = 0.0f;
+                    int symv = 0;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        e[m] = fmaf(t[m].x, t[m].x, t[m].y * t[m].y);
+                        sum += e[m];
+                    }
+                    mx = e[0];
+#pragma unroll
+                    for (int m = 1; m < M; ++m)
+                        if (e[m] > mx) {
+                            mx = e[m];
+                            symv = m;
+                        }
+                    second = -1.0f;
+#pragma unroll
+                    for (int m = 0; m < M; ++m)
+                        if (m != symv && e[m] > second) second = e[m];
+                    if (mx - second <= cfg.g_sym * (mx + second) && mx > 0.0f) { /* a 0 == 0 tie (zero input) is exact */
+                        fl |= FLAG_SYM;
+                        atomicAdd(&ms->nflag_sym, 1);
+                    }
+                    if (bo) {
+                        if (M == 2)
+                            bo[sym] = (unsigned char)(symv == 1);
+                        else {
+                            bo[2 * sym + 1] = (unsigned char)(symv & 1);
+                            bo[2 * sym] = (unsigned char)((symv & 2) >> 1);
+                        }
+                    }
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const float rf = sqrtf(e[m]);
+                        filt[m * Nsym + sym] = rf;
+                        if (fo) fo[m * Nsym + sym] = rf;
+                    }
+                    s_sig += mx;
+                    s_nse += (sum - mx) / (float)(M - 1);
+                    s_mean += sqrtf(mx);
+                }
+            }
+            s_sig = warp_sum(s_sig);
+            s_nse = warp_sum(s_nse);
+            s_mean = warp_sum(s_mean);
+            if (lane == 0) {
+                ms->red[warp][2] = s_sig;
+                ms->red[warp][3] = s_nse;
+                ms->red[warp][4] = s_mean;
+            }
+            if (fl) atomicOr(&ms->fflags, fl);
+        }
+        __syncthreads();
+
+        /* ---- a decision inside its margin: replay the frame exactly (rare) ---- */
+        bool replayed = false;
+        if (ms->fflags && args.mbox) {
+            replayed = exact_frame_replay<M, FMT>(cfg, args, smem, cap, frame, nin, pos);
+            if (!replayed && tid == 0 && args.replays) atomicAdd(args.replays + 1, 1);
+        }
+
+        /* ---- stats of the frame, the record, loop control (thread 0) ---- */
+        if (tid == 0 && !replayed) {
+            const float nsymf = (float)Nsym;
+            const float sig = (ms->red[0][2] + ms->red[1][2]) / nsymf;
+            const float nse = (1e-12f + ms->red[0][3] + ms->red[1][3]) / nsymf;
+            float meanebno = (ms->red[0][4] + ms->red[1][4]) / nsymf;
+            float stdebno = sig - meanebno * meanebno;
+            stdebno = stdebno > 0.0f ? sqrtf(stdebno) : 0.0f;
+            ms->rx_sig_pow = sig;
+            ms->rx_nse_pow = nse;
+            ms->v_est = sqrtf(sig - nse);
+            ms->SNRest = sig / nse;
+            ms->EbNodB = -6.0f + 20.0f * log10f((1e-6f + meanebno) / (1e-6f + stdebno));
+            ms->snr_est = 0.5f * ms->snr_est + 0.5f * ms->EbNodB;
+        }
+        if (tid == 0) {
+            if (ms->fflags && !replayed) ms->flags |= ms->fflags;
+            ms->fflags = 0;
+            const float sig = ms->rx_sig_pow, nse = ms->rx_nse_pow;
+            const float *fe = cfg.est_type ? ms->f2_est : ms->f_est;
+            ms->foff = (float)((cfg.f1_tx + cfg.f1_tx + cfg.tone_spacing) / 2) - (fe[0] + fe[1]) / 2.0f;
+            if (args.stats) {
+                pirip_frame_stats *st = &args.stats[cap * args.max_frames + (size_t)frame];
+                for (int m = 0; m < 4; ++m) {
+                    st->f_est[m] = m < M ? ms->f_est[m] : 0.0f;
+                    st->f2_est[m] = m < M ? ms->f2_est[m] : 0.0f;
+                }
+                st->norm_rx_timing = ms->norm_rx_timing;
+                st->ppm = ms->ppm;
+                st->SNRest = ms->SNRest;
+                st->v_est = ms->v_est;
+                st->rx_sig_pow = sig;
+                st->rx_nse_pow = nse;
+                st->EbNodB = ms->EbNodB;
+                st->snr_est = ms->snr_est;
+                st->foff = ms->foff;
+                st->rx_timing = ms->rx_timing;
+                st->nin_next = ms->nin_next;
+                st->sample_offset = (int32_t)pos;
+            }
+            /* advance */
+            for (int m = 0; m < M; ++m) ms->acc[m] += (unsigned)nin * ms->step32[m];
+            ms->nin_prev = nin;
+            ms->pos_prev = pos;
+            ms->pos = pos + (u64)nin;
+            ms->nin = ms->nin_next;
+            ms->frame = frame + 1;
+            int cont = ((size_t)(frame + 1) < args.max_frames && ms->pos + (u64)ms->nin <= args.nsamples) ? 1 : 0;
+            if (ms->flags && cfg.exit_on_flag) cont = 0;
+            if (ms->flags && (ms->flags >> 8) == 0) ms->flags |= ((frame + 1) & 0xfff) << 8;
+            ms->cont = cont;
+        }
+        __syncthreads();
+
+        /* ---- A12: LLRs (fast) ---- */
+        if (cfg.soft && args.llr) {
+            float *lo = args.llr + (cap * args.max_frames + (size_t)frame) * (size_t)cfg.Nbits;
+            const float scale = 2.0f * ms->SNRest, v = ms->v_est;
+            for (int sym = tid; sym < Nsym; sym += T) {
+                constexpr int BPS = M == 2 ? 1 : 2;
+                float num[2] = { -1000000.0f, -1000000.0f }, den[2] = { -1000000.0f, -1000000.0f };
+#pragma unroll
+                for (int m = 0; m < M; ++m) {
+                    const float yr = filt[m * Nsym + sym];
+                    const float env = sqrtf(yr * yr / (v * v));
+                    const float metric = logbessi0_f(scale * env);
+                    int mask = 1 << (BPS - 1);
+#pragma unroll
+                    for (int k = 0; k < BPS; ++k) {
+                        if (mask & m)
+                            num[k] = max_star0_f(num[k], metric);
+                        else
+                            den[k] = max_star0_f(den[k], metric);
+                        mask >>= 1;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < BPS; ++k) lo[sym * BPS + k] = -(num[k] - den[k]);
+            }
+        }
+        /* ---- keep the tail of the baseband memory for the next frame ---- */
+        {
+            const int nold2 = Nmem - ms->nin; /* ms->nin is already the next frame's nin */
+            for (int i = tid; i < M * nold2; i += T) {
+                const int m = i / nold2, k = i - m * nold2;
+                fdc[m * fdcS + k] = fdc[m * fdcS + (Nmem - nold2) + k];
+            }
+        }
+        __syncthreads();
+    }
+
+    /* a bulk copy still in flight must land before the CTA retires */
+    if (ms->pending && ms->use_tma) mbar_wait(&ms->bar, (unsigned)ms->parity);
+    if (tid == 0) {
+        if (args.mbox) {
+            st_relaxed_u64(args.mbox + cap * (args.max_frames + 1) + ms->frame, MBOX_VALID | MBOX_END);
+            st_relaxed_s32(args.afin + cap, 1);
+        }
+        if (args.nframes) args.nframes[cap] = ms->frame;
+        int fl = ms->flags;
+        if (fl) fl |= (ms->nflag_sym > 2047 ? 2047 : ms->nflag_sym) << 20; /* bits 20..30: symbols inside the margin */
+        if (args.flags) args.flags[cap] = fl;
+        if (fl && args.flag_list && args.flag_count) {
+            const int slot = atomicAdd(args.flag_count, 1);
+            args.flag_list[slot] = (int)cap;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ host side */
+struct cpx {
+    float re, im;
+};
+inline cpx cmulf(cpx a, cpx b) { return cpx{ a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re }; }
+
+inline int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct FskFastPlan {
+    FastCfg cfg;
+    int M, fmt, device;
+    float *d_hannS = nullptr;
+    float2 *d_ideal = nullptr, *d_corr = nullptr;
+    OscEntry *d_osc = nullptr;
+    int *d_flags = nullptr, *d_list = nullptr, *d_count = nullptr; /* d_count: one counter per chunk of a host-buffer call */
+    size_t cap_flags = 0;
+    /* exact-oscillator side chain */
+    u64 *d_mbox = nullptr;
+    float4 *d_ckpt = nullptr;
+    int *d_afin = nullptr, *d_replays = nullptr;
+    size_t cap_mbox = 0, cap_chain = 0;
+    int ckpt_per_frame = 0;
+    bool chain = true;
+    size_t chain_smem = 0;
+    static const int kSide = 4;
+    cudaStream_t side[kSide] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t ev_a[kSide] = { nullptr, nullptr, nullptr, nullptr }, ev_b[kSide] = { nullptr, nullptr, nullptr, nullptr };
+    std::string desc;
+};
+
+template <int M, int FMT, bool STEP1>
+static cudaError_t fast_launch_t(const FskFastPlan *p, const FastArgs &a, cudaStream_t stream, bool prepare_only) {
+    auto kern = fsk_fast_kernel<M, FMT, STEP1>;
+    if (prepare_only) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p->cfg.smem_bytes);
+    kern<<<(unsigned)a.n_captures, T, (size_t)p->cfg.smem_bytes, stream>>>(p->cfg, a);
+    return cudaGetLastError();
+}
+
+static cudaError_t fast_dispatch(const FskFastPlan *p, const FastArgs &a, cudaStream_t stream, bool prepare_only) {
+    /* the paired integrator needs step == 1 and even Ts, RO, nint */
+    const bool s1 = p->cfg.step == 1 && (p->cfg.Ts & 1) == 0 && (p->cfg.RO & 1) == 0 && (p->cfg.nint & 1) == 0;
+#define D(MM, FF)                                                                                       \
+    if (p->M == MM && p->fmt == FF)                                                                     \
+        return s1 ? fast_launch_t<MM, FF, true>(p, a, stream, prepare_only) : fast_launch_t<MM, FF, false>(p, a, stream, prepare_only);
+    D(2, PIRIP_FMT_U8)
+    D(2, PIRIP_FMT_S16)
+    D(2, PIRIP_FMT_F32)
+    D(4, PIRIP_FMT_U8)
+    D(4, PIRIP_FMT_S16)
+    D(4, PIRIP_FMT_F32)
+#undef D
+    return cudaErrorInvalidValue;
+}
+
+void fsk_fast_plan_destroy(FskFastPlan *p) {
+    if (!p) return;
+    cudaFree(p->d_hannS);
+    cudaFree(p->d_ideal);
+    cudaFree(p->d_corr);
+    cudaFree(p->d_osc);
+    cudaFree(p->d_flags);
+    cudaFree(p->d_list);
+    cudaFree(p->d_count);
+    cudaFree(p->d_mbox);
+    cudaFree(p->d_ckpt);
+    cudaFree(p->d_afin);
+    cudaFree(p->d_replays);
+    for (int i = 0; i < FskFastPlan::kSide; ++i) {
+        if (p->side[i]) cudaStreamDestroy(p->side[i]);
+        if (p->ev_a[i]) cudaEventDestroy(p->ev_a[i]);
+        if (p->ev_b[i]) cudaEventDestroy(p->ev_b[i]);
+    }
+    delete p;
+}
+
+FskFastPlan *fsk_fast_plan_create(const pirip_fsk_cfg &c, const FskDevCfg &d, const float *h_hann, const float2 *h_phi_ft, int device,
+                                  std::string &why) {
+    FskFastPlan *p = new FskFastPlan();
+    p->M = c.M;
+    p->fmt = c.fmt;
+    p->device = device;
+    FastCfg &f = p->cfg;
+    memset(&f, 0, sizeof f);
+    f.Fs = d.Fs; f.Rs = d.Rs; f.P = d.P; f.Nsym = d.Nsym; f.Ts = d.Ts; f.N = d.N; f.Nmem = d.Nmem; f.Ndft = d.Ndft;
+    f.Nbits = d.Nbits; f.nint = d.nint; f.step = d.Ts / d.P;
+    f.st = d.st; f.en = d.en; f.nb = d.en - d.st; f.f_zero = d.f_zero; f.est_type = d.est_type;
+    f.tone_spacing = d.tone_spacing; f.f1_tx = d.f1_tx; f.fixed_nin = (d.burst_mode || d.lock_nin) ? 1 : 0; f.soft = d.soft;
+    f.nmask = d.nmask; f.len_mask = d.len_mask;
+    for (int i = 0; i < FSK_MAX_MASK; ++i) f.mask_pos[i] = d.mask_pos[i];
+    f.log2_ndft = d.log2_ndft; f.nfac = d.nfac;
+    for (int i = 0; i < FSK_MAX_FFT_FACTORS; ++i) {
+        f.fac_p[i] = d.fac_p[i];
+        f.fac_m[i] = d.fac_m[i];
+        f.fac_fstride[i] = d.fac_fstride[i];
+    }
+    f.nin_max = d.N + d.Ts / 4;
+    f.nin_min = d.N - d.Ts / 4;
+    f.bps = c.fmt == PIRIP_FMT_U8 ? 2 : (c.fmt == PIRIP_FMT_S16 ? 4 : 8);
+    f.fs_over_ndft = d.fs_over_ndft;
+    f.in_scale = c.fmt == PIRIP_FMT_U8 ? 0.0078125f : 1.0f;
+    f.g_sym = 2e-5f;
+    f.g_tim = 1e-5f;
+    if (const char *e = getenv("PIRIP_FSK_GUARD_SYM")) f.g_sym = (float)atof(e);
+    if (const char *e = getenv("PIRIP_FSK_GUARD_TIM")) f.g_tim = (float)atof(e);
+    f.exit_on_flag = 1;
+    if (const char *e = getenv("PIRIP_FSK_FAST_NO_EXIT")) f.exit_on_flag = atoi(e) ? 0 : 1;
+    if (f.nb <= 0 || f.step < 1 || d.Nsym < 3 || f.nint > T * 256) {
+        why = "configuration outside the fast kernel's range";
+        delete p;
+        return nullptr;
+    }
+    /* integrator outputs per thread: even (16-byte aligned window starts), half of it odd (bank spread) */
+    f.RO = (f.nint + T - 1) / T;
+    if (f.RO & 1) f.RO++;
+    f.tailpad = align_up(2 * d.Ts + d.Ts / 4 + 2, TAILPAD_MIN);
+    if (f.tailpad < 16) f.tailpad = 16;
+
+    /* shared memory layout */
+    f.raw_bytes = align_up(f.nin_max * f.bps + 32, 16);
+    f.fdcS = align_up(d.Nmem, 8) + 8;
+    while ((f.fdcS & 15) != 8) f.fdcS += 2;
+    /* scratch row must hold the FFT exchange / generic FFT blocks, the magnitude row the magnitudes of a round */
+    const int row_free = (f.fdcS - f.tailpad) * 8;
+    int off = 0;
+    off = 16; /* a pair of samples may start one sample before the frame */
+    f.off_raw = off; off += f.raw_bytes;
+    f.off_fdc = off; off += c.M * f.fdcS * 8;
+    f.off_Sf = off; off += align_up(f.nb * 4, 16);
+    f.off_hann = off; off += align_up(d.Ndft * 4, 16);
+    f.off_filt = off; off += align_up(c.M * d.Nsym * 4, 16);
+    f.off_ideal = off; off += align_up((d.P + 1) * 8, 16);
+    f.off_misc = off; off += align_up((int)sizeof(Misc), 16);
+    f.smem_bytes = off;
+    const int numffts_max = f.nin_max / (d.Ndft / 2) - 1;
+    if (d.log2_ndft == 8) {
+        int per = row_free / (272 * 8);
+        const int permag = row_free / (f.nb * 4);
+        if (permag < per) per = permag;
+        if (per > T / 16) per = T / 16;
+        if (per < 1) {
+            why = "fast kernel: scratch rows too small";
+            delete p;
+            return nullptr;
+        }
+        f.fft_blocks_per_round = per;
+        f.prune = (f.st >= 128 && f.en <= 128 + 32) ? 1 : 0;
+        if (getenv("PIRIP_FSK_FAST_NO_PRUNE")) f.prune = 0;
+    } else {
+        int per = row_free / (d.Ndft * 8);
+        const int permag = f.nb > 0 ? row_free / (f.nb * 4) : per;
+        if (permag < per) per = permag;
+        if (per < 1 && numffts_max > 0) {
+            why = "fast kernel: an FFT block does not fit the scratch row";
+            delete p;
+            return nullptr;
+        }
+        f.fft_blocks_per_round = per < 1 ? 1 : per;
+    }
+    if (f.smem_bytes > 227 * 1024) {
+        why = "fast kernel: more than 227 KB of shared memory";
+        delete p;
+        return nullptr;
+    }
+
+    /* tables */
+    std::vector<float> hs((size_t)d.Ndft);
+    for (int i = 0; i < d.Ndft; ++i) hs[(size_t)i] = h_hann[i] * f.in_scale; /* exact: power-of-two scale */
+    std::vector<OscEntry> osc((size_t)d.Ndft * 4);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int b = 0; b < d.Ndft; ++b)
+        for (int m = 0; m < 4; ++m) {
+            float fest;
+            if (d.est_type) {
+                const float foff = (float)((b - d.Ndft / 2) * d.Fs / d.Ndft);
+                fest = foff + (float)(m * d.tone_spacing);
+            } else
+                fest = (float)(b - d.Ndft / 2) * d.fs_over_ndft;
+            /* [U fsk.c::fsk_demod_core] dphi_m = comp_exp_j(2*M_PI*(f_est/(float)Fs)) */
+            const float th = (float)(2 * M_PI * ((fest) / (float)(d.Fs)));
+            const float cf = em_cosf(th), sf = em_sinf(th);
+            const double ang = atan2((double)sf, (double)cf);
+            const double lng = 0.5 * log((double)cf * cf + (double)sf * sf);
+            OscEntry e;
+            e.dphi = make_float2(cf, sf);
+            const double turns = ang / two_pi;
+            const double tfrac = turns - floor(turns);
+            e.step32 = (unsigned)(unsigned long long)llround(tfrac * 4294967296.0);
+            const double n2 = 2.0 * T;
+            const double gs = exp(lng * n2);
+            e.dstride = make_float2((float)(gs * cos(ang * n2)), (float)(gs * sin(ang * n2)));
+            e.lng = (float)lng;
+            e.f = fest;
+            e.pad = 0.0f;
+            osc[(size_t)b * 4 + m] = e;
+        }
+    std::vector<float2> ideal((size_t)d.P), corr((size_t)T);
+    for (int k = 0; k < d.P; ++k) ideal[(size_t)k] = make_float2((float)cos(two_pi * k / d.P), (float)sin(two_pi * k / d.P));
+    (void)cmulf;
+    for (int r = 0; r < T; ++r) {
+        double sr = 0, si = 0;
+        int cnt = 0;
+        for (int i = r * f.RO; i < (r + 1) * f.RO && i < f.nint; ++i, ++cnt) {
+            const double ir = cos(two_pi * (i % d.P) / d.P), ii = sin(two_pi * (i % d.P) / d.P);
+            /* phi_ft[i] * conj(ideal) */
+            sr += (double)h_phi_ft[i].x * ir + (double)h_phi_ft[i].y * ii;
+            si += (double)h_phi_ft[i].y * ir - (double)h_phi_ft[i].x * ii;
+        }
+        corr[(size_t)r] = cnt ? make_float2((float)(sr / cnt), (float)(si / cnt)) : make_float2(1.0f, 0.0f);
+    }
+    if (d.log2_ndft == 8) {
+        const double pi = 3.141592653589793238462643383279502884197169399375105820974944;
+        for (int k = 1; k < 4; ++k)
+            for (int j = 1; j < 4; ++j) {
+                const double phase = -2 * pi * (16 * k * j) / 256;
+                f.tw_l2[3 * (k - 1) + (j - 1)] = make_float2((float)cos(phase), (float)sin(phase));
+            }
+    }
+    bool ok = pirip::cuda_ok(cudaSetDevice(device), "cudaSetDevice") &&
+              pirip::cuda_ok(cudaMalloc(&p->d_hannS, sizeof(float) * hs.size()), "cudaMalloc hannS") &&
+              pirip::cuda_ok(cudaMalloc(&p->d_osc, sizeof(OscEntry) * osc.size()), "cudaMalloc osc") &&
+              pirip::cuda_ok(cudaMalloc(&p->d_ideal, sizeof(float2) * ideal.size()), "cudaMalloc ideal") &&
+              pirip::cuda_ok(cudaMalloc(&p->d_corr, sizeof(float2) * corr.size()), "cudaMalloc corr") &&
+              pirip::cuda_ok(cudaMalloc(&p->d_count, sizeof(int) * 64), "cudaMalloc flag count") &&
+              pirip::cuda_ok(cudaMemset(p->d_count, 0, sizeof(int) * 64), "memset flag count") &&
+              pirip::cuda_ok(cudaMemcpy(p->d_hannS, hs.data(), sizeof(float) * hs.size(), cudaMemcpyHostToDevice), "copy hannS") &&
+              pirip::cuda_ok(cudaMemcpy(p->d_osc, osc.data(), sizeof(OscEntry) * osc.size(), cudaMemcpyHostToDevice), "copy osc") &&
+              pirip::cuda_ok(cudaMemcpy(p->d_ideal, ideal.data(), sizeof(float2) * ideal.size(), cudaMemcpyHostToDevice), "copy ideal") &&
+              pirip::cuda_ok(cudaMemcpy(p->d_corr, corr.data(), sizeof(float2) * corr.size(), cudaMemcpyHostToDevice), "copy corr");
+    f.hannS = p->d_hannS;
+    f.twiddle = d.twiddle;
+    f.osc = p->d_osc;
+    f.ftideal = p->d_ideal;
+    f.ftcorr = p->d_corr;
+    f.phi_ft = d.phi_ft;
+    p->ckpt_per_frame = ck_chunks(f.nin_max) + 1;
+    /* the side chain needs launches to be asynchronous and the two kernels to run side by side: not under tools that
+       serialise kernels (Nsight Compute replay, compute-sanitizer, CUDA_LAUNCH_BLOCKING) - there the fast kernel flags and
+       the exact kernel re-runs the flagged captures */
+    p->chain = getenv("PIRIP_FSK_NO_CHAIN") == nullptr && getenv("CUDA_INJECTION64_PATH") == nullptr &&
+               getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") == nullptr &&
+               !(getenv("CUDA_LAUNCH_BLOCKING") != nullptr && atoi(getenv("CUDA_LAUNCH_BLOCKING")) != 0);
+    p->chain_smem = 0; /* 0: chain warps share SMs with the fast kernel */
+    if (const char *ev = getenv("PIRIP_FSK_CHAIN_SMEM_KB")) p->chain_smem = (size_t)atoi(ev) * 1024;
+    if (p->chain_smem > 0)
+        ok = ok && pirip::cuda_ok(c.M == 2 ? cudaFuncSetAttribute(fsk_osc_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->chain_smem)
+                                           : cudaFuncSetAttribute(fsk_osc_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->chain_smem),
+                                  "cudaFuncSetAttribute (chain kernel)");
+    ok = ok && pirip::cuda_ok(cudaMalloc(&p->d_replays, sizeof(int) * 8), "cudaMalloc replays") &&
+         pirip::cuda_ok(cudaMemset(p->d_replays, 0, sizeof(int) * 8), "memset replays");
+    FastArgs dummy;
+    memset(&dummy, 0, sizeof dummy);
+    ok = ok && pirip::cuda_ok(fast_dispatch(p, dummy, nullptr, true), "cudaFuncSetAttribute (fast kernel)");
+    if (!ok) {
+        why = pirip::last_error();
+        fsk_fast_plan_destroy(p);
+        return nullptr;
+    }
+    char buf[256];
+    snprintf(buf, sizeof buf, "fsk_fast_kernel<M=%d>: one CTA of %d threads per capture, %d B dynamic smem, guards sym %.1e tim %.1e; flagged captures re-run by the exact kernel",
+             c.M, T, f.smem_bytes, (double)f.g_sym, (double)f.g_tim);
+    p->desc = buf;
+    return p;
+}
+
+const char *fsk_fast_plan_desc(const FskFastPlan *p) { return p ? p->desc.c_str() : ""; }
+
+/* device buffers for the flags of a launch: [n] flags, [n] list, count */
+cudaError_t fsk_fast_flag_buffers(FskFastPlan *p, size_t n, int **flags, int **list, int **count) {
+    if (n > p->cap_flags) {
+        cudaFree(p->d_flags);
+        cudaFree(p->d_list);
+        p->d_flags = p->d_list = nullptr;
+        p->cap_flags = 0;
+        cudaError_t e = cudaMalloc(&p->d_flags, sizeof(int) * n);
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc(&p->d_list, sizeof(int) * n);
+        if (e != cudaSuccess) return e;
+        p->cap_flags = n;
+    }
+    *flags = p->d_flags;
+    *list = p->d_list;
+    *count = p->d_count;
+    return cudaSuccess;
+}
+
+/* replays of the plan so far: [0] frames replayed exactly, [1] replays that could not be done (side chain late / absent) */
+cudaError_t fsk_fast_replay_counts(FskFastPlan *p, int out[8]) { return cudaMemcpy(out, p->d_replays, sizeof(int) * 8, cudaMemcpyDeviceToHost); }
+
+static cudaError_t chain_buffers(FskFastPlan *p, size_t n, size_t max_frames) {
+    const size_t need_mbox = n * (max_frames + 1);
+    if (need_mbox > p->cap_mbox) {
+        cudaFree(p->d_mbox);
+        p->d_mbox = nullptr;
+        p->cap_mbox = 0;
+        cudaError_t e = cudaMalloc(&p->d_mbox, sizeof(u64) * need_mbox);
+        if (e != cudaSuccess) return e;
+        p->cap_mbox = need_mbox;
+    }
+    if (n > p->cap_chain) {
+        cudaFree(p->d_ckpt);
+        cudaFree(p->d_afin);
+        p->d_ckpt = nullptr;
+        p->d_afin = nullptr;
+        p->cap_chain = 0;
+        cudaError_t e = cudaMalloc(&p->d_ckpt, sizeof(float4) * n * 2 * p->ckpt_per_frame * 4);
+        if (e != cudaSuccess) return e;
+        e = cudaMalloc(&p->d_afin, sizeof(int) * n);
+        if (e != cudaSuccess) return e;
+        p->cap_chain = n;
+    }
+    return cudaSuccess;
+}
+
+/* `off` / `total`: position of this launch's captures inside the buffers of a chunked host-buffer call; `slot`: which side
+   stream / event pair the chunk uses */
+cudaError_t fsk_fast_launch(FskFastPlan *p, const FskBatchArgs &b, int *d_flags, int *d_list, int *d_count, cudaStream_t stream,
+                            size_t off, size_t total, size_t slot) {
+    FastArgs a;
+    memset(&a, 0, sizeof a);
+    a.iq = b.iq;
+    a.stride = b.capture_stride_bytes;
+    a.nsamples = b.samples_per_capture;
+    a.max_frames = b.max_frames;
+    a.n_captures = b.n_captures;
+    a.alloc_end = (reinterpret_cast<size_t>(b.iq) + (b.n_captures - 1) * b.capture_stride_bytes + b.samples_per_capture * (size_t)p->cfg.bps) & ~(size_t)15;
+    a.bits = b.bits;
+    a.llr = b.llr;
+    a.rx_filt = b.rx_filt;
+    a.stats = b.stats;
+    a.nframes = b.nframes;
+    a.flags = d_flags;
+    a.flag_list = d_list;
+    a.flag_count = d_count;
+    a.tma_ok = b.tma_ok;
+    a.ckpt_per_frame = p->ckpt_per_frame;
+    if (total < off + b.n_captures) total = off + b.n_captures;
+    const int k = (int)(slot % FskFastPlan::kSide);
+    bool chain = p->chain;
+    cudaError_t e;
+    if (chain) {
+        if ((e = chain_buffers(p, total, b.max_frames)) != cudaSuccess) return e;
+        if (!p->side[k]) {
+            if ((e = cudaStreamCreateWithFlags(&p->side[k], cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&p->ev_a[k], cudaEventDisableTiming)) != cudaSuccess) return e;
+            if ((e = cudaEventCreateWithFlags(&p->ev_b[k], cudaEventDisableTiming)) != cudaSuccess) return e;
+        }
+        a.mbox = p->d_mbox + off * (b.max_frames + 1);
+        a.ckpt = p->d_ckpt + off * (size_t)(2 * p->ckpt_per_frame * 4);
+        a.afin = p->d_afin + off;
+        a.replays = p->d_replays;
+        if ((e = cudaMemsetAsync(a.mbox, 0, sizeof(u64) * b.n_captures * (b.max_frames + 1), stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(a.ckpt, 0, sizeof(float4) * b.n_captures * 2 * p->ckpt_per_frame * 4, stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(a.afin, 0, sizeof(int) * b.n_captures, stream)) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(p->ev_a[k], stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(p->side[k], p->ev_a[k], 0)) != cudaSuccess) return e;
+        /* chain warps get SMs of their own (see the kernel): about 9 warps per CTA, one CTA per SM through a shared-memory
+           request nothing else fits beside */
+        const unsigned per = (unsigned)(32 / p->M);
+        const unsigned warps = (unsigned)((b.n_captures + per - 1) / per);
+        unsigned wpc = 9;
+        if (const char *ev = getenv("PIRIP_FSK_CHAIN_WPC"))
+            if (atoi(ev) >= 1 && atoi(ev) <= 32) wpc = (unsigned)atoi(ev);
+        if (warps < wpc) wpc = warps;
+        const unsigned grid = (warps + wpc - 1) / wpc;
+        const size_t chain_smem = p->chain_smem;
+        if (p->M == 2)
+            fsk_osc_chain_kernel<2><<<grid, 32 * wpc, chain_smem, p->side[k]>>>(p->cfg, a);
+        else
+            fsk_osc_chain_kernel<4><<<grid, 32 * wpc, chain_smem, p->side[k]>>>(p->cfg, a);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((e = cudaEventRecord(p->ev_b[k], p->side[k])) != cudaSuccess) return e;
+    }
+    if ((e = fast_dispatch(p, a, stream, false)) != cudaSuccess) return e;
+    if (chain && (e = cudaStreamWaitEvent(stream, p->ev_b[k], 0)) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+int fsk_fast_uses_chain(const FskFastPlan *p) { return p && p->chain ? 1 : 0; }

@@ -110,6 +110,10 @@ struct pirip_fsk_plan {
     unsigned short *d_perm = nullptr;
     std::vector<float> h_hann;
     std::string kernel_desc;
+    FskFastPlan *fast = nullptr; /* tolerance-mode batch kernel (fsk_fast.cu); NULL when the configuration is outside its range */
+    int mode = 1;                /* 1: fast kernel + exact re-run of flagged captures; 0: exact kernel only */
+    size_t last_n = 0;           /* captures of the last fast launch sequence (for pirip_fsk_plan_flagged) */
+    size_t last_chunks = 0;
     /* reusable device buffers of the host-buffer entry point */
     struct Work {
         static const int kStreams = 3;
@@ -450,6 +454,7 @@ static bool derive_cfg(const pirip_fsk_cfg &c, int burst_mode, int lock_nin, int
 static void plan_free(pirip_fsk_plan *p) {
     if (!p) return;
     cudaSetDevice(p->device);
+    fsk_fast_plan_destroy(p->fast);
     cudaFree(p->d_hann);
     cudaFree(p->d_tw);
     cudaFree(p->d_phi_ft);
@@ -468,7 +473,8 @@ static void plan_free(pirip_fsk_plan *p) {
     delete p;
 }
 
-static pirip_fsk_plan *plan_build(const pirip_fsk_cfg &cfg, int device, int burst_mode, int lock_nin, int max_g = FSK_MAX_G) {
+static pirip_fsk_plan *plan_build(const pirip_fsk_cfg &cfg, int device, int burst_mode, int lock_nin, int max_g = FSK_MAX_G,
+                                  bool want_fast = false) {
     std::string why;
     if (!cfg_valid(cfg, why)) {
         pirip::set_error(why);
@@ -508,6 +514,13 @@ static pirip_fsk_plan *plan_build(const pirip_fsk_cfg &cfg, int device, int burs
     p->dev.twiddle = p->d_tw;
     p->dev.phi_ft = p->d_phi_ft;
     p->dev.perm = p->d_perm;
+    /* the fast kernel hands flagged captures to the batch kernel's list mode, so it needs that kernel too */
+    if (want_fast && p->dev.k2.ok) {
+        std::string why_not;
+        p->fast = fsk_fast_plan_create(cfg, p->dev, p->h_hann.data(), pf.data(), device, why_not);
+        if (!p->fast) pirip::set_error("");
+    }
+    if (const char *e = getenv("PIRIP_FSK_MODE")) p->mode = (strcmp(e, "exact") == 0 || strcmp(e, "0") == 0) ? 0 : 1;
     return p;
 }
 
@@ -516,8 +529,56 @@ extern "C" pirip_fsk_plan *pirip_fsk_plan_create(const pirip_fsk_cfg *cfg, int d
         pirip::set_error("cfg is NULL");
         return nullptr;
     }
-    return plan_build(*cfg, device, 0, 0);
+    return plan_build(*cfg, device, 0, 0, FSK_MAX_G, true);
 }
+
+extern "C" int pirip_fsk_plan_set_mode(pirip_fsk_plan *plan, int mode) {
+    if (!plan) return pirip::fail(-1, "plan is NULL");
+    if (mode != PIRIP_FSK_MODE_EXACT && mode != PIRIP_FSK_MODE_FAST) return pirip::fail(-2, "unknown mode");
+    if (mode == PIRIP_FSK_MODE_FAST && !plan->fast) return pirip::fail(-3, "configuration outside the fast kernel's range");
+    plan->mode = mode;
+    return 0;
+}
+
+/* flags of the last batch call (fast mode): synchronises the device, copies the per-capture flag words and returns how
+   many captures were re-run by the exact kernel; 0 in exact mode */
+extern "C" long pirip_fsk_plan_flagged(pirip_fsk_plan *plan, int32_t *flags_out, size_t n) {
+    if (!plan) return pirip::fail(-1, "plan is NULL");
+    if (!(plan->fast && plan->mode) || plan->last_n == 0) return 0;
+    if (!pirip::cuda_ok(cudaSetDevice(plan->device), "cudaSetDevice")) return -10;
+    if (!pirip::cuda_ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return -13;
+    int *d_flags = nullptr, *d_list = nullptr, *d_count = nullptr;
+    if (!pirip::cuda_ok(fsk_fast_flag_buffers(plan->fast, plan->last_n, &d_flags, &d_list, &d_count), "flag buffers")) return -12;
+    int counts[64];
+    const size_t nch = plan->last_chunks < 64 ? plan->last_chunks : 64;
+    if (!pirip::cuda_ok(cudaMemcpy(counts, d_count, sizeof(int) * nch, cudaMemcpyDeviceToHost), "D2H flag counts")) return -12;
+    long total = 0;
+    for (size_t i = 0; i < nch; ++i) total += counts[i];
+    if (flags_out) {
+        const size_t m = n < plan->last_n ? n : plan->last_n;
+        if (!pirip::cuda_ok(cudaMemcpy(flags_out, d_flags, sizeof(int32_t) * m, cudaMemcpyDeviceToHost), "D2H flags")) return -12;
+    }
+    return total;
+}
+
+/* exact in-kernel frame replays of this plan so far (synchronises): out[0] replayed, out[1] replays that fell back to flagging */
+extern "C" int pirip_fsk_plan_replays(pirip_fsk_plan *plan, int32_t out[2]) {
+    if (!plan || !out) return pirip::fail(-1, "plan / out is NULL");
+    out[0] = out[1] = 0;
+    if (!plan->fast) return 0;
+    if (!pirip::cuda_ok(cudaSetDevice(plan->device), "cudaSetDevice")) return -10;
+    if (!pirip::cuda_ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return -13;
+    int v[8];
+    if (!pirip::cuda_ok(fsk_fast_replay_counts(plan->fast, v), "D2H replay counts")) return -12;
+    out[0] = v[0];
+    out[1] = v[1];
+    if (getenv("PIRIP_FSK_CHAIN_DIAG"))
+        fprintf(stderr, "side chain: replays %d failed %d, lag at capture end (max frames) %d, replay wait kcycles %d, lag at a replay (max frames) %d\n", v[0],
+                v[1], v[2], v[3], v[4]);
+    return 0;
+}
+
+extern "C" int pirip_fsk_plan_mode(const pirip_fsk_plan *plan) { return plan ? ((plan->fast && plan->mode) ? 1 : 0) : -1; }
 
 extern "C" void pirip_fsk_plan_destroy(pirip_fsk_plan *plan) { plan_free(plan); }
 
@@ -525,6 +586,10 @@ extern "C" const char *pirip_fsk_plan_kernel(const pirip_fsk_plan *plan) {
     if (!plan) return "";
     pirip_fsk_plan *p = const_cast<pirip_fsk_plan *>(plan);
     char buf[256];
+    if (plan->fast && plan->mode) {
+        p->kernel_desc = fsk_fast_plan_desc(plan->fast);
+        return p->kernel_desc.c_str();
+    }
     if (plan->dev.k2.ok)
         snprintf(buf, sizeof buf, "fsk2_kernel<M=%d, %d warps>: one persistent CTA per SM (%d SMs), up to %d captures in lockstep, %d B dynamic smem",
                  plan->dev.M, plan->dev.k2.threads / 32, plan->dev.k2.num_sms, plan->dev.k2.gmax, plan->dev.k2.smem_bytes);
@@ -549,12 +614,16 @@ static size_t bytes_per_sample(int fmt) { return fmt == PIRIP_FMT_U8 ? 2 : (fmt 
 static int batch_dev(pirip_fsk_plan *plan, const void *d_iq, size_t n_captures, size_t samples_per_capture,
                      size_t capture_stride_bytes, uint8_t *d_bits, float *d_llr, float *d_rx_filt,
                      struct pirip_frame_stats *d_stats, int32_t *d_nframes, size_t max_frames, void *stream,
-                     const unsigned long long *d_landed);
+                     const unsigned long long *d_landed, size_t flag_off = 0, size_t flag_total = 0, size_t chunk = 0);
 
 extern "C" int pirip_fsk_demod_batch_dev(pirip_fsk_plan *plan, const void *d_iq, size_t n_captures,
                                          size_t samples_per_capture, size_t capture_stride_bytes, uint8_t *d_bits,
                                          float *d_llr, float *d_rx_filt, struct pirip_frame_stats *d_stats,
                                          int32_t *d_nframes, size_t max_frames, void *stream) {
+    if (plan) {
+        plan->last_n = n_captures;
+        plan->last_chunks = 1;
+    }
     return batch_dev(plan, d_iq, n_captures, samples_per_capture, capture_stride_bytes, d_bits, d_llr, d_rx_filt, d_stats,
                      d_nframes, max_frames, stream, nullptr);
 }
@@ -562,7 +631,7 @@ extern "C" int pirip_fsk_demod_batch_dev(pirip_fsk_plan *plan, const void *d_iq,
 static int batch_dev(pirip_fsk_plan *plan, const void *d_iq, size_t n_captures, size_t samples_per_capture,
                      size_t capture_stride_bytes, uint8_t *d_bits, float *d_llr, float *d_rx_filt,
                      struct pirip_frame_stats *d_stats, int32_t *d_nframes, size_t max_frames, void *stream,
-                     const unsigned long long *d_landed) {
+                     const unsigned long long *d_landed, size_t flag_off, size_t flag_total, size_t chunk) {
     if (!plan) return pirip::fail(-1, "plan is NULL");
     if (n_captures == 0) return 0;
     if (!d_iq) return pirip::fail(-2, "d_iq is NULL");
@@ -585,6 +654,32 @@ static int batch_dev(pirip_fsk_plan *plan, const void *d_iq, size_t n_captures, 
     a.n_captures = n_captures;
     a.tma_ok = (reinterpret_cast<size_t>(d_iq) & 15) == 0 && getenv("PIRIP_FSK_NO_TMA") == nullptr;
     a.landed = plan->dev.k2.ok ? d_landed : nullptr;
+    if (plan->fast && plan->mode) {
+        /* fast kernel over every capture, then the exact kernel over the captures it flagged (list on the device) */
+        if (chunk >= 64) return pirip::fail(-6, "too many chunks");
+        int *d_flags = nullptr, *d_list = nullptr, *d_count = nullptr;
+        if (!pirip::cuda_ok(fsk_fast_flag_buffers(plan->fast, flag_total ? flag_total : n_captures, &d_flags, &d_list, &d_count), "cudaMalloc flags"))
+            return -12;
+        d_flags += flag_off;
+        d_list += flag_off;
+        d_count += chunk;
+        a.landed = nullptr;
+        if (!pirip::cuda_ok(cudaMemsetAsync(d_count, 0, sizeof(int), (cudaStream_t)stream), "reset flag count")) return -11;
+        if (!pirip::cuda_ok(fsk_fast_launch(plan->fast, a, d_flags, d_list, d_count, (cudaStream_t)stream, flag_off, flag_total, chunk),
+                            "fsk_fast_kernel launch"))
+            return -11;
+        pirip::count_launch(fsk_fast_uses_chain(plan->fast) ? 2 : 1);
+        FskBatchArgs x = a;
+        x.cap_list = d_list;
+        x.cap_count = d_count;
+        x.total_captures = n_captures;
+        /* launch bound of the re-run: one resident group per SM is more than the guards ever flag; the rest of a longer
+           list (never seen) would still be processed, group after group */
+        if (getenv("PIRIP_FSK_FAST_NO_RERUN") != nullptr) return 0; /* diagnostics: the fast kernel's own results for every capture */
+        if (!pirip::cuda_ok(fsk2_launch_demod(plan->dev, x, n_captures, (cudaStream_t)stream), "fsk2_kernel (flagged captures) launch")) return -11;
+        pirip::count_launch();
+        return 0;
+    }
     if (plan->dev.k2.ok) {
         if (!pirip::cuda_ok(fsk2_launch_demod(plan->dev, a, n_captures, (cudaStream_t)stream), "fsk2_kernel launch")) return -11;
     } else if (!pirip::cuda_ok(fsk_launch_demod(plan->dev, a, n_captures, (cudaStream_t)stream), "fsk_demod_kernel launch"))
@@ -643,8 +738,19 @@ extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_
         const size_t resident = (size_t)plan->dev.k2.num_sms * (size_t)plan->dev.k2.gmax;
         nchunks = (n_captures + resident - 1) / resident;
     }
+    const bool fast = plan->fast && plan->mode;
+    if (fast) {
+        /* the fast kernel is several times quicker than PCIe delivers the captures: split the batch by captures, copy
+           chunk k + 1 while chunk k is demodulated (plain stream order, no kernel ever waits for a copy issued after it) */
+        nchunks = 8;
+        if (const char *e = getenv("PIRIP_FSK_E2E_CHUNKS"))
+            if (atoi(e) >= 1 && atoi(e) <= 64) nchunks = (size_t)atoi(e);
+        while (nchunks > 1 && n_captures / nchunks < 64) nchunks /= 2;
+    }
     if (nchunks < 1) nchunks = 1;
     const size_t per = (n_captures + nchunks - 1) / nchunks;
+    plan->last_n = n_captures;
+    plan->last_chunks = (n_captures + per - 1) / per;
     /* Streamed ingest (batch kernel, one launch): the captures go to the device in time slices on the copy stream while
        the kernel already demodulates the first ones on the compute stream; the kernel reads d_landed before it fetches
        a frame.  PCIe and the SMs work at the same time although the batch is a single launch. */
@@ -661,7 +767,7 @@ extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_
        serialise the launch on the host, which would leave the kernel waiting for ever: copy first, then run. */
     const bool injected = getenv("CUDA_INJECTION64_PATH") != nullptr || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
                           (getenv("CUDA_LAUNCH_BLOCKING") != nullptr && atoi(getenv("CUDA_LAUNCH_BLOCKING")) != 0);
-    const bool streamed = plan->dev.k2.ok && nchunks == 1 && nslices > 1 && !injected && getenv("PIRIP_FSK_NO_STREAM_INGEST") == nullptr;
+    const bool streamed = !fast && plan->dev.k2.ok && nchunks == 1 && nslices > 1 && !injected && getenv("PIRIP_FSK_NO_STREAM_INGEST") == nullptr;
     if (rc == 0 && streamed) {
         if (!w.d_landed) CK(cudaMalloc(&w.d_landed, sizeof(unsigned long long)), "cudaMalloc landed");
         if (!w.h_marks) CK(cudaHostAlloc(&w.h_marks, 72 * sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc marks");
@@ -703,8 +809,8 @@ extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_
                                  cudaMemcpyHostToDevice, s),
                "H2D iq");
             if (rc == 0)
-                rc = pirip_fsk_demod_batch_dev(plan, d_iq, nc, samples_per_capture, stride, d_bits, d_llr, d_filt, d_stats, d_nf,
-                                               max_frames, s);
+                rc = batch_dev(plan, d_iq, nc, samples_per_capture, stride, d_bits, d_llr, d_filt, d_stats, d_nf, max_frames, s, nullptr,
+                               c0, n_captures, ci);
         }
         if (bits) CK(cudaMemcpyAsync(bits + c0 * max_frames * nb, d_bits, nc * max_frames * nb, cudaMemcpyDeviceToHost, s), "D2H bits");
         if (llr) CK(cudaMemcpyAsync(llr + c0 * max_frames * nb, d_llr, sizeof(float) * nc * max_frames * nb, cudaMemcpyDeviceToHost, s), "D2H llr");

@@ -574,7 +574,8 @@ __device__ void stage_issue(const FskDevCfg &cfg, const FskBatchArgs &args, cons
     const size_t want = (size_t)(cfg.N + cfg.Ts / 4) * bps;
     const size_t lo = a & ~(size_t)15;
     size_t hi = (a + want + 15) & ~(size_t)15;
-    const size_t safe = (base + (args.n_captures - 1) * args.capture_stride_bytes + args.samples_per_capture * bps) & ~(size_t)15;
+    const size_t batch = args.total_captures ? args.total_captures : args.n_captures;
+    const size_t safe = (base + (batch - 1) * args.capture_stride_bytes + args.samples_per_capture * bps) & ~(size_t)15;
     if (hi > safe) hi = safe;
     if (hi <= lo) return;
     const unsigned bytes = (unsigned)(hi - lo);
@@ -711,7 +712,12 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
     }
     for (int i = tid; i < nint; i += nthreads) phi_ft[i] = cfg.phi_ft[i];
 
-    const size_t ncap = args.n_captures;
+    /* list mode: only the captures the fast kernel flagged (their count is known on the device only) */
+    size_t ncap = args.n_captures;
+    if (args.cap_count) {
+        const size_t n = (size_t)*args.cap_count;
+        ncap = n < ncap ? n : ncap;
+    }
     const int grid = (int)gridDim.x;
     const int ncap_cta = ncap > blockIdx.x ? (int)((ncap - blockIdx.x + grid - 1) / grid) : 0;
 #ifdef FSK2_TIMING
@@ -784,6 +790,7 @@ __global__ void __launch_bounds__(NW * 32, 1) fsk2_kernel(const __grid_constant_
                 cs->sf_turn = 0;
                 cs->est_done = 0;
                 cs->cap = (int)(blockIdx.x + (size_t)(k0 + g) * grid);
+                if (args.cap_list) cs->cap = args.cap_list[cs->cap];
                 cs->stg_valid[0] = cs->stg_valid[1] = 0;
                 cs->stg_fills[0] = cs->stg_fills[1] = 0;
                 cs->fast = 0;

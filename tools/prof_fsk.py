@@ -35,3 +35,7 @@ e1.record(s)
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1)
 print("captures %d x %d samples: %.3f ms, %.1f Msamples/s" % (a.captures, nsamp, ms, a.captures * nsamp / ms / 1e3))
+import numpy as np
+cnt, fl = plan.flagged(a.captures)
+print("mode", plan.mode, "flagged", cnt, "reasons", {k: int(((fl & v) != 0).sum()) for k, v in (("sym", 1), ("tim", 2), ("ppm", 4), ("nan", 8))},
+      "first-frame-0:", int((((fl >> 8) & 0xfff) == 1).sum()), "replays(ok,failed)", plan.replays(), plan.kernel())
