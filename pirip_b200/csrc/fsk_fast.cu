@@ -66,6 +66,7 @@ struct FastCfg {
     const float2 *ftcorr;   /* [T] mean of (timing oscillator of the scalar recursion) / ideal over a thread's run of outputs */
     const float2 *phi_ft;   /* [nint] the timing oscillator exactly as the scalar float recursion produces it (exact replay) */
     int off_raw, raw_bytes, off_fdc, fdcS, off_Sf, off_hann, off_filt, off_ideal, off_misc, smem_bytes;
+    int group_stride;         /* shared memory per capture group (bytes, 128-byte multiple) */
     int fft_blocks_per_round; /* blocks transformed at a time: as many as fit the scratch row */
     int prune;                /* 256-point FFT: the estimator window lies inside output bins k < 32 */
     int exit_on_flag;
@@ -90,6 +91,9 @@ struct FastArgs {
     int *afin;          /* [n_captures] set by the fast kernel when it has finished a capture */
     int *replays;       /* [2] counters: frames replayed exactly, replays that failed (side chain not available in time) */
     int ckpt_per_frame;
+    /* launch geometry: the first chain_ctas CTAs run the exact-oscillator chains (chain_wpc warps each), every other CTA
+       holds G capture groups */
+    int G, chain_ctas, chain_wpc;
 };
 
 enum { FLAG_SYM = 1, FLAG_TIM = 2, FLAG_PPM = 4, FLAG_NAN = 8 };
@@ -131,6 +135,11 @@ __host__ __device__ __forceinline__ int ck_of(int nin, int j) { /* chunk holding
 }
 
 /* ------------------------------------------------------------------ small device helpers */
+/* One CTA holds up to 9 capture GROUPS of T = 64 threads; the threads of a group meet at the group's own hardware barrier
+   (bar.sync id, 64), so the groups of a CTA run independently of each other. */
+__device__ __forceinline__ void group_sync() { asm volatile("bar.sync %0, %1;" ::"r"((int)(threadIdx.x >> 6) + 1), "r"(64) : "memory"); }
+#define GSYNC() group_sync()
+
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -335,7 +344,7 @@ __device__ void fft_generic(const FastCfg &cfg, int tid, const unsigned char *fr
         const float h = hannS[n];
         buf[e] = make_float2(__fmul_rn(h, x.x), __fmul_rn(h, x.y));
     }
-    __syncthreads();
+    GSYNC();
     for (int s = cfg.nfac - 1; s >= 0; --s) {
         const int p = cfg.fac_p[s], m = cfg.fac_m[s], fs = cfg.fac_fstride[s];
         const int per_blk = Ndft / p;
@@ -357,14 +366,14 @@ __device__ void fft_generic(const FastCfg &cfg, int tid, const unsigned char *fr
                 F[0] = xadd(f0, t);
             }
         }
-        __syncthreads();
+        GSYNC();
     }
     for (int e = tid; e < nblk * cfg.nb; e += T) {
         const int b = e / cfg.nb, i = cfg.st + (e - b * cfg.nb);
         const float2 v = buf[(size_t)b * Ndft + ((i + half) & (Ndft - 1))];
         mag[(size_t)b * cfg.nb + (i - cfg.st)] = __fsqrt_rn(__fadd_rn(__fmul_rn(v.x, v.x), __fmul_rn(v.y, v.y)));
     }
-    __syncthreads();
+    GSYNC();
 }
 
 /* float log I0(x) ([U mpdecode_core.c::bessi0] polynomial in the log domain), tolerance mode */
@@ -428,14 +437,17 @@ __device__ __forceinline__ float2 ocmul(float2 a, float2 b) {
    kernel gives up after ~100 ms without any (a tool serialising the two kernels): the fast kernel then falls back to
    flagging, i.e. to the exact kernel. */
 template <int M>
-__global__ void fsk_osc_chain_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ FastArgs args) {
-    /* lane = (capture, tone): 32 / M captures per warp, every lane one serial chain of dependent multiply-adds.  The CTAs of
-       this kernel ask for most of an SM's shared memory so that they get SMs of their own: a chain warp that shares its
-       scheduler with the fast kernel's warps falls behind the frames it is meant to shadow. */
+__device__ __noinline__ void osc_chain_role(const FastCfg &cfg, const FastArgs &args) {
+    /* lane = (capture, tone): 32 / M captures per warp, every lane one serial chain of dependent multiply-adds.  The chain
+       CTAs have their SMs to themselves (one CTA per SM): a chain warp that shares its scheduler with demodulating warps
+       falls behind the frames it is meant to shadow.  A lane takes captures lane0, lane0 + LB, ... one after the other, in
+       the order the demodulating groups take them. */
+    if ((int)(threadIdx.x >> 5) >= args.chain_wpc) return;
     const int lane = threadIdx.x & 31;
     const int m = lane % M;
-    const size_t gw = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const size_t cap = gw * (32 / M) + lane / M;
+    const size_t gw = (size_t)blockIdx.x * args.chain_wpc + (threadIdx.x >> 5);
+    const size_t LB = (size_t)args.chain_ctas * args.chain_wpc * (32 / M);
+    size_t cap = gw * (32 / M) + lane / M;
     bool done = cap >= args.n_captures, have = false;
     float2 phi = make_float2(1.0f, 0.0f), dphi = make_float2(1.0f, 0.0f);
     int f = 0, k = 0, K = 0, base = 0, rem = 0;
@@ -497,10 +509,11 @@ __global__ void fsk_osc_chain_kernel(const __grid_constant__ FastCfg cfg, const 
             fin += never;
             w += (u64)never;
         }
-        if (poll_fin && fin) done = true, have = false; /* the fast kernel has finished this capture: nobody will ask any more */
+        bool next = false;
+        if (poll_fin && fin) next = true, have = false; /* the demodulator has finished this capture: nobody will ask any more */
         if (poll_box && (w & MBOX_VALID)) {
             if (w & MBOX_END)
-                done = true;
+                next = true;
             else {
                 const int code = (int)((w >> 48) & 3);
                 const int nin = code == 0 ? cfg.nin_min : (code == 1 ? cfg.N : cfg.nin_max);
@@ -510,6 +523,18 @@ __global__ void fsk_osc_chain_kernel(const __grid_constant__ FastCfg cfg, const 
                 dphi = cfg.osc[(w >> (12 * m)) & 0xfff].dphi;
                 have = true;
                 k = 0;
+            }
+        }
+        if (next) {
+            cap += LB;
+            if (cap >= args.n_captures)
+                done = true;
+            else {
+                phi = make_float2(1.0f, 0.0f);
+                f = 0;
+                box = args.mbox + cap * (args.max_frames + 1);
+                ck = args.ckpt + cap * (size_t)(2 * args.ckpt_per_frame * 4) + m;
+                afin = args.afin + cap;
             }
         }
     }
@@ -527,7 +552,7 @@ __global__ void fsk_osc_chain_kernel(const __grid_constant__ FastCfg cfg, const 
 template <int M, int FMT>
 __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastArgs &args, unsigned char *smem, size_t cap, int frame,
                                                 int nin, u64 pos) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x & (T - 1), lane = tid & 31, warp = tid >> 5;
     float2 *fdc = reinterpret_cast<float2 *>(smem + cfg.off_fdc);
     float *filt = reinterpret_cast<float *>(smem + cfg.off_filt);
     Misc *ms = reinterpret_cast<Misc *>(smem + cfg.off_misc);
@@ -544,6 +569,8 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
     const int nct = frame > 0 ? ck_chunks(nprev) - ct0 : 0;
     const int ncn = ck_chunks(nin);
     {
+        if (tid == 0) ms->rp_ok = 1;
+        GSYNC();
         int ok = (args.ckpt && Nsym <= T && cfg.tailpad <= 64) ? 1 : 0;
         const long long t0 = clock64();
         for (int task = tid; ok && task < M * (nct + ncn); task += T) {
@@ -561,7 +588,9 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
             }
         }
         if (tid == 0 && args.replays) atomicAdd(args.replays + 3, (int)((clock64() - t0) >> 10));
-        if (!__syncthreads_and(ok)) return false;
+        if (!ok) ms->rp_ok = 0;
+        GSYNC();
+        if (!ms->rp_ok) return false;
     }
 
     /* keep the fast baseband memory the next frame's tail is taken from */
@@ -573,7 +602,7 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
         const int m = e / cfg.tailpad, k = e - m * cfg.tailpad;
         keep[i] = (m < M) ? fdc[m * fdcS + Nmem - cfg.tailpad + k] : make_float2(0.0f, 0.0f);
     }
-    __syncthreads();
+    GSYNC();
 
     /* exact f_dc: the tail comes from the previous frame's last nold samples (its oscillator), then the nin new samples */
     {
@@ -606,7 +635,7 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
             }
         }
     }
-    __syncthreads();
+    GSYNC();
 
     /* window energies and the timing line, accumulated in the scalar order (warp 0; lane 0 carries the sum) */
     if (warp == 0) {
@@ -659,7 +688,7 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
             ms->fflags = fl;
         }
     }
-    __syncthreads();
+    GSYNC();
     if (ms->fflags) {
         /* not settled (NaN input, ppm threshold): leave the frame flagged */
 #pragma unroll
@@ -668,7 +697,7 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
             const int m = e / cfg.tailpad, k = e - m * cfg.tailpad;
             if (m < M) fdc[m * fdcS + Nmem - cfg.tailpad + k] = keep[i];
         }
-        __syncthreads();
+        GSYNC();
         return false;
     }
 
@@ -743,7 +772,7 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
                 ms->red[1][3] = s_mean;
             }
         }
-        __syncthreads();
+        GSYNC();
     }
     if (tid == 0) {
         const float nsymf = (float)Nsym;
@@ -766,17 +795,24 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
         const int m = e / cfg.tailpad, k = e - m * cfg.tailpad;
         if (m < M) fdc[m * fdcS + Nmem - cfg.tailpad + k] = keep[i];
     }
-    __syncthreads();
+    GSYNC();
     return true;
 }
 
 /* ------------------------------------------------------------------ the kernel */
 template <int M, int FMT, bool STEP1>
-__global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ FastArgs args) {
-    extern __shared__ __align__(128) unsigned char smem[];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const size_t cap = blockIdx.x;
-    if (cap >= args.n_captures) return;
+__global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ FastArgs args) {
+    extern __shared__ __align__(128) unsigned char smem_all[];
+    /* roles: the first chain_ctas CTAs run the exact-oscillator chains, the others demodulate (one CTA per SM either way) */
+    if ((int)blockIdx.x < args.chain_ctas) {
+        osc_chain_role<M>(cfg, args);
+        return;
+    }
+    const int grp = threadIdx.x >> 6;
+    if (grp >= args.G) return;
+    unsigned char *smem = smem_all + (size_t)grp * cfg.group_stride;
+    const int tid = threadIdx.x & (T - 1), lane = tid & 31, warp = tid >> 5;
+    const int cta_a = (int)blockIdx.x - args.chain_ctas, n_a = (int)gridDim.x - args.chain_ctas;
 
     unsigned char *raw = smem + cfg.off_raw;
     float2 *fdc = reinterpret_cast<float2 *>(smem + cfg.off_fdc);
@@ -788,7 +824,6 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
 
     const int Ndft = cfg.Ndft, half = Ndft >> 1, nb = cfg.nb, Ts = cfg.Ts, P = cfg.P, Nsym = cfg.Nsym, Nmem = cfg.Nmem, fdcS = cfg.fdcS;
     const int step = cfg.step, nint = cfg.nint, bps = cfg.bps;
-    const unsigned char *cap_base = args.iq + cap * args.stride;
 
     /* per-thread constants: FFT twiddles of the last two levels (256-point path), timing-line correction */
     float2 t3[3], t4[4][3];
@@ -804,8 +839,12 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
     const float2 ftc = cfg.ftcorr[tid];
 
     for (int i = tid; i < Ndft; i += T) hannS[i] = cfg.hannS[i];
-    for (int i = tid; i < nb; i += T) Sf[i] = 0.0f;
     for (int i = tid; i <= P; i += T) ideal[i] = cfg.ftideal[i % P];
+    /* group (cta_a, grp) takes captures grp * n_a + cta_a, then every n_a * G-th one after it */
+    for (size_t cap = (size_t)grp * n_a + cta_a; cap < args.n_captures; cap += (size_t)n_a * args.G) {
+    const unsigned char *cap_base = args.iq + cap * args.stride;
+    GSYNC();
+    for (int i = tid; i < nb; i += T) Sf[i] = 0.0f;
     for (int i = tid; i < M * fdcS; i += T) fdc[i] = make_float2(0.0f, 0.0f);
     if (tid == 0) {
         mbar_init(&ms->bar, 1);
@@ -825,7 +864,7 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
         ms->norm_rx_timing = ms->ppm = ms->snr_est = 0.0f;
         for (int m = 0; m < 4; ++m) ms->acc[m] = 0u;
     }
-    __syncthreads();
+    GSYNC();
 
     /* issue the copy of raw samples [pos, pos + nin_max) (16-byte aligned superset) into `raw`; thread 0 only */
     auto issue_raw = [&](u64 pos) {
@@ -852,7 +891,7 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
         ms->cont = (args.max_frames > 0 && (u64)cfg.N <= args.nsamples) ? 1 : 0;
         if (ms->cont) issue_raw(0);
     }
-    __syncthreads();
+    GSYNC();
 
     while (ms->cont) {
         const int nin = ms->nin, nold = Nmem - nin, frame = ms->frame;
@@ -867,7 +906,7 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
             const size_t nbytes = (size_t)cfg.nin_max * bps < have ? (size_t)cfg.nin_max * bps : have;
             for (size_t i = tid; i < nbytes; i += T) raw[ms->roff + i] = g[i];
         }
-        __syncthreads();
+        GSYNC();
         const unsigned char *fr = raw + ms->roff; /* sample 0 of the frame */
 
         /* ---- A7: tone frequency estimate (exact) ---- */
@@ -882,14 +921,14 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
                     const int j = j0 + (tid >> 4);
                     if ((tid >> 4) < gpr && j < numffts)
                         fft256_block<FMT>(cfg, tid & 15, fr + (size_t)j * half * bps, hannS, scratch + (tid >> 4) * 272, mag + (size_t)(tid >> 4) * nb, t3, t4);
-                    __syncthreads();
+                    GSYNC();
                     const int nr = numffts - j0 < gpr ? numffts - j0 : gpr;
                     for (int b = tid; b < nb; b += T) {
                         float s = Sf[b];
                         for (int r = 0; r < nr; ++r) s = __fadd_rn(__fmul_rn(s, c9), __fmul_rn(mag[r * nb + b], tc));
                         Sf[b] = s;
                     }
-                    __syncthreads();
+                    GSYNC();
                 }
             } else {
                 const int per = cfg.fft_blocks_per_round;
@@ -901,7 +940,7 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
                         for (int r = 0; r < nr; ++r) s = __fadd_rn(__fmul_rn(s, c9), __fmul_rn(mag[r * nb + b], tc));
                         Sf[b] = s;
                     }
-                    __syncthreads();
+                    GSYNC();
                 }
             }
             /* peak picking with blanking (warp 0) and the mask correlation (warp 1), on Sf[st, en) */
@@ -985,7 +1024,7 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
                     for (int m = 0; m < M; ++m) ms->f2_est[m] = __fadd_rn(foff, (float)(m * cfg.tone_spacing));
                 }
             }
-            __syncthreads();
+            GSYNC();
             if (tid < M) {
                 const int m = tid;
                 const int ei = cfg.est_type ? ms->bmax * 4 + m : (ms->freqi[m] + half) * 4;
@@ -997,7 +1036,7 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
                 ms->lng[m] = e.lng;
                 ms->osc_idx[m] = ei;
             }
-            __syncthreads();
+            GSYNC();
             if (tid == 0 && args.mbox) {
                 /* tell the exact-oscillator side chain what this frame is */
                 u64 w = MBOX_VALID | ((u64)(nin == cfg.nin_min ? 0 : (nin == cfg.N ? 1 : 2)) << 48);
@@ -1051,7 +1090,7 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
                 }
             }
         }
-        __syncthreads();
+        GSYNC();
         /* raw is free: fetch the next frame (its start is known, its length is not: fetch the longest) */
         if (tid == 0) {
             const u64 npos = pos + (u64)nin;
@@ -1145,7 +1184,7 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
                 ms->red[warp][1] = ti;
             }
         }
-        __syncthreads();
+        GSYNC();
 
         /* ---- A10: timing estimate, nin for the next call, interpolation weights (thread 0) ---- */
         if (tid == 0) {
@@ -1174,7 +1213,7 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
             ms->rx_timing = rx_timing;
             ms->fflags = fl;
         }
-        __syncthreads();
+        GSYNC();
 
         /* ---- A11: resample at the timing instant, decide, per-symbol statistics (fast, guarded) ---- */
         {
@@ -1276,7 +1315,7 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
             }
             if (fl) atomicOr(&ms->fflags, fl);
         }
-        __syncthreads();
+        GSYNC();
 
         /* ---- a decision inside its margin: replay the frame exactly (rare) ---- */
         bool replayed = false;
@@ -1337,7 +1376,7 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
             if (ms->flags && (ms->flags >> 8) == 0) ms->flags |= ((frame + 1) & 0xfff) << 8;
             ms->cont = cont;
         }
-        __syncthreads();
+        GSYNC();
 
         /* ---- A12: LLRs (fast) ---- */
         if (cfg.soft && args.llr) {
@@ -1373,7 +1412,7 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
                 fdc[m * fdcS + k] = fdc[m * fdcS + (Nmem - nold2) + k];
             }
         }
-        __syncthreads();
+        GSYNC();
     }
 
     /* a bulk copy still in flight must land before the CTA retires */
@@ -1392,6 +1431,7 @@ __global__ void __launch_bounds__(T, (M == 2 ? 9 : 4)) fsk_fast_kernel(const __g
             args.flag_list[slot] = (int)cap;
         }
     }
+    } /* captures of this group */
 }
 
 /* ------------------------------------------------------------------ host side */
@@ -1419,27 +1459,35 @@ struct FskFastPlan {
     size_t cap_mbox = 0, cap_chain = 0;
     int ckpt_per_frame = 0;
     bool chain = true;
-    size_t chain_smem = 0;
-    static const int kSide = 4;
-    cudaStream_t side[kSide] = { nullptr, nullptr, nullptr, nullptr };
-    cudaEvent_t ev_a[kSide] = { nullptr, nullptr, nullptr, nullptr }, ev_b[kSide] = { nullptr, nullptr, nullptr, nullptr };
+    int gmax = 1;   /* capture groups per CTA: what shared memory and registers allow (at most 9 / 5) */
+    int num_sms = 148;
     std::string desc;
 };
 
 template <int M, int FMT, bool STEP1>
-static cudaError_t fast_launch_t(const FskFastPlan *p, const FastArgs &a, cudaStream_t stream, bool prepare_only) {
+static cudaError_t fast_launch_t(const FskFastPlan *p, const FastArgs &a, cudaStream_t stream, int mode, unsigned grid, unsigned block, size_t smem,
+                                 int *regs) {
     auto kern = fsk_fast_kernel<M, FMT, STEP1>;
-    if (prepare_only) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p->cfg.smem_bytes);
-    kern<<<(unsigned)a.n_captures, T, (size_t)p->cfg.smem_bytes, stream>>>(p->cfg, a);
+    if (mode == 1) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (mode == 2) {
+        cudaFuncAttributes at;
+        cudaError_t e = cudaFuncGetAttributes(&at, kern);
+        if (e == cudaSuccess) *regs = at.numRegs;
+        return e;
+    }
+    kern<<<grid, block, smem, stream>>>(p->cfg, a);
     return cudaGetLastError();
 }
 
-static cudaError_t fast_dispatch(const FskFastPlan *p, const FastArgs &a, cudaStream_t stream, bool prepare_only) {
+/* mode 0: launch, 1: set the shared-memory attribute, 2: query registers per thread */
+static cudaError_t fast_dispatch(const FskFastPlan *p, const FastArgs &a, cudaStream_t stream, int mode, unsigned grid = 0, unsigned block = 0,
+                                 size_t smem = 0, int *regs = nullptr) {
     /* the paired integrator needs step == 1 and even Ts, RO, nint */
     const bool s1 = p->cfg.step == 1 && (p->cfg.Ts & 1) == 0 && (p->cfg.RO & 1) == 0 && (p->cfg.nint & 1) == 0;
-#define D(MM, FF)                                                                                       \
-    if (p->M == MM && p->fmt == FF)                                                                     \
-        return s1 ? fast_launch_t<MM, FF, true>(p, a, stream, prepare_only) : fast_launch_t<MM, FF, false>(p, a, stream, prepare_only);
+#define D(MM, FF)                                                                                                   \
+    if (p->M == MM && p->fmt == FF)                                                                                 \
+        return s1 ? fast_launch_t<MM, FF, true>(p, a, stream, mode, grid, block, smem, regs)                       \
+                  : fast_launch_t<MM, FF, false>(p, a, stream, mode, grid, block, smem, regs);
     D(2, PIRIP_FMT_U8)
     D(2, PIRIP_FMT_S16)
     D(2, PIRIP_FMT_F32)
@@ -1463,11 +1511,6 @@ void fsk_fast_plan_destroy(FskFastPlan *p) {
     cudaFree(p->d_ckpt);
     cudaFree(p->d_afin);
     cudaFree(p->d_replays);
-    for (int i = 0; i < FskFastPlan::kSide; ++i) {
-        if (p->side[i]) cudaStreamDestroy(p->side[i]);
-        if (p->ev_a[i]) cudaEventDestroy(p->ev_a[i]);
-        if (p->ev_b[i]) cudaEventDestroy(p->ev_b[i]);
-    }
     delete p;
 }
 
@@ -1529,6 +1572,7 @@ FskFastPlan *fsk_fast_plan_create(const pirip_fsk_cfg &c, const FskDevCfg &d, co
     f.off_ideal = off; off += align_up((d.P + 1) * 8, 16);
     f.off_misc = off; off += align_up((int)sizeof(Misc), 16);
     f.smem_bytes = off;
+    f.group_stride = align_up(off, 128);
     const int numffts_max = f.nin_max / (d.Ndft / 2) - 1;
     if (d.log2_ndft == 8) {
         int per = row_free / (272 * 8);
@@ -1631,31 +1675,40 @@ FskFastPlan *fsk_fast_plan_create(const pirip_fsk_cfg &c, const FskDevCfg &d, co
     f.ftcorr = p->d_corr;
     f.phi_ft = d.phi_ft;
     p->ckpt_per_frame = ck_chunks(f.nin_max) + 1;
-    /* the side chain needs launches to be asynchronous and the two kernels to run side by side: not under tools that
-       serialise kernels (Nsight Compute replay, compute-sanitizer, CUDA_LAUNCH_BLOCKING) - there the fast kernel flags and
-       the exact kernel re-runs the flagged captures */
-    p->chain = getenv("PIRIP_FSK_NO_CHAIN") == nullptr && getenv("CUDA_INJECTION64_PATH") == nullptr &&
-               getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") == nullptr &&
-               !(getenv("CUDA_LAUNCH_BLOCKING") != nullptr && atoi(getenv("CUDA_LAUNCH_BLOCKING")) != 0);
-    p->chain_smem = 0; /* 0: chain warps share SMs with the fast kernel */
-    if (const char *ev = getenv("PIRIP_FSK_CHAIN_SMEM_KB")) p->chain_smem = (size_t)atoi(ev) * 1024;
-    if (p->chain_smem > 0)
-        ok = ok && pirip::cuda_ok(c.M == 2 ? cudaFuncSetAttribute(fsk_osc_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->chain_smem)
-                                           : cudaFuncSetAttribute(fsk_osc_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->chain_smem),
-                                  "cudaFuncSetAttribute (chain kernel)");
+    p->chain = getenv("PIRIP_FSK_NO_CHAIN") == nullptr;
     ok = ok && pirip::cuda_ok(cudaMalloc(&p->d_replays, sizeof(int) * 8), "cudaMalloc replays") &&
          pirip::cuda_ok(cudaMemset(p->d_replays, 0, sizeof(int) * 8), "memset replays");
     FastArgs dummy;
     memset(&dummy, 0, sizeof dummy);
-    ok = ok && pirip::cuda_ok(fast_dispatch(p, dummy, nullptr, true), "cudaFuncSetAttribute (fast kernel)");
+    ok = ok && pirip::cuda_ok(fast_dispatch(p, dummy, nullptr, 1), "cudaFuncSetAttribute (fast kernel)");
+    int regs = 128;
+    ok = ok && pirip::cuda_ok(fast_dispatch(p, dummy, nullptr, 2, 0, 0, 0, &regs), "cudaFuncGetAttributes (fast kernel)");
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) p->num_sms = sms;
+        int g = (227 * 1024) / f.group_stride;
+        const int greg = 65536 / (T * (regs > 0 ? regs : 128));
+        if (greg < g) g = greg;
+        const int gcap = c.M == 2 ? 9 : 5; /* __launch_bounds__ of the kernel */
+        if (g > gcap) g = gcap;
+        if (const char *ev = getenv("PIRIP_FSK_FAST_G"))
+            if (atoi(ev) >= 1 && atoi(ev) < g) g = atoi(ev);
+        p->gmax = g;
+        if (g < 1) {
+            pirip::set_error("fast kernel: a capture group does not fit an SM");
+            ok = false;
+        }
+    }
     if (!ok) {
         why = pirip::last_error();
         fsk_fast_plan_destroy(p);
         return nullptr;
     }
     char buf[256];
-    snprintf(buf, sizeof buf, "fsk_fast_kernel<M=%d>: one CTA of %d threads per capture, %d B dynamic smem, guards sym %.1e tim %.1e; flagged captures re-run by the exact kernel",
-             c.M, T, f.smem_bytes, (double)f.g_sym, (double)f.g_tim);
+    snprintf(buf, sizeof buf,
+             "fsk_fast_kernel<M=%d>: one CTA per SM, up to %d capture groups of %d threads (%d B smem each), exact-oscillator chain CTAs %s; guards sym %.1e "
+             "tim %.1e; decisions inside a margin are replayed exactly in the kernel",
+             c.M, p->gmax, T, f.group_stride, p->chain ? "on" : "off", (double)f.g_sym, (double)f.g_tim);
     p->desc = buf;
     return p;
 }
@@ -1709,10 +1762,10 @@ static cudaError_t chain_buffers(FskFastPlan *p, size_t n, size_t max_frames) {
     return cudaSuccess;
 }
 
-/* `off` / `total`: position of this launch's captures inside the buffers of a chunked host-buffer call; `slot`: which side
-   stream / event pair the chunk uses */
+/* `off` / `total`: position of this launch's captures inside the buffers of a chunked host-buffer call */
 cudaError_t fsk_fast_launch(FskFastPlan *p, const FskBatchArgs &b, int *d_flags, int *d_list, int *d_count, cudaStream_t stream,
                             size_t off, size_t total, size_t slot) {
+    (void)slot;
     FastArgs a;
     memset(&a, 0, sizeof a);
     a.iq = b.iq;
@@ -1732,45 +1785,49 @@ cudaError_t fsk_fast_launch(FskFastPlan *p, const FskBatchArgs &b, int *d_flags,
     a.tma_ok = b.tma_ok;
     a.ckpt_per_frame = p->ckpt_per_frame;
     if (total < off + b.n_captures) total = off + b.n_captures;
-    const int k = (int)(slot % FskFastPlan::kSide);
-    bool chain = p->chain;
+    const size_t n = b.n_captures;
+    /* geometry: one CTA per SM.  Demodulating CTAs hold up to gmax capture groups; with fewer captures than groups the
+       captures are spread over the SMs first.  Chain CTAs: one lane per (capture, tone) that can be in flight at once,
+       about 9 warps per CTA (a warp needs ~60% of a scheduler's issue slots to keep pace: two per scheduler is the most). */
+    const int sms = p->num_sms;
+    int chain_ctas = 0, wpc = 0;
+    if (p->chain) {
+        size_t inflight = (size_t)sms * p->gmax;
+        if (inflight > n) inflight = n;
+        const size_t warps = (inflight * p->M + 31) / 32;
+        wpc = 9;
+        if (const char *ev = getenv("PIRIP_FSK_CHAIN_WPC"))
+            if (atoi(ev) >= 1 && atoi(ev) <= 18) wpc = atoi(ev);
+        if ((size_t)wpc > warps) wpc = (int)warps;
+        if (wpc > 2 * p->gmax) wpc = 2 * p->gmax; /* the CTA has 2 * G warps */
+        chain_ctas = (int)((warps + wpc - 1) / wpc);
+        if (chain_ctas > sms / 4) chain_ctas = sms / 4; /* a longer list is worked off lane by lane */
+    }
+    int n_a = sms - chain_ctas;
+    if ((size_t)n_a > n) n_a = (int)n;
+    int G = (int)((n + n_a - 1) / n_a);
+    if (G > p->gmax) G = p->gmax;
+    int block_groups = G;
+    if (chain_ctas && 2 * block_groups < wpc) block_groups = (wpc + 1) / 2;
+    a.G = G;
+    a.chain_ctas = chain_ctas;
+    a.chain_wpc = wpc;
     cudaError_t e;
-    if (chain) {
+    if (chain_ctas) {
         if ((e = chain_buffers(p, total, b.max_frames)) != cudaSuccess) return e;
-        if (!p->side[k]) {
-            if ((e = cudaStreamCreateWithFlags(&p->side[k], cudaStreamNonBlocking)) != cudaSuccess) return e;
-            if ((e = cudaEventCreateWithFlags(&p->ev_a[k], cudaEventDisableTiming)) != cudaSuccess) return e;
-            if ((e = cudaEventCreateWithFlags(&p->ev_b[k], cudaEventDisableTiming)) != cudaSuccess) return e;
-        }
         a.mbox = p->d_mbox + off * (b.max_frames + 1);
         a.ckpt = p->d_ckpt + off * (size_t)(2 * p->ckpt_per_frame * 4);
         a.afin = p->d_afin + off;
         a.replays = p->d_replays;
-        if ((e = cudaMemsetAsync(a.mbox, 0, sizeof(u64) * b.n_captures * (b.max_frames + 1), stream)) != cudaSuccess) return e;
-        if ((e = cudaMemsetAsync(a.ckpt, 0, sizeof(float4) * b.n_captures * 2 * p->ckpt_per_frame * 4, stream)) != cudaSuccess) return e;
-        if ((e = cudaMemsetAsync(a.afin, 0, sizeof(int) * b.n_captures, stream)) != cudaSuccess) return e;
-        if ((e = cudaEventRecord(p->ev_a[k], stream)) != cudaSuccess) return e;
-        if ((e = cudaStreamWaitEvent(p->side[k], p->ev_a[k], 0)) != cudaSuccess) return e;
-        /* chain warps get SMs of their own (see the kernel): about 9 warps per CTA, one CTA per SM through a shared-memory
-           request nothing else fits beside */
-        const unsigned per = (unsigned)(32 / p->M);
-        const unsigned warps = (unsigned)((b.n_captures + per - 1) / per);
-        unsigned wpc = 9;
-        if (const char *ev = getenv("PIRIP_FSK_CHAIN_WPC"))
-            if (atoi(ev) >= 1 && atoi(ev) <= 32) wpc = (unsigned)atoi(ev);
-        if (warps < wpc) wpc = warps;
-        const unsigned grid = (warps + wpc - 1) / wpc;
-        const size_t chain_smem = p->chain_smem;
-        if (p->M == 2)
-            fsk_osc_chain_kernel<2><<<grid, 32 * wpc, chain_smem, p->side[k]>>>(p->cfg, a);
-        else
-            fsk_osc_chain_kernel<4><<<grid, 32 * wpc, chain_smem, p->side[k]>>>(p->cfg, a);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if ((e = cudaEventRecord(p->ev_b[k], p->side[k])) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(a.mbox, 0, sizeof(u64) * n * (b.max_frames + 1), stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(a.ckpt, 0, sizeof(float4) * n * 2 * p->ckpt_per_frame * 4, stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(a.afin, 0, sizeof(int) * n, stream)) != cudaSuccess) return e;
     }
-    if ((e = fast_dispatch(p, a, stream, false)) != cudaSuccess) return e;
-    if (chain && (e = cudaStreamWaitEvent(stream, p->ev_b[k], 0)) != cudaSuccess) return e;
-    return cudaSuccess;
+    /* more than half an SM's shared memory per CTA: never two CTAs on one SM, so every CTA of the grid is resident at once
+       (the chain lanes and the replays wait for each other across CTAs) */
+    size_t smem = (size_t)block_groups * p->cfg.group_stride;
+    if (smem < 116 * 1024) smem = 116 * 1024;
+    return fast_dispatch(p, a, stream, 0, (unsigned)(n_a + chain_ctas), (unsigned)(block_groups * T), smem);
 }
 
 int fsk_fast_uses_chain(const FskFastPlan *p) { return p && p->chain ? 1 : 0; }

@@ -668,7 +668,7 @@ static int batch_dev(pirip_fsk_plan *plan, const void *d_iq, size_t n_captures, 
         if (!pirip::cuda_ok(fsk_fast_launch(plan->fast, a, d_flags, d_list, d_count, (cudaStream_t)stream, flag_off, flag_total, chunk),
                             "fsk_fast_kernel launch"))
             return -11;
-        pirip::count_launch(fsk_fast_uses_chain(plan->fast) ? 2 : 1);
+        pirip::count_launch();
         FskBatchArgs x = a;
         x.cap_list = d_list;
         x.cap_count = d_count;
