@@ -234,6 +234,11 @@ int pirip_fsk_plan_replays(pirip_fsk_plan *plan, int32_t out[2]);
    (static storage inside the plan; valid until the plan is destroyed) */
 const char *pirip_fsk_plan_kernel(const pirip_fsk_plan *plan);
 
+/* Pack nbits one-bit-per-byte values (device memory, nbits a multiple of 8, d_bits 16-byte aligned) into nbits/8 bytes, MSB
+   first - the bit order of codec2's freedv_pack as pirip uses it ([R tx/rpitx_fsk.cpp:38,75-83]).  Used to gather the decoded
+   bit streams of a sharded batch with an eighth of the bytes.  Asynchronous on `stream`. */
+int pirip_pack_bits_dev(const uint8_t *d_bits, size_t nbits, uint8_t *d_packed, void *stream);
+
 /* number of kernel launches issued by this library so far (bench.py gpu_launches) */
 uint64_t pirip_kernel_launches(void);
 /* last error message of the calling thread ("" if none) */

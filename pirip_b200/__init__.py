@@ -22,5 +22,6 @@ from ._lib import (  # noqa: F401
     kernel_launches,
     lib,
     lib_path,
+    pack_bits_dev,
     version,
 )

@@ -71,6 +71,8 @@ def lib():
     L.pirip_fsk_plan_replays.argtypes = [C.c_void_p, C.c_void_p]
     L.pirip_fsk_plan_kernel.restype = C.c_char_p
     L.pirip_fsk_plan_kernel.argtypes = [C.c_void_p]
+    L.pirip_pack_bits_dev.restype = C.c_int
+    L.pirip_pack_bits_dev.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
     L.pirip_kernel_launches.restype = C.c_uint64
     L.pirip_last_error.restype = C.c_char_p
     L.pirip_version.restype = C.c_char_p
@@ -84,6 +86,13 @@ def version():
 
 def kernel_launches():
     return int(lib().pirip_kernel_launches())
+
+
+def pack_bits_dev(d_bits, nbits, d_packed, stream=None):
+    """Device pointers in, MSB-first packing (freedv_pack order); asynchronous on `stream`."""
+    rc = lib().pirip_pack_bits_dev(d_bits, nbits, d_packed, stream)
+    if rc != 0:
+        raise _err("pirip_pack_bits_dev", rc)
 
 
 def _err(what, rc=None):

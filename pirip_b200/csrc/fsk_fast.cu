@@ -70,6 +70,7 @@ struct FastCfg {
     int fft_blocks_per_round; /* blocks transformed at a time: as many as fit the scratch row */
     int prune;                /* 256-point FFT: the estimator window lies inside output bins k < 32 */
     int exit_on_flag;
+    int diag; /* PIRIP_FSK_FAST_DIAG: the stats record carries the timing-line strength in `foff` */
 };
 
 struct FastArgs {
@@ -116,6 +117,8 @@ struct Misc {
     float2 dphi_prev[4];
     float2 xtc;         /* exact timing-line sum */
     int osc_idx[4];
+    float rho, dfr;
+    int near;
 };
 
 #define MBOX_VALID (1ull << 63)
@@ -571,7 +574,7 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
     {
         if (tid == 0) ms->rp_ok = 1;
         GSYNC();
-        int ok = (args.ckpt && Nsym <= T && cfg.tailpad <= 64) ? 1 : 0;
+        int ok = (args.ckpt && Nsym <= T && cfg.tailpad <= 128) ? 1 : 0;
         const long long t0 = clock64();
         for (int task = tid; ok && task < M * (nct + ncn); task += T) {
             const int m = task / (nct + ncn), seg = task - m * (nct + ncn);
@@ -594,7 +597,7 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
     }
 
     /* keep the fast baseband memory the next frame's tail is taken from */
-    constexpr int KEEP = (M * 64 + T - 1) / T; /* tailpad <= 64 */
+    constexpr int KEEP = (M * 128 + T - 1) / T; /* tailpad <= 128 */
     float2 keep[KEEP];
 #pragma unroll
     for (int i = 0; i < KEEP; ++i) {
@@ -785,7 +788,7 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
         float stdebno = __fsub_rn(__fdiv_rn(ms->red[1][2], nsymf), __fmul_rn(meanebno, meanebno));
         stdebno = (double)stdebno > 0.0 ? (float)sqrt((double)stdebno) : 0.0f;
         ms->EbNodB = __fadd_rn(-6.0f, __fmul_rn(20.0f, em_log10f((float)((1e-6 + (double)meanebno) / (1e-6 + (double)stdebno)))));
-        ms->snr_est = (float)(.5 * (double)ms->red[0][5] + .5 * (double)ms->EbNodB); /* red[0][5]: snr_est before this frame */
+        ms->snr_est = (float)(.5 * (double)ms->snr_est + .5 * (double)ms->EbNodB); /* still the value before this frame */
         if (args.replays) atomicAdd(args.replays, 1);
     }
     /* the fast baseband memory of the frame's end, for the next frame's tail */
@@ -1105,7 +1108,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
 
         /* ---- A9/A10: sliding-window integrators, window energies, timing line (fast) ---- */
         {
-            float tr = 0.0f, ti = 0.0f;
+            float tr = 0.0f, ti = 0.0f, esum = 0.0f;
             const int i0 = tid * cfg.RO;
             if (i0 < nint) {
                 const int cnt = nint - i0 < cfg.RO ? nint - i0 : cfg.RO;
@@ -1139,6 +1142,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                         }
                         const float2 w0 = ideal[ip], w1 = ideal[ip + 1]; /* the table holds P + 1 entries: no wrap inside a pair */
                         if (o + 1 >= cnt) e1 = 0.0f;
+                        esum += e0 + e1;
                         tr = fmaf(e0, w0.x, tr);
                         ti = fmaf(e0, w0.y, ti);
                         tr = fmaf(e1, w1.x, tr);
@@ -1162,6 +1166,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
 #pragma unroll
                         for (int m = 0; m < M; ++m) e += fmaf(S[m].x, S[m].x, S[m].y * S[m].y);
                         const float2 w = ideal[ip];
+                        esum += e;
                         tr = fmaf(e, w.x, tr);
                         ti = fmaf(e, w.y, ti);
                         ip = ip + 1 == P ? 0 : ip + 1;
@@ -1179,9 +1184,11 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             }
             tr = warp_sum(tr);
             ti = warp_sum(ti);
+            esum = warp_sum(esum);
             if (lane == 0) {
                 ms->red[warp][0] = tr;
                 ms->red[warp][1] = ti;
+                ms->red[warp][5] = esum;
             }
         }
         GSYNC();
@@ -1189,19 +1196,25 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
         /* ---- A10: timing estimate, nin for the next call, interpolation weights (thread 0) ---- */
         if (tid == 0) {
             const float tcr = ms->red[0][0] + ms->red[1][0], tci = ms->red[0][1] + ms->red[1][1];
+            const float esum = ms->red[0][5] + ms->red[1][5];
+            ms->rho = sqrtf(tcr * tcr + tci * tci) / fmaxf(esum, 1e-30f); /* strength of the timing line: conditioning of the estimate */
             int fl = 0;
             if (isnan(tcr) || isnan(tci)) fl |= FLAG_NAN;
+            /* How far the scalar algorithm's norm_rx_timing can be from this one: both timing-line sums carry an absolute
+               error of a few 1e-7 of the summed window energies, so the angle is uncertain by that over the line's relative
+               strength rho (measured: |d norm| * rho <= 9.2e-8 over every test configuration; 4e-7 used). */
+            const float dn = cfg.g_tim / fmaxf(ms->rho, 1e-9f) + 2e-7f;
             const float norm = atan2f(tci, tcr) * 0.15915494309189535f;
             const float rx_timing = norm * (float)P;
             const float d = norm - ms->norm_rx_timing;
             ms->red[0][7] = ms->norm_rx_timing; /* for an exact replay of this frame */
             ms->red[0][6] = ms->ppm;
             ms->norm_rx_timing = norm;
-            if (fabsf(fabsf(d) - 0.2f) < cfg.g_tim) fl |= FLAG_PPM;
+            if (fabsf(fabsf(d) - 0.2f) < 2.0f * dn) fl |= FLAG_PPM;
             if (fabsf(d) < 0.2f) ms->ppm = 0.9f * ms->ppm + 0.1f * (1e6f * d / (float)Nsym);
             int nn = nin;
             if (!cfg.fixed_nin) {
-                if (fabsf(fabsf(norm) - 0.25f) < cfg.g_tim) fl |= FLAG_TIM;
+                if (fabsf(fabsf(norm) - 0.25f) < dn) fl |= FLAG_TIM;
                 nn = norm > 0.25f ? cfg.N + Ts / 4 : (norm < -0.25f ? cfg.N - Ts / 4 : cfg.N);
             }
             ms->nin_next = nn;
@@ -1210,6 +1223,11 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             ms->high = (int)ceilf(rx_timing);
             ms->fract = rx_timing - lowf;
             ms->omf = 1.0f - ms->fract;
+            /* uncertainty of the interpolation weight.  Next to an integer timing offset the scalar algorithm may interpolate
+               between the neighbouring pair of integrator outputs (same value to first order: the resampled output is
+               continuous in the timing); the symbol guard then also covers that pair's difference (near = -1 / +1). */
+            ms->dfr = (float)P * dn;
+            ms->near = ms->fract < ms->dfr ? -1 : (ms->fract > 1.0f - ms->dfr ? 1 : 0);
             ms->rx_timing = rx_timing;
             ms->fflags = fl;
         }
@@ -1218,43 +1236,59 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
         /* ---- A11: resample at the timing instant, decide, per-symbol statistics (fast, guarded) ---- */
         {
             const int low = ms->low;
-            const float fr_w = ms->fract, omf = ms->omf;
-            const int L = Ts + step, per = (L + 3) >> 2;
+            const float fr_w = ms->fract;
+            /* t = (1 - fract) W(low) + fract W(high) = sum_{k < Ts} v_k + fract (sum_{Ts <= k < Ts + step} v_k - sum_{k < step} v_k):
+               the four lanes of a symbol add a quarter of the window each (packed adds), lane 3 the correction */
+            const int per = (Ts + 3) >> 2;
             float s_sig = 0.0f, s_nse = 0.0f, s_mean = 0.0f;
             int fl = 0;
             unsigned char *bo = args.bits ? args.bits + (cap * args.max_frames + (size_t)frame) * (size_t)cfg.Nbits : nullptr;
             float *fo = args.rx_filt ? args.rx_filt + (cap * args.max_frames + (size_t)frame) * (size_t)(M * Nsym) : nullptr;
             const int ntask = (Nsym * 4 + 31) & ~31;
+            const bool two = ms->high != low; /* an integer timing offset: W(high) is W(low), fract is 0 */
+            const int near = ms->near;
             for (int task = tid; task < ntask; task += T) {
                 const int sym = task >> 2, sub = task & 3;
                 const bool valid = sym < Nsym;
                 const int base = ((sym + 1) * P + low) * step;
-                const int k0 = sub * per, k1 = (k0 + per < L) ? k0 + per : L;
+                const int k0 = sub * per, k1 = (k0 + per < Ts) ? k0 + per : Ts;
                 float2 t[M];
+                float uu[M];
 #pragma unroll
-                for (int m = 0; m < M; ++m) t[m] = make_float2(0.0f, 0.0f);
+                for (int m = 0; m < M; ++m) t[m] = make_float2(0.0f, 0.0f), uu[m] = 0.0f;
                 if (valid) {
-                    /* entries [0, step) leave the window (weight 1 - fract), [Ts, Ts + step) enter it (weight fract) */
-                    int k = k0;
-                    for (; k < k1 && k < step; ++k)
+                    const float2 *f = fdc + base;
+#pragma unroll 2
+                    for (int k = k0; k < k1; ++k)
+#pragma unroll
+                        for (int m = 0; m < M; ++m) t[m] = xadd(t[m], f[m * fdcS + k]);
+                    if (sub == 3 && two) {
+                        float2 u[M];
+#pragma unroll
+                        for (int m = 0; m < M; ++m) u[m] = make_float2(0.0f, 0.0f);
+                        for (int k = 0; k < step; ++k)
+#pragma unroll
+                            for (int m = 0; m < M; ++m) u[m] = xadd(u[m], xsub(f[m * fdcS + Ts + k], f[m * fdcS + k]));
 #pragma unroll
                         for (int m = 0; m < M; ++m) {
-                            const float2 v = fdc[m * fdcS + base + k];
-                            t[m].x = fmaf(omf, v.x, t[m].x);
-                            t[m].y = fmaf(omf, v.y, t[m].y);
+                            t[m].x = fmaf(fr_w, u[m].x, t[m].x);
+                            t[m].y = fmaf(fr_w, u[m].y, t[m].y);
+                            uu[m] = fmaf(u[m].x, u[m].x, u[m].y * u[m].y); /* |dt/dfract|^2 */
                         }
-                    const int kmid = k1 < Ts ? k1 : Ts;
-                    for (; k < kmid; ++k)
-#pragma unroll
-                        for (int m = 0; m < M; ++m) t[m] = xadd(t[m], fdc[m * fdcS + base + k]);
-                    for (; k < k1; ++k)
+                    }
+                    if (sub == 3 && near != 0) {
+                        /* the neighbouring pair: W(low) - W(low-1) below, W(low+2) - W(low+1) above */
+                        const float2 *g = near < 0 ? f - step : f + (two ? step : 0);
 #pragma unroll
                         for (int m = 0; m < M; ++m) {
-                            const float2 v = fdc[m * fdcS + base + k];
-                            t[m].x = fmaf(fr_w, v.x, t[m].x);
-                            t[m].y = fmaf(fr_w, v.y, t[m].y);
+                            float2 u2 = make_float2(0.0f, 0.0f);
+                            for (int k = 0; k < step; ++k) u2 = xadd(u2, xsub(g[m * fdcS + Ts + k], g[m * fdcS + k]));
+                            uu[m] = fmaxf(uu[m], fmaf(u2.x, u2.x, u2.y * u2.y));
                         }
+                    }
                 }
+#pragma unroll
+                for (int m = 0; m < M; ++m) uu[m] = __shfl_down_sync(0xffffffffu, uu[m], 3); /* lane 3 of the symbol -> its lane 0 */
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
                     t[m].x += __shfl_xor_sync(0xffffffffu, t[m].x, 1);
@@ -1279,10 +1313,18 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                             symv = m;
                         }
                     second = -1.0f;
+                    float uub = uu[0], uus = 0.0f;
 #pragma unroll
-                    for (int m = 0; m < M; ++m)
-                        if (m != symv && e[m] > second) second = e[m];
-                    if (mx - second <= cfg.g_sym * (mx + second) && mx > 0.0f) { /* a 0 == 0 tie (zero input) is exact */
+                    for (int m = 0; m < M; ++m) {
+                        if (m == symv) uub = uu[m];
+                        if (m != symv && e[m] > second) second = e[m], uus = uu[m];
+                    }
+                    /* the scalar algorithm's energies differ from these by rounding (g_sym, relative) and by the uncertainty dfr
+                       of the interpolation weight: d|t|^2 <= dfr (2 |t| |u| + |u|^2 dfr) */
+                    const float dfr = ms->dfr;
+                    const float slack = cfg.g_sym * (mx + second) +
+                                        dfr * (2.0f * (sqrtf(mx * uub) + sqrtf(second * uus)) + (uub + uus) * dfr);
+                    if (mx - second <= slack && mx > 0.0f) { /* a 0 == 0 tie (zero input) is exact */
                         fl |= FLAG_SYM;
                         atomicAdd(&ms->nflag_sym, 1);
                     }
@@ -1359,7 +1401,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                 st->rx_nse_pow = nse;
                 st->EbNodB = ms->EbNodB;
                 st->snr_est = ms->snr_est;
-                st->foff = ms->foff;
+                st->foff = cfg.diag ? ms->rho : ms->foff;
                 st->rx_timing = ms->rx_timing;
                 st->nin_next = ms->nin_next;
                 st->sample_offset = (int32_t)pos;
@@ -1539,10 +1581,11 @@ FskFastPlan *fsk_fast_plan_create(const pirip_fsk_cfg &c, const FskDevCfg &d, co
     f.bps = c.fmt == PIRIP_FMT_U8 ? 2 : (c.fmt == PIRIP_FMT_S16 ? 4 : 8);
     f.fs_over_ndft = d.fs_over_ndft;
     f.in_scale = c.fmt == PIRIP_FMT_U8 ? 0.0078125f : 1.0f;
-    f.g_sym = 2e-5f;
-    f.g_tim = 1e-5f;
+    f.g_sym = 4e-6f; /* rounding of the energies at a given timing */
+    f.g_tim = 4e-7f; /* timing-line sums: absolute error relative to the summed window energies (observed <= 9.2e-8) */
     if (const char *e = getenv("PIRIP_FSK_GUARD_SYM")) f.g_sym = (float)atof(e);
     if (const char *e = getenv("PIRIP_FSK_GUARD_TIM")) f.g_tim = (float)atof(e);
+    f.diag = getenv("PIRIP_FSK_FAST_DIAG") ? 1 : 0;
     f.exit_on_flag = 1;
     if (const char *e = getenv("PIRIP_FSK_FAST_NO_EXIT")) f.exit_on_flag = atoi(e) ? 0 : 1;
     if (f.nb <= 0 || f.step < 1 || d.Nsym < 3 || f.nint > T * 256) {

@@ -28,3 +28,11 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture
+def exact_mode(monkeypatch):
+    """Plans created inside the test use the exact-order kernel (PIRIP_FSK_MODE_EXACT): the tests that compare every float
+    with the oracle bit for bit.  The default mode of the batch entry points is the tolerance-mode kernel, which has its own
+    tests (tests/test_fsk_fast_gpu.py)."""
+    monkeypatch.setenv("PIRIP_FSK_MODE", "exact")

@@ -6,7 +6,7 @@ import pytest
 import orc
 import synth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("exact_mode")]
 
 
 def test_taps_match_oracle_bit_for_bit():

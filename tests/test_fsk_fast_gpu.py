@@ -1,0 +1,190 @@
+"""GPU parity of the tolerance-mode demodulator (fsk_fast.cu, the default of the batch entry points) against the CPU oracle.
+
+Contract (BASELINE.json north_star: "hard-decision bits and frame indices bit-exact, freq/timing estimates and LLRs within a
+stated float tolerance"):
+  identical   frame counts, sample offsets, nin decisions, hard bits, f_est / f2_est (uint32 patterns)
+  tolerance   norm_rx_timing: 1e-3 absolute (observed <= 4e-5, only in frames whose timing line is < 1e-3 of the summed window
+              energy); rx_filt and LLRs: 1e-3 of the frame's largest magnitude (observed <= 3e-4); SNRest / v_est / rx_sig_pow:
+              1e-3 relative; ppm (a filtered derivative of the timing: 1e6/Nsym times its frame-to-frame difference): 1.0 absolute
+              (observed <= 0.15).
+The kernel keeps the discrete outputs identical by checking every decision against a margin derived from the frame's own
+conditioning and replaying the frame with the scalar operation sequence when a decision is inside it
+(tests check the replay actually happens and that nothing is left to the host-side fallback).
+"""
+import os
+import threading
+import zlib
+
+import numpy as np
+import pytest
+
+import orc
+import synth
+from test_fsk_gpu import CONFIGS, make_batch, oracle_cfg
+
+pytestmark = pytest.mark.gpu
+
+TOL_NORM, TOL_REL, TOL_PPM = 1e-3, 1e-3, 1.0
+
+
+def oracle_batch(cfg, iq):
+    out = [None] * iq.shape[0]
+    nthr = os.cpu_count() or 4
+
+    def work(rows):
+        for r in rows:
+            out[r] = orc.fsk_demod_stream(cfg, iq[r])
+
+    ths = [threading.Thread(target=work, args=(range(t, iq.shape[0], nthr),)) for t in range(nthr)]
+    for t in ths:
+        t.start()
+    for t in ths:
+        t.join()
+    return out
+
+
+def compare_fast(plan, pk, iq, out, refs=None, floats=True):
+    cfg = oracle_cfg(pk)
+    refs = refs or oracle_batch(cfg, iq)
+    worst = dict(norm=0.0, filt=0.0, llr=0.0, snr=0.0)
+    for c in range(iq.shape[0]):
+        ref = refs[c]
+        nf = ref["nframes"]
+        assert out["nframes"][c] == nf, f"capture {c}: frame count {out['nframes'][c]} != {nf}"
+        nbad = int((out["bits"][c, :nf * plan.nbits] != ref["bits"]).sum())
+        assert nbad == 0, f"capture {c}: {nbad} hard-bit mismatches"
+        if not floats:
+            continue
+        st, rs = out["stats"][c, :nf], ref["stats"]
+        assert np.array_equal(st["nin_next"], rs["nin_next"]), f"capture {c}: nin decisions differ"
+        assert np.array_equal(st["sample_offset"], rs["sample_offset"])
+        for k in ("f_est", "f2_est"):
+            assert np.array_equal(st[k].view(np.uint32), rs[k].view(np.uint32)), f"capture {c}: {k} differs"
+        dn = np.abs(st["norm_rx_timing"].astype(np.float64) - rs["norm_rx_timing"])
+        dn = np.minimum(dn, 1.0 - dn)
+        worst["norm"] = max(worst["norm"], float(dn.max()) if nf else 0.0)
+        assert (dn <= TOL_NORM).all(), f"capture {c}: norm_rx_timing off by {dn.max()}"
+        assert (np.abs(st["ppm"] - rs["ppm"]) <= TOL_PPM).all(), f"capture {c}: ppm"
+        for k in ("SNRest", "v_est", "rx_sig_pow", "rx_nse_pow"):
+            a, b = st[k].astype(np.float64), rs[k].astype(np.float64)
+            rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-30)
+            worst["snr"] = max(worst["snr"], float(rel.max()) if nf else 0.0)
+            assert (rel <= TOL_REL).all(), f"capture {c}: {k} off by {rel.max()} relative"
+        gf = out["rx_filt"][c, :nf * plan.nfilt].reshape(nf, -1).astype(np.float64)
+        rf = ref["rx_filt"].reshape(nf, -1).astype(np.float64)
+        rel = np.abs(gf - rf) / np.maximum(rf.max(axis=1, keepdims=True), 1e-30)
+        worst["filt"] = max(worst["filt"], float(rel.max()) if nf else 0.0)
+        assert (rel <= TOL_REL).all(), f"capture {c}: rx_filt off by {rel.max()} of the frame maximum"
+        if pk.get("soft"):
+            gl = out["llr"][c, :nf * plan.nbits].reshape(nf, -1).astype(np.float64)
+            rl = ref["llr"].reshape(nf, -1).astype(np.float64)
+            rel = np.abs(gl - rl) / np.maximum(np.abs(rl).max(axis=1, keepdims=True), 1e-30)
+            worst["llr"] = max(worst["llr"], float(rel.max()) if nf else 0.0)
+            assert (rel <= TOL_REL).all(), f"capture {c}: LLR off by {rel.max()} of the frame maximum"
+    return worst
+
+
+@pytest.mark.parametrize("name", list(CONFIGS))
+def test_fast_batch_matches_oracle(name):
+    import pirip_b200 as pb
+    pk, gk = CONFIGS[name]
+    plan = pb.FskPlan(**pk)
+    assert plan.mode == "fast", plan.kernel()
+    iq = make_batch(pk, gk, ncap=48, nbits=4000 * (2 if pk["M"] == 4 else 1) if pk["Rs"] > 1000 else 1500,
+                    ebnos=[None, 12.0, 9.0, 6.0, 4.0, 2.0], seed0=11000 + zlib.crc32(name.encode()) % 1000)
+    out = plan.demod_batch(iq, want_llr=pk.get("soft", False), want_rx_filt=True, want_stats=True)
+    worst = compare_fast(plan, pk, iq, out)
+    nflag, _ = plan.flagged(iq.shape[0])
+    print(name, "worst", worst, "flagged", nflag, "replays", plan.replays())
+    plan.close()
+
+
+def test_fast_kernel_replays_and_settles_everything_itself():
+    """Noisy 4FSK captures with non-orthogonal tones put decisions inside their margins every few hundred frames: the kernel
+    must replay those frames itself (replays > 0, none failed) and leave nothing to the exact-kernel fallback."""
+    import pirip_b200 as pb
+    pk, gk = CONFIGS["c3_4fsk_literal"]
+    plan = pb.FskPlan(**pk)
+    iq = make_batch(pk, gk, ncap=64, nbits=6000, ebnos=[6.0, 4.0, 3.0], seed0=12345)
+    out = plan.demod_batch(iq, want_llr=True, want_rx_filt=True, want_stats=True)
+    compare_fast(plan, pk, iq, out)
+    ok, failed = plan.replays()
+    nflag, _ = plan.flagged(iq.shape[0])
+    assert ok > 0 and failed == 0 and nflag == 0, (ok, failed, nflag)
+    plan.close()
+
+
+def test_fast_fallback_without_the_oscillator_chain(monkeypatch):
+    """Without the exact-oscillator chain (PIRIP_FSK_NO_CHAIN) a frame cannot be replayed in the kernel: the capture is flagged
+    and re-run by the exact kernel inside the same call - results are the oracle's all the same."""
+    import pirip_b200 as pb
+    monkeypatch.setenv("PIRIP_FSK_NO_CHAIN", "1")
+    pk, gk = CONFIGS["c3_4fsk_literal"]
+    plan = pb.FskPlan(**pk)
+    iq = make_batch(pk, gk, ncap=64, nbits=6000, ebnos=[6.0, 4.0, 3.0], seed0=12345)
+    out = plan.demod_batch(iq, want_llr=True, want_rx_filt=True, want_stats=True)
+    compare_fast(plan, pk, iq, out)
+    nflag, flags = plan.flagged(iq.shape[0])
+    assert nflag > 0 and nflag == int((flags != 0).sum())
+    plan.close()
+
+
+def test_fast_equals_exact_on_discrete_outputs_ragged_and_short():
+    """Edge cases of the capture loop: captures shorter than one frame, exactly one frame, lengths that end inside a frame,
+    odd sample counts; fast and exact kernels agree on frame counts and bits."""
+    import pirip_b200 as pb
+    pk, gk = CONFIGS["c1_2fsk_240k_10k_p24_limits"]
+    full = make_batch(pk, gk, ncap=8, nbits=1500, ebnos=[None, 9.0, 6.0], seed0=777)
+    for nsamp in (0, 100, 1199, 1200, 1201, 2399, 2401, 3611, 12345):
+        iq = np.ascontiguousarray(full[:, :2 * nsamp])
+        if nsamp == 0:
+            continue
+        pf, pe = pb.FskPlan(**pk), pb.FskPlan(**pk)
+        pe.set_mode("exact")
+        a = pf.demod_batch(iq, want_stats=True)
+        b = pe.demod_batch(iq, want_stats=True)
+        assert np.array_equal(a["nframes"], b["nframes"]), nsamp
+        assert np.array_equal(a["bits"], b["bits"]), nsamp
+        assert np.array_equal(a["stats"]["nin_next"], b["stats"]["nin_next"]), nsamp
+        pf.close()
+        pe.close()
+
+
+@pytest.mark.parametrize("fmt", ["s16", "f32"])
+def test_fast_other_input_formats(fmt):
+    """fsk_demod -c (cs16) and the COMP float input through the fast kernel."""
+    import pirip_b200 as pb
+    pk, gk = CONFIGS["c1_2fsk_240k_10k_p24_limits"]
+    u8 = make_batch(pk, gk, ncap=12, nbits=2000, ebnos=[None, 9.0, 6.0], seed0=4242)
+    x = (u8.astype(np.float32) - 127.0)
+    if fmt == "s16":
+        iq = np.ascontiguousarray((x * 60.0).astype(np.int16))
+        pfmt, ofmt = pb.FMT_S16, orc.FMT_S16
+    else:
+        iq = np.ascontiguousarray((x / 128.0).astype(np.float32)).view(np.complex64)  # COMP samples
+        pfmt, ofmt = pb.FMT_F32, orc.FMT_F32
+    kw = dict(pk, fmt=pfmt)
+    plan = pb.FskPlan(**kw)
+    assert plan.mode == "fast"
+    out = plan.demod_batch(iq, want_rx_filt=True, want_stats=True)
+    compare_fast(plan, dict(pk, fmt=ofmt), iq, out)
+    plan.close()
+
+
+def test_fast_full_c5_batch_bits_equal_oracle():
+    """The benchmark batch itself (BASELINE.json config 5 at the C1 settings): 1250 x 1-s captures, every capture checked
+    against the oracle: frame counts, nin, hard bits, tone estimates identical; timing / SNR within the tolerance."""
+    import torch
+    import bench
+    import pirip_b200 as pb
+    ncap, nsamp = 1250, 240000
+    iq = bench.gen_captures(torch, ncap, nsamp, seed=0, device=torch.device("cuda", 0)).cpu().numpy()
+    pk = dict(Fs=bench.FS, Rs=bench.RS, M=bench.M, P=bench.P, limits=bench.LIMITS)
+    plan = pb.FskPlan(**pk)
+    out = plan.demod_batch(iq, want_rx_filt=True, want_stats=True)
+    worst = compare_fast(plan, pk, iq, out)
+    nflag, _ = plan.flagged(ncap)
+    ok, failed = plan.replays()
+    print("C5 batch: worst", worst, "flagged", nflag, "replays", (ok, failed))
+    assert failed == 0 and nflag == 0
+    plan.close()

@@ -13,7 +13,7 @@ import pytest
 import orc
 import synth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("exact_mode")]
 
 # name -> (plan kwargs, generator kwargs)
 CONFIGS = {

@@ -10,7 +10,7 @@ import pytest
 import orc
 import synth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("exact_mode")]
 
 C1 = dict(Fs=240000, Rs=10000, M=2, P=24, limits=(500, 25000))
 

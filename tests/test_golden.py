@@ -42,10 +42,11 @@ def test_oracle_reproduces_golden(name):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", list(CFGS))
-def test_cuda_reproduces_golden(name):
+def test_cuda_reproduces_golden(name, exact_mode):
     import pirip_b200 as pb
     kw, g = CFGS[name], load(name)
     plan = pb.FskPlan(**kw)
+    assert plan.mode == "exact"
     out = plan.demod_batch(g["iq"], want_llr=kw.get("soft", False), want_rx_filt=True, want_stats=True)
     for c in range(g["iq"].shape[0]):
         nf = int(g["nframes"][c])

@@ -7,7 +7,7 @@ import pytest
 import orc
 import synth
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("exact_mode")]
 CODES = ["HRA_112_112", "H_256_512_4", "H_128_256_5"]
 
 

@@ -69,7 +69,7 @@ def probe(name, pk, gk, ncap, nbits, ebnos, threads):
     r = dict(config=name, captures=ncap, frames=0, symbols=0, flagged=int(nflag), nframes_mismatch=0, nin_mismatch=0, f_est_mismatch=0,
              bit_mismatch=0, captures_with_bit_mismatch=0, unflagged_bad_captures=0, max_dnorm=0.0, max_filt_rel=0.0,
              max_margin_err=0.0, max_llr_rel=0.0, max_dsnr_rel=0.0)
-    merrs, dn_all, worst = [], [], []
+    merrs, dn_all, worst, rho_all = [], [], [], []
     for c in range(ncap):
         ref = refs[c]
         nf = min(ref["nframes"], int(out["nframes"][c]))
@@ -103,6 +103,9 @@ def probe(name, pk, gk, ncap, nbits, ebnos, threads):
         dn = np.abs(st["norm_rx_timing"][:ok_upto].astype(np.float64) - rs["norm_rx_timing"][:ok_upto])
         dn = np.minimum(dn, 1.0 - dn)  # wrap at +-0.5
         dn_all.append(dn)
+        if os.environ.get("PIRIP_FSK_FAST_DIAG"):
+            rho = st["foff"][:ok_upto].astype(np.float64)
+            rho_all.append(rho)
         gf = out["rx_filt"][c, :ok_upto * plan.nfilt].reshape(ok_upto, -1).astype(np.float64)
         rf = ref["rx_filt"][:ok_upto * plan.nfilt].reshape(ok_upto, -1).astype(np.float64)
         scale = np.maximum(rf.max(axis=1, keepdims=True), 1e-30)
@@ -127,6 +130,14 @@ def probe(name, pk, gk, ncap, nbits, ebnos, threads):
     r["margin_err_pct"] = {p: float(np.percentile(me, p)) for p in (50, 99, 99.99)}
     r["max_dnorm"] = float(dn.max())
     r["dnorm_pct"] = {p: float(np.percentile(dn, p)) for p in (50, 99, 99.99)}
+    if rho_all:
+        rho = np.concatenate(rho_all)
+        k = dn * rho
+        r["rho_pct"] = {p: float(np.percentile(rho, p)) for p in (0.01, 1, 50)}
+        r["dnorm_x_rho_pct"] = {p: float(np.percentile(k, p)) for p in (50, 99, 99.99, 100)}
+        # per rho-decade: max dnorm
+        r["dnorm_by_rho"] = [(float(lo), int(((rho >= lo) & (rho < lo * 10)).sum()), float(dn[(rho >= lo) & (rho < lo * 10)].max()) if ((rho >= lo) & (rho < lo * 10)).any() else 0.0)
+                             for lo in (1e-4, 1e-3, 1e-2, 1e-1)]
     r["flag_reasons"] = {k: int(((flags & v) != 0).sum()) for k, v in (("sym", 1), ("tim", 2), ("ppm", 4), ("nan", 8))}
     r["flag_words"] = [(c, ebnos[c % len(ebnos)], int(flags[c] & 0xff), int((flags[c] >> 8) & 0xfff) - 1, int(flags[c] >> 20)) for c in range(ncap) if flags[c]]
     worst.sort(reverse=True)
