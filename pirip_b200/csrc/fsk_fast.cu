@@ -85,6 +85,8 @@ struct FastArgs {
     int *flag_list;  /* compacted indices of flagged captures */
     int *flag_count;
     int tma_ok;
+    const u64 *landed; /* optional: samples of every capture already in device memory (the host streams the captures in while the
+                          kernel runs); a frame is fetched only when it has landed */
     /* exact-oscillator side chain (fsk_osc_chain_kernel): NULL when it does not run beside this launch */
     u64 *mbox;          /* [n_captures][max_frames + 1] per-frame mailbox: what the side chain needs to run frame f */
     float4 *ckpt;       /* [n_captures][2][ckpt_per_frame][4] records {phi.x, phi.y, tag, ~tag}: oscillator state before every 64th
@@ -97,7 +99,7 @@ struct FastArgs {
     int G, chain_ctas, chain_wpc;
 };
 
-enum { FLAG_SYM = 1, FLAG_TIM = 2, FLAG_PPM = 4, FLAG_NAN = 8 };
+enum { FLAG_SYM = 1, FLAG_TIM = 2, FLAG_PPM = 4, FLAG_NAN = 8, FLAG_INGEST = 16 };
 
 struct Misc {
     u64 bar;
@@ -871,6 +873,24 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
 
     /* issue the copy of raw samples [pos, pos + nin_max) (16-byte aligned superset) into `raw`; thread 0 only */
     auto issue_raw = [&](u64 pos) {
+        if (args.landed) {
+            /* streamed ingest: wait until the copy engine has delivered this frame (longest form) for every capture.  The wait
+               sleeps, costs no issue slots to speak of, and gives up after ~2 s without the samples (a tool that serialises
+               copies behind the kernel): the capture is then flagged and re-run by the exact kernel after the copies. */
+            u64 need = pos + (u64)cfg.nin_max;
+            if (need > args.nsamples) need = args.nsamples;
+            const volatile u64 *lw = args.landed;
+            if (*lw < need) {
+                const long long t0 = clock64();
+                while (*lw < need) {
+                    __nanosleep(1000);
+                    if (clock64() - t0 > 4000000000ll) {
+                        ms->flags |= FLAG_INGEST;
+                        break;
+                    }
+                }
+            }
+        }
         const size_t a = reinterpret_cast<size_t>(cap_base) + pos * bps;
         size_t want_end = a + (size_t)cfg.nin_max * bps;
         const size_t cap_end = reinterpret_cast<size_t>(cap_base) + args.nsamples * bps;
@@ -1414,7 +1434,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             ms->nin = ms->nin_next;
             ms->frame = frame + 1;
             int cont = ((size_t)(frame + 1) < args.max_frames && ms->pos + (u64)ms->nin <= args.nsamples) ? 1 : 0;
-            if (ms->flags && cfg.exit_on_flag) cont = 0;
+            if ((ms->flags && cfg.exit_on_flag) || (ms->flags & FLAG_INGEST)) cont = 0;
             if (ms->flags && (ms->flags >> 8) == 0) ms->flags |= ((frame + 1) & 0xfff) << 8;
             ms->cont = cont;
         }
@@ -1826,6 +1846,7 @@ cudaError_t fsk_fast_launch(FskFastPlan *p, const FskBatchArgs &b, int *d_flags,
     a.flag_list = d_list;
     a.flag_count = d_count;
     a.tma_ok = b.tma_ok;
+    a.landed = b.landed;
     a.ckpt_per_frame = p->ckpt_per_frame;
     if (total < off + b.n_captures) total = off + b.n_captures;
     const size_t n = b.n_captures;

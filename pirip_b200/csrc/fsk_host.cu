@@ -614,7 +614,7 @@ static size_t bytes_per_sample(int fmt) { return fmt == PIRIP_FMT_U8 ? 2 : (fmt 
 static int batch_dev(pirip_fsk_plan *plan, const void *d_iq, size_t n_captures, size_t samples_per_capture,
                      size_t capture_stride_bytes, uint8_t *d_bits, float *d_llr, float *d_rx_filt,
                      struct pirip_frame_stats *d_stats, int32_t *d_nframes, size_t max_frames, void *stream,
-                     const unsigned long long *d_landed, size_t flag_off = 0, size_t flag_total = 0, size_t chunk = 0);
+                     const unsigned long long *d_landed, size_t flag_off = 0, size_t flag_total = 0, size_t chunk = 0, int phases = 3);
 
 extern "C" int pirip_fsk_demod_batch_dev(pirip_fsk_plan *plan, const void *d_iq, size_t n_captures,
                                          size_t samples_per_capture, size_t capture_stride_bytes, uint8_t *d_bits,
@@ -631,7 +631,7 @@ extern "C" int pirip_fsk_demod_batch_dev(pirip_fsk_plan *plan, const void *d_iq,
 static int batch_dev(pirip_fsk_plan *plan, const void *d_iq, size_t n_captures, size_t samples_per_capture,
                      size_t capture_stride_bytes, uint8_t *d_bits, float *d_llr, float *d_rx_filt,
                      struct pirip_frame_stats *d_stats, int32_t *d_nframes, size_t max_frames, void *stream,
-                     const unsigned long long *d_landed, size_t flag_off, size_t flag_total, size_t chunk) {
+                     const unsigned long long *d_landed, size_t flag_off, size_t flag_total, size_t chunk, int phases) {
     if (!plan) return pirip::fail(-1, "plan is NULL");
     if (n_captures == 0) return 0;
     if (!d_iq) return pirip::fail(-2, "d_iq is NULL");
@@ -663,13 +663,19 @@ static int batch_dev(pirip_fsk_plan *plan, const void *d_iq, size_t n_captures, 
         d_flags += flag_off;
         d_list += flag_off;
         d_count += chunk;
-        a.landed = nullptr;
-        if (!pirip::cuda_ok(cudaMemsetAsync(d_count, 0, sizeof(int), (cudaStream_t)stream), "reset flag count")) return -11;
-        if (!pirip::cuda_ok(fsk_fast_launch(plan->fast, a, d_flags, d_list, d_count, (cudaStream_t)stream, flag_off, flag_total, chunk),
-                            "fsk_fast_kernel launch"))
-            return -11;
-        pirip::count_launch();
+        a.landed = d_landed;
+        /* phases: 1 = the fast kernel, 2 = the exact kernel over the captures it flagged (the host-buffer call puts the end of
+           its streamed copies between the two) */
+        if (phases & 1) {
+            if (!pirip::cuda_ok(cudaMemsetAsync(d_count, 0, sizeof(int), (cudaStream_t)stream), "reset flag count")) return -11;
+            if (!pirip::cuda_ok(fsk_fast_launch(plan->fast, a, d_flags, d_list, d_count, (cudaStream_t)stream, flag_off, flag_total, chunk),
+                                "fsk_fast_kernel launch"))
+                return -11;
+            pirip::count_launch();
+        }
+        if (!(phases & 2)) return 0;
         FskBatchArgs x = a;
+        x.landed = nullptr; /* the host makes the re-run wait for the last copy */
         x.cap_list = d_list;
         x.cap_count = d_count;
         x.total_captures = n_captures;
@@ -740,9 +746,10 @@ extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_
     }
     const bool fast = plan->fast && plan->mode;
     if (fast) {
-        /* the fast kernel is several times quicker than PCIe delivers the captures: split the batch by captures, copy
-           chunk k + 1 while chunk k is demodulated (plain stream order, no kernel ever waits for a copy issued after it) */
-        nchunks = 8;
+        /* one launch for the whole batch (a launch costs 200 frames of per-frame latency however few captures it has), the
+           captures streamed in by time slices beside it - see below.  PIRIP_FSK_E2E_CHUNKS > 1 selects plain chunking by
+           captures instead (copy chunk k + 1 while chunk k is demodulated). */
+        nchunks = 1;
         if (const char *e = getenv("PIRIP_FSK_E2E_CHUNKS"))
             if (atoi(e) >= 1 && atoi(e) <= 64) nchunks = (size_t)atoi(e);
         while (nchunks > 1 && n_captures / nchunks < 64) nchunks /= 2;
@@ -767,7 +774,7 @@ extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_
        serialise the launch on the host, which would leave the kernel waiting for ever: copy first, then run. */
     const bool injected = getenv("CUDA_INJECTION64_PATH") != nullptr || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
                           (getenv("CUDA_LAUNCH_BLOCKING") != nullptr && atoi(getenv("CUDA_LAUNCH_BLOCKING")) != 0);
-    const bool streamed = !fast && plan->dev.k2.ok && nchunks == 1 && nslices > 1 && !injected && getenv("PIRIP_FSK_NO_STREAM_INGEST") == nullptr;
+    const bool streamed = plan->dev.k2.ok && nchunks == 1 && nslices > 1 && !injected && getenv("PIRIP_FSK_NO_STREAM_INGEST") == nullptr;
     if (rc == 0 && streamed) {
         if (!w.d_landed) CK(cudaMalloc(&w.d_landed, sizeof(unsigned long long)), "cudaMalloc landed");
         if (!w.h_marks) CK(cudaHostAlloc(&w.h_marks, 72 * sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc marks");
@@ -791,9 +798,12 @@ extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_
             cudaStream_t cs = w.streams[(ci + 1) % pirip_fsk_plan::Work::kStreams]; /* copy stream */
             CK(cudaMemsetAsync(w.d_landed, 0, sizeof(unsigned long long), s), "reset landed");
             CK(cudaEventRecord(w.ev_reset, s), "event record");
-            if (rc == 0)
+            bool launched = false;
+            if (rc == 0) {
                 rc = batch_dev(plan, d_iq, nc, samples_per_capture, stride, d_bits, d_llr, d_filt, d_stats, d_nf, max_frames, s,
-                               w.d_landed);
+                               w.d_landed, c0, n_captures, ci, fast ? 1 : 3);
+                launched = rc == 0;
+            }
             CK(cudaStreamWaitEvent(cs, w.ev_reset, 0), "stream wait");
             const size_t per_slice = ((samples_per_capture + nslices - 1) / nslices + 7) / 8 * 8;
             for (size_t k = 0, s0 = 0; rc == 0 && s0 < samples_per_capture; ++k, s0 += per_slice) {
@@ -803,6 +813,21 @@ extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_
                    "H2D iq slice");
                 w.h_marks[k] = (unsigned long long)s1;
                 CK(cudaMemcpyAsync(w.d_landed, &w.h_marks[k], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs), "publish landed");
+            }
+            if (rc != 0 && launched) {
+                /* a copy failed after the kernel was launched: release the kernel (it would otherwise wait for samples that never
+                   come until its own time-out); the call still reports the error */
+                w.h_marks[71] = (unsigned long long)samples_per_capture;
+                cudaMemcpyAsync(w.d_landed, &w.h_marks[71], sizeof(unsigned long long), cudaMemcpyHostToDevice, cs);
+            }
+            if (fast && launched) {
+                /* the exact re-run of flagged captures (normally none) reads the captures: after the last copy */
+                cudaError_t e1 = cudaEventRecord(w.ev_reset, cs);
+                cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(s, w.ev_reset, 0) : e1;
+                if (rc == 0 && !pirip::cuda_ok(e2, "wait for the streamed copies")) rc = -12;
+                if (rc == 0)
+                    rc = batch_dev(plan, d_iq, nc, samples_per_capture, stride, d_bits, d_llr, d_filt, d_stats, d_nf, max_frames, s, nullptr,
+                                   c0, n_captures, ci, 2);
             }
         } else {
             CK(cudaMemcpy2DAsync(d_iq, stride, (const unsigned char *)iq + c0 * cap_bytes, cap_bytes, cap_bytes, nc,
