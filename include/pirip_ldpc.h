@@ -107,6 +107,20 @@ void freedv_fsk_ldpc_rx_info(struct freedv *f, int info[6]);
 typedef struct pirip_ldpc_plan pirip_ldpc_plan;
 pirip_ldpc_plan *pirip_ldpc_plan_create(const struct LDPC *ldpc, int device);
 void pirip_ldpc_plan_destroy(pirip_ldpc_plan *plan);
+/* Check-node update of the batched decoder (all modes honour the code's iteration cap - 15 for FSK_LDPC [R README.md:211] -
+ * and stop at the first iteration whose parity checks all pass):
+ *   PIRIP_LDPC_SUM_PRODUCT (default): [U mpdecode_core.c::SumProduct] with its phi0 in double - decoded bits, `iter` and
+ *     `pcc` identical to the CPU evaluation;
+ *   PIRIP_LDPC_SUM_PRODUCT_FAST: the same update with phi0 in single precision (hardware exp / log): same bits on every
+ *     word that converges, `iter` may differ by one now and then;
+ *   PIRIP_LDPC_MIN_SUM: normalised min-sum (scale 0.75): no transcendentals; same payload on converged words, a few tenths
+ *     of a dB earlier breakdown at threshold.
+ * PIRIP_LDPC_MODE=minsum|fast in the environment selects the mode of plans created afterwards. */
+#define PIRIP_LDPC_SUM_PRODUCT 0
+#define PIRIP_LDPC_SUM_PRODUCT_FAST 1
+#define PIRIP_LDPC_MIN_SUM 2
+int pirip_ldpc_plan_set_mode(pirip_ldpc_plan *plan, int mode);
+int pirip_ldpc_plan_mode(const pirip_ldpc_plan *plan);
 /* d_llr [n_codewords][CodeLength] float (positive = bit 0); outputs (device): d_bits
  * [n_codewords][CodeLength] one bit per byte, d_iter [n_codewords], d_pcc [n_codewords]
  * (either count may be NULL).  Asynchronous on `stream`.  Returns 0 or a negative code. */

@@ -430,6 +430,16 @@ class LdpcPlan:
         if not self._h:
             raise _err("pirip_ldpc_plan_create")
 
+    MODES = {"sum_product": 0, "sum_product_fast": 1, "min_sum": 2}
+
+    def set_mode(self, mode):
+        """'sum_product' (exact, default), 'sum_product_fast' or 'min_sum' (include/pirip_ldpc.h)."""
+        self.L.pirip_ldpc_plan_set_mode.restype = C.c_int
+        self.L.pirip_ldpc_plan_set_mode.argtypes = [C.c_void_p, C.c_int]
+        rc = self.L.pirip_ldpc_plan_set_mode(self._h, self.MODES[mode])
+        if rc != 0:
+            raise _err("pirip_ldpc_plan_set_mode", rc)
+
     def decode(self, llr):
         llr = np.ascontiguousarray(llr, np.float32).reshape(-1, self.N)
         n = llr.shape[0]

@@ -36,7 +36,13 @@ struct LdpcGraph {
     int N, NPB, E, max_iter;
     const uint16_t *c_off;  /* [NPB+1] first edge of every check */
     const uint16_t *v_off;  /* [N+1] first entry of every variable in v_edge */
-    const uint16_t *v_edge; /* [E] edge ids of every variable, in the variable's table order */
+    const uint16_t *c_vpos; /* [E] check order: position of the edge in variable order */
+    const unsigned *v_rec;  /* [E] variable order: check << 8 | position of the edge in its check */
+    /* shared-memory layout of the decoder kernel (bytes): tables once per CTA, then one block per warp (codeword) */
+    int off_voff, off_vedge, off_echk, tables_bytes;
+    int w_q, w_chk, w_llr, warp_bytes;
+    int warps;  /* codewords per CTA */
+    float ms_scale; /* normalisation of the min-sum check update */
 };
 
 /* [U mpdecode_core.c::phi0] CML closed form with the coarse steps above 5 */
@@ -51,85 +57,177 @@ __device__ __forceinline__ float phi0(float x) {
     const float z = (float)em_exp((double)x);
     return (float)em_log((double)((z + 1.0f) / (z - 1.0f)));
 }
+/* the same function in single precision with the hardware exponential / logarithm (tolerance mode) */
+__device__ __forceinline__ float phi0_fast(float x) {
+    if (x > 10.0f) return 0.0f;
+    if (x < 9.08e-5f) return 10.0f;
+    if (x > 9.0f) return 1.6881e-4f;
+    if (x > 8.0f) return 4.5887e-4f;
+    if (x > 7.0f) return 1.2473e-3f;
+    if (x > 6.0f) return 3.3906e-3f;
+    if (x > 5.0f) return 9.2168e-3f;
+    const float z = __expf(x);
+    return __logf(__fdividef(z + 1.0f, z - 1.0f));
+}
 
-constexpr int kLdpcThreads = 128;
+enum { LDPC_SP_EXACT = 0, LDPC_SP_FAST = 1, LDPC_MINSUM = 2 };
+constexpr int kLdpcMaxWarps = 8;
 
-__global__ void __launch_bounds__(kLdpcThreads) ldpc_decode_kernel(const __grid_constant__ LdpcGraph g, const float *llr_in,
-                                                                   unsigned char *bits_out, int *iter_out, int *pcc_out) {
+/* One WARP per codeword, up to 8 codewords per CTA, the Tanner graph tables loaded once per CTA.
+   A lane owns whole check nodes in the check phase and whole variable nodes in the variable phase and walks their edges
+   in table order, so in the exact mode every float sum is formed in the order of the scalar algorithm
+   ([U mpdecode_core.c::SumProduct]) and bits / iterations / parity-check counts are identical to it.  Messages: one float per
+   edge (the variable-to-check message: phi0(|q|) with the sign of q in the sign bit, or q itself for min-sum); the
+   check-to-variable messages are never stored - a check leaves its sum (or its two smallest magnitudes) and sign parity, and
+   the variable phase forms r from them.  The parity-check count is a warp reduction; the loop ends as soon as it reaches
+   NumberParityBits (early exit per codeword, no CTA barrier inside the iterations). */
+/* check-to-variable message from what the check left behind (cs: sum / smallest magnitude with the parity in the sign bit;
+   ca: min-sum only, second smallest magnitude with the position of the smallest in its 6 low mantissa bits) */
+template <int MODE>
+__device__ __forceinline__ float r_msg(float qe, float cs, float ca, int pos) {
+    const unsigned neg = (__float_as_uint(cs) ^ __float_as_uint(qe)) & 0x80000000u;
+    float mag;
+    if (MODE == LDPC_MINSUM) {
+        const unsigned a2 = __float_as_uint(ca);
+        mag = ((int)(a2 & 63u) == pos) ? __uint_as_float(a2 & ~63u) : fabsf(cs);
+    } else {
+        const float d = __fsub_rn(fabsf(cs), fabsf(qe));
+        mag = MODE == LDPC_SP_EXACT ? phi0(d) : phi0_fast(d);
+    }
+    return __uint_as_float(__float_as_uint(mag) ^ neg);
+}
+/* variable-to-check message as stored: phi0(|t|) (or |t| for min-sum) with the sign the scalar code gives t (t > 0 ? 0 : 1) */
+template <int MODE>
+__device__ __forceinline__ float q_store(float t) {
+    const float a = MODE == LDPC_MINSUM ? fabsf(t) : (MODE == LDPC_SP_EXACT ? phi0(fabsf(t)) : phi0_fast(fabsf(t)));
+    return t > 0.0f ? a : -a;
+}
+
+/* One WARP per codeword, up to 8 codewords per CTA, the Tanner graph tables loaded once per CTA.
+   A lane owns whole check nodes in the check phase and whole variable nodes in the variable phase and walks their edges
+   in table order, so in the exact mode every float sum is formed in the order of the scalar algorithm
+   ([U mpdecode_core.c::SumProduct]) and bits / iterations / parity-check counts are identical to it.  Messages: one float per
+   edge, stored in VARIABLE order (the variable phase reads and writes them sequentially; the check phase gathers them through
+   an index table): the variable-to-check message phi0(|q|) with the sign of q in the sign bit, or q itself for min-sum.
+   The check-to-variable messages are never stored - a check leaves its sum (or its two smallest magnitudes) and sign parity,
+   and the variable phase forms r from them.  The parity-check count is a warp reduction; the loop ends as soon as it reaches
+   NumberParityBits (early exit per codeword, no CTA barrier inside the iterations). */
+template <int MODE>
+__global__ void __launch_bounds__(32 * kLdpcMaxWarps) ldpc_decode_warp_kernel(const __grid_constant__ LdpcGraph g, const float *llr_in, size_t n_cw,
+                                                                              unsigned char *bits_out, int *iter_out, int *pcc_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *llr = reinterpret_cast<float *>(smem_raw);
-    float *q_msg = llr + g.N;
-    float *r_msg = q_msg + g.E;
-    uint16_t *c_off = reinterpret_cast<uint16_t *>(r_msg + g.E);
-    uint16_t *v_off = c_off + (g.NPB + 1);
-    uint16_t *v_edge = v_off + (g.N + 1);
-    unsigned char *q_sign = reinterpret_cast<unsigned char *>(v_edge + g.E);
-    unsigned char *dec = q_sign + g.E;
-    __shared__ int ssum;
-    const int tid = threadIdx.x;
-    const size_t cw = blockIdx.x;
-
-    for (int i = tid; i <= g.NPB; i += kLdpcThreads) c_off[i] = g.c_off[i];
-    for (int i = tid; i <= g.N; i += kLdpcThreads) v_off[i] = g.v_off[i];
-    for (int i = tid; i < g.E; i += kLdpcThreads) v_edge[i] = g.v_edge[i];
-    for (int i = tid; i < g.N; i += kLdpcThreads) llr[i] = llr_in[cw * g.N + i];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint16_t *c_off = reinterpret_cast<uint16_t *>(smem_raw);
+    uint16_t *v_off = reinterpret_cast<uint16_t *>(smem_raw + g.off_voff);
+    uint16_t *c_vpos = reinterpret_cast<uint16_t *>(smem_raw + g.off_vedge);  /* [E] check order -> position in variable order */
+    unsigned *v_rec = reinterpret_cast<unsigned *>(smem_raw + g.off_echk);    /* [E] variable order: check << 8 | position in the check */
+    for (int i = threadIdx.x; i <= g.NPB; i += blockDim.x) c_off[i] = g.c_off[i];
+    for (int i = threadIdx.x; i <= g.N; i += blockDim.x) v_off[i] = g.v_off[i];
+    for (int i = threadIdx.x; i < g.E; i += blockDim.x) {
+        c_vpos[i] = g.c_vpos[i];
+        v_rec[i] = g.v_rec[i];
+    }
     __syncthreads();
-    /* initial variable-to-check messages: the channel LLR on every edge */
-    for (int v = tid; v < g.N; v += kLdpcThreads) {
-        const float x = llr[v];
-        const float ph = phi0(fabsf(x));
-        const unsigned char sg = x < 0.0f ? 1 : 0;
-        for (int j = v_off[v]; j < v_off[v + 1]; ++j) {
-            q_msg[v_edge[j]] = ph;
-            q_sign[v_edge[j]] = sg;
-        }
-        dec[v] = 0;
-    }
-    int result = g.max_iter, pcc = 0;
-    for (int iter = 0; iter < g.max_iter; ++iter) {
-        if (tid == 0) ssum = 0;
-        __syncthreads();
-        /* check-node update */
-        int local = 0;
-        for (int c = tid; c < g.NPB; c += kLdpcThreads) {
-            const int e0 = c_off[c], e1 = c_off[c + 1];
-            int sign = q_sign[e0];
-            float phi_sum = q_msg[e0];
-            for (int e = e0 + 1; e < e1; ++e) {
-                phi_sum += q_msg[e];
-                sign ^= q_sign[e];
+    if (warp >= g.warps) return;
+    unsigned char *wb = smem_raw + g.tables_bytes + (size_t)warp * g.warp_bytes;
+    float *q = reinterpret_cast<float *>(wb + g.w_q);        /* [E] variable order */
+    float2 *chk = reinterpret_cast<float2 *>(wb + g.w_chk);  /* [NPB] what a check leaves behind (see r_msg) */
+    float *llr = reinterpret_cast<float *>(wb + g.w_llr);    /* [N] */
+
+    for (size_t cw = (size_t)blockIdx.x * g.warps + warp; cw < n_cw; cw += (size_t)gridDim.x * g.warps) {
+        const float *in = llr_in + cw * g.N;
+        for (int v = lane; v < g.N; v += 32) {
+            const float x = in[v];
+            llr[v] = x;
+            float m;
+            if (MODE == LDPC_MINSUM)
+                m = x;
+            else {
+                const float ph = MODE == LDPC_SP_EXACT ? phi0(fabsf(x)) : phi0_fast(fabsf(x));
+                m = x < 0.0f ? -ph : ph;
             }
-            if (sign == 0) local++;
-            for (int e = e0; e < e1; ++e) {
-                const float r = phi0(phi_sum - q_msg[e]);
-                r_msg[e] = (sign ^ q_sign[e]) ? -r : r;
+            for (int j = v_off[v]; j < v_off[v + 1]; ++j) q[j] = m;
+        }
+        __syncwarp();
+        int result = g.max_iter, pcc = 0;
+        for (int iter = 0; iter < g.max_iter; ++iter) {
+            /* check-node phase */
+            int local = 0;
+            for (int c = lane; c < g.NPB; c += 32) {
+                const int e0 = c_off[c], e1 = c_off[c + 1];
+                unsigned sign = 0;
+                if (MODE == LDPC_MINSUM) {
+                    float m1 = 3.0e38f, m2 = 3.0e38f;
+                    int pos = 0;
+                    for (int e = e0; e < e1; ++e) {
+                        const float v = q[c_vpos[e]];
+                        const float a = fabsf(v);
+                        sign ^= __float_as_uint(v) & 0x80000000u;
+                        if (a < m1) {
+                            m2 = m1;
+                            m1 = a;
+                            pos = e - e0;
+                        } else if (a < m2)
+                            m2 = a;
+                    }
+                    chk[c] = make_float2(__uint_as_float(__float_as_uint(m1 * g.ms_scale) | sign),
+                                         __uint_as_float((__float_as_uint(m2 * g.ms_scale) & ~63u) | (unsigned)(pos & 63)));
+                } else {
+                    const float v0 = q[c_vpos[e0]];
+                    float phi_sum = fabsf(v0);
+                    sign = __float_as_uint(v0) & 0x80000000u;
+                    for (int e = e0 + 1; e < e1; ++e) {
+                        const float v = q[c_vpos[e]];
+                        phi_sum = __fadd_rn(phi_sum, fabsf(v));
+                        sign ^= __float_as_uint(v) & 0x80000000u;
+                    }
+                    chk[c] = make_float2(__uint_as_float(__float_as_uint(phi_sum) | sign), 0.0f);
+                }
+                if (sign == 0) local++;
+            }
+            pcc = __reduce_add_sync(0xffffffffu, local);
+            __syncwarp();
+            const bool last = pcc == g.NPB || iter == g.max_iter - 1;
+            /* variable-node phase */
+            for (int v = lane; v < g.N; v += 32) {
+                const int j0 = v_off[v], j1 = v_off[v + 1];
+                float Qi = llr[v];
+                float r[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (j0 + k < j1) {
+                        const unsigned rec = v_rec[j0 + k];
+                        const float2 cs = chk[rec >> 8];
+                        r[k] = r_msg<MODE>(q[j0 + k], cs.x, cs.y, (int)(rec & 63u));
+                        Qi = __fadd_rn(Qi, r[k]);
+                    }
+                /* variables with more than 8 edges (none of codec2's codes): the rest of the sum */
+                for (int j = j0 + 8; j < j1; ++j) {
+                    const unsigned rec = v_rec[j];
+                    const float2 cs = chk[rec >> 8];
+                    Qi = __fadd_rn(Qi, r_msg<MODE>(q[j], cs.x, cs.y, (int)(rec & 63u)));
+                }
+                if (last) bits_out[cw * g.N + v] = Qi < 0.0f ? 1 : 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (j0 + k < j1) q[j0 + k] = q_store<MODE>(__fsub_rn(Qi, r[k]));
+                for (int j = j0 + 8; j < j1; ++j) {
+                    const unsigned rec = v_rec[j];
+                    const float2 cs = chk[rec >> 8];
+                    q[j] = q_store<MODE>(__fsub_rn(Qi, r_msg<MODE>(q[j], cs.x, cs.y, (int)(rec & 63u))));
+                }
+            }
+            __syncwarp();
+            if (pcc == g.NPB) {
+                result = iter + 1;
+                break;
             }
         }
-        if (local) atomicAdd(&ssum, local);
-        __syncthreads();
-        /* variable-node update */
-        for (int v = tid; v < g.N; v += kLdpcThreads) {
-            float Qi = llr[v];
-            for (int j = v_off[v]; j < v_off[v + 1]; ++j) Qi += r_msg[v_edge[j]];
-            dec[v] = Qi < 0.0f ? 1 : 0;
-            for (int j = v_off[v]; j < v_off[v + 1]; ++j) {
-                const int e = v_edge[j];
-                const float t = Qi - r_msg[e];
-                q_msg[e] = phi0(fabsf(t));
-                q_sign[e] = t > 0.0f ? 0 : 1;
-            }
+        if (lane == 0) {
+            if (iter_out) iter_out[cw] = result;
+            if (pcc_out) pcc_out[cw] = pcc;
         }
-        pcc = ssum;
-        __syncthreads();
-        if (pcc == g.NPB) {
-            result = iter + 1;
-            break;
-        }
-    }
-    for (int v = tid; v < g.N; v += kLdpcThreads) bits_out[cw * g.N + v] = dec[v];
-    if (tid == 0) {
-        if (iter_out) iter_out[cw] = result;
-        if (pcc_out) pcc_out[cw] = pcc;
+        __syncwarp();
     }
 }
 
@@ -257,7 +355,10 @@ bool build_graph(const struct LDPC *l, std::vector<uint16_t> &c_off, std::vector
 struct pirip_ldpc_plan {
     LdpcGraph g;
     int device, smem;
-    uint16_t *d_c_off = nullptr, *d_v_off = nullptr, *d_v_edge = nullptr;
+    int mode = LDPC_SP_EXACT;
+    int num_sms = 148;
+    uint16_t *d_c_off = nullptr, *d_v_off = nullptr, *d_c_vpos = nullptr;
+    unsigned *d_v_rec = nullptr;
     float *d_llr = nullptr;
     unsigned char *d_bits = nullptr;
     int *d_iter = nullptr, *d_pcc = nullptr;
@@ -281,36 +382,103 @@ extern "C" pirip_ldpc_plan *pirip_ldpc_plan_create(const struct LDPC *l, int dev
     p->g.NPB = l->NumberParityBits;
     p->g.E = (int)v_edge.size();
     p->g.max_iter = l->max_iter > 0 ? l->max_iter : 15;
-    p->smem = (p->g.N + 2 * p->g.E) * 4 + ((p->g.NPB + 1) + (p->g.N + 1) + p->g.E) * 2 + p->g.E + p->g.N + 16;
-    p->smem = (p->smem + 15) / 16 * 16;
-    if (p->smem > 227 * 1024) {
+    /* v_edge[j] = edge id (check order) of the j-th entry in variable order */
+    std::vector<uint16_t> c_vpos((size_t)p->g.E);
+    std::vector<unsigned> v_rec((size_t)p->g.E);
+    {
+        std::vector<int> e_chk((size_t)p->g.E);
+        for (int c = 0; c < p->g.NPB; ++c)
+            for (int e = c_off[(size_t)c]; e < c_off[(size_t)c + 1]; ++e) e_chk[(size_t)e] = c;
+        for (int j = 0; j < p->g.E; ++j) {
+            const int e = v_edge[(size_t)j], c = e_chk[(size_t)e];
+            c_vpos[(size_t)e] = (uint16_t)j;
+            v_rec[(size_t)j] = ((unsigned)c << 8) | (unsigned)(e - c_off[(size_t)c]);
+        }
+    }
+    {
+        auto al = [](int v) { return (v + 15) / 16 * 16; };
+        LdpcGraph &g = p->g;
+        int o = al((g.NPB + 1) * 2);
+        g.off_voff = o;
+        o += al((g.N + 1) * 2);
+        g.off_vedge = o;
+        o += al(g.E * 2);
+        g.off_echk = o;
+        o += al(g.E * 4);
+        g.tables_bytes = o;
+        int w = 0;
+        g.w_q = w;
+        w += al(g.E * 4);
+        g.w_chk = w;
+        w += al(g.NPB * 8);
+        g.w_llr = w;
+        w += al(g.N * 4);
+        g.warp_bytes = w;
+        int warps = (227 * 1024 - g.tables_bytes) / w;
+        /* two CTAs per SM when they fit: 8 codewords each */
+        if (warps > kLdpcMaxWarps) warps = kLdpcMaxWarps;
+        while (warps > 1 && 2 * (g.tables_bytes + warps * w + 1024) > 228 * 1024 && warps > 4) --warps;
+        g.warps = warps;
+        g.ms_scale = 0.75f;
+        p->smem = g.tables_bytes + (warps > 0 ? warps : 0) * w;
+    }
+    if (p->g.warps < 1) {
         pirip::set_error("code too large for one CTA's shared memory");
         delete p;
         return nullptr;
     }
+    for (int c = 0; c < p->g.NPB; ++c)
+        if (c_off[(size_t)c + 1] - c_off[(size_t)c] > 64) {
+            pirip::set_error("check nodes with more than 64 edges are not supported");
+            delete p;
+            return nullptr;
+        }
+    {
+        int sms = 0;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) p->num_sms = sms;
+    }
+    if (const char *e = getenv("PIRIP_LDPC_MODE")) {
+        if (!strcmp(e, "minsum")) p->mode = LDPC_MINSUM;
+        else if (!strcmp(e, "fast")) p->mode = LDPC_SP_FAST;
+    }
     if (!pirip::cuda_ok(cudaSetDevice(device), "cudaSetDevice") ||
         !pirip::cuda_ok(cudaMalloc(&p->d_c_off, 2 * c_off.size()), "cudaMalloc") ||
         !pirip::cuda_ok(cudaMalloc(&p->d_v_off, 2 * v_off.size()), "cudaMalloc") ||
-        !pirip::cuda_ok(cudaMalloc(&p->d_v_edge, 2 * v_edge.size()), "cudaMalloc") ||
+        !pirip::cuda_ok(cudaMalloc(&p->d_c_vpos, 2 * c_vpos.size()), "cudaMalloc") ||
+        !pirip::cuda_ok(cudaMalloc(&p->d_v_rec, 4 * v_rec.size()), "cudaMalloc") ||
         !pirip::cuda_ok(cudaMemcpy(p->d_c_off, c_off.data(), 2 * c_off.size(), cudaMemcpyHostToDevice), "copy") ||
         !pirip::cuda_ok(cudaMemcpy(p->d_v_off, v_off.data(), 2 * v_off.size(), cudaMemcpyHostToDevice), "copy") ||
-        !pirip::cuda_ok(cudaMemcpy(p->d_v_edge, v_edge.data(), 2 * v_edge.size(), cudaMemcpyHostToDevice), "copy") ||
-        !pirip::cuda_ok(cudaFuncSetAttribute(ldpc_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem), "smem attr")) {
+        !pirip::cuda_ok(cudaMemcpy(p->d_c_vpos, c_vpos.data(), 2 * c_vpos.size(), cudaMemcpyHostToDevice), "copy") ||
+        !pirip::cuda_ok(cudaMemcpy(p->d_v_rec, v_rec.data(), 4 * v_rec.size(), cudaMemcpyHostToDevice), "copy") ||
+        !pirip::cuda_ok(cudaFuncSetAttribute(ldpc_decode_warp_kernel<LDPC_SP_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem), "smem attr") ||
+        !pirip::cuda_ok(cudaFuncSetAttribute(ldpc_decode_warp_kernel<LDPC_SP_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem), "smem attr") ||
+        !pirip::cuda_ok(cudaFuncSetAttribute(ldpc_decode_warp_kernel<LDPC_MINSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem), "smem attr")) {
         pirip_ldpc_plan_destroy(p);
         return nullptr;
     }
     p->g.c_off = p->d_c_off;
     p->g.v_off = p->d_v_off;
-    p->g.v_edge = p->d_v_edge;
+    p->g.c_vpos = p->d_c_vpos;
+    p->g.v_rec = p->d_v_rec;
     return p;
 }
+
+extern "C" int pirip_ldpc_plan_set_mode(pirip_ldpc_plan *p, int mode) {
+    if (!p) return pirip::fail(-1, "plan is NULL");
+    if (mode != LDPC_SP_EXACT && mode != LDPC_SP_FAST && mode != LDPC_MINSUM) return pirip::fail(-2, "unknown decoder mode");
+    p->mode = mode;
+    return 0;
+}
+
+extern "C" int pirip_ldpc_plan_mode(const pirip_ldpc_plan *p) { return p ? p->mode : -1; }
 
 extern "C" void pirip_ldpc_plan_destroy(pirip_ldpc_plan *p) {
     if (!p) return;
     cudaSetDevice(p->device);
     cudaFree(p->d_c_off);
     cudaFree(p->d_v_off);
-    cudaFree(p->d_v_edge);
+    cudaFree(p->d_c_vpos);
+    cudaFree(p->d_v_rec);
     cudaFree(p->d_llr);
     cudaFree(p->d_bits);
     cudaFree(p->d_iter);
@@ -324,9 +492,19 @@ extern "C" int pirip_ldpc_decode_batch_dev(pirip_ldpc_plan *p, const float *d_ll
     if (n == 0) return 0;
     if (!d_llr || !d_bits) return pirip::fail(-2, "NULL buffer");
     if (!pirip::cuda_ok(cudaSetDevice(p->device), "cudaSetDevice")) return -10;
-    ldpc_decode_kernel<<<(unsigned)n, kLdpcThreads, p->smem, (cudaStream_t)stream>>>(p->g, d_llr, d_bits, d_iter, d_pcc);
+    const size_t ctas_needed = (n + p->g.warps - 1) / p->g.warps;
+    const size_t resident = (size_t)p->num_sms * ((p->smem + 1024) * 2 <= 228 * 1024 ? 2 : 1);
+    const unsigned grid = (unsigned)(ctas_needed < 4 * resident ? ctas_needed : 4 * resident); /* a CTA loops over codewords */
+    const unsigned block = 32u * (unsigned)p->g.warps;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (p->mode == LDPC_MINSUM)
+        ldpc_decode_warp_kernel<LDPC_MINSUM><<<grid, block, p->smem, st>>>(p->g, d_llr, n, d_bits, d_iter, d_pcc);
+    else if (p->mode == LDPC_SP_FAST)
+        ldpc_decode_warp_kernel<LDPC_SP_FAST><<<grid, block, p->smem, st>>>(p->g, d_llr, n, d_bits, d_iter, d_pcc);
+    else
+        ldpc_decode_warp_kernel<LDPC_SP_EXACT><<<grid, block, p->smem, st>>>(p->g, d_llr, n, d_bits, d_iter, d_pcc);
     pirip::count_launch();
-    return pirip::cuda_ok(cudaGetLastError(), "ldpc_decode_kernel launch") ? 0 : -11;
+    return pirip::cuda_ok(cudaGetLastError(), "ldpc_decode_warp_kernel launch") ? 0 : -11;
 }
 
 extern "C" int pirip_ldpc_decode_batch(pirip_ldpc_plan *p, const float *llr, size_t n, uint8_t *bits, int32_t *iter, int32_t *pcc) {
@@ -352,7 +530,7 @@ extern "C" int pirip_ldpc_decode_batch(pirip_ldpc_plan *p, const float *llr, siz
     if (!pirip::cuda_ok(cudaMemcpy(p->d_llr, llr, sizeof(float) * n * p->g.N, cudaMemcpyHostToDevice), "H2D")) return -12;
     const int rc = pirip_ldpc_decode_batch_dev(p, p->d_llr, n, p->d_bits, p->d_iter, p->d_pcc, nullptr);
     if (rc) return rc;
-    if (!pirip::cuda_ok(cudaMemcpy(bits, p->d_bits, n * p->g.N, cudaMemcpyDeviceToHost), "ldpc_decode_kernel")) return -13;
+    if (!pirip::cuda_ok(cudaMemcpy(bits, p->d_bits, n * p->g.N, cudaMemcpyDeviceToHost), "ldpc_decode_warp_kernel")) return -13;
     if (iter && !pirip::cuda_ok(cudaMemcpy(iter, p->d_iter, sizeof(int) * n, cudaMemcpyDeviceToHost), "D2H")) return -13;
     if (pcc && !pirip::cuda_ok(cudaMemcpy(pcc, p->d_pcc, sizeof(int) * n, cudaMemcpyDeviceToHost), "D2H")) return -13;
     return 0;
