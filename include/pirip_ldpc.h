@@ -24,6 +24,8 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include "pirip_fsk.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -129,6 +131,29 @@ int pirip_ldpc_decode_batch_dev(pirip_ldpc_plan *plan, const float *d_llr, size_
 /* host buffers, synchronous */
 int pirip_ldpc_decode_batch(pirip_ldpc_plan *plan, const float *llr, size_t n_codewords, uint8_t *bits, int32_t *iter,
                             int32_t *pcc);
+
+/* ---- layer 2: the coded receive chain of a batch of captures on the device (BASELINE.json config 4) ---------------
+ * u8 / s16 / f32 IQ captures -> FSK demodulation with LLR output -> per capture: 32-bit UW search over a two-frame
+ * window, sync state machine, LDPC decode of the frame behind the UW, CRC-16 -> per MODEM FRAME one rx_status byte
+ * (FREEDV_RX_*) and, where FREEDV_RX_BITS is set, the packed payload: the record stream `rtl_fsk --code <name> -b` writes
+ * ([R README.md:184,292]; consumer [R tx/frame_repeater.c:55-62]), for every capture of the batch in two launches (the
+ * demodulator, then ONE launch that runs framing + LDPC + CRC for all captures).  The LDPC update is the ldpc plan's mode
+ * (pirip_ldpc_plan_set_mode on pirip_fsk_ldpc_rx_plan_ldpc()); the demodulator's numerics mode likewise. */
+typedef struct pirip_rx_plan pirip_rx_plan;
+pirip_rx_plan *pirip_fsk_ldpc_rx_plan_create(const struct pirip_fsk_cfg *cfg, const char *codename, int device);
+void pirip_fsk_ldpc_rx_plan_destroy(pirip_rx_plan *plan);
+pirip_fsk_plan *pirip_fsk_ldpc_rx_plan_fsk(pirip_rx_plan *plan);
+pirip_ldpc_plan *pirip_fsk_ldpc_rx_plan_ldpc(pirip_rx_plan *plan);
+int pirip_fsk_ldpc_rx_plan_payload_bytes(const pirip_rx_plan *plan);
+/* host buffers: status [n][max_frames], payload [n][max_frames][payload_bytes], nframes [n] (may be NULL), info (may be
+ * NULL) [n][max_frames][4] = uw_loc (-1: no frame step at this modem frame), uw_err, iter, pcc - the fields of the
+ * `rtl_fsk -v` log line [R README.md:200].  max_frames from pirip_fsk_plan_max_frames().  Synchronous. */
+int pirip_fsk_ldpc_rx_batch(pirip_rx_plan *plan, const void *iq, size_t n_captures, size_t samples_per_capture, uint8_t *status,
+                            uint8_t *payload, int32_t *nframes, int32_t *info, size_t max_frames);
+/* device buffers (d_llr [n][max_frames * Nbits] scratch), asynchronous on `stream` */
+int pirip_fsk_ldpc_rx_batch_dev(pirip_rx_plan *plan, const void *d_iq, size_t n_captures, size_t samples_per_capture,
+                                size_t capture_stride_bytes, float *d_llr, int32_t *d_nframes, uint8_t *d_status, uint8_t *d_payload,
+                                int32_t *d_info, size_t max_frames, void *stream);
 
 #ifdef __cplusplus
 }

@@ -209,6 +209,7 @@ void orc_deframer_destroy(struct orc_deframer *d);
 /* push nbits new LLRs; returns rx_status; payload_bits (data_bits bytes, 1 bit/byte)
    is written when ORC_RX_BITS is set */
 int orc_deframer_push(struct orc_deframer *d, const float llr[], int nbits, uint8_t payload_bits[]);
+void orc_deframer_info(const struct orc_deframer *d, int info[6]);
 
 /* ------------------------------------------------------------------ misc */
 /* which math backend the oracle was built with: 0 = exact_math.h, 1 = glibc libm */

@@ -200,6 +200,16 @@ int orc_deframer_push(struct orc_deframer *d, const float llr[], int nbits, uint
     return rx_status;
 }
 
+/* fields of the `rtl_fsk -v` log line of the last push [R README.md:200]: state, uw_loc, uw_err, iter, pcc, nbits queued */
+void orc_deframer_info(const struct orc_deframer *d, int info[6]) {
+    info[0] = d->state;
+    info[1] = d->best_location;
+    info[2] = d->last_uw_errors;
+    info[3] = d->last_iter;
+    info[4] = d->last_pcc;
+    info[5] = d->frame_llr_nbits;
+}
+
 /* ---------------------------------------------------------------- math probes */
 int orc_math_backend(void) { return ORC_MATH_BACKEND; }
 float orc_cosf(float x) { return om_cosf(x); }

@@ -16,6 +16,7 @@ from ._lib import (  # noqa: F401
     DecimPlan,
     FskLdpcModem,
     LdpcPlan,
+    RxPlan,
     ldpc_code,
     ldpc_encode,
     PiripError,

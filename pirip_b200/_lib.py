@@ -463,6 +463,87 @@ class LdpcPlan:
             pass
 
 
+class RxPlan:
+    """pirip_fsk_ldpc_rx_plan_*: the coded receive chain of a batch of captures (config 4): demodulation with LLRs, UW sync,
+    LDPC, CRC-16 on the device; per modem frame a status byte and the packed payload (the `rtl_fsk --code ... -b` records)."""
+
+    def __init__(self, codename, Fs, Rs, M, P=8, Nsym=50, f1_tx=1200, tone_spacing=400, limits=None, mask=False, fmt=FMT_U8,
+                 device=0, demod_mode=None, ldpc_mode=None):
+        L = _ldpc_protos()
+        lib()
+        L.pirip_fsk_ldpc_rx_plan_create.restype = C.c_void_p
+        L.pirip_fsk_ldpc_rx_plan_create.argtypes = [C.POINTER(FskCfg), C.c_char_p, C.c_int]
+        L.pirip_fsk_ldpc_rx_plan_destroy.argtypes = [C.c_void_p]
+        L.pirip_fsk_ldpc_rx_plan_fsk.restype = C.c_void_p
+        L.pirip_fsk_ldpc_rx_plan_fsk.argtypes = [C.c_void_p]
+        L.pirip_fsk_ldpc_rx_plan_ldpc.restype = C.c_void_p
+        L.pirip_fsk_ldpc_rx_plan_ldpc.argtypes = [C.c_void_p]
+        L.pirip_fsk_ldpc_rx_plan_payload_bytes.restype = C.c_int
+        L.pirip_fsk_ldpc_rx_plan_payload_bytes.argtypes = [C.c_void_p]
+        L.pirip_fsk_ldpc_rx_batch.restype = C.c_int
+        L.pirip_fsk_ldpc_rx_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_size_t]
+        L.pirip_fsk_ldpc_rx_batch_dev.restype = C.c_int
+        L.pirip_fsk_ldpc_rx_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        L.pirip_ldpc_plan_set_mode.restype = C.c_int
+        L.pirip_ldpc_plan_set_mode.argtypes = [C.c_void_p, C.c_int]
+        self.L = L
+        self.cfg = FskCfg(Fs=Fs, Rs=Rs, M=M, P=P, Nsym=Nsym, f1_tx=f1_tx, tone_spacing=tone_spacing,
+                          est_min=limits[0] if limits else 0, est_max=limits[1] if limits else 0,
+                          have_limits=1 if limits else 0, freq_est_type=1 if mask else 0, fmt=fmt, soft=1)
+        self._h = L.pirip_fsk_ldpc_rx_plan_create(C.byref(self.cfg), codename.encode(), device)
+        if not self._h:
+            raise _err("pirip_fsk_ldpc_rx_plan_create")
+        self.payload_bytes = L.pirip_fsk_ldpc_rx_plan_payload_bytes(self._h)
+        self._fsk = L.pirip_fsk_ldpc_rx_plan_fsk(self._h)
+        self._ldpc = L.pirip_fsk_ldpc_rx_plan_ldpc(self._h)
+        self.nbits = lib().pirip_fsk_plan_nbits(self._fsk)
+        self.bytes_per_sample = {FMT_U8: 2, FMT_S16: 4, FMT_F32: 8}[fmt]
+        if demod_mode:
+            rc = lib().pirip_fsk_plan_set_mode(self._fsk, {"exact": MODE_EXACT, "fast": MODE_FAST}[demod_mode])
+            if rc != 0:
+                raise _err("pirip_fsk_plan_set_mode", rc)
+        if ldpc_mode:
+            rc = L.pirip_ldpc_plan_set_mode(self._ldpc, LdpcPlan.MODES[ldpc_mode])
+            if rc != 0:
+                raise _err("pirip_ldpc_plan_set_mode", rc)
+
+    def max_frames(self, samples_per_capture):
+        return int(lib().pirip_fsk_plan_max_frames(self._fsk, samples_per_capture))
+
+    def rx_batch(self, iq, want_info=False):
+        """iq [n_captures, ...] one capture per row.  Returns dict(status[n, mf], payload[n, mf, bytes], nframes[n], info)."""
+        iq = np.ascontiguousarray(iq)
+        n = iq.shape[0]
+        spc = iq.shape[1] * iq.dtype.itemsize // self.bytes_per_sample
+        mf = self.max_frames(spc)
+        status = np.zeros((n, mf), np.uint8)
+        payload = np.zeros((n, mf, self.payload_bytes), np.uint8)
+        nframes = np.zeros(n, np.int32)
+        info = np.zeros((n, mf, 4), np.int32) if want_info else None
+        rc = self.L.pirip_fsk_ldpc_rx_batch(self._h, _ptr(iq), n, spc, _ptr(status), _ptr(payload), _ptr(nframes), _ptr(info), mf)
+        if rc != 0:
+            raise _err("pirip_fsk_ldpc_rx_batch", rc)
+        return dict(status=status, payload=payload, nframes=nframes, info=info, max_frames=mf)
+
+    def rx_batch_dev(self, d_iq, n, spc, stride, d_llr, d_nframes, d_status, d_payload, max_frames, d_info=None, stream=None):
+        rc = self.L.pirip_fsk_ldpc_rx_batch_dev(self._h, d_iq, n, spc, stride, d_llr, d_nframes, d_status, d_payload, d_info, max_frames, stream)
+        if rc != 0:
+            raise _err("pirip_fsk_ldpc_rx_batch_dev", rc)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.L.pirip_fsk_ldpc_rx_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class FskLdpcModem:
     """freedv_open_advanced(FREEDV_MODE_FSK_LDPC) handle: framer ([R tx/rpitx_fsk.cpp:395]) and the
     receive-side deframer fed with LLRs."""

@@ -27,209 +27,11 @@
 #include "exact_math.h"
 #include "host_util.h"
 #include "llr_dev.h"
+#include "ldpc_dev.h"
 
 namespace {
 
 /* ------------------------------------------------------------------ device side */
-
-struct LdpcGraph {
-    int N, NPB, E, max_iter;
-    const uint16_t *c_off;  /* [NPB+1] first edge of every check */
-    const uint16_t *v_off;  /* [N+1] first entry of every variable in v_edge */
-    const uint16_t *c_vpos; /* [E] check order: position of the edge in variable order */
-    const unsigned *v_rec;  /* [E] variable order: check << 8 | position of the edge in its check */
-    /* shared-memory layout of the decoder kernel (bytes): tables once per CTA, then one block per warp (codeword) */
-    int off_voff, off_vedge, off_echk, tables_bytes;
-    int w_q, w_chk, w_llr, warp_bytes;
-    int warps;  /* codewords per CTA */
-    float ms_scale; /* normalisation of the min-sum check update */
-};
-
-/* [U mpdecode_core.c::phi0] CML closed form with the coarse steps above 5 */
-__device__ __forceinline__ float phi0(float x) {
-    if (x > 10.0f) return 0.0f;
-    if ((double)x < 9.08e-5) return 10.0f;
-    if (x > 9.0f) return (float)1.6881e-4;
-    if (x > 8.0f) return (float)4.5887e-4;
-    if (x > 7.0f) return (float)1.2473e-3;
-    if (x > 6.0f) return (float)3.3906e-3;
-    if (x > 5.0f) return (float)9.2168e-3;
-    const float z = (float)em_exp((double)x);
-    return (float)em_log((double)((z + 1.0f) / (z - 1.0f)));
-}
-/* the same function in single precision with the hardware exponential / logarithm (tolerance mode) */
-__device__ __forceinline__ float phi0_fast(float x) {
-    if (x > 10.0f) return 0.0f;
-    if (x < 9.08e-5f) return 10.0f;
-    if (x > 9.0f) return 1.6881e-4f;
-    if (x > 8.0f) return 4.5887e-4f;
-    if (x > 7.0f) return 1.2473e-3f;
-    if (x > 6.0f) return 3.3906e-3f;
-    if (x > 5.0f) return 9.2168e-3f;
-    const float z = __expf(x);
-    return __logf(__fdividef(z + 1.0f, z - 1.0f));
-}
-
-enum { LDPC_SP_EXACT = 0, LDPC_SP_FAST = 1, LDPC_MINSUM = 2 };
-constexpr int kLdpcMaxWarps = 8;
-
-/* One WARP per codeword, up to 8 codewords per CTA, the Tanner graph tables loaded once per CTA.
-   A lane owns whole check nodes in the check phase and whole variable nodes in the variable phase and walks their edges
-   in table order, so in the exact mode every float sum is formed in the order of the scalar algorithm
-   ([U mpdecode_core.c::SumProduct]) and bits / iterations / parity-check counts are identical to it.  Messages: one float per
-   edge (the variable-to-check message: phi0(|q|) with the sign of q in the sign bit, or q itself for min-sum); the
-   check-to-variable messages are never stored - a check leaves its sum (or its two smallest magnitudes) and sign parity, and
-   the variable phase forms r from them.  The parity-check count is a warp reduction; the loop ends as soon as it reaches
-   NumberParityBits (early exit per codeword, no CTA barrier inside the iterations). */
-/* check-to-variable message from what the check left behind (cs: sum / smallest magnitude with the parity in the sign bit;
-   ca: min-sum only, second smallest magnitude with the position of the smallest in its 6 low mantissa bits) */
-template <int MODE>
-__device__ __forceinline__ float r_msg(float qe, float cs, float ca, int pos) {
-    const unsigned neg = (__float_as_uint(cs) ^ __float_as_uint(qe)) & 0x80000000u;
-    float mag;
-    if (MODE == LDPC_MINSUM) {
-        const unsigned a2 = __float_as_uint(ca);
-        mag = ((int)(a2 & 63u) == pos) ? __uint_as_float(a2 & ~63u) : fabsf(cs);
-    } else {
-        const float d = __fsub_rn(fabsf(cs), fabsf(qe));
-        mag = MODE == LDPC_SP_EXACT ? phi0(d) : phi0_fast(d);
-    }
-    return __uint_as_float(__float_as_uint(mag) ^ neg);
-}
-/* variable-to-check message as stored: phi0(|t|) (or |t| for min-sum) with the sign the scalar code gives t (t > 0 ? 0 : 1) */
-template <int MODE>
-__device__ __forceinline__ float q_store(float t) {
-    const float a = MODE == LDPC_MINSUM ? fabsf(t) : (MODE == LDPC_SP_EXACT ? phi0(fabsf(t)) : phi0_fast(fabsf(t)));
-    return t > 0.0f ? a : -a;
-}
-
-/* One WARP per codeword, up to 8 codewords per CTA, the Tanner graph tables loaded once per CTA.
-   A lane owns whole check nodes in the check phase and whole variable nodes in the variable phase and walks their edges
-   in table order, so in the exact mode every float sum is formed in the order of the scalar algorithm
-   ([U mpdecode_core.c::SumProduct]) and bits / iterations / parity-check counts are identical to it.  Messages: one float per
-   edge, stored in VARIABLE order (the variable phase reads and writes them sequentially; the check phase gathers them through
-   an index table): the variable-to-check message phi0(|q|) with the sign of q in the sign bit, or q itself for min-sum.
-   The check-to-variable messages are never stored - a check leaves its sum (or its two smallest magnitudes) and sign parity,
-   and the variable phase forms r from them.  The parity-check count is a warp reduction; the loop ends as soon as it reaches
-   NumberParityBits (early exit per codeword, no CTA barrier inside the iterations). */
-template <int MODE>
-__global__ void __launch_bounds__(32 * kLdpcMaxWarps) ldpc_decode_warp_kernel(const __grid_constant__ LdpcGraph g, const float *llr_in, size_t n_cw,
-                                                                              unsigned char *bits_out, int *iter_out, int *pcc_out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint16_t *c_off = reinterpret_cast<uint16_t *>(smem_raw);
-    uint16_t *v_off = reinterpret_cast<uint16_t *>(smem_raw + g.off_voff);
-    uint16_t *c_vpos = reinterpret_cast<uint16_t *>(smem_raw + g.off_vedge);  /* [E] check order -> position in variable order */
-    unsigned *v_rec = reinterpret_cast<unsigned *>(smem_raw + g.off_echk);    /* [E] variable order: check << 8 | position in the check */
-    for (int i = threadIdx.x; i <= g.NPB; i += blockDim.x) c_off[i] = g.c_off[i];
-    for (int i = threadIdx.x; i <= g.N; i += blockDim.x) v_off[i] = g.v_off[i];
-    for (int i = threadIdx.x; i < g.E; i += blockDim.x) {
-        c_vpos[i] = g.c_vpos[i];
-        v_rec[i] = g.v_rec[i];
-    }
-    __syncthreads();
-    if (warp >= g.warps) return;
-    unsigned char *wb = smem_raw + g.tables_bytes + (size_t)warp * g.warp_bytes;
-    float *q = reinterpret_cast<float *>(wb + g.w_q);        /* [E] variable order */
-    float2 *chk = reinterpret_cast<float2 *>(wb + g.w_chk);  /* [NPB] what a check leaves behind (see r_msg) */
-    float *llr = reinterpret_cast<float *>(wb + g.w_llr);    /* [N] */
-
-    for (size_t cw = (size_t)blockIdx.x * g.warps + warp; cw < n_cw; cw += (size_t)gridDim.x * g.warps) {
-        const float *in = llr_in + cw * g.N;
-        for (int v = lane; v < g.N; v += 32) {
-            const float x = in[v];
-            llr[v] = x;
-            float m;
-            if (MODE == LDPC_MINSUM)
-                m = x;
-            else {
-                const float ph = MODE == LDPC_SP_EXACT ? phi0(fabsf(x)) : phi0_fast(fabsf(x));
-                m = x < 0.0f ? -ph : ph;
-            }
-            for (int j = v_off[v]; j < v_off[v + 1]; ++j) q[j] = m;
-        }
-        __syncwarp();
-        int result = g.max_iter, pcc = 0;
-        for (int iter = 0; iter < g.max_iter; ++iter) {
-            /* check-node phase */
-            int local = 0;
-            for (int c = lane; c < g.NPB; c += 32) {
-                const int e0 = c_off[c], e1 = c_off[c + 1];
-                unsigned sign = 0;
-                if (MODE == LDPC_MINSUM) {
-                    float m1 = 3.0e38f, m2 = 3.0e38f;
-                    int pos = 0;
-                    for (int e = e0; e < e1; ++e) {
-                        const float v = q[c_vpos[e]];
-                        const float a = fabsf(v);
-                        sign ^= __float_as_uint(v) & 0x80000000u;
-                        if (a < m1) {
-                            m2 = m1;
-                            m1 = a;
-                            pos = e - e0;
-                        } else if (a < m2)
-                            m2 = a;
-                    }
-                    chk[c] = make_float2(__uint_as_float(__float_as_uint(m1 * g.ms_scale) | sign),
-                                         __uint_as_float((__float_as_uint(m2 * g.ms_scale) & ~63u) | (unsigned)(pos & 63)));
-                } else {
-                    const float v0 = q[c_vpos[e0]];
-                    float phi_sum = fabsf(v0);
-                    sign = __float_as_uint(v0) & 0x80000000u;
-                    for (int e = e0 + 1; e < e1; ++e) {
-                        const float v = q[c_vpos[e]];
-                        phi_sum = __fadd_rn(phi_sum, fabsf(v));
-                        sign ^= __float_as_uint(v) & 0x80000000u;
-                    }
-                    chk[c] = make_float2(__uint_as_float(__float_as_uint(phi_sum) | sign), 0.0f);
-                }
-                if (sign == 0) local++;
-            }
-            pcc = __reduce_add_sync(0xffffffffu, local);
-            __syncwarp();
-            const bool last = pcc == g.NPB || iter == g.max_iter - 1;
-            /* variable-node phase */
-            for (int v = lane; v < g.N; v += 32) {
-                const int j0 = v_off[v], j1 = v_off[v + 1];
-                float Qi = llr[v];
-                float r[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (j0 + k < j1) {
-                        const unsigned rec = v_rec[j0 + k];
-                        const float2 cs = chk[rec >> 8];
-                        r[k] = r_msg<MODE>(q[j0 + k], cs.x, cs.y, (int)(rec & 63u));
-                        Qi = __fadd_rn(Qi, r[k]);
-                    }
-                /* variables with more than 8 edges (none of codec2's codes): the rest of the sum */
-                for (int j = j0 + 8; j < j1; ++j) {
-                    const unsigned rec = v_rec[j];
-                    const float2 cs = chk[rec >> 8];
-                    Qi = __fadd_rn(Qi, r_msg<MODE>(q[j], cs.x, cs.y, (int)(rec & 63u)));
-                }
-                if (last) bits_out[cw * g.N + v] = Qi < 0.0f ? 1 : 0;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (j0 + k < j1) q[j0 + k] = q_store<MODE>(__fsub_rn(Qi, r[k]));
-                for (int j = j0 + 8; j < j1; ++j) {
-                    const unsigned rec = v_rec[j];
-                    const float2 cs = chk[rec >> 8];
-                    q[j] = q_store<MODE>(__fsub_rn(Qi, r_msg<MODE>(q[j], cs.x, cs.y, (int)(rec & 63u))));
-                }
-            }
-            __syncwarp();
-            if (pcc == g.NPB) {
-                result = iter + 1;
-                break;
-            }
-        }
-        if (lane == 0) {
-            if (iter_out) iter_out[cw] = result;
-            if (pcc_out) pcc_out[cw] = pcc;
-        }
-        __syncwarp();
-    }
-}
 
 __global__ void llr_kernel(const float *rx_filt, float *llr, float v_est, float SNRest, int M, int nsyms) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -413,6 +215,8 @@ extern "C" pirip_ldpc_plan *pirip_ldpc_plan_create(const struct LDPC *l, int dev
         w += al(g.NPB * 8);
         g.w_llr = w;
         w += al(g.N * 4);
+        g.w_scr = w; /* 256 words of scratch for the receive-chain kernel: hard-bit words of two frames, decoded bits */
+        w += 1024;
         g.warp_bytes = w;
         int warps = (227 * 1024 - g.tables_bytes) / w;
         /* two CTAs per SM when they fit: 8 codewords each */
@@ -827,3 +631,319 @@ extern "C" void freedv_fsk_ldpc_rx_info(struct freedv *f, int info[6]) {
     info[4] = f->last_pcc;
     info[5] = f->frame_llr_nbits;
 }
+
+/* ------------------------------------------------------------------ batched coded receive chain (config 4) */
+
+namespace {
+
+struct RxArgs {
+    const float *llr;      /* [ncap][llr_stride] the demodulator's LLR stream of every capture */
+    size_t llr_stride;
+    const int32_t *nframes; /* [ncap] modem frames demodulated */
+    size_t ncap, max_frames;
+    int Nbits, bpf, K, thresh1, thresh2, baduw_thresh;
+    unsigned uw_word;      /* bit u = UW bit u */
+    uint8_t *status;       /* [ncap][max_frames] rx_status of every modem frame */
+    uint8_t *payload;      /* [ncap][max_frames][K/8] packed payload where FREEDV_RX_BITS is set (zero elsewhere) */
+    int32_t *info;         /* optional [ncap][max_frames][4]: uw_loc, uw_err, iter, pcc of the frame step taken at that modem frame */
+};
+
+/* FSK_LDPC receive side of every capture of a batch in ONE launch ([U freedv_fsk.c::freedv_rx_fsk_ldpc_data], the state
+   machine of freedv_fsk_ldpc_rx_llrs below; `rtl_fsk --code H_256_512_4 -b` [R README.md:184,292], record layout
+   [R tx/frame_repeater.c:55-62]).  One WARP per capture: it walks the capture's modem frames, runs the UW search over the
+   two-frame window (hard bits packed by ballot, 32 start positions per step), the sync state machine, the LDPC decoder
+   (ldpc_decode_one, the same routine as the batch decoder) on the frame after the UW, and the CRC-16 check; it writes one
+   status byte and - when the CRC passes - the packed payload per modem frame.  The two-frame window and the LLR queue of
+   the scalar code are views of the capture's LLR stream, so nothing is buffered. */
+template <int MODE>
+__global__ void __launch_bounds__(32 * kLdpcMaxWarps) fsk_ldpc_rx_kernel(const __grid_constant__ LdpcGraph g, const __grid_constant__ RxArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    ldpc_load_tables(g, smem_raw);
+    __syncthreads();
+    if (warp >= g.warps) return;
+    const LdpcSmem m = ldpc_smem_view(g, smem_raw, warp);
+    unsigned *hw = m.scr;        /* hard-bit words of the two-frame window */
+    unsigned *dec = m.scr + 160; /* decoded bits, bit v of word v / 32 */
+    const int bpf = a.bpf, nhw = (2 * bpf + 31) / 32;
+    for (size_t cap = (size_t)blockIdx.x * g.warps + warp; cap < a.ncap; cap += (size_t)gridDim.x * g.warps) {
+        const float *S = a.llr + cap * a.llr_stride;
+        const int nf = a.nframes[cap];
+        int state = 0, best_loc = 0, baduw = 0, t = 0;
+        long long nq = 0;
+        for (int f = 0; f < nf; ++f) {
+            nq += a.Nbits;
+            int rx_status = 0;
+            int uw_err = 0, iters = 0, pccv = 0, stepped = 0;
+            if (nq >= bpf) {
+                stepped = 1;
+                const long long base = (long long)(t - 1) * bpf; /* stream index of the window's first LLR (zeros before the stream) */
+                for (int k = 0; k < nhw; ++k) {
+                    const int i = 32 * k + lane;
+                    const long long idx = base + i;
+                    const float x = (idx >= 0 && i < 2 * bpf) ? S[idx] : 0.0f;
+                    const unsigned w = __ballot_sync(0xffffffffu, x < 0.0f);
+                    if (lane == 0) hw[k] = w;
+                }
+                if (lane == 0) hw[nhw] = 0;
+                __syncwarp();
+                auto uw_errors = [&](int i) {
+                    const unsigned lo = hw[i >> 5], hi = hw[(i >> 5) + 1];
+                    const unsigned win = __funnelshift_r(lo, hi, i & 31);
+                    return __popc(win ^ a.uw_word);
+                };
+                int next_state = state, errors = 0;
+                if (state == 0) {
+                    int be = 32, bl = 0;
+                    for (int i = lane; i < bpf; i += 32) {
+                        const int e = uw_errors(i);
+                        if (e < be) {
+                            be = e;
+                            bl = i;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        const int oe = __shfl_xor_sync(0xffffffffu, be, o), ol = __shfl_xor_sync(0xffffffffu, bl, o);
+                        if (oe < be || (oe == be && ol < bl)) {
+                            be = oe;
+                            bl = ol;
+                        }
+                    }
+                    best_loc = be < 32 ? bl : 0; /* the scalar search starts from best_errors = 32, location 0 */
+                    if (be <= a.thresh1) {
+                        errors = be;
+                        next_state = 1;
+                        baduw = 0;
+                    }
+                } else {
+                    errors = uw_errors(best_loc);
+                    if (errors > a.thresh2) {
+                        baduw++;
+                        if (baduw >= a.baduw_thresh) next_state = 0;
+                    } else
+                        baduw = 0;
+                }
+                uw_err = errors;
+                if (next_state == 1) {
+                    for (int k = lane; k < (g.N + 31) / 32; k += 32) dec[k] = 0;
+                    __syncwarp();
+                    const long long cw0 = base + best_loc + 32;
+                    iters = ldpc_decode_one<MODE>(
+                        g, m, lane, [&](int v) { return (cw0 + v >= 0) ? S[cw0 + v] : 0.0f; },
+                        [&](int v, int bit) {
+                            if (bit) atomicOr(&dec[v >> 5], 1u << (v & 31));
+                        },
+                        &pccv);
+                    __syncwarp();
+                    if (pccv != g.NPB) rx_status |= FREEDV_RX_BIT_ERRORS;
+                    /* CRC-16/CCITT-FALSE of the payload but its last two bytes ([U freedv_api.c::freedv_gen_crc16]); bytes MSB first */
+                    const int nbytes = a.K / 8;
+                    auto byte_at = [&](int b) { return (unsigned)(__brev((dec[b >> 2] >> (8 * (b & 3))) & 0xffu) >> 24); };
+                    int crc_ok = 0;
+                    if (lane == 0) {
+                        unsigned crc = 0xFFFF;
+                        for (int b = 0; b < nbytes - 2; ++b) {
+                            unsigned x = ((crc >> 8) ^ byte_at(b)) & 0xff;
+                            x ^= x >> 4;
+                            crc = ((crc << 8) ^ (x << 12) ^ (x << 5) ^ x) & 0xffff;
+                        }
+                        crc_ok = crc == ((byte_at(nbytes - 2) << 8) | byte_at(nbytes - 1));
+                    }
+                    crc_ok = __shfl_sync(0xffffffffu, crc_ok, 0);
+                    if (crc_ok) {
+                        rx_status |= FREEDV_RX_BITS;
+                        uint8_t *po = a.payload + (cap * a.max_frames + (size_t)f) * (size_t)nbytes;
+                        for (int b = lane; b < nbytes; b += 32) po[b] = (uint8_t)byte_at(b);
+                    } else if (state == 0)
+                        next_state = 0; /* CRC failed on the first frame after a UW hit: dud UW */
+                }
+                state = next_state;
+                t++;
+                nq -= bpf;
+            }
+            if (state == 1) rx_status |= FREEDV_RX_SYNC;
+            if (lane == 0) {
+                a.status[cap * a.max_frames + (size_t)f] = (uint8_t)rx_status;
+                if (a.info) {
+                    int32_t *io = a.info + (cap * a.max_frames + (size_t)f) * 4;
+                    io[0] = stepped ? best_loc : -1;
+                    io[1] = uw_err;
+                    io[2] = iters;
+                    io[3] = pccv;
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace
+
+struct pirip_rx_plan {
+    pirip_fsk_plan *fsk = nullptr;
+    pirip_ldpc_plan *ldpc = nullptr;
+    struct LDPC code;
+    pirip_fsk_cfg cfg;
+    int device = 0, Nbits = 0, bpf = 0, K = 0;
+    /* device buffers of the host-buffer entry point */
+    unsigned char *d_iq = nullptr;
+    float *d_llr = nullptr;
+    uint8_t *d_status = nullptr, *d_payload = nullptr;
+    int32_t *d_nf = nullptr, *d_info = nullptr;
+    size_t cap_iq = 0, cap_llr = 0, cap_out = 0, cap_n = 0;
+    cudaStream_t stream = nullptr;
+};
+
+extern "C" void pirip_fsk_ldpc_rx_plan_destroy(pirip_rx_plan *p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    pirip_fsk_plan_destroy(p->fsk);
+    pirip_ldpc_plan_destroy(p->ldpc);
+    cudaFree(p->d_iq);
+    cudaFree(p->d_llr);
+    cudaFree(p->d_status);
+    cudaFree(p->d_payload);
+    cudaFree(p->d_nf);
+    cudaFree(p->d_info);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    delete p;
+}
+
+extern "C" pirip_rx_plan *pirip_fsk_ldpc_rx_plan_create(const struct pirip_fsk_cfg *cfg, const char *codename, int device) {
+    if (!cfg || !codename) {
+        pirip::set_error("cfg / codename is NULL");
+        return nullptr;
+    }
+    std::string name(codename);
+    if (ldpc_codes_find(&name[0]) < 0) {
+        pirip::set_error("unknown LDPC code " + name);
+        return nullptr;
+    }
+    pirip_rx_plan *p = new pirip_rx_plan();
+    p->device = device;
+    p->cfg = *cfg;
+    p->cfg.soft = 1;
+    ldpc_codes_setup(&p->code, &name[0]);
+    p->fsk = pirip_fsk_plan_create(&p->cfg, device);
+    p->ldpc = p->fsk ? pirip_ldpc_plan_create(&p->code, device) : nullptr;
+    if (!p->fsk || !p->ldpc) {
+        pirip_fsk_ldpc_rx_plan_destroy(p);
+        return nullptr;
+    }
+    p->Nbits = pirip_fsk_plan_nbits(p->fsk);
+    p->K = p->code.CodeLength - p->code.NumberParityBits;
+    p->bpf = 32 + p->code.CodeLength;
+    if (2 * p->bpf / 32 + 2 > 160 || (p->code.CodeLength + 31) / 32 > 96 || (p->K % 8) != 0) {
+        pirip::set_error("code too long for the receive-chain kernel's scratch");
+        pirip_fsk_ldpc_rx_plan_destroy(p);
+        return nullptr;
+    }
+    if (!pirip::cuda_ok(cudaFuncSetAttribute(fsk_ldpc_rx_kernel<LDPC_SP_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->ldpc->smem), "smem attr") ||
+        !pirip::cuda_ok(cudaFuncSetAttribute(fsk_ldpc_rx_kernel<LDPC_SP_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->ldpc->smem), "smem attr") ||
+        !pirip::cuda_ok(cudaFuncSetAttribute(fsk_ldpc_rx_kernel<LDPC_MINSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->ldpc->smem), "smem attr")) {
+        pirip_fsk_ldpc_rx_plan_destroy(p);
+        return nullptr;
+    }
+    return p;
+}
+
+extern "C" pirip_fsk_plan *pirip_fsk_ldpc_rx_plan_fsk(pirip_rx_plan *p) { return p ? p->fsk : nullptr; }
+extern "C" pirip_ldpc_plan *pirip_fsk_ldpc_rx_plan_ldpc(pirip_rx_plan *p) { return p ? p->ldpc : nullptr; }
+extern "C" int pirip_fsk_ldpc_rx_plan_payload_bytes(const pirip_rx_plan *p) { return p ? p->K / 8 : -1; }
+
+extern "C" int pirip_fsk_ldpc_rx_batch_dev(pirip_rx_plan *p, const void *d_iq, size_t n_captures, size_t samples_per_capture,
+                                           size_t capture_stride_bytes, float *d_llr, int32_t *d_nframes, uint8_t *d_status, uint8_t *d_payload,
+                                           int32_t *d_info, size_t max_frames, void *stream) {
+    if (!p) return pirip::fail(-1, "plan is NULL");
+    if (n_captures == 0) return 0;
+    if (!d_iq || !d_llr || !d_nframes || !d_status || !d_payload) return pirip::fail(-2, "NULL buffer");
+    cudaStream_t st = (cudaStream_t)stream;
+    /* demodulate: LLRs of every modem frame, [n][max_frames * Nbits] */
+    int rc = pirip_fsk_demod_batch_dev(p->fsk, d_iq, n_captures, samples_per_capture, capture_stride_bytes, nullptr, d_llr, nullptr, nullptr,
+                                       d_nframes, max_frames, st);
+    if (rc) return rc;
+    const size_t nbytes = (size_t)p->K / 8;
+    if (!pirip::cuda_ok(cudaMemsetAsync(d_payload, 0, n_captures * max_frames * nbytes, st), "memset payload") ||
+        !pirip::cuda_ok(cudaMemsetAsync(d_status, 0, n_captures * max_frames, st), "memset status"))
+        return -12;
+    RxArgs a;
+    memset(&a, 0, sizeof a);
+    a.llr = d_llr;
+    a.llr_stride = max_frames * (size_t)p->Nbits;
+    a.nframes = d_nframes;
+    a.ncap = n_captures;
+    a.max_frames = max_frames;
+    a.Nbits = p->Nbits;
+    a.bpf = p->bpf;
+    a.K = p->K;
+    a.thresh1 = 5;
+    a.thresh2 = 6;
+    a.baduw_thresh = 1;
+    a.uw_word = 0;
+    for (int u = 0; u < 32; ++u) a.uw_word |= (unsigned)fsk_ldpc_uw[u] << u;
+    a.status = d_status;
+    a.payload = d_payload;
+    a.info = d_info;
+    const LdpcGraph &g = p->ldpc->g;
+    const size_t ctas_needed = (n_captures + g.warps - 1) / g.warps;
+    const size_t resident = (size_t)p->ldpc->num_sms * ((p->ldpc->smem + 1024) * 2 <= 228 * 1024 ? 2 : 1);
+    const unsigned grid = (unsigned)(ctas_needed < resident ? ctas_needed : resident);
+    const unsigned block = 32u * (unsigned)g.warps;
+    if (p->ldpc->mode == LDPC_MINSUM)
+        fsk_ldpc_rx_kernel<LDPC_MINSUM><<<grid, block, p->ldpc->smem, st>>>(g, a);
+    else if (p->ldpc->mode == LDPC_SP_FAST)
+        fsk_ldpc_rx_kernel<LDPC_SP_FAST><<<grid, block, p->ldpc->smem, st>>>(g, a);
+    else
+        fsk_ldpc_rx_kernel<LDPC_SP_EXACT><<<grid, block, p->ldpc->smem, st>>>(g, a);
+    pirip::count_launch();
+    return pirip::cuda_ok(cudaGetLastError(), "fsk_ldpc_rx_kernel launch") ? 0 : -11;
+}
+
+extern "C" int pirip_fsk_ldpc_rx_batch(pirip_rx_plan *p, const void *iq, size_t n, size_t samples_per_capture, uint8_t *status, uint8_t *payload,
+                                       int32_t *nframes, int32_t *info, size_t max_frames) {
+    if (!p) return pirip::fail(-1, "plan is NULL");
+    if (n == 0) return 0;
+    if (!iq || !status || !payload) return pirip::fail(-2, "NULL buffer");
+    if (!pirip::cuda_ok(cudaSetDevice(p->device), "cudaSetDevice")) return -10;
+    const size_t bps = p->cfg.fmt == PIRIP_FMT_U8 ? 2 : (p->cfg.fmt == PIRIP_FMT_S16 ? 4 : 8);
+    const size_t cap_bytes = samples_per_capture * bps, stride = (cap_bytes + 15) / 16 * 16;
+    const size_t nbytes = (size_t)p->K / 8;
+    auto ensure = [&](void **ptr, size_t &have, size_t need) {
+        if (need <= have && *ptr) return true;
+        cudaFree(*ptr);
+        *ptr = nullptr;
+        have = 0;
+        if (!pirip::cuda_ok(cudaMalloc(ptr, need), "cudaMalloc")) return false;
+        have = need;
+        return true;
+    };
+    if (!p->stream && !pirip::cuda_ok(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return -12;
+    if (!ensure((void **)&p->d_iq, p->cap_iq, stride * n) || !ensure((void **)&p->d_llr, p->cap_llr, sizeof(float) * n * max_frames * p->Nbits))
+        return -12;
+    if (n * max_frames > p->cap_out) {
+        size_t c1 = 0, c2 = 0, c3 = 0;
+        if (!ensure((void **)&p->d_status, c1, n * max_frames) || !ensure((void **)&p->d_payload, c2, n * max_frames * nbytes) ||
+            !ensure((void **)&p->d_info, c3, sizeof(int32_t) * 4 * n * max_frames))
+            return -12;
+        p->cap_out = n * max_frames;
+    }
+    if (n > p->cap_n) {
+        size_t c4 = 0;
+        if (!ensure((void **)&p->d_nf, c4, sizeof(int32_t) * n)) return -12;
+        p->cap_n = n;
+    }
+    cudaStream_t st = p->stream;
+    if (!pirip::cuda_ok(cudaMemcpy2DAsync(p->d_iq, stride, iq, cap_bytes, cap_bytes, n, cudaMemcpyHostToDevice, st), "H2D iq")) return -12;
+    if (!pirip::cuda_ok(cudaMemsetAsync(p->d_llr, 0, sizeof(float) * n * max_frames * p->Nbits, st), "memset llr")) return -12;
+    const int rc = pirip_fsk_ldpc_rx_batch_dev(p, p->d_iq, n, samples_per_capture, stride, p->d_llr, p->d_nf, p->d_status, p->d_payload,
+                                               info ? p->d_info : nullptr, max_frames, st);
+    if (rc) return rc;
+    if (!pirip::cuda_ok(cudaMemcpyAsync(status, p->d_status, n * max_frames, cudaMemcpyDeviceToHost, st), "D2H status") ||
+        !pirip::cuda_ok(cudaMemcpyAsync(payload, p->d_payload, n * max_frames * nbytes, cudaMemcpyDeviceToHost, st), "D2H payload") ||
+        (nframes && !pirip::cuda_ok(cudaMemcpyAsync(nframes, p->d_nf, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st), "D2H nframes")) ||
+        (info && !pirip::cuda_ok(cudaMemcpyAsync(info, p->d_info, sizeof(int32_t) * 4 * n * max_frames, cudaMemcpyDeviceToHost, st), "D2H info")))
+        return -12;
+    return pirip::cuda_ok(cudaStreamSynchronize(st), "receive chain") ? 0 : -13;
+}
+

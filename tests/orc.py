@@ -96,6 +96,7 @@ def lib(libm=False):
     L.orc_deframer_destroy.argtypes = [C.c_void_p]
     L.orc_deframer_push.restype = C.c_int
     L.orc_deframer_push.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_deframer_info.argtypes = [C.c_void_p, C.c_void_p]
     L.orc_fft_alloc.restype = C.c_void_p
     L.orc_fft_alloc.argtypes = [C.c_int]
     L.orc_fft_free.argtypes = [C.c_void_p]
@@ -258,6 +259,12 @@ class Deframer:
         out = np.zeros(self.K, np.uint8)
         st = self.L.orc_deframer_push(self.h, _ptr(llr), llr.size, _ptr(out))
         return st, out
+
+    def info(self):
+        """state, uw_loc, uw_err, iter, pcc, nbits queued after the last push (the `rtl_fsk -v` log fields)"""
+        a = np.zeros(6, np.int32)
+        self.L.orc_deframer_info(self.h, _ptr(a))
+        return a
 
     def close(self):
         if self.h:

@@ -48,7 +48,7 @@ def test_loopback_rtl_sdr_shaped_pipeline(tmp_path, batch):
     cmd = [os.path.join(BIN, "fsk_demod"), "-d", "-p", "24"] + (["--batch"] if batch else []) + ["2", str(Fs), str(Rb), str(f), "-"]
     dem = subprocess.run(cmd, capture_output=True, check=True)
     rx = np.frombuffer(dem.stdout, np.uint8)
-    ref = orc.fsk_demod_stream(orc.demod_cfg(Fs, Rb, 2, P=24), iq)
+    ref = orc.fsk_demod_stream(orc.demod_cfg(Fs, Rb, 2, P=24, limits=(-Fs // 2, Fs // 2)), iq)  # complex input, no --fsk_lower: whole spectrum
     assert np.array_equal(rx, ref["bits"])  # the CLI output is the oracle's, byte for byte
     put = subprocess.run([os.path.join(BIN, "fsk_put_test_bits"), "-q", "-p", "90", "-"], input=dem.stdout, capture_output=True)
     assert put.returncode == 0, put.stderr.decode()

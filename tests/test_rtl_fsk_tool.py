@@ -119,7 +119,8 @@ def test_uncoded_decimating_front_end_matches_the_csdr_pipeline(tmp_path):
     got = np.frombuffer(rx.stdout, np.uint8)
     # oracle: csdr stage in floats, then the demodulator on complex float input
     dec, _ = orc.csdr_decimate_stream(iq, 45)
-    ref = orc.fsk_demod_stream(orc.demod_cfg(Fs, Rs, 2, P=8, limits=(500, Fs // 2), fmt=orc.FMT_F32), dec)
+    # no -p on upstream's command line: P is derived from Ts = 40 (halved while even and above 10 -> 10)
+    ref = orc.fsk_demod_stream(orc.demod_cfg(Fs, Rs, 2, P=10, limits=(500, Fs // 2), fmt=orc.FMT_F32), dec)
     assert np.array_equal(got, ref["bits"][:got.size]) and got.size >= ref["bits"].size - 50
     put = subprocess.run([os.path.join(BIN, "fsk_put_test_bits"), "-q", "-p", "8", "-"], input=rx.stdout, capture_output=True)
     assert put.returncode == 0, put.stderr.decode()
@@ -197,3 +198,34 @@ def test_transmitter_test_modes(tmp_path):
                          check=True, capture_output=True).stdout
     put = subprocess.run([os.path.join(BIN, "fsk_put_test_bits"), "-q", "-p", "25", "-"], input=dem, capture_output=True)
     assert put.returncode == 0, put.stderr.decode()
+
+
+@pytest.mark.parametrize("args,Fs,Rs,M", [
+    # the reference's own command lines, options exactly as written (tuner options are accepted and ignored; the file source
+    # replaces the dongle): [R README.md:114], [R README.md:152], [R README.md:172], [R README.md:196], [R README.md:262],
+    # [R README.md:286], [R script/frame_repeater:23], [R test/loopback_rtl_fsk.sh:10]
+    ("-g 49 -f 144490000 - -n 480000", 240000, 10000, 2),
+    ("-w 500E3 -e ff8 -r 1000 -f 144490000 - -u localhost", 240000, 1000, 2),
+    ("-s 2400000 -a 80000 -w 500E3 -e ff8 -r 10000 -f 144490000 - -u 127.0.0.1", 80000, 10000, 2),
+    ("-g 1 -f 144490000 - -a 100000 -r 10000 --code H_256_512_4 -v -u localhost --testframes", 100000, 10000, 2),
+    ("-g 49 -f 144490000 - -a 200000 -r 10000 -m 4 --code H_256_512_4 -v -u localhost --testframes --mask 10000 -e 0xfff", 200000, 10000, 4),
+    ("-g 30 -f 144490000 - -r 10000 -m 2 -a 180000 --code H_256_512_4 -v -u localhost --testframes -m 4 --mask 10000", 180000, 10000, 4),
+    ("-g 49 -f 144490000 - -a 40000 -r 1000 --code H_256_512_4 -L /dev/null", 40000, 1000, 2),
+    ("-g 1 -s 240000 -f 144490000 - -n 240000 -u localhost", 240000, 10000, 2),
+])
+def test_reference_command_lines_run_verbatim(args, Fs, Rs, M, tmp_path):
+    """every rtl_fsk command line of the reference's README / scripts must parse and run (it used to exit with usage()
+    or 'Ts/P must be an integer'); the sample source is stdin in place of the dongle."""
+    build_tools()
+    tuner = Fs if "-s" not in args.split() else int(args.split()[args.split().index("-s") + 1])
+    nsec = 0.25 if Rs >= 10000 else 1.0
+    x = synth.fsk_mod(synth.test_bits(int(Rs * nsec) * (1 if M == 2 else 2)), M, tuner, Rs, Rs, Rs, timing_offset=3.0)
+    iq = synth.to_u8(synth.add_awgn(x, 15.0, tuner // Rs, M, synth.rng(5)), amp=60.0)
+    r = subprocess.run([os.path.join(BIN, "rtl_fsk")] + args.split(), input=iq.tobytes(), capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()
+    assert b"modem frames" in r.stderr
+    if "--code" not in args:
+        assert len(r.stdout) > 0
+        if "-n" in args.split():
+            n = int(args.split()[args.split().index("-n") + 1])
+            assert len(r.stdout) <= n // (Fs // Rs)

@@ -34,7 +34,7 @@ static void usage(const char *p) {
 }
 
 int main(int argc, char *argv[]) {
-    int fmt = PIRIP_FMT_S16, real_input = 1, P = 0, nsym = FSK_DEFAULT_NSYM, lower = -1, upper = -1, mask = 0, soft = 0, batch = 0;
+    int fmt = PIRIP_FMT_S16, real_input = 1, P = 0, nsym = FSK_DEFAULT_NSYM, lower = 0, upper = 0, user_lower = 0, user_upper = 0, mask = 0, soft = 0, batch = 0;
     int stats_every = 0;
     static struct option lo[] = { { "fsk_lower", required_argument, 0, 'b' }, { "fsk_upper", required_argument, 0, 'u' },
                                   { "mask", required_argument, 0, 'm' },      { "nsym", required_argument, 0, 'n' },
@@ -50,8 +50,8 @@ int main(int argc, char *argv[]) {
             case 'p': P = atoi(optarg); break;
             case 's': soft = 1; break;
             case 't': stats_every = optarg ? atoi(optarg) : 8; if (stats_every < 1) stats_every = 8; break;
-            case 'b': lower = atoi(optarg); break;
-            case 'u': upper = atoi(optarg); break;
+            case 'b': lower = atoi(optarg); user_lower = 1; break;
+            case 'u': upper = atoi(optarg); user_upper = 1; break;
             case 'm': mask = atoi(optarg); break;
             case 'n': nsym = atoi(optarg); break;
             case 'B': batch = 1; break;
@@ -73,10 +73,15 @@ int main(int argc, char *argv[]) {
         fprintf(stderr, "Couldn't open files\n");
         return 1;
     }
-    const int have_limits = lower >= 0 || upper >= 0;
-    if (have_limits) {
-        if (lower < 0) lower = 0;
-        if (upper < 0) upper = Fs / 2;
+    /* the estimator window is always set, as upstream's fsk_demod does ([U fsk_demod.c], M-confidence): without
+       --fsk_lower the whole negative half is searched as well when the input is complex (-c / -d / -f), --fsk_upper defaults
+       to Fs/2 */
+    const int have_limits = 1;
+    if (!user_lower) lower = real_input ? 0 : -Fs / 2;
+    if (!user_upper) upper = Fs / 2;
+    if (lower < -Fs / 2 || upper > Fs / 2 || upper <= lower) {
+        fprintf(stderr, "fsk_demod: estimator limits must satisfy -Fs/2 <= lower < upper <= Fs/2\n");
+        return 1;
     }
     const int tone_spacing = mask ? mask : 400;
     const size_t bps = real_input ? 2 : (fmt == PIRIP_FMT_U8 ? 2 : (fmt == PIRIP_FMT_S16 ? 4 : 8));

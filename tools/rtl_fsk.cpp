@@ -8,7 +8,8 @@
  * `rtl_fsk ... | fsk_put_test_bits -` run as in pirip's scripts:
  *
  *   rtl_fsk [-i iqfile] [-s rtlFs] [-a modemFs] -r Rs -m M [-p P] [--code NAME] [--mask spacing]
- *           [--fsk_lower Hz] [--fsk_upper Hz] [--filter addr] [--testframes] [-b] [-q] [-v] [-u host] [-f Hz] [-g gain] [-L] out
+ *           [--fsk_lower Hz] [--fsk_upper Hz] [--filter addr] [--testframes] [-b] [-q] [-v] [-u host] [-n samples]
+ *           [-f Hz] [-g gain] [-w bw] [-e reg] [-L logfile] out
  *
  *   uncoded          Nbits bytes per modem frame, one bit per byte                       [R README.md:114]
  *   --code NAME      packed payload bytes of every frame whose CRC checks                [R README.md:184,297]
@@ -42,7 +43,8 @@
 static void usage(const char *p) {
     fprintf(stderr,
             "usage: %s [-i iqfile] [-s rtlFs] [-a modemFs] -r Rs -m M [-p P] [--code NAME] [--mask spacing] [--fsk_lower Hz]\n"
-            "          [--fsk_upper Hz] [--filter addr] [--testframes] [-b] [-q] [-v] [-u host] [-f Hz] [-g gain] [-L] OutputFile\n",
+            "          [--fsk_upper Hz] [--filter addr] [--testframes] [-b] [-q] [-v] [-u host] [-n samples] [-f Hz] [-g gain] [-w bw] [-e reg]\n"
+            "          [-L logfile] OutputFile\n",
             p);
     exit(1);
 }
@@ -50,13 +52,14 @@ static void usage(const char *p) {
 int main(int argc, char *argv[]) {
     int Fs_rtl = 0, Fs = 0, Rs = 10000, M = 2, P = 0, lower = -1, upper = -1, mask = 0, filter_addr = -1;
     int burst_records = 0, quiet = 0, verbose = 0, testframes = 0;
+    long long max_samples = -1; /* -n: stop after this many input samples (at the tuner rate) [R README.md:114] */
     const char *code = nullptr, *inname = "-", *dash_host = nullptr;
     static struct option lo[] = { { "code", required_argument, 0, 'c' },      { "mask", required_argument, 0, 'k' },
                                   { "fsk_lower", required_argument, 0, 'l' }, { "fsk_upper", required_argument, 0, 'U' },
                                   { "filter", required_argument, 0, 'F' },    { "testframes", no_argument, 0, 't' },
                                   { "help", no_argument, 0, 'h' },            { 0, 0, 0, 0 } };
     int o;
-    while ((o = getopt_long(argc, argv, "i:s:a:r:m:p:f:g:u:bqvLh", lo, NULL)) != -1) {
+    while ((o = getopt_long(argc, argv, "i:s:a:r:m:p:f:g:u:n:e:w:L:d:bqvh", lo, NULL)) != -1) {
         switch (o) {
             case 'i': inname = optarg; break;
             case 's': Fs_rtl = atoi(optarg); break;
@@ -74,7 +77,10 @@ int main(int argc, char *argv[]) {
             case 'q': quiet = 1; break;
             case 'v': verbose = 1; break;
             case 'u': dash_host = optarg; break;
-            case 'f': case 'g': case 'L': break; /* tuner frequency / gain / logging: nothing to tune in a file */
+            case 'n': max_samples = (long long)atof(optarg); break;
+            /* tuner frequency / gain / device, tuner bandwidth (-w) and register tweak (-e) [R README.md:152,172,239], log file
+               (-L file [R script/frame_repeater:23]): accepted as upstream spells them, nothing to tune in a file */
+            case 'f': case 'g': case 'd': case 'e': case 'w': case 'L': break;
             default: usage(argv[0]);
         }
     }
@@ -85,7 +91,12 @@ int main(int argc, char *argv[]) {
     if (Fs_rtl == 0) Fs_rtl = Fs;
     if ((M != 2 && M != 4) || Rs <= 0 || Fs % Rs || Fs_rtl % Fs) usage(argv[0]);
     const int D = Fs_rtl / Fs; /* csdr decimation ratio, e.g. 1.8M -> 40k = 45 [R README.md:109], 2.4M -> 80k = 30 [R README.md:172] */
-    if (P == 0) P = FSK_DEFAULT_P;
+    if (P == 0) {
+        /* upstream takes no -p: the oversampling is derived from Ts the way the FSK_LDPC modem open does ([U freedv_fsk.c::
+           freedv_fsk_open], M-confidence: Ts halved while it is even and above 10): Ts 24 -> 6, 20 -> 10, 40 -> 10, 240 -> 15, 8 -> 8 */
+        P = Fs / Rs;
+        while (P > 10 && (P % 2) == 0) P /= 2;
+    }
     if ((Fs / Rs) % P || P < 4) {
         fprintf(stderr, "rtl_fsk: Ts/P must be an integer and P >= 4\n");
         return 1;
@@ -160,8 +171,11 @@ int main(int argc, char *argv[]) {
     long frames = 0, packets = 0, test_errs = 0, test_bits_n = 0;
     double since_dash = 0.0;
 
+    long long consumed = 0; /* input samples handed to the modem chain so far */
     for (;;) {
         const int nin = (int)fsk_nin(fsk);
+        if (max_samples >= 0 && consumed + (long long)D * nin > max_samples) break;
+        consumed += (long long)D * nin;
         if (D == 1) {
             raw.resize((size_t)nin * 2);
             if (fread(raw.data(), 2, (size_t)nin, fin) != (size_t)nin) break; /* short read ends the loop */
