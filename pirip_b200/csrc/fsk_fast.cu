@@ -69,6 +69,7 @@ struct FastCfg {
     int group_stride;         /* shared memory per capture group (bytes, 128-byte multiple) */
     int fft_blocks_per_round; /* blocks transformed at a time: as many as fit the scratch row */
     int prune;                /* 256-point FFT: the estimator window lies inside output bins k < 32 */
+    int fft_merged;           /* 256-point FFT: the magnitude row holds every block of a frame, one IIR pass per frame */
     int exit_on_flag;
     int diag; /* PIRIP_FSK_FAST_DIAG: the stats record carries the timing-line strength in `foff` */
 };
@@ -260,6 +261,14 @@ __device__ __forceinline__ float2 raw_cvt(const unsigned char *p) {
     } else {
         return *reinterpret_cast<const float2 *>(p);
     }
+}
+
+/* square root for FAST quantities (MUFU, relative error ~1e-7): the translation unit is built with -prec-sqrt=true, where
+   sqrtf() is a ~20-instruction IEEE sequence */
+__device__ __forceinline__ float fsqrt_fast(float x) {
+    float r;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -805,7 +814,9 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
 }
 
 /* ------------------------------------------------------------------ the kernel */
-template <int M, int FMT, bool STEP1>
+/* SPEC = 1: the benchmark shape (config 1 / 5: Ts = P = 24, Nsym = 50, Ndft = 256) with its sizes as compile-time constants, so
+   that the integrator, decision and mixing loops unroll; SPEC = 0: every size from cfg. */
+template <int M, int FMT, bool STEP1, int SPEC>
 __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ FastArgs args) {
     extern __shared__ __align__(128) unsigned char smem_all[];
     /* roles: the first chain_ctas CTAs run the exact-oscillator chains, the others demodulate (one CTA per SM either way) */
@@ -827,8 +838,10 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
     float2 *ideal = reinterpret_cast<float2 *>(smem + cfg.off_ideal);
     Misc *ms = reinterpret_cast<Misc *>(smem + cfg.off_misc);
 
-    const int Ndft = cfg.Ndft, half = Ndft >> 1, nb = cfg.nb, Ts = cfg.Ts, P = cfg.P, Nsym = cfg.Nsym, Nmem = cfg.Nmem, fdcS = cfg.fdcS;
-    const int step = cfg.step, nint = cfg.nint, bps = cfg.bps;
+    constexpr bool S1 = SPEC == 1;
+    const int Ndft = S1 ? 256 : cfg.Ndft, half = Ndft >> 1, nb = cfg.nb, Ts = S1 ? 24 : cfg.Ts, P = S1 ? 24 : cfg.P, Nsym = S1 ? 50 : cfg.Nsym;
+    const int Nmem = S1 ? 1248 : cfg.Nmem, fdcS = cfg.fdcS;
+    const int step = S1 ? 1 : cfg.step, nint = S1 ? 1224 : cfg.nint, bps = S1 ? 2 : cfg.bps;
 
     /* per-thread constants: FFT twiddles of the last two levels (256-point path), timing-line correction */
     float2 t3[3], t4[4][3];
@@ -940,6 +953,22 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             const float tc = 0.1f, c9 = __fsub_rn(1.0f, tc);
             if (cfg.log2_ndft == 8) {
                 const int gpr = cfg.fft_blocks_per_round; /* thread groups (blocks) per round: as many as the scratch row holds */
+                if (cfg.fft_merged) {
+                    /* every block of the frame first (a half-warp reuses its exchange buffer round after round, ordered by the
+                       block routine's own __syncwarp), then ONE pass of the IIR over the blocks in order */
+                    for (int j0 = 0; j0 < numffts; j0 += gpr) {
+                        const int j = j0 + (tid >> 4);
+                        if ((tid >> 4) < gpr && j < numffts)
+                            fft256_block<FMT>(cfg, tid & 15, fr + (size_t)j * half * bps, hannS, scratch + (tid >> 4) * 272, mag + (size_t)j * nb, t3, t4);
+                    }
+                    GSYNC();
+                    for (int b = tid; b < nb; b += T) {
+                        float s = Sf[b];
+                        for (int r = 0; r < numffts; ++r) s = __fadd_rn(__fmul_rn(s, c9), __fmul_rn(mag[r * nb + b], tc));
+                        Sf[b] = s;
+                    }
+                    GSYNC();
+                } else
                 for (int j0 = 0; j0 < numffts; j0 += gpr) {
                     const int j = j0 + (tid >> 4);
                     if ((tid >> 4) < gpr && j < numffts)
@@ -969,12 +998,20 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             /* peak picking with blanking (warp 0) and the mask correlation (warp 1), on Sf[st, en) */
             float *tmp = mag; /* scratch copy for the blanking */
             if (warp == 0) {
-                for (int b = lane; b < nb; b += 32) tmp[b] = Sf[b];
+                const bool inreg = nb <= 32; /* a window of at most 32 bins: one bin per lane, blanking in registers */
+                float myv = 0.0f;
+                if (inreg)
+                    myv = lane < nb ? Sf[lane] : 0.0f;
+                else
+                    for (int b = lane; b < nb; b += 32) tmp[b] = Sf[b];
                 __syncwarp();
                 int fq[4];
                 for (int it = 0; it < M; ++it) {
                     float best = 0.0f;
                     int bi = 0;
+                    if (inreg) {
+                        if (myv > 0.0f) best = myv, bi = cfg.st + lane;
+                    } else
                     for (int b = lane; b < nb; b += 32) {
                         const float v = tmp[b];
                         if (v > best) {
@@ -995,8 +1032,12 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                     int lo = imax - cfg.f_zero, hi = imax + cfg.f_zero;
                     lo = lo < cfg.st ? cfg.st : lo;
                     hi = hi > cfg.en ? cfg.en : hi;
-                    for (int b = lo + lane; b < hi; b += 32) tmp[b - cfg.st] = 0.0f;
-                    __syncwarp();
+                    if (inreg) {
+                        if (cfg.st + lane >= lo && cfg.st + lane < hi) myv = 0.0f;
+                    } else {
+                        for (int b = lo + lane; b < hi; b += 32) tmp[b - cfg.st] = 0.0f;
+                        __syncwarp();
+                    }
                     fq[it] = imax - half;
                 }
                 if (lane == 0) {
@@ -1087,17 +1128,50 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             const bool al4 = FMT == PIRIP_FMT_U8 && (((ms->roff - 2 * par) & 3) == 0);
             const unsigned char *p = fr + (ptrdiff_t)j0 * bps;
             float2 *dst = fdc + nold + j0;
+            if (al4) {
+                /* u8 pairs on 4-byte boundaries (the usual case): the complete pairs in a loop without predicates, the next
+                   pair's bytes loaded before the current pair is mixed; the pair before sample 0 (odd nold, thread 0) and the
+                   half pair at the end on their own */
+                const int qfull = (nin + par) >> 1; /* pairs q < qfull hold two samples of the frame (but for q = 0 when par) */
+                /* mode 0: both samples, 1: the first only, 2: the second only */
+                auto mixpair = [&](unsigned w, float2 *dd, int mode) {
+                    const float2 x0 = make_float2(u8m127(w, 0), u8m127(w, 1)), x1 = make_float2(u8m127(w, 2), u8m127(w, 3));
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const float2 y0 = fmix(x0, p0[m]), y1 = fmix(x1, p1[m]);
+                        if (mode == 0)
+                            *reinterpret_cast<float4 *>(dd + m * fdcS) = make_float4(y0.x, y0.y, y1.x, y1.y);
+                        else if (mode == 1)
+                            dd[m * fdcS] = y0;
+                        else
+                            dd[m * fdcS + 1] = y1;
+                        p0[m] = fcmul(p0[m], D[m]);
+                        p1[m] = fcmul(p1[m], D[m]);
+                    }
+                };
+                int q = tid;
+                if (par && tid == 0) {
+                    mixpair(*reinterpret_cast<const unsigned *>(p), dst, 2);
+                    q += T, p += 2 * T * 2, dst += 2 * T;
+                }
+                if (q < qfull) {
+                    unsigned w = *reinterpret_cast<const unsigned *>(p);
+#pragma unroll 2
+                    for (; q + T < qfull; q += T, dst += 2 * T) {
+                        p += 2 * T * 2;
+                        const unsigned wn = *reinterpret_cast<const unsigned *>(p);
+                        mixpair(w, dst, 0);
+                        w = wn;
+                    }
+                    mixpair(w, dst, 0);
+                    q += T, p += 2 * T * 2, dst += 2 * T;
+                }
+                if (q == qfull && q < npairs) mixpair(*reinterpret_cast<const unsigned *>(p), dst, 1);
+            } else
             for (int q = tid; q < npairs; q += T, p += 2 * T * bps, dst += 2 * T) {
                 const int j = 2 * q - par;
-                float2 x0, x1;
-                if (al4) {
-                    const unsigned w = *reinterpret_cast<const unsigned *>(p);
-                    x0 = make_float2(u8m127(w, 0), u8m127(w, 1));
-                    x1 = make_float2(u8m127(w, 2), u8m127(w, 3));
-                } else {
-                    x0 = j >= 0 ? raw_cvt<FMT>(p) : make_float2(0.0f, 0.0f);
-                    x1 = raw_cvt<FMT>(p + bps);
-                }
+                const float2 x0 = j >= 0 ? raw_cvt<FMT>(p) : make_float2(0.0f, 0.0f);
+                const float2 x1 = raw_cvt<FMT>(p + bps);
                 const bool full = j >= 0 && j + 1 < nin;
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
@@ -1129,9 +1203,10 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
         /* ---- A9/A10: sliding-window integrators, window energies, timing line (fast) ---- */
         {
             float tr = 0.0f, ti = 0.0f, esum = 0.0f;
-            const int i0 = tid * cfg.RO;
+            const int RO = cfg.RO;
+            const int i0 = tid * RO;
             if (i0 < nint) {
-                const int cnt = nint - i0 < cfg.RO ? nint - i0 : cfg.RO;
+                const int cnt = nint - i0 < RO ? nint - i0 : RO;
                 if (STEP1) {
                     /* step == 1, Ts even, RO even: two outputs per iteration, 16-byte loads (window starts are even) */
                     const float4 *r4[M];
@@ -1151,14 +1226,16 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                     int ip = i0 % P;
 #pragma unroll 2
                     for (int o = 0; o < cnt; o += 2) {
-                        float e0 = 0.0f, e1 = 0.0f;
+                        float e0, e1;
 #pragma unroll
                         for (int m = 0; m < M; ++m) {
                             const float4 ov = r4[m][o >> 1], nv = r4[m][hTs + (o >> 1)];
-                            e0 += fmaf(S[m].x, S[m].x, S[m].y * S[m].y);
-                            const float2 S1 = xadd(S[m], xsub(make_float2(nv.x, nv.y), make_float2(ov.x, ov.y)));
-                            e1 += fmaf(S1.x, S1.x, S1.y * S1.y);
-                            S[m] = xadd(S1, xsub(make_float2(nv.z, nv.w), make_float2(ov.z, ov.w)));
+                            const float ea = fmaf(S[m].x, S[m].x, S[m].y * S[m].y);
+                            const float2 Sn = xadd(S[m], xsub(make_float2(nv.x, nv.y), make_float2(ov.x, ov.y)));
+                            const float eb = fmaf(Sn.x, Sn.x, Sn.y * Sn.y);
+                            S[m] = xadd(Sn, xsub(make_float2(nv.z, nv.w), make_float2(ov.z, ov.w)));
+                            e0 = m ? e0 + ea : ea;
+                            e1 = m ? e1 + eb : eb;
                         }
                         const float2 w0 = ideal[ip], w1 = ideal[ip + 1]; /* the table holds P + 1 entries: no wrap inside a pair */
                         if (o + 1 >= cnt) e1 = 0.0f;
@@ -1258,95 +1335,117 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             const int low = ms->low;
             const float fr_w = ms->fract;
             /* t = (1 - fract) W(low) + fract W(high) = sum_{k < Ts} v_k + fract (sum_{Ts <= k < Ts + step} v_k - sum_{k < step} v_k):
-               the four lanes of a symbol add a quarter of the window each (packed adds), lane 3 the correction */
+               the four lanes of a symbol add a quarter of the window each (packed adds), lane 3 the correction.  The sums of a
+               pass (16 symbols per group of 64 threads) end in the first lane of every symbol; four passes are gathered so that
+               every lane of a warp holds ONE symbol - lane L of warp w the symbol 16 (L >> 3) + 8 w + (L & 7) of the round - and
+               the decision, its guard and the statistics run once per round with full warps. */
             const int per = (Ts + 3) >> 2;
             float s_sig = 0.0f, s_nse = 0.0f, s_mean = 0.0f;
             int fl = 0;
             unsigned char *bo = args.bits ? args.bits + (cap * args.max_frames + (size_t)frame) * (size_t)cfg.Nbits : nullptr;
             float *fo = args.rx_filt ? args.rx_filt + (cap * args.max_frames + (size_t)frame) * (size_t)(M * Nsym) : nullptr;
-            const int ntask = (Nsym * 4 + 31) & ~31;
             const bool two = ms->high != low; /* an integer timing offset: W(high) is W(low), fract is 0 */
             const int near = ms->near;
-            for (int task = tid; task < ntask; task += T) {
-                const int sym = task >> 2, sub = task & 3;
-                const bool valid = sym < Nsym;
-                const int base = ((sym + 1) * P + low) * step;
-                const int k0 = sub * per, k1 = (k0 + per < Ts) ? k0 + per : Ts;
-                float2 t[M];
-                float uu[M];
+            const float dfr = ms->dfr;
+            const int sub = tid & 3;
+            const int k0 = sub * per, k1 = (k0 + per < Ts) ? k0 + per : Ts;
+            for (int sym0 = 0; sym0 < Nsym; sym0 += 64) {
+                float E[M], U[M]; /* this lane's symbol of the round: tone energies, |dt/dfract|^2 */
 #pragma unroll
-                for (int m = 0; m < M; ++m) t[m] = make_float2(0.0f, 0.0f), uu[m] = 0.0f;
-                if (valid) {
-                    const float2 *f = fdc + base;
+                for (int m = 0; m < M; ++m) E[m] = U[m] = 0.0f;
+#pragma unroll
+                for (int pass = 0; pass < 4; ++pass) {
+                    if (sym0 + 16 * pass >= Nsym) break; /* uniform */
+                    const int sym = sym0 + 16 * pass + (tid >> 2);
+                    const bool valid = sym < Nsym;
+                    const int base = ((sym + 1) * P + low) * step;
+                    float2 t[M];
+                    float uu[M];
+#pragma unroll
+                    for (int m = 0; m < M; ++m) t[m] = make_float2(0.0f, 0.0f), uu[m] = 0.0f;
+                    if (valid) {
+                        const float2 *f = fdc + base;
+                        if (S1) {
+#pragma unroll
+                            for (int k = 0; k < 6; ++k)
+#pragma unroll
+                                for (int m = 0; m < M; ++m) t[m] = xadd(t[m], f[m * fdcS + k0 + k]);
+                        } else {
 #pragma unroll 2
-                    for (int k = k0; k < k1; ++k)
+                            for (int k = k0; k < k1; ++k)
 #pragma unroll
-                        for (int m = 0; m < M; ++m) t[m] = xadd(t[m], f[m * fdcS + k]);
-                    if (sub == 3 && two) {
-                        float2 u[M];
+                                for (int m = 0; m < M; ++m) t[m] = xadd(t[m], f[m * fdcS + k]);
+                        }
+                        if (sub == 3 && two) {
+                            float2 u[M];
 #pragma unroll
-                        for (int m = 0; m < M; ++m) u[m] = make_float2(0.0f, 0.0f);
-                        for (int k = 0; k < step; ++k)
+                            for (int m = 0; m < M; ++m) u[m] = make_float2(0.0f, 0.0f);
+                            for (int k = 0; k < step; ++k)
 #pragma unroll
-                            for (int m = 0; m < M; ++m) u[m] = xadd(u[m], xsub(f[m * fdcS + Ts + k], f[m * fdcS + k]));
+                                for (int m = 0; m < M; ++m) u[m] = xadd(u[m], xsub(f[m * fdcS + Ts + k], f[m * fdcS + k]));
 #pragma unroll
-                        for (int m = 0; m < M; ++m) {
-                            t[m].x = fmaf(fr_w, u[m].x, t[m].x);
-                            t[m].y = fmaf(fr_w, u[m].y, t[m].y);
-                            uu[m] = fmaf(u[m].x, u[m].x, u[m].y * u[m].y); /* |dt/dfract|^2 */
+                            for (int m = 0; m < M; ++m) {
+                                t[m].x = fmaf(fr_w, u[m].x, t[m].x);
+                                t[m].y = fmaf(fr_w, u[m].y, t[m].y);
+                                uu[m] = fmaf(u[m].x, u[m].x, u[m].y * u[m].y); /* |dt/dfract|^2 */
+                            }
+                        }
+                        if (sub == 3 && near != 0) {
+                            /* the neighbouring pair: W(low) - W(low-1) below, W(low+2) - W(low+1) above */
+                            const float2 *g = near < 0 ? f - step : f + (two ? step : 0);
+#pragma unroll
+                            for (int m = 0; m < M; ++m) {
+                                float2 u2 = make_float2(0.0f, 0.0f);
+                                for (int k = 0; k < step; ++k) u2 = xadd(u2, xsub(g[m * fdcS + Ts + k], g[m * fdcS + k]));
+                                uu[m] = fmaxf(uu[m], fmaf(u2.x, u2.x, u2.y * u2.y));
+                            }
                         }
                     }
-                    if (sub == 3 && near != 0) {
-                        /* the neighbouring pair: W(low) - W(low-1) below, W(low+2) - W(low+1) above */
-                        const float2 *g = near < 0 ? f - step : f + (two ? step : 0);
 #pragma unroll
-                        for (int m = 0; m < M; ++m) {
-                            float2 u2 = make_float2(0.0f, 0.0f);
-                            for (int k = 0; k < step; ++k) u2 = xadd(u2, xsub(g[m * fdcS + Ts + k], g[m * fdcS + k]));
-                            uu[m] = fmaxf(uu[m], fmaf(u2.x, u2.x, u2.y * u2.y));
-                        }
+                    for (int m = 0; m < M; ++m) {
+                        t[m].x += __shfl_xor_sync(0xffffffffu, t[m].x, 1);
+                        t[m].y += __shfl_xor_sync(0xffffffffu, t[m].y, 1);
+                        t[m].x += __shfl_xor_sync(0xffffffffu, t[m].x, 2);
+                        t[m].y += __shfl_xor_sync(0xffffffffu, t[m].y, 2);
+                    }
+                    /* gather: the symbol of lanes 4k .. 4k+3 goes to lane 8 pass + k (energies from any of the four lanes, the
+                       correction term from the symbol's lane 3) */
+                    const int src = 4 * (lane & 7);
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        const float e = fmaf(t[m].x, t[m].x, t[m].y * t[m].y);
+                        const float ge = __shfl_sync(0xffffffffu, e, src), gu = __shfl_sync(0xffffffffu, uu[m], src + 3);
+                        if ((lane >> 3) == pass) E[m] = ge, U[m] = gu;
                     }
                 }
-#pragma unroll
-                for (int m = 0; m < M; ++m) uu[m] = __shfl_down_sync(0xffffffffu, uu[m], 3); /* lane 3 of the symbol -> its lane 0 */
-#pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    t[m].x += __shfl_xor_sync(0xffffffffu, t[m].x, 1);
-                    t[m].y += __shfl_xor_sync(0xffffffffu, t[m].y, 1);
-                    t[m].x += __shfl_xor_sync(0xffffffffu, t[m].x, 2);
-                    t[m].y += __shfl_xor_sync(0xffffffffu, t[m].y, 2);
-                }
-                if (valid && sub == 0) {
-                    float e[M];
-                    float mx = 0.0f, sum = 0.0f, second = 0.0f;
+                const int sym = sym0 + 16 * (lane >> 3) + 8 * warp + (lane & 7);
+                if (sym < Nsym) {
+                    float mx = E[0], sum = 0.0f, second = -1.0f;
                     int symv = 0;
 #pragma unroll
-                    for (int m = 0; m < M; ++m) {
-                        e[m] = fmaf(t[m].x, t[m].x, t[m].y * t[m].y);
-                        sum += e[m];
-                    }
-                    mx = e[0];
+                    for (int m = 0; m < M; ++m) sum += E[m];
 #pragma unroll
                     for (int m = 1; m < M; ++m)
-                        if (e[m] > mx) {
-                            mx = e[m];
+                        if (E[m] > mx) {
+                            mx = E[m];
                             symv = m;
                         }
-                    second = -1.0f;
-                    float uub = uu[0], uus = 0.0f;
+                    float uub = U[0], uus = 0.0f;
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
-                        if (m == symv) uub = uu[m];
-                        if (m != symv && e[m] > second) second = e[m], uus = uu[m];
+                        if (m == symv) uub = U[m];
+                        if (m != symv && E[m] > second) second = E[m], uus = U[m];
                     }
                     /* the scalar algorithm's energies differ from these by rounding (g_sym, relative) and by the uncertainty dfr
-                       of the interpolation weight: d|t|^2 <= dfr (2 |t| |u| + |u|^2 dfr) */
-                    const float dfr = ms->dfr;
-                    const float slack = cfg.g_sym * (mx + second) +
-                                        dfr * (2.0f * (sqrtf(mx * uub) + sqrtf(second * uus)) + (uub + uus) * dfr);
-                    if (mx - second <= slack && mx > 0.0f) { /* a 0 == 0 tie (zero input) is exact */
-                        fl |= FLAG_SYM;
-                        atomicAdd(&ms->nflag_sym, 1);
+                       of the interpolation weight: d|t|^2 <= dfr (2 |t| |u| + |u|^2 dfr).  2 sqrt(a b) <= a + b gives a bound
+                       without square roots that clears nearly every symbol; the tight bound decides the rest. */
+                    const float gs = cfg.g_sym * (mx + second);
+                    if (mx - second <= gs + dfr * ((mx + second) + (uub + uus) * (1.0f + dfr)) && mx > 0.0f) {
+                        const float slack = gs + dfr * (2.0f * (sqrtf(mx * uub) + sqrtf(second * uus)) + (uub + uus) * dfr);
+                        if (mx - second <= slack) { /* a 0 == 0 tie (zero input) is exact */
+                            fl |= FLAG_SYM;
+                            atomicAdd(&ms->nflag_sym, 1);
+                        }
                     }
                     if (bo) {
                         if (M == 2)
@@ -1356,15 +1455,17 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                             bo[2 * sym] = (unsigned char)((symv & 2) >> 1);
                         }
                     }
+                    float rmx = 0.0f;
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
-                        const float rf = sqrtf(e[m]);
+                        const float rf = fsqrt_fast(E[m]);
                         filt[m * Nsym + sym] = rf;
                         if (fo) fo[m * Nsym + sym] = rf;
+                        if (m == symv) rmx = rf;
                     }
                     s_sig += mx;
-                    s_nse += (sum - mx) / (float)(M - 1);
-                    s_mean += sqrtf(mx);
+                    s_nse += (sum - mx) * (1.0f / (float)(M - 1));
+                    s_mean += rmx;
                 }
             }
             s_sig = warp_sum(s_sig);
@@ -1469,10 +1570,9 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
         /* ---- keep the tail of the baseband memory for the next frame ---- */
         {
             const int nold2 = Nmem - ms->nin; /* ms->nin is already the next frame's nin */
-            for (int i = tid; i < M * nold2; i += T) {
-                const int m = i / nold2, k = i - m * nold2;
-                fdc[m * fdcS + k] = fdc[m * fdcS + (Nmem - nold2) + k];
-            }
+#pragma unroll
+            for (int m = 0; m < M; ++m)
+                for (int k = tid; k < nold2; k += T) fdc[m * fdcS + k] = fdc[m * fdcS + (Nmem - nold2) + k];
         }
         GSYNC();
     }
@@ -1526,10 +1626,10 @@ struct FskFastPlan {
     std::string desc;
 };
 
-template <int M, int FMT, bool STEP1>
+template <int M, int FMT, bool STEP1, int SPEC>
 static cudaError_t fast_launch_t(const FskFastPlan *p, const FastArgs &a, cudaStream_t stream, int mode, unsigned grid, unsigned block, size_t smem,
                                  int *regs) {
-    auto kern = fsk_fast_kernel<M, FMT, STEP1>;
+    auto kern = fsk_fast_kernel<M, FMT, STEP1, SPEC>;
     if (mode == 1) return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     if (mode == 2) {
         cudaFuncAttributes at;
@@ -1546,10 +1646,15 @@ static cudaError_t fast_dispatch(const FskFastPlan *p, const FastArgs &a, cudaSt
                                  size_t smem = 0, int *regs = nullptr) {
     /* the paired integrator needs step == 1 and even Ts, RO, nint */
     const bool s1 = p->cfg.step == 1 && (p->cfg.Ts & 1) == 0 && (p->cfg.RO & 1) == 0 && (p->cfg.nint & 1) == 0;
+    /* the benchmark shape has a kernel of its own with the sizes compiled in */
+    const FastCfg &c = p->cfg;
+    if (s1 && p->M == 2 && p->fmt == PIRIP_FMT_U8 && c.Ts == 24 && c.P == 24 && c.Nsym == 50 && c.Ndft == 256 && c.Nmem == 1248 && c.nint == 1224 &&
+        c.bps == 2 && !getenv("PIRIP_FSK_FAST_NO_SPEC"))
+        return fast_launch_t<2, PIRIP_FMT_U8, true, 1>(p, a, stream, mode, grid, block, smem, regs);
 #define D(MM, FF)                                                                                                   \
     if (p->M == MM && p->fmt == FF)                                                                                 \
-        return s1 ? fast_launch_t<MM, FF, true>(p, a, stream, mode, grid, block, smem, regs)                       \
-                  : fast_launch_t<MM, FF, false>(p, a, stream, mode, grid, block, smem, regs);
+        return s1 ? fast_launch_t<MM, FF, true, 0>(p, a, stream, mode, grid, block, smem, regs)                    \
+                  : fast_launch_t<MM, FF, false, 0>(p, a, stream, mode, grid, block, smem, regs);
     D(2, PIRIP_FMT_U8)
     D(2, PIRIP_FMT_S16)
     D(2, PIRIP_FMT_F32)
@@ -1616,6 +1721,9 @@ FskFastPlan *fsk_fast_plan_create(const pirip_fsk_cfg &c, const FskDevCfg &d, co
     /* integrator outputs per thread: even (16-byte aligned window starts), half of it odd (bank spread) */
     f.RO = (f.nint + T - 1) / T;
     if (f.RO & 1) f.RO++;
+    /* step 1: a thread reads its run with 16-byte loads, eight lanes per shared-memory wavefront.  Runs RO * 8 bytes apart fall
+       on distinct 16-byte bank groups only when RO / 2 is odd (RO = 20: every load is a 2-way conflict; 22: none) */
+    if (f.step == 1 && ((f.RO >> 1) & 1) == 0 && !getenv("PIRIP_FSK_FAST_RO_EVEN")) f.RO += 2;
     f.tailpad = align_up(2 * d.Ts + d.Ts / 4 + 2, TAILPAD_MIN);
     if (f.tailpad < 16) f.tailpad = 16;
 
@@ -1637,6 +1745,7 @@ FskFastPlan *fsk_fast_plan_create(const pirip_fsk_cfg &c, const FskDevCfg &d, co
     f.smem_bytes = off;
     f.group_stride = align_up(off, 128);
     const int numffts_max = f.nin_max / (d.Ndft / 2) - 1;
+    f.fft_merged = (d.log2_ndft == 8 && numffts_max * f.nb * 4 <= row_free && !getenv("PIRIP_FSK_FAST_NO_MERGE")) ? 1 : 0;
     if (d.log2_ndft == 8) {
         int per = row_free / (272 * 8);
         const int permag = row_free / (f.nb * 4);

@@ -55,7 +55,73 @@ struct CodeEntry {
     std::string name;
     int max_iter, CodeLength, NumberParityBits, NumberRowsHcols, max_row_weight, max_col_weight;
     std::vector<uint16_t> H_rows, H_cols;
+    bool standin = false; /* a generated table of the same shape, NOT codec2's matrix */
+    bool warned = false;
 };
+
+/* codec2's generated table files (src/H_256_512_4.h + .c and friends) as text: `#define <NAME>_<FIELD> n` and
+   `<NAME>_H_rows[] = { ... }` / `<NAME>_H_cols[] = { ... }`.  Every name with both arrays and its dimensions becomes an entry. */
+static void parse_codec2_tables(const std::string &txt, std::vector<CodeEntry> &out) {
+    auto is_id = [](char c) { return (c >= 'a' && c <= 'z') || (c >= 'A' && c <= 'Z') || (c >= '0' && c <= '9') || c == '_'; };
+    auto define_of = [&](const std::string &name, const char *field, int dflt) {
+        const std::string key = name + "_" + field;
+        size_t pos = 0;
+        while ((pos = txt.find(key, pos)) != std::string::npos) {
+            const size_t end = pos + key.size();
+            if ((pos == 0 || !is_id(txt[pos - 1])) && end < txt.size() && !is_id(txt[end])) return atoi(txt.c_str() + end);
+            pos = end;
+        }
+        return dflt;
+    };
+    auto array_of = [&](const std::string &name, const char *suffix, std::vector<uint16_t> &v) {
+        const std::string key = name + suffix;
+        size_t pos = 0;
+        while ((pos = txt.find(key, pos)) != std::string::npos) {
+            size_t q = pos + key.size();
+            pos = q;
+            while (q < txt.size() && (txt[q] == ' ' || txt[q] == '[' || txt[q] == ']')) ++q;
+            if (q >= txt.size() || txt[q] != '=') continue; /* a declaration (extern ...;), not the definition */
+            const size_t open = txt.find('{', q), close = txt.find('}', q);
+            if (open == std::string::npos || close == std::string::npos || close < open) return false;
+            v.clear();
+            for (size_t i = open + 1; i < close;) {
+                if (txt[i] >= '0' && txt[i] <= '9') {
+                    v.push_back((uint16_t)strtoul(txt.c_str() + i, nullptr, 10));
+                    while (i < close && txt[i] >= '0' && txt[i] <= '9') ++i;
+                } else
+                    ++i;
+            }
+            return !v.empty();
+        }
+        return false;
+    };
+    size_t pos = 0;
+    const std::string tag = "_H_rows";
+    while ((pos = txt.find(tag, pos)) != std::string::npos) {
+        size_t b = pos;
+        while (b > 0 && is_id(txt[b - 1])) --b;
+        const std::string name = txt.substr(b, pos - b);
+        pos += tag.size();
+        bool have = false;
+        for (const CodeEntry &e : out) have = have || e.name == name;
+        if (name.empty() || have) continue;
+        CodeEntry e;
+        e.name = name;
+        if (!array_of(name, "_H_rows", e.H_rows) || !array_of(name, "_H_cols", e.H_cols)) continue;
+        e.CodeLength = define_of(name, "CODELENGTH", 0);
+        e.NumberParityBits = define_of(name, "NUMBERPARITYBITS", 0);
+        e.NumberRowsHcols = define_of(name, "NUMBERROWSHCOLS", 0);
+        e.max_row_weight = define_of(name, "MAX_ROW_WEIGHT", 0);
+        e.max_col_weight = define_of(name, "MAX_COL_WEIGHT", 0);
+        e.max_iter = define_of(name, "MAX_ITER", 15);
+        if (e.CodeLength <= 0 || e.NumberParityBits <= 0 || e.NumberRowsHcols <= 0 || e.max_row_weight <= 0 || e.max_col_weight <= 0 ||
+            e.H_rows.size() != (size_t)e.NumberParityBits * e.max_row_weight || e.H_cols.size() != (size_t)e.NumberRowsHcols * e.max_col_weight) {
+            fprintf(stderr, "pirip_b200: PIRIP_LDPC_TABLES: table %s is incomplete (dimensions / array sizes), ignored\n", name.c_str());
+            continue;
+        }
+        out.push_back(std::move(e));
+    }
+}
 
 std::mutex g_codes_mu;
 std::vector<CodeEntry> &codes() {
@@ -72,8 +138,41 @@ std::vector<CodeEntry> &codes() {
             e.max_col_weight = b.max_col_weight;
             e.H_rows.assign(b.H_rows, b.H_rows + (size_t)b.NumberParityBits * b.max_row_weight);
             e.H_cols.assign(b.H_cols, b.H_cols + (size_t)b.NumberRowsHcols * b.max_col_weight);
+            e.standin = true;
             w.push_back(std::move(e));
         }
+        /* PIRIP_LDPC_TABLES=<codec2>/src/H_256_512_4.h:<codec2>/src/H_256_512_4.c[:...]: codec2's own tables take the genuine
+           names; the stand-in of the same name stays reachable as <name>_STANDIN */
+        if (const char *ev = getenv("PIRIP_LDPC_TABLES")) {
+            std::string txt, list(ev);
+            size_t a = 0;
+            while (a <= list.size()) {
+                size_t b = list.find(':', a);
+                if (b == std::string::npos) b = list.size();
+                const std::string path = list.substr(a, b - a);
+                if (!path.empty()) {
+                    FILE *fp = fopen(path.c_str(), "rb");
+                    if (!fp)
+                        fprintf(stderr, "pirip_b200: PIRIP_LDPC_TABLES: cannot read %s\n", path.c_str());
+                    else {
+                        char buf[1 << 14];
+                        size_t n;
+                        while ((n = fread(buf, 1, sizeof buf, fp)) > 0) txt.append(buf, n);
+                        fclose(fp);
+                        txt.push_back('\n');
+                    }
+                }
+                a = b + 1;
+            }
+            std::vector<CodeEntry> real;
+            parse_codec2_tables(txt, real);
+            for (CodeEntry &r : real) {
+                for (CodeEntry &e : w)
+                    if (e.name == r.name && e.standin) e.name += "_STANDIN";
+                w.push_back(std::move(r));
+            }
+        }
+        w.reserve(64); /* keep table pointers handed out by ldpc_codes_setup stable */
         return w;
     }();
     return v;
@@ -357,10 +456,27 @@ extern "C" void ldpc_codes_list(void) {
     fprintf(stderr, "\n");
 }
 
+/* A stand-in answers to the genuine name (pirip's command lines run unchanged, [R README.md:184]) but says so, loudly, once:
+   frames coded with it do not interoperate with codec2 / real pirip radios.  `<name>_STANDIN` selects it silently. */
 extern "C" int ldpc_codes_find(char name[]) {
+    if (!name) return -1;
     std::lock_guard<std::mutex> lk(g_codes_mu);
-    for (size_t i = 0; i < codes().size(); ++i)
-        if (codes()[i].name == name) return (int)i;
+    const std::string want(name);
+    for (size_t i = 0; i < codes().size(); ++i) {
+        CodeEntry &e = codes()[i];
+        if (e.name == want) {
+            if (e.standin && !e.warned && !getenv("PIRIP_LDPC_STANDIN_OK")) {
+                e.warned = true;
+                fprintf(stderr,
+                        "pirip_b200: WARNING: LDPC code %s is a STAND-IN table (same N, K and layout, NOT codec2's parity-check matrix):\n"
+                        "pirip_b200: WARNING: frames coded with it do not decode on codec2 / real pirip radios and theirs do not decode here.\n"
+                        "pirip_b200: WARNING: load codec2's table with PIRIP_LDPC_TABLES=<codec2>/src/%s.h:<codec2>/src/%s.c or ldpc_codes_add().\n",
+                        name, name, name);
+            }
+            return (int)i;
+        }
+        if (e.standin && e.name + "_STANDIN" == want) return (int)i;
+    }
     return -1;
 }
 
@@ -404,6 +520,8 @@ extern "C" int ldpc_codes_add(const char *name, int max_iter, int CodeLength, in
     e.H_cols.assign(H_cols, H_cols + (size_t)NumberRowsHcols * max_col_weight);
     std::lock_guard<std::mutex> lk(g_codes_mu);
     codes().reserve(64); /* keep table pointers handed out by ldpc_codes_setup stable */
+    for (CodeEntry &o : codes())
+        if (o.name == e.name && o.standin) o.name += "_STANDIN"; /* a real table takes the genuine name over */
     codes().push_back(std::move(e));
     return (int)codes().size() - 1;
 }
