@@ -15,6 +15,8 @@ A "step" is one pass of the demodulator over the whole per-GPU batch.
   e2e    : the same metric through the host-buffer C-ABI call pirip_fsk_demod_batch(): pinned
            host u8 in -> H2D -> kernel -> D2H bits, every step
   roofline / cpu_baseline / clocks / gpu_launches: see DESIGN.md "Measurement".
+  secondary (N = 1): chain_c4 (config 4: demodulator + UW sync + LDPC + CRC on the device), c3_4fsk_llr (config 3),
+           c1_single_stream (config 1 through the command-line tool, CPU port on one thread beside it)
 
 `--impl reference` times the CPU implementation of the path (the oracle restatement of codec2's
 fsk_demod, all host cores) on a bounded sample of the same workload.
@@ -165,6 +167,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=1.0, help="capture length")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary lines (chain_c4, c3_4fsk_llr, c1_single_stream)")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
     # stdout carries exactly ONE line, the JSON: libraries that write to file descriptor 1 themselves (NCCL prints its
@@ -436,6 +439,17 @@ def main():
             "cpu_baseline": cpu_baseline,
             "parity": {"captures_checked": nchk, "captures_per_gpu": ncap, "captures_mismatching": int(sum(mism)),
                        "bits_and_frames_equal_oracle": bool(ok), "ber_by_ebno_db": ber_by_ebno}}
+    # secondary lines at N = 1: the coded chain of config 4, config 3 with LLR output, config 1 as ONE
+    # stream through the command-line tool; each with its own roofline / CPU-port figure (tools/bench_secondary.py)
+    if world == 1 and not args.no_secondary and ncap == 1250 and nsamp == 240000:
+        del iq, bits, bits_dense
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_secondary
+        try:
+            line["secondary"] = bench_secondary.run_all(torch, pb, dev, cores, cpu=not args.no_cpu)
+        except Exception as e:  # the headline line must not be lost to a secondary leg
+            line["secondary"] = {"error": repr(e)}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -145,6 +145,8 @@ void fsk_stats_normalise_eye(struct FSK *fsk, int normalise_enable);
 /* replaces codec2 src/fsk.h::fsk_mod / fsk_mod_c (Tx side, host only) */
 void fsk_mod(struct FSK *fsk, float fsk_out[], uint8_t tx_bits[], int nbits);
 void fsk_mod_c(struct FSK *fsk, COMP fsk_out[], uint8_t tx_bits[], int nbits);
+/* replaces codec2 src/fsk.h::fsk_mod_ext_vco: per-sample tone frequency (Hz) for an external VCO, Ts values per symbol */
+void fsk_mod_ext_vco(struct FSK *fsk, float vco_out[], uint8_t tx_bits[], int nbits);
 
 /* ---- layer 2: batched extension ------------------------------------------- */
 

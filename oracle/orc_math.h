@@ -4,9 +4,10 @@
  * Default: the bit-reproducible functions of pirip_b200/csrc/exact_math.h, so the
  * CUDA path can be compared with the oracle float for float (same IEEE op
  * sequence on both machines).  With -DORC_USE_LIBM the oracle calls glibc's
- * cosf/sinf/atan2f/expf/logf/log10f exactly as upstream codec2 does; the CPU test
- * tests/test_oracle_libm.py checks the two builds agree (hard bits identical,
- * floats within a few ulp) so the exact-math substitution is itself pinned.
+ * cosf/sinf/atan2f/expf/logf/log10f exactly as upstream codec2 does; the CPU tests
+ * tests/test_exact_math.py check the two builds agree (every function within 1 ulp
+ * of glibc; hard bits / nin / f_est identical and floats within 1e-4 on noisy
+ * captures), so the exact-math substitution is itself pinned.
  */
 #ifndef ORC_MATH_H
 #define ORC_MATH_H

@@ -262,6 +262,22 @@ class FskStream:
         self.L.fsk_demod_sd(self.fsk, _ptr(filt), _ptr(samples))
         return filt
 
+    def clear_estimators(self):
+        self.L.fsk_clear_estimators.argtypes = [C.POINTER(FSK)]
+        self.L.fsk_clear_estimators(self.fsk)
+
+    def enable_burst_mode(self):
+        self.L.fsk_enable_burst_mode.argtypes = [C.POINTER(FSK)]
+        self.L.fsk_enable_burst_mode(self.fsk)
+
+    def mod_ext_vco(self, bits):
+        """fsk_mod_ext_vco: per-sample tone frequency for an external VCO."""
+        bits = np.ascontiguousarray(bits, np.uint8)
+        self.L.fsk_mod_ext_vco.argtypes = [C.POINTER(FSK), C.c_void_p, C.c_void_p, C.c_int]
+        out = np.zeros(bits.size // (self.s.mode >> 1) * self.s.Ts, np.float32)
+        self.L.fsk_mod_ext_vco(self.fsk, _ptr(out), _ptr(bits), bits.size)
+        return out
+
     def close(self):
         if self.fsk:
             self.L.fsk_destroy(self.fsk)

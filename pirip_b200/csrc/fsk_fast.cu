@@ -940,7 +940,9 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             const unsigned char *g = cap_base + pos * bps;
             const size_t have = (args.nsamples - pos) * bps;
             const size_t nbytes = (size_t)cfg.nin_max * bps < have ? (size_t)cfg.nin_max * bps : have;
-            for (size_t i = tid; i < nbytes; i += T) raw[ms->roff + i] = g[i];
+            /* past L1: with streamed ingest the copy engine may still be writing the rest of a 32-byte sector that an earlier
+               frame's read brought into L1 */
+            for (size_t i = tid; i < nbytes; i += T) raw[ms->roff + i] = __ldcg(g + i);
         }
         GSYNC();
         const unsigned char *fr = raw + ms->roff; /* sample 0 of the frame */

@@ -774,7 +774,12 @@ extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_
        serialise the launch on the host, which would leave the kernel waiting for ever: copy first, then run. */
     const bool injected = getenv("CUDA_INJECTION64_PATH") != nullptr || getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") != nullptr ||
                           (getenv("CUDA_LAUNCH_BLOCKING") != nullptr && atoi(getenv("CUDA_LAUNCH_BLOCKING")) != 0);
-    const bool streamed = plan->dev.k2.ok && nchunks == 1 && nslices > 1 && !injected && getenv("PIRIP_FSK_NO_STREAM_INGEST") == nullptr;
+    /* Only the fast kernel runs behind the copies by default: when its samples do not arrive (a second client on the GPU, a tool
+       that serialises copies behind the kernel) it flags the capture after ~2 s and the capture is re-run by the exact kernel
+       once the copies are done - the call still succeeds.  The exact kernel's device-side wait can only fail the launch
+       (correctness by time-out), so the exact mode copies first unless PIRIP_FSK_EXACT_STREAM_INGEST=1 asks for the overlap. */
+    const bool streamed = plan->dev.k2.ok && nchunks == 1 && nslices > 1 && !injected && getenv("PIRIP_FSK_NO_STREAM_INGEST") == nullptr &&
+                          (fast || getenv("PIRIP_FSK_EXACT_STREAM_INGEST") != nullptr);
     if (rc == 0 && streamed) {
         if (!w.d_landed) CK(cudaMalloc(&w.d_landed, sizeof(unsigned long long)), "cudaMalloc landed");
         if (!w.h_marks) CK(cudaHostAlloc(&w.h_marks, 72 * sizeof(unsigned long long), cudaHostAllocDefault), "cudaHostAlloc marks");
@@ -1190,4 +1195,23 @@ extern "C" void fsk_mod(struct FSK *fsk, float fsk_out[], uint8_t tx_bits[], int
     std::vector<COMP> tmp((size_t)n);
     fsk_mod_c(fsk, tmp.data(), tx_bits, nbits);
     for (int i = 0; i < n; ++i) fsk_out[i] = tmp[(size_t)i].real;
+}
+
+/* Tx side, host only: the drive signal of an external VCO - the tone frequency of every sample, f1_tx + tone_spacing * symbol, Ts
+   values per symbol ([U fsk.c::fsk_mod_ext_vco]).  pirip's own transmitter derives its tone table the same way
+   ([R tx/rpitx_fsk.cpp:127-143]). */
+extern "C" void fsk_mod_ext_vco(struct FSK *fsk, float vco_out[], uint8_t tx_bits[], int nbits) {
+    const int Ts = fsk->Ts, M = fsk->mode;
+    assert(fsk->f1_tx > 0);
+    assert(fsk->tone_spacing > 0);
+    int bit_i = 0;
+    const int nsym = nbits / (M >> 1);
+    for (int i = 0; i < nsym; ++i) {
+        int sym = 0;
+        for (int m = M; m >>= 1;) {
+            sym = (sym << 1) | (tx_bits[bit_i] == 1 ? 1 : 0);
+            bit_i++;
+        }
+        for (int j = 0; j < Ts; ++j) vco_out[i * Ts + j] = (float)fsk->f1_tx + (float)fsk->tone_spacing * (float)sym;
+    }
 }

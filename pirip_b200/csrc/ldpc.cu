@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -259,7 +260,6 @@ struct pirip_ldpc_plan {
     int mode = LDPC_SP_EXACT;
     int num_sms = 148;
     uint16_t *d_c_off = nullptr, *d_v_off = nullptr, *d_c_vpos = nullptr;
-    unsigned *d_v_rec = nullptr;
     float *d_llr = nullptr;
     unsigned char *d_bits = nullptr;
     int *d_iter = nullptr, *d_pcc = nullptr;
@@ -285,16 +285,8 @@ extern "C" pirip_ldpc_plan *pirip_ldpc_plan_create(const struct LDPC *l, int dev
     p->g.max_iter = l->max_iter > 0 ? l->max_iter : 15;
     /* v_edge[j] = edge id (check order) of the j-th entry in variable order */
     std::vector<uint16_t> c_vpos((size_t)p->g.E);
-    std::vector<unsigned> v_rec((size_t)p->g.E);
     {
-        std::vector<int> e_chk((size_t)p->g.E);
-        for (int c = 0; c < p->g.NPB; ++c)
-            for (int e = c_off[(size_t)c]; e < c_off[(size_t)c + 1]; ++e) e_chk[(size_t)e] = c;
-        for (int j = 0; j < p->g.E; ++j) {
-            const int e = v_edge[(size_t)j], c = e_chk[(size_t)e];
-            c_vpos[(size_t)e] = (uint16_t)j;
-            v_rec[(size_t)j] = ((unsigned)c << 8) | (unsigned)(e - c_off[(size_t)c]);
-        }
+        for (int j = 0; j < p->g.E; ++j) c_vpos[(size_t)v_edge[(size_t)j]] = (uint16_t)j;
     }
     {
         auto al = [](int v) { return (v + 15) / 16 * 16; };
@@ -304,24 +296,25 @@ extern "C" pirip_ldpc_plan *pirip_ldpc_plan_create(const struct LDPC *l, int dev
         o += al((g.N + 1) * 2);
         g.off_vedge = o;
         o += al(g.E * 2);
-        g.off_echk = o;
-        o += al(g.E * 4);
         g.tables_bytes = o;
         int w = 0;
         g.w_q = w;
         w += al(g.E * 4);
-        g.w_chk = w;
-        w += al(g.NPB * 8);
         g.w_llr = w;
         w += al(g.N * 4);
         g.w_scr = w; /* 256 words of scratch for the receive-chain kernel: hard-bit words of two frames, decoded bits */
         w += 1024;
         g.warp_bytes = w;
         int warps = (227 * 1024 - g.tables_bytes) / w;
-        /* two CTAs per SM when they fit: 8 codewords each */
+        /* one CTA per SM with as many codewords (warps) as shared memory holds: the tables are loaded once for all of them */
         if (warps > kLdpcMaxWarps) warps = kLdpcMaxWarps;
-        while (warps > 1 && 2 * (g.tables_bytes + warps * w + 1024) > 228 * 1024 && warps > 4) --warps;
         g.warps = warps;
+        g.max_vdeg = 0;
+        for (int v = 0; v < g.N; ++v) g.max_vdeg = std::max(g.max_vdeg, (int)v_off[(size_t)v + 1] - (int)v_off[(size_t)v]);
+        g.v_split = g.N;
+        while (g.v_split > 0 && (int)v_off[(size_t)g.v_split] - (int)v_off[(size_t)g.v_split - 1] <= 2) --g.v_split;
+        g.v_split = (g.v_split + 31) / 32 * 32; /* whole rounds of lanes on either side */
+        if (g.v_split > g.N) g.v_split = g.N;
         g.ms_scale = 0.75f;
         p->smem = g.tables_bytes + (warps > 0 ? warps : 0) * w;
     }
@@ -348,11 +341,9 @@ extern "C" pirip_ldpc_plan *pirip_ldpc_plan_create(const struct LDPC *l, int dev
         !pirip::cuda_ok(cudaMalloc(&p->d_c_off, 2 * c_off.size()), "cudaMalloc") ||
         !pirip::cuda_ok(cudaMalloc(&p->d_v_off, 2 * v_off.size()), "cudaMalloc") ||
         !pirip::cuda_ok(cudaMalloc(&p->d_c_vpos, 2 * c_vpos.size()), "cudaMalloc") ||
-        !pirip::cuda_ok(cudaMalloc(&p->d_v_rec, 4 * v_rec.size()), "cudaMalloc") ||
         !pirip::cuda_ok(cudaMemcpy(p->d_c_off, c_off.data(), 2 * c_off.size(), cudaMemcpyHostToDevice), "copy") ||
         !pirip::cuda_ok(cudaMemcpy(p->d_v_off, v_off.data(), 2 * v_off.size(), cudaMemcpyHostToDevice), "copy") ||
         !pirip::cuda_ok(cudaMemcpy(p->d_c_vpos, c_vpos.data(), 2 * c_vpos.size(), cudaMemcpyHostToDevice), "copy") ||
-        !pirip::cuda_ok(cudaMemcpy(p->d_v_rec, v_rec.data(), 4 * v_rec.size(), cudaMemcpyHostToDevice), "copy") ||
         !pirip::cuda_ok(cudaFuncSetAttribute(ldpc_decode_warp_kernel<LDPC_SP_EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem), "smem attr") ||
         !pirip::cuda_ok(cudaFuncSetAttribute(ldpc_decode_warp_kernel<LDPC_SP_FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem), "smem attr") ||
         !pirip::cuda_ok(cudaFuncSetAttribute(ldpc_decode_warp_kernel<LDPC_MINSUM>, cudaFuncAttributeMaxDynamicSharedMemorySize, p->smem), "smem attr")) {
@@ -362,7 +353,6 @@ extern "C" pirip_ldpc_plan *pirip_ldpc_plan_create(const struct LDPC *l, int dev
     p->g.c_off = p->d_c_off;
     p->g.v_off = p->d_v_off;
     p->g.c_vpos = p->d_c_vpos;
-    p->g.v_rec = p->d_v_rec;
     return p;
 }
 
@@ -381,7 +371,6 @@ extern "C" void pirip_ldpc_plan_destroy(pirip_ldpc_plan *p) {
     cudaFree(p->d_c_off);
     cudaFree(p->d_v_off);
     cudaFree(p->d_c_vpos);
-    cudaFree(p->d_v_rec);
     cudaFree(p->d_llr);
     cudaFree(p->d_bits);
     cudaFree(p->d_iter);
@@ -397,7 +386,7 @@ extern "C" int pirip_ldpc_decode_batch_dev(pirip_ldpc_plan *p, const float *d_ll
     if (!pirip::cuda_ok(cudaSetDevice(p->device), "cudaSetDevice")) return -10;
     const size_t ctas_needed = (n + p->g.warps - 1) / p->g.warps;
     const size_t resident = (size_t)p->num_sms * ((p->smem + 1024) * 2 <= 228 * 1024 ? 2 : 1);
-    const unsigned grid = (unsigned)(ctas_needed < 4 * resident ? ctas_needed : 4 * resident); /* a CTA loops over codewords */
+    const unsigned grid = (unsigned)(ctas_needed < resident ? ctas_needed : resident); /* persistent CTAs loop over the codewords */
     const unsigned block = 32u * (unsigned)p->g.warps;
     cudaStream_t st = (cudaStream_t)stream;
     if (p->mode == LDPC_MINSUM)

@@ -8,6 +8,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "exact_math.h"
 
 struct LdpcGraph {
@@ -15,11 +17,12 @@ struct LdpcGraph {
     const uint16_t *c_off;  /* [NPB+1] first edge of every check */
     const uint16_t *v_off;  /* [N+1] first entry of every variable in v_edge */
     const uint16_t *c_vpos; /* [E] check order: position of the edge in variable order */
-    const unsigned *v_rec;  /* [E] variable order: check << 8 | position of the edge in its check */
     /* shared-memory layout of the decoder kernel (bytes): tables once per CTA, then one block per warp (codeword) */
-    int off_voff, off_vedge, off_echk, tables_bytes;
-    int w_q, w_chk, w_llr, w_scr, warp_bytes;
+    int off_voff, off_vedge, tables_bytes;
+    int w_q, w_llr, w_scr, warp_bytes;
     int warps;  /* codewords per CTA */
+    int max_vdeg; /* largest number of edges of a variable */
+    int v_split;  /* variables from here on have at most two edges (the parity part of a repeat-accumulate code) */
     float ms_scale; /* normalisation of the min-sum check update */
 };
 
@@ -49,7 +52,7 @@ __device__ __forceinline__ float phi0_fast(float x) {
 }
 
 enum { LDPC_SP_EXACT = 0, LDPC_SP_FAST = 1, LDPC_MINSUM = 2 };
-constexpr int kLdpcMaxWarps = 8;
+constexpr int kLdpcMaxWarps = 24;
 
 /* One WARP per codeword, up to 8 codewords per CTA, the Tanner graph tables loaded once per CTA.
    A lane owns whole check nodes in the check phase and whole variable nodes in the variable phase and walks their edges
@@ -84,9 +87,7 @@ __device__ __forceinline__ float q_store(float t) {
 /* Per-CTA view of the graph tables in shared memory and one warp's message storage */
 struct LdpcSmem {
     const uint16_t *c_off, *v_off, *c_vpos;
-    const unsigned *v_rec;
-    float *q;      /* [E] variable order */
-    float2 *chk;   /* [NPB] what a check leaves behind (see r_msg) */
+    float *q;      /* [E] variable order: q on the way to the checks, r on the way back */
     float *llr;    /* [N] */
     unsigned *scr; /* [256] scratch words (receive-chain kernel) */
 };
@@ -96,23 +97,17 @@ __device__ __forceinline__ void ldpc_load_tables(const LdpcGraph &g, unsigned ch
     uint16_t *c_off = reinterpret_cast<uint16_t *>(smem_raw);
     uint16_t *v_off = reinterpret_cast<uint16_t *>(smem_raw + g.off_voff);
     uint16_t *c_vpos = reinterpret_cast<uint16_t *>(smem_raw + g.off_vedge);
-    unsigned *v_rec = reinterpret_cast<unsigned *>(smem_raw + g.off_echk);
     for (int i = threadIdx.x; i <= g.NPB; i += blockDim.x) c_off[i] = g.c_off[i];
     for (int i = threadIdx.x; i <= g.N; i += blockDim.x) v_off[i] = g.v_off[i];
-    for (int i = threadIdx.x; i < g.E; i += blockDim.x) {
-        c_vpos[i] = g.c_vpos[i];
-        v_rec[i] = g.v_rec[i];
-    }
+    for (int i = threadIdx.x; i < g.E; i += blockDim.x) c_vpos[i] = g.c_vpos[i];
 }
 __device__ __forceinline__ LdpcSmem ldpc_smem_view(const LdpcGraph &g, unsigned char *smem_raw, int warp) {
     LdpcSmem m;
     m.c_off = reinterpret_cast<const uint16_t *>(smem_raw);
     m.v_off = reinterpret_cast<const uint16_t *>(smem_raw + g.off_voff);
     m.c_vpos = reinterpret_cast<const uint16_t *>(smem_raw + g.off_vedge);
-    m.v_rec = reinterpret_cast<const unsigned *>(smem_raw + g.off_echk);
     unsigned char *wb = smem_raw + g.tables_bytes + (size_t)warp * g.warp_bytes;
     m.q = reinterpret_cast<float *>(wb + g.w_q);
-    m.chk = reinterpret_cast<float2 *>(wb + g.w_chk);
     m.llr = reinterpret_cast<float *>(wb + g.w_llr);
     m.scr = reinterpret_cast<unsigned *>(wb + g.w_scr);
     return m;
@@ -128,104 +123,146 @@ __device__ __forceinline__ LdpcSmem ldpc_smem_view(const LdpcGraph &g, unsigned 
    and the variable phase forms r from them.  The parity-check count is a warp reduction; the loop ends as soon as it reaches
    NumberParityBits.  `load(v)` delivers the channel LLR of variable v; `store(v, bit)` receives the decisions of the last
    iteration (every lane calls it for its variables).  Returns the iteration count, *pcc_out the parity checks passed. */
+/* The messages of a codeword live in ONE array of E floats in variable order, used in place by both phases:
+     check phase     reads the variable-to-check messages q of its edges (gathered through c_vpos, up to 8 in flight before they are
+                     combined, and the next check's behind them), forms sign parity and sum / two smallest magnitudes, and writes the
+                     check-to-variable message r of every edge back to the edge's slot;
+     variable phase  reads its r's sequentially, Q = llr + sum r in edge order, decision, writes q = Q - r back.
+   A pad of +0 (sum-product: x + 0 = x exactly, sign unchanged) or of the largest float (min-sum) stands in for the edges a check
+   does not have, so sums and minima are those of the scalar order ([U mpdecode_core.c::SumProduct]).
+   The variable phase is unrolled VA wide for the variables below g.v_split and 2 wide from there on (the degree-2 parity
+   variables of a repeat-accumulate code); edges beyond the unrolled width take a loop. */
+template <int MODE, int VA, class Load, class Store>
+__device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSmem &m, int lane, Load load, Store store, int *pcc_out) {
+    const uint16_t *c_off = m.c_off, *v_off = m.v_off, *c_vpos = m.c_vpos;
+    float *q = m.q, *llr = m.llr;
+    for (int v = lane; v < g.N; v += 32) {
+        const float x = load(v);
+        llr[v] = x;
+        float mm;
+        if (MODE == LDPC_MINSUM)
+            mm = x;
+        else {
+            const float ph = MODE == LDPC_SP_EXACT ? phi0(fabsf(x)) : phi0_fast(fabsf(x));
+            mm = x < 0.0f ? -ph : ph;
+        }
+        for (int j = v_off[v]; j < v_off[v + 1]; ++j) q[j] = mm;
+    }
+    __syncwarp();
+    int result = g.max_iter, pcc = 0;
+    for (int iter = 0; iter < g.max_iter; ++iter) {
+        /* check-node phase */
+        int local = 0;
+        for (int c = lane; c < g.NPB; c += 32) {
+            const int e0 = c_off[c], e1 = c_off[c + 1];
+            const float pad = MODE == LDPC_MINSUM ? 3.0e38f : 0.0f;
+            int idx[8];
+            float v[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) idx[k] = (e0 + k < e1) ? c_vpos[e0 + k] : -1;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[k] = idx[k] >= 0 ? q[idx[k]] : pad;
+            unsigned sign = 0;
+            if (MODE == LDPC_MINSUM) {
+                float m1 = 3.0e38f, m2 = 3.0e38f;
+                int pos = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const float a = fabsf(v[k]);
+                    sign ^= __float_as_uint(v[k]) & 0x80000000u;
+                    if (a < m1) {
+                        m2 = m1;
+                        m1 = a;
+                        pos = k;
+                    } else if (a < m2)
+                        m2 = a;
+                }
+                for (int e = e0 + 8; e < e1; ++e) {
+                    const float w = q[c_vpos[e]];
+                    const float a = fabsf(w);
+                    sign ^= __float_as_uint(w) & 0x80000000u;
+                    if (a < m1) {
+                        m2 = m1;
+                        m1 = a;
+                        pos = e - e0;
+                    } else if (a < m2)
+                        m2 = a;
+                }
+                const float s1 = m1 * g.ms_scale, s2 = m2 * g.ms_scale;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (idx[k] >= 0) {
+                        const unsigned neg = (sign ^ __float_as_uint(v[k])) & 0x80000000u;
+                        q[idx[k]] = __uint_as_float(__float_as_uint(k == pos ? s2 : s1) ^ neg);
+                    }
+                for (int e = e0 + 8; e < e1; ++e) {
+                    const int j = c_vpos[e];
+                    const unsigned neg = (sign ^ __float_as_uint(q[j])) & 0x80000000u;
+                    q[j] = __uint_as_float(__float_as_uint((e - e0) == pos ? s2 : s1) ^ neg);
+                }
+            } else {
+                float phi_sum = fabsf(v[0]);
+                sign = __float_as_uint(v[0]) & 0x80000000u;
+#pragma unroll
+                for (int k = 1; k < 8; ++k) {
+                    phi_sum = __fadd_rn(phi_sum, fabsf(v[k]));
+                    sign ^= __float_as_uint(v[k]) & 0x80000000u;
+                }
+                for (int e = e0 + 8; e < e1; ++e) {
+                    const float w = q[c_vpos[e]];
+                    phi_sum = __fadd_rn(phi_sum, fabsf(w));
+                    sign ^= __float_as_uint(w) & 0x80000000u;
+                }
+                const float cs = __uint_as_float(__float_as_uint(phi_sum) | sign);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    if (idx[k] >= 0) q[idx[k]] = r_msg<MODE>(v[k], cs, 0.0f, k);
+                for (int e = e0 + 8; e < e1; ++e) {
+                    const int j = c_vpos[e];
+                    q[j] = r_msg<MODE>(q[j], cs, 0.0f, e - e0);
+                }
+            }
+            if (sign == 0) local++;
+        }
+        pcc = __reduce_add_sync(0xffffffffu, local);
+        __syncwarp();
+        const bool last = pcc == g.NPB || iter == g.max_iter - 1;
+        /* variable-node phase */
+        auto vnode = [&](int v, auto W) {
+            constexpr int VW = decltype(W)::value;
+            const int j0 = v_off[v], j1 = v_off[v + 1];
+            float Qi = llr[v];
+            float r[VW];
+#pragma unroll
+            for (int k = 0; k < VW; ++k)
+                if (j0 + k < j1) {
+                    r[k] = q[j0 + k];
+                    Qi = __fadd_rn(Qi, r[k]);
+                }
+            for (int j = j0 + VW; j < j1; ++j) Qi = __fadd_rn(Qi, q[j]);
+            if (last) store(v, Qi < 0.0f ? 1 : 0);
+#pragma unroll
+            for (int k = 0; k < VW; ++k)
+                if (j0 + k < j1) q[j0 + k] = q_store<MODE>(__fsub_rn(Qi, r[k]));
+            for (int j = j0 + VW; j < j1; ++j) q[j] = q_store<MODE>(__fsub_rn(Qi, q[j]));
+        };
+        for (int v = lane; v < g.v_split; v += 32) vnode(v, std::integral_constant<int, VA>());
+        for (int v = g.v_split + lane; v < g.N; v += 32) vnode(v, std::integral_constant<int, 2>());
+        __syncwarp();
+        if (pcc == g.NPB) {
+            result = iter + 1;
+            break;
+        }
+    }
+    __syncwarp();
+    *pcc_out = pcc;
+    return result;
+}
+
 template <int MODE, class Load, class Store>
 __device__ __forceinline__ int ldpc_decode_one(const LdpcGraph &g, const LdpcSmem &m, int lane, Load load, Store store, int *pcc_out) {
-    const uint16_t *c_off = m.c_off, *v_off = m.v_off, *c_vpos = m.c_vpos;
-    const unsigned *v_rec = m.v_rec;
-    float *q = m.q, *llr = m.llr;
-    float2 *chk = m.chk;
-    {
-        for (int v = lane; v < g.N; v += 32) {
-            const float x = load(v);
-            llr[v] = x;
-            float mm;
-            if (MODE == LDPC_MINSUM)
-                mm = x;
-            else {
-                const float ph = MODE == LDPC_SP_EXACT ? phi0(fabsf(x)) : phi0_fast(fabsf(x));
-                mm = x < 0.0f ? -ph : ph;
-            }
-            for (int j = v_off[v]; j < v_off[v + 1]; ++j) q[j] = mm;
-        }
-        __syncwarp();
-        int result = g.max_iter, pcc = 0;
-        for (int iter = 0; iter < g.max_iter; ++iter) {
-            /* check-node phase */
-            int local = 0;
-            for (int c = lane; c < g.NPB; c += 32) {
-                const int e0 = c_off[c], e1 = c_off[c + 1];
-                unsigned sign = 0;
-                if (MODE == LDPC_MINSUM) {
-                    float m1 = 3.0e38f, m2 = 3.0e38f;
-                    int pos = 0;
-                    for (int e = e0; e < e1; ++e) {
-                        const float v = q[c_vpos[e]];
-                        const float a = fabsf(v);
-                        sign ^= __float_as_uint(v) & 0x80000000u;
-                        if (a < m1) {
-                            m2 = m1;
-                            m1 = a;
-                            pos = e - e0;
-                        } else if (a < m2)
-                            m2 = a;
-                    }
-                    chk[c] = make_float2(__uint_as_float(__float_as_uint(m1 * g.ms_scale) | sign),
-                                         __uint_as_float((__float_as_uint(m2 * g.ms_scale) & ~63u) | (unsigned)(pos & 63)));
-                } else {
-                    const float v0 = q[c_vpos[e0]];
-                    float phi_sum = fabsf(v0);
-                    sign = __float_as_uint(v0) & 0x80000000u;
-                    for (int e = e0 + 1; e < e1; ++e) {
-                        const float v = q[c_vpos[e]];
-                        phi_sum = __fadd_rn(phi_sum, fabsf(v));
-                        sign ^= __float_as_uint(v) & 0x80000000u;
-                    }
-                    chk[c] = make_float2(__uint_as_float(__float_as_uint(phi_sum) | sign), 0.0f);
-                }
-                if (sign == 0) local++;
-            }
-            pcc = __reduce_add_sync(0xffffffffu, local);
-            __syncwarp();
-            const bool last = pcc == g.NPB || iter == g.max_iter - 1;
-            /* variable-node phase */
-            for (int v = lane; v < g.N; v += 32) {
-                const int j0 = v_off[v], j1 = v_off[v + 1];
-                float Qi = llr[v];
-                float r[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (j0 + k < j1) {
-                        const unsigned rec = v_rec[j0 + k];
-                        const float2 cs = chk[rec >> 8];
-                        r[k] = r_msg<MODE>(q[j0 + k], cs.x, cs.y, (int)(rec & 63u));
-                        Qi = __fadd_rn(Qi, r[k]);
-                    }
-                /* variables with more than 8 edges (none of codec2's codes): the rest of the sum */
-                for (int j = j0 + 8; j < j1; ++j) {
-                    const unsigned rec = v_rec[j];
-                    const float2 cs = chk[rec >> 8];
-                    Qi = __fadd_rn(Qi, r_msg<MODE>(q[j], cs.x, cs.y, (int)(rec & 63u)));
-                }
-                if (last) store(v, Qi < 0.0f ? 1 : 0);
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    if (j0 + k < j1) q[j0 + k] = q_store<MODE>(__fsub_rn(Qi, r[k]));
-                for (int j = j0 + 8; j < j1; ++j) {
-                    const unsigned rec = v_rec[j];
-                    const float2 cs = chk[rec >> 8];
-                    q[j] = q_store<MODE>(__fsub_rn(Qi, r_msg<MODE>(q[j], cs.x, cs.y, (int)(rec & 63u))));
-                }
-            }
-            __syncwarp();
-            if (pcc == g.NPB) {
-                result = iter + 1;
-                break;
-            }
-        }
-        __syncwarp();
-        *pcc_out = pcc;
-        return result;
-    }
+    if (g.max_vdeg <= 4) return ldpc_decode_impl<MODE, 4>(g, m, lane, load, store, pcc_out);
+    return ldpc_decode_impl<MODE, 8>(g, m, lane, load, store, pcc_out);
 }
 
 /* Batch decoder: one warp per codeword, up to 8 codewords per CTA, the Tanner graph tables loaded once per CTA; a CTA loops

@@ -149,6 +149,80 @@ def fsk_demod_stream(cfg, iq, libm=False):
                 rx_filt=rx_filt[:nf * cfg.M * cfg.Nsym], stats=stats[:nf])
 
 
+class OrcComp(C.Structure):
+    _fields_ = [("real", C.c_float), ("imag", C.c_float)]
+
+
+class OrcFsk(C.Structure):
+    """struct orc_fsk of oracle/oracle.h ([U fsk.h::struct FSK])."""
+    _fields_ = [("Ndft", C.c_int), ("Fs", C.c_int), ("N", C.c_int), ("Rs", C.c_int), ("Ts", C.c_int), ("Nmem", C.c_int),
+                ("P", C.c_int), ("Nsym", C.c_int), ("Nbits", C.c_int), ("f1_tx", C.c_int), ("tone_spacing", C.c_int),
+                ("mode", C.c_int), ("tc", C.c_float), ("est_min", C.c_int), ("est_max", C.c_int), ("est_space", C.c_int),
+                ("hann_table", C.c_void_p), ("Sf", C.POINTER(C.c_float)), ("phi_c", OrcComp * 4), ("f_dc", C.c_void_p),
+                ("fft_cfg", C.c_void_p), ("norm_rx_timing", C.c_float), ("tx_phase_c", OrcComp), ("EbNodB", C.c_float),
+                ("f_est", C.c_float * 4), ("f2_est", C.c_float * 4), ("freq_est_type", C.c_int), ("ppm", C.c_float),
+                ("SNRest", C.c_float), ("v_est", C.c_float), ("rx_sig_pow", C.c_float), ("rx_nse_pow", C.c_float),
+                ("nin", C.c_int), ("burst_mode", C.c_int), ("lock_nin", C.c_int), ("stats_snr_est", C.c_float),
+                ("stats_foff", C.c_float), ("stats_rx_timing", C.c_float), ("stats_clock_offset", C.c_float),
+                ("normalise_eye", C.c_int)]
+
+
+class FskStream:
+    """The oracle's per-stream demodulator object, call for call like codec2's struct FSK API (the mirror of
+    pirip_b200.FskStream): create_hbr / nin / demod / demod_sd / clear_estimators / enable_burst_mode."""
+
+    def __init__(self, Fs, Rs, M, P=8, Nsym=50, f1_tx=1200, tone_spacing=400, limits=None, mask=False):
+        L = lib()
+        L.orc_fsk_create_hbr.restype = C.POINTER(OrcFsk)
+        L.orc_fsk_create_hbr.argtypes = [C.c_int] * 7
+        L.orc_fsk_destroy.argtypes = [C.POINTER(OrcFsk)]
+        L.orc_fsk_nin.restype = C.c_uint32
+        L.orc_fsk_nin.argtypes = [C.POINTER(OrcFsk)]
+        L.orc_fsk_demod.argtypes = [C.POINTER(OrcFsk), C.c_void_p, C.c_void_p]
+        L.orc_fsk_demod_sd.argtypes = [C.POINTER(OrcFsk), C.c_void_p, C.c_void_p]
+        L.orc_fsk_set_freq_est_limits.argtypes = [C.POINTER(OrcFsk), C.c_int, C.c_int]
+        L.orc_fsk_set_freq_est_alg.argtypes = [C.POINTER(OrcFsk), C.c_int]
+        L.orc_fsk_clear_estimators.argtypes = [C.POINTER(OrcFsk)]
+        L.orc_fsk_enable_burst_mode.argtypes = [C.POINTER(OrcFsk)]
+        self.L = L
+        self.fsk = L.orc_fsk_create_hbr(Fs, Rs, M, P, Nsym, f1_tx, tone_spacing)
+        if limits:
+            L.orc_fsk_set_freq_est_limits(self.fsk, limits[0], limits[1])
+        if mask:
+            L.orc_fsk_set_freq_est_alg(self.fsk, 1)
+
+    @property
+    def s(self):
+        return self.fsk.contents
+
+    def nin(self):
+        return int(self.L.orc_fsk_nin(self.fsk))
+
+    def demod(self, samples):
+        samples = np.ascontiguousarray(samples, np.complex64)
+        assert samples.size == self.nin()
+        bits = np.zeros(self.s.Nbits, np.uint8)
+        self.L.orc_fsk_demod(self.fsk, _ptr(bits), _ptr(samples))
+        return bits
+
+    def demod_sd(self, samples):
+        samples = np.ascontiguousarray(samples, np.complex64)
+        filt = np.zeros(self.s.mode * self.s.Nsym, np.float32)
+        self.L.orc_fsk_demod_sd(self.fsk, _ptr(filt), _ptr(samples))
+        return filt
+
+    def clear_estimators(self):
+        self.L.orc_fsk_clear_estimators(self.fsk)
+
+    def enable_burst_mode(self):
+        self.L.orc_fsk_enable_burst_mode(self.fsk)
+
+    def close(self):
+        if self.fsk:
+            self.L.orc_fsk_destroy(self.fsk)
+            self.fsk = None
+
+
 def csdr_decimate_stream(iq_u8, decimation, transition_bw=0.05, libm=False):
     L = lib(libm)
     iq_u8 = np.ascontiguousarray(iq_u8, np.uint8)

@@ -168,3 +168,98 @@ def test_front_team_pipelined_schedule_is_bit_identical(monkeypatch):
         assert np.array_equal(out["bits"][c, :nf * 50], ref["bits"])
         assert np.array_equal(out["stats"][c, :nf].view(np.uint8), ref["stats"].view(np.uint8))
     plan.close()
+
+
+def _both_streams(kw, **extra):
+    import pirip_b200 as pb
+    return pb.FskStream(**kw, **extra), orc.FskStream(**kw, **extra)
+
+
+def _run_streams(g, o, x, hook=None, nframes=10 ** 9):
+    """Feed both objects the same samples, call for call; every hard bit, nin and norm_rx_timing must agree (uint32 patterns)."""
+    pos, k = 0, 0
+    while k < nframes and pos + g.nin() <= x.size:
+        assert g.nin() == o.nin(), k
+        n = g.nin()
+        if hook:
+            hook(k, g, o)
+        bg, bo = g.demod(x[pos:pos + n]), o.demod(x[pos:pos + n])
+        assert np.array_equal(bg, bo), k
+        assert np.float32(g.s.norm_rx_timing).view(np.uint32) == np.float32(o.s.norm_rx_timing).view(np.uint32), k
+        assert [np.float32(v).view(np.uint32) for v in g.s.f_est[:g.s.mode]] == [np.float32(v).view(np.uint32) for v in o.s.f_est[:o.s.mode]], k
+        pos += n
+        k += 1
+    return k
+
+
+def _signal(seed, nbits, kw, ebno=9.0, ppm=80.0):
+    x = synth.fsk_mod(synth.test_bits(nbits), kw["M"], kw["Fs"], kw["Rs"], kw["Rs"], kw["Rs"], timing_offset=2.3, phase0=0.7, ppm=ppm)
+    x = synth.add_awgn(x, ebno, kw["Fs"] // kw["Rs"], kw["M"], synth.rng(seed))
+    return (0.4 * x).astype(np.complex64)
+
+
+def test_burst_mode_fixes_nin_and_matches_the_oracle():
+    """fsk_enable_burst_mode ([U fsk.c]): nin stays N whatever the timing estimate says (exported but untested)."""
+    kw = dict(Fs=80000, Rs=10000, M=2, P=8)
+    g, o = _both_streams(kw, limits=(500, 39000))
+    g.enable_burst_mode()
+    o.enable_burst_mode()
+    x = _signal(1, 3000, kw, ppm=400.0)  # a clock offset that would force nin slips within a few frames
+    seen = []
+    n = _run_streams(g, o, x, hook=lambda k, a, b: seen.append(a.nin()))
+    assert n >= 50 and set(seen) == {g.s.N}
+    g.close()
+    o.close()
+
+
+def test_lock_nin_and_clear_estimators_match_the_oracle():
+    kw = dict(Fs=80000, Rs=10000, M=2, P=8)
+    g, o = _both_streams(kw, limits=(500, 39000))
+    x = _signal(2, 4000, kw, ppm=400.0)
+
+    def hook(k, a, b):
+        if k == 20:  # struct FSK's public field, as rtl_fsk-style callers set it
+            a.s.lock_nin = 1
+            b.s.lock_nin = 1
+        if k == 45:
+            a.s.lock_nin = 0
+            b.s.lock_nin = 0
+        if k == 30:  # fsk_clear_estimators between bursts ([U fsk.c]): Sf and the timing history start again
+            a.clear_estimators()
+            b.clear_estimators()
+    nins = []
+    n = _run_streams(g, o, x, hook=lambda k, a, b: (hook(k, a, b), nins.append(a.nin())))
+    assert n >= 70
+    assert set(nins[21:45]) == {g.s.N} and len(set(nins)) > 1  # locked in between, slipping outside
+    g.close()
+    o.close()
+
+
+@pytest.mark.parametrize("Nsym", [32, 100])
+def test_other_nsym_stream_and_batch(Nsym):
+    """Nsym != 50 through fsk_create_hbr and through the batch plan."""
+    import pirip_b200 as pb
+    kw = dict(Fs=80000, Rs=10000, M=2, P=8)
+    g, o = _both_streams(kw, limits=(500, 39000), Nsym=Nsym)
+    assert (g.s.N, g.s.Nbits, g.s.Ndft) == (o.s.N, o.s.Nbits, o.s.Ndft)
+    x = _signal(3, 40 * Nsym, kw)
+    assert _run_streams(g, o, x) >= 30
+    g.close()
+    o.close()
+    u8, _ = synth.capture_u8(31, 40 * Nsym, 2, 80000, 10000, 10000, 10000, ebno_db=8.0)
+    plan = pb.FskPlan(**kw, Nsym=Nsym, limits=(500, 39000))
+    out = plan.demod_batch(np.stack([u8, u8[::-1].copy()]))
+    ref = orc.fsk_demod_stream(orc.demod_cfg(80000, 10000, 2, P=8, Nsym=Nsym, limits=(500, 39000)), u8)
+    nf = int(out["nframes"][0])
+    assert nf == ref["nframes"] and np.array_equal(out["bits"][0, :nf * plan.nbits], ref["bits"])
+    plan.close()
+
+
+def test_fsk_mod_ext_vco_tone_frequencies():
+    import pirip_b200 as pb
+    st = pb.FskStream(80000, 10000, 4, P=8, f1_tx=1200, tone_spacing=800)
+    bits = np.array([0, 0, 0, 1, 1, 0, 1, 1], np.uint8)
+    vco = st.mod_ext_vco(bits)
+    assert vco.size == 4 * 8
+    assert vco.reshape(4, 8).tolist() == [[1200.0] * 8, [2000.0] * 8, [2800.0] * 8, [3600.0] * 8]
+    st.close()

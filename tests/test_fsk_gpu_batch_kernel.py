@@ -77,8 +77,9 @@ def test_streamed_ingest_equals_copy_then_run():
     # long enough for sixteen time slices (>= 4 * nin_max samples per slice)
     iq = _batch(40, 3400)
     assert iq.shape[1] // 2 >= 64 * 1206
-    a = _run(iq, {"PIRIP_FSK_K2": "1", "PIRIP_FSK_NO_STREAM_INGEST": None})
-    b = _run(iq, {"PIRIP_FSK_K2": "1", "PIRIP_FSK_NO_STREAM_INGEST": "1"})
+    # the exact kernel copies first by default (its device-side wait can only fail the launch); the overlap is opt-in
+    a = _run(iq, {"PIRIP_FSK_K2": "1", "PIRIP_FSK_NO_STREAM_INGEST": None, "PIRIP_FSK_EXACT_STREAM_INGEST": "1"})
+    b = _run(iq, {"PIRIP_FSK_K2": "1", "PIRIP_FSK_NO_STREAM_INGEST": "1", "PIRIP_FSK_EXACT_STREAM_INGEST": None})
     _same(a, b)
     _oracle_sample(iq, a, [0, 7, 39])
 

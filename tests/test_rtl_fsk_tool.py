@@ -205,7 +205,7 @@ def test_transmitter_test_modes(tmp_path):
     # replaces the dongle): [R README.md:114], [R README.md:152], [R README.md:172], [R README.md:196], [R README.md:262],
     # [R README.md:286], [R script/frame_repeater:23], [R test/loopback_rtl_fsk.sh:10]
     ("-g 49 -f 144490000 - -n 480000", 240000, 10000, 2),
-    ("-w 500E3 -e ff8 -r 1000 -f 144490000 - -u localhost", 240000, 1000, 2),
+    ("-w 500E3 -e ff8 -r 1000 -f 144490000 - -u localhost", 240000, 1000, 2),  # modem rate chosen by the tool: 40 kHz
     ("-s 2400000 -a 80000 -w 500E3 -e ff8 -r 10000 -f 144490000 - -u 127.0.0.1", 80000, 10000, 2),
     ("-g 1 -f 144490000 - -a 100000 -r 10000 --code H_256_512_4 -v -u localhost --testframes", 100000, 10000, 2),
     ("-g 49 -f 144490000 - -a 200000 -r 10000 -m 4 --code H_256_512_4 -v -u localhost --testframes --mask 10000 -e 0xfff", 200000, 10000, 4),

@@ -74,12 +74,14 @@ def oracle_chain(cfg, code, u8, Nbits, libm=False):
     return ref["nframes"], st, pl, info
 
 
-def make_captures(name, M, n, seed0, ebnos, nsamp):
+def make_captures(name, M, n, seed0, ebnos, nsamp, **kw):
     import pirip_b200 as pb
     _, v = pb.ldpc_code(name)
+    if M == 4:
+        kw.setdefault("f1", 5000)  # 5, 15, 25, 35 kHz: four tones Rs apart below the 40 kHz Nyquist rate
     caps, sent = [], []
     for c in range(n):
-        u8, s = coded_capture(seed0 + c, v, M, ebnos[c % len(ebnos)], nsamp=nsamp)
+        u8, s = coded_capture(seed0 + c, v, M, ebnos[c % len(ebnos)], nsamp=nsamp, **kw)
         caps.append(u8)
         sent.append(s)
     return v, np.stack(caps), sent
@@ -151,3 +153,29 @@ def test_rx_batch_tolerance_modes_deliver_the_same_packets(ldpc_mode):
                 assert o1["payload"][c, k].tobytes() in sent_set, (c, k)
     print(ldpc_mode, "packets: exact chain", n0, "tolerance chain", n1)
     assert n1 >= (0.97 if ldpc_mode == "sum_product_fast" else 0.85) * n0
+
+
+def test_per_versus_ebno_sanity_point_4fsk():
+    """[R README.md:239-251]: 4FSK + H_256_512_4 loses about 10 % of its packets at Eb/N0 = 6 dB (Eb per INFORMATION bit: rate 1/2,
+    two bits per symbol; measured there one dB worse than theory, bursts with acquisition at their start).  The GPU chain's
+    packet error rate must cross 10 % inside 6 +- 1 dB.  The code table is the repo's STAND-IN for H_256_512_4 (same (512, 256)
+    repeat-accumulate shape, not codec2's matrix: DESIGN.md 5), so this is a sanity point, not a parity claim."""
+    import pirip_b200 as pb
+    name, M, per_pt = "H_256_512_4", 4, 48
+    kw = dict(Fs=FS, Rs=RS, M=M, P=P, limits=(500, 39000))
+    plan = pb.RxPlan(name, **kw, demod_mode="exact", ldpc_mode="sum_product")
+    per = {}
+    for info_ebno in (5.0, 7.0):
+        # add_awgn's Eb is per CHANNEL bit: 3 dB below the information bit's at rate 1/2
+        v, iq, sent = make_captures(name, M, per_pt, 3000, [info_ebno - 3.0], 40000, nbursts=2, frames_per_burst=(4, 4))
+        out = plan.rx_batch(iq)
+        tot = got = 0
+        for c in range(per_pt):
+            ss = {s.tobytes() for s in sent[c]}
+            tot += len(sent[c])
+            nf = int(out["nframes"][c])
+            got += sum(1 for k in range(nf) if out["status"][c, k] & pb._lib.RX_BITS and out["payload"][c, k].tobytes() in ss)
+        per[info_ebno] = 1.0 - got / tot
+        print("4FSK H_256_512_4 (stand-in) Eb/N0 %.1f dB: %d of %d packets, PER %.3f" % (info_ebno, got, tot, per[info_ebno]))
+    plan.close()
+    assert per[5.0] > 0.10 > per[7.0], per

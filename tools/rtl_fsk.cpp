@@ -86,8 +86,22 @@ int main(int argc, char *argv[]) {
     }
     if (argc - optind < 1) usage(argv[0]);
     const char *outname = argv[optind];
-    if (Fs_rtl == 0 && Fs == 0) Fs = Fs_rtl = 240000;
-    if (Fs == 0) Fs = Fs_rtl;
+    if (Fs_rtl == 0 && Fs == 0) Fs_rtl = 240000;
+    if (Fs == 0) {
+        /* no -a: the modem runs at the tuner rate ([R README.md:114]) - unless that puts more than 100 samples into a symbol
+           (`-r 1000` at the default 240 kHz, [R README.md:152,184]: a 12000-sample modem frame and a 4096-point estimator, beyond
+           what one capture group of the GPU kernels holds).  Then the csdr stage in front decimates to the lowest rate that keeps
+           40 samples per symbol, the rate pirip's own scripts pick for that symbol rate (-a 40000 -r 1000, [R script/ping:47]). */
+        Fs = Fs_rtl;
+        if (Rs > 0 && Fs_rtl / Rs > 100) {
+            for (int D2 = Fs_rtl / (40 * Rs); D2 >= 1; --D2)
+                if (Fs_rtl % D2 == 0 && (Fs_rtl / D2) % Rs == 0 && Fs_rtl / D2 >= 40 * Rs) {
+                    Fs = Fs_rtl / D2;
+                    break;
+                }
+            if (Fs != Fs_rtl && !quiet) fprintf(stderr, "rtl_fsk: modem sample rate %d Hz (tuner %d Hz / %d); -a overrides\n", Fs, Fs_rtl, Fs_rtl / Fs);
+        }
+    }
     if (Fs_rtl == 0) Fs_rtl = Fs;
     if ((M != 2 && M != 4) || Rs <= 0 || Fs % Rs || Fs_rtl % Fs) usage(argv[0]);
     const int D = Fs_rtl / Fs; /* csdr decimation ratio, e.g. 1.8M -> 40k = 45 [R README.md:109], 2.4M -> 80k = 30 [R README.md:172] */
