@@ -213,6 +213,13 @@ int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_t n_capture
                           size_t samples_per_capture, uint8_t *bits, float *llr, float *rx_filt,
                           struct pirip_frame_stats *stats, int32_t *nframes, size_t max_frames);
 
+/* One process, several GPUs (BASELINE.json config 5: independent captures shard across the GPUs of a box): plans[r]
+ * was created on device r' of the caller's choice; the batch is cut into n_plans contiguous blocks whose sizes differ by at most
+ * one, every device demodulates its block from and to the caller's host buffers at the same time, and the decoded bit streams
+ * arrive in `bits` in capture order (the gather is the device-to-host copy of every shard).  No data-path collective. */
+int pirip_fsk_demod_batch_multi(pirip_fsk_plan *const *plans, int n_plans, const void *iq, size_t n_captures,
+                                size_t samples_per_capture, uint8_t *bits, float *llr, int32_t *nframes, size_t max_frames);
+
 /* Numerics mode of the batch entry points.
  *   PIRIP_FSK_MODE_FAST (default where the configuration allows it): the tolerance-mode kernel — tone estimates exact,
  *     integrators / timing / LLRs within the float tolerance stated in DESIGN.md, every discrete decision guarded by a

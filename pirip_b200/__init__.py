@@ -20,6 +20,7 @@ from ._lib import (  # noqa: F401
     ldpc_code,
     ldpc_encode,
     PiripError,
+    demod_batch_multi,
     kernel_launches,
     lib,
     lib_path,

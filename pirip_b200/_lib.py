@@ -198,6 +198,28 @@ class FskPlan:
             raise _err("pirip_fsk_demod_batch_dev", rc)
 
 
+def demod_batch_multi(plans, iq, want_llr=False):
+    """pirip_fsk_demod_batch_multi: one host process, one plan per GPU; the captures (rows of iq) are cut into contiguous blocks,
+    every device takes one, the bit streams come back in capture order."""
+    iq = np.ascontiguousarray(iq)
+    ncap = iq.shape[0]
+    p0 = plans[0]
+    spc = iq.shape[1] * iq.dtype.itemsize // p0.bytes_per_sample
+    mf = p0.max_frames(spc)
+    bits = np.zeros((ncap, mf * p0.nbits), np.uint8)
+    nframes = np.zeros(ncap, np.int32)
+    llr = np.zeros((ncap, mf * p0.nbits), np.float32) if want_llr else None
+    L = lib()
+    L.pirip_fsk_demod_batch_multi.restype = C.c_int
+    L.pirip_fsk_demod_batch_multi.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_size_t]
+    arr = (C.c_void_p * len(plans))(*[p._h for p in plans])
+    rc = L.pirip_fsk_demod_batch_multi(arr, len(plans), _ptr(iq), ncap, spc, _ptr(bits), _ptr(llr), _ptr(nframes), mf)
+    if rc != 0:
+        raise _err("pirip_fsk_demod_batch_multi", rc)
+    return dict(bits=bits, nframes=nframes, llr=llr, max_frames=mf)
+
+
 # ---- codec2 `struct FSK` API (include/pirip_fsk.h layer 1) -------------------------------------
 
 class COMP(C.Structure):

@@ -212,6 +212,7 @@ cudaError_t fsk_fast_launch(FskFastPlan *p, const FskBatchArgs &b, int *d_flags,
                             size_t off, size_t total, size_t slot);
 cudaError_t fsk_fast_replay_counts(FskFastPlan *p, int out[8]);
 int fsk_fast_uses_chain(const FskFastPlan *p);
+size_t fsk_fast_round_captures(const FskFastPlan *p);
 #endif
 
 /* defined in fsk_kernel.cu */

@@ -865,6 +865,9 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
     for (int i = tid; i < nb; i += T) Sf[i] = 0.0f;
     for (int i = tid; i < M * fdcS; i += T) fdc[i] = make_float2(0.0f, 0.0f);
     if (tid == 0) {
+        /* a group takes several captures one after the other when the batch is larger than the resident groups: the barrier
+           object of the previous capture is invalidated before it is initialised again (PTX: initialising a live mbarrier is undefined) */
+        if (cap != (size_t)grp * n_a + cta_a) asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(&ms->bar)) : "memory");
         mbar_init(&ms->bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         ms->pos = 0;
@@ -2006,3 +2009,24 @@ cudaError_t fsk_fast_launch(FskFastPlan *p, const FskBatchArgs &b, int *d_flags,
 }
 
 int fsk_fast_uses_chain(const FskFastPlan *p) { return p && p->chain ? 1 : 0; }
+
+/* captures one launch keeps resident (every group one capture): larger batches are cut into launches of this size by the
+   callers - a group that takes a second capture in the same launch left the next launch waiting on its bulk-copy barrier
+   (seen with 1400 and 2600 captures on B200), and a round of launches costs no more than the in-kernel loop did */
+size_t fsk_fast_round_captures(const FskFastPlan *p) {
+    /* the largest n that fsk_fast_launch's geometry holds with one capture per group: (SMs - chain CTAs for n) * gmax >= n */
+    const int sms = p->num_sms;
+    for (size_t n = (size_t)sms * p->gmax; n > 1; --n) {
+        int chain_ctas = 0;
+        if (p->chain) {
+            const size_t warps = (n * p->M + 31) / 32;
+            int wpc = 9;
+            if ((size_t)wpc > warps) wpc = (int)warps;
+            if (wpc > 2 * p->gmax) wpc = 2 * p->gmax;
+            chain_ctas = (int)((warps + wpc - 1) / wpc);
+            if (chain_ctas > sms / 4) chain_ctas = sms / 4;
+        }
+        if ((size_t)(sms - chain_ctas) * (size_t)p->gmax >= n) return n;
+    }
+    return 1;
+}

@@ -16,6 +16,7 @@
 
 #include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "exact_math.h"
@@ -654,6 +655,23 @@ static int batch_dev(pirip_fsk_plan *plan, const void *d_iq, size_t n_captures, 
     a.n_captures = n_captures;
     a.tma_ok = (reinterpret_cast<size_t>(d_iq) & 15) == 0 && getenv("PIRIP_FSK_NO_TMA") == nullptr;
     a.landed = plan->dev.k2.ok ? d_landed : nullptr;
+    if (plan->fast && plan->mode && flag_total == 0 && n_captures > fsk_fast_round_captures(plan->fast)) {
+        /* more captures than one launch keeps resident: rounds of launches, each with its own flag list and counter */
+        const size_t R = fsk_fast_round_captures(plan->fast);
+        const size_t rounds = (n_captures + R - 1) / R;
+        if (rounds > 64) return pirip::fail(-6, "too many captures for one call of the fast kernel (64 rounds)");
+        const size_t nb = (size_t)plan->dev.Nbits, nfl = (size_t)plan->dev.M * plan->dev.Nsym;
+        plan->last_chunks = rounds;
+        for (size_t r = 0, c0 = 0; c0 < n_captures; ++r, c0 += R) {
+            const size_t nc = c0 + R <= n_captures ? R : n_captures - c0;
+            const int rc = batch_dev(plan, (const unsigned char *)d_iq + c0 * capture_stride_bytes, nc, samples_per_capture, capture_stride_bytes,
+                                     d_bits ? d_bits + c0 * max_frames * nb : nullptr, d_llr ? d_llr + c0 * max_frames * nb : nullptr,
+                                     d_rx_filt ? d_rx_filt + c0 * max_frames * nfl : nullptr, d_stats ? d_stats + c0 * max_frames : nullptr,
+                                     d_nframes + c0, max_frames, stream, d_landed, c0, n_captures, r, phases);
+            if (rc) return rc;
+        }
+        return 0;
+    }
     if (plan->fast && plan->mode) {
         /* fast kernel over every capture, then the exact kernel over the captures it flagged (list on the device) */
         if (chunk >= 64) return pirip::fail(-6, "too many chunks");
@@ -749,7 +767,7 @@ extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_
         /* one launch for the whole batch (a launch costs 200 frames of per-frame latency however few captures it has), the
            captures streamed in by time slices beside it - see below.  PIRIP_FSK_E2E_CHUNKS > 1 selects plain chunking by
            captures instead (copy chunk k + 1 while chunk k is demodulated). */
-        nchunks = 1;
+        nchunks = (n_captures + fsk_fast_round_captures(plan->fast) - 1) / fsk_fast_round_captures(plan->fast);
         if (const char *e = getenv("PIRIP_FSK_E2E_CHUNKS"))
             if (atoi(e) >= 1 && atoi(e) <= 64) nchunks = (size_t)atoi(e);
         while (nchunks > 1 && n_captures / nchunks < 64) nchunks /= 2;
@@ -852,6 +870,46 @@ extern "C" int pirip_fsk_demod_batch(pirip_fsk_plan *plan, const void *iq, size_
         if (w.streams[i] && !pirip::cuda_ok(cudaStreamSynchronize(w.streams[i]), "kernel execution") && rc == 0) rc = -13;
 #undef CK
     return rc;
+}
+
+/* ---------------------------------------------------------------- one process, several GPUs */
+
+/* Captures are independent, so a batch shards over the devices with no data-path collective (BASELINE.json
+   config 5): plan r (one per device, each created with its own device index) demodulates the contiguous block
+   [r n / W + min(r, n mod W), ...) - block sizes differ by at most one - from and to the caller's host buffers, all devices at
+   once (one host thread per device: the host-buffer call is synchronous).  The "gather" of the decoded bit streams is the
+   device-to-host copy of every shard into its place in `bits`.  Returns 0 or the first failing device's code. */
+extern "C" int pirip_fsk_demod_batch_multi(pirip_fsk_plan *const *plans, int n_plans, const void *iq, size_t n_captures,
+                                           size_t samples_per_capture, uint8_t *bits, float *llr, int32_t *nframes, size_t max_frames) {
+    if (!plans || n_plans < 1) return pirip::fail(-1, "no plans");
+    for (int r = 0; r < n_plans; ++r) {
+        if (!plans[r]) return pirip::fail(-1, "plan is NULL");
+        if (plans[r]->dev.Nbits != plans[0]->dev.Nbits || plans[r]->dev.fmt != plans[0]->dev.fmt || plans[r]->dev.N != plans[0]->dev.N)
+            return pirip::fail(-3, "the plans of a multi-device call must share one configuration");
+    }
+    if (n_captures == 0) return 0;
+    if (!iq) return pirip::fail(-2, "iq is NULL");
+    const size_t cap_bytes = samples_per_capture * bytes_per_sample(plans[0]->dev.fmt);
+    const size_t nb = (size_t)plans[0]->dev.Nbits;
+    const size_t base = n_captures / (size_t)n_plans, extra = n_captures % (size_t)n_plans;
+    std::vector<int> rcs((size_t)n_plans, 0);
+    std::vector<std::string> errs((size_t)n_plans);
+    std::vector<std::thread> ths;
+    for (int r = 0; r < n_plans; ++r) {
+        const size_t c0 = (size_t)r * base + ((size_t)r < extra ? (size_t)r : extra);
+        const size_t nc = base + ((size_t)r < extra ? 1 : 0);
+        if (nc == 0) continue;
+        ths.emplace_back([=, &rcs, &errs] {
+            rcs[(size_t)r] = pirip_fsk_demod_batch(plans[r], (const unsigned char *)iq + c0 * cap_bytes, nc, samples_per_capture,
+                                                   bits ? bits + c0 * max_frames * nb : nullptr, llr ? llr + c0 * max_frames * nb : nullptr, nullptr,
+                                                   nullptr, nframes ? nframes + c0 : nullptr, max_frames);
+            if (rcs[(size_t)r]) errs[(size_t)r] = pirip_last_error(); /* the error text is per thread */
+        });
+    }
+    for (std::thread &t : ths) t.join();
+    for (int r = 0; r < n_plans; ++r)
+        if (rcs[(size_t)r]) return pirip::fail(rcs[(size_t)r], "device " + std::to_string(plans[r]->device) + ": " + errs[(size_t)r]);
+    return 0;
 }
 
 /* ---------------------------------------------------------------- codec2 struct FSK API */

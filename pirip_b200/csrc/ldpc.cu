@@ -315,6 +315,18 @@ extern "C" pirip_ldpc_plan *pirip_ldpc_plan_create(const struct LDPC *l, int dev
         while (g.v_split > 0 && (int)v_off[(size_t)g.v_split] - (int)v_off[(size_t)g.v_split - 1] <= 2) --g.v_split;
         g.v_split = (g.v_split + 31) / 32 * 32; /* whole rounds of lanes on either side */
         if (g.v_split > g.N) g.v_split = g.N;
+        g.max_cdeg = 0;
+        for (int c = 0; c < g.NPB; ++c) g.max_cdeg = std::max(g.max_cdeg, (int)c_off[(size_t)c + 1] - (int)c_off[(size_t)c]);
+        g.v_deg_a = g.v_split > 0 ? (int)v_off[1] - (int)v_off[0] : 0;
+        for (int v = 0; v < g.v_split; ++v)
+            if ((int)v_off[(size_t)v + 1] - (int)v_off[(size_t)v] != g.v_deg_a) g.v_deg_a = 0;
+        g.v_tail_base = g.v_split < g.N ? (int)v_off[(size_t)g.v_split] : 0;
+        g.v_tail_regular = g.v_split < g.N ? 1 : 0;
+        for (int v = g.v_split; v < g.N; ++v) {
+            const int d = (int)v_off[(size_t)v + 1] - (int)v_off[(size_t)v];
+            if (!(d == 2 || (v == g.N - 1 && d >= 1 && d <= 2)) || (int)v_off[(size_t)v] != g.v_tail_base + 2 * (v - g.v_split)) g.v_tail_regular = 0;
+        }
+        if (getenv("PIRIP_LDPC_NO_REGULAR")) g.v_deg_a = 0, g.v_tail_regular = 0;
         g.ms_scale = 0.75f;
         p->smem = g.tables_bytes + (warps > 0 ? warps : 0) * w;
     }

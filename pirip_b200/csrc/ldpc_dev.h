@@ -23,6 +23,9 @@ struct LdpcGraph {
     int warps;  /* codewords per CTA */
     int max_vdeg; /* largest number of edges of a variable */
     int v_split;  /* variables from here on have at most two edges (the parity part of a repeat-accumulate code) */
+    int max_cdeg; /* largest number of edges of a check */
+    int v_deg_a;  /* > 0: every variable below v_split has exactly this many edges */
+    int v_tail_regular, v_tail_base; /* variables from v_split on: two edges each (the last one may have one), first entry v_tail_base */
     float ms_scale; /* normalisation of the min-sum check update */
 };
 
@@ -132,7 +135,7 @@ __device__ __forceinline__ LdpcSmem ldpc_smem_view(const LdpcGraph &g, unsigned 
    does not have, so sums and minima are those of the scalar order ([U mpdecode_core.c::SumProduct]).
    The variable phase is unrolled VA wide for the variables below g.v_split and 2 wide from there on (the degree-2 parity
    variables of a repeat-accumulate code); edges beyond the unrolled width take a loop. */
-template <int MODE, int VA, class Load, class Store>
+template <int MODE, int VA, int CD, class Load, class Store>
 __device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSmem &m, int lane, Load load, Store store, int *pcc_out) {
     const uint16_t *c_off = m.c_off, *v_off = m.v_off, *c_vpos = m.c_vpos;
     float *q = m.q, *llr = m.llr;
@@ -156,18 +159,18 @@ __device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSm
         for (int c = lane; c < g.NPB; c += 32) {
             const int e0 = c_off[c], e1 = c_off[c + 1];
             const float pad = MODE == LDPC_MINSUM ? 3.0e38f : 0.0f;
-            int idx[8];
-            float v[8];
+            int idx[CD];
+            float v[CD];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) idx[k] = (e0 + k < e1) ? c_vpos[e0 + k] : -1;
+            for (int k = 0; k < CD; ++k) idx[k] = (e0 + k < e1) ? c_vpos[e0 + k] : -1;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) v[k] = idx[k] >= 0 ? q[idx[k]] : pad;
+            for (int k = 0; k < CD; ++k) v[k] = idx[k] >= 0 ? q[idx[k]] : pad;
             unsigned sign = 0;
             if (MODE == LDPC_MINSUM) {
                 float m1 = 3.0e38f, m2 = 3.0e38f;
                 int pos = 0;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
+                for (int k = 0; k < CD; ++k) {
                     const float a = fabsf(v[k]);
                     sign ^= __float_as_uint(v[k]) & 0x80000000u;
                     if (a < m1) {
@@ -177,7 +180,7 @@ __device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSm
                     } else if (a < m2)
                         m2 = a;
                 }
-                for (int e = e0 + 8; e < e1; ++e) {
+                for (int e = e0 + CD; e < e1; ++e) {
                     const float w = q[c_vpos[e]];
                     const float a = fabsf(w);
                     sign ^= __float_as_uint(w) & 0x80000000u;
@@ -190,12 +193,12 @@ __device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSm
                 }
                 const float s1 = m1 * g.ms_scale, s2 = m2 * g.ms_scale;
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
+                for (int k = 0; k < CD; ++k)
                     if (idx[k] >= 0) {
                         const unsigned neg = (sign ^ __float_as_uint(v[k])) & 0x80000000u;
                         q[idx[k]] = __uint_as_float(__float_as_uint(k == pos ? s2 : s1) ^ neg);
                     }
-                for (int e = e0 + 8; e < e1; ++e) {
+                for (int e = e0 + CD; e < e1; ++e) {
                     const int j = c_vpos[e];
                     const unsigned neg = (sign ^ __float_as_uint(q[j])) & 0x80000000u;
                     q[j] = __uint_as_float(__float_as_uint((e - e0) == pos ? s2 : s1) ^ neg);
@@ -204,20 +207,20 @@ __device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSm
                 float phi_sum = fabsf(v[0]);
                 sign = __float_as_uint(v[0]) & 0x80000000u;
 #pragma unroll
-                for (int k = 1; k < 8; ++k) {
+                for (int k = 1; k < CD; ++k) {
                     phi_sum = __fadd_rn(phi_sum, fabsf(v[k]));
                     sign ^= __float_as_uint(v[k]) & 0x80000000u;
                 }
-                for (int e = e0 + 8; e < e1; ++e) {
+                for (int e = e0 + CD; e < e1; ++e) {
                     const float w = q[c_vpos[e]];
                     phi_sum = __fadd_rn(phi_sum, fabsf(w));
                     sign ^= __float_as_uint(w) & 0x80000000u;
                 }
                 const float cs = __uint_as_float(__float_as_uint(phi_sum) | sign);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
+                for (int k = 0; k < CD; ++k)
                     if (idx[k] >= 0) q[idx[k]] = r_msg<MODE>(v[k], cs, 0.0f, k);
-                for (int e = e0 + 8; e < e1; ++e) {
+                for (int e = e0 + CD; e < e1; ++e) {
                     const int j = c_vpos[e];
                     q[j] = r_msg<MODE>(q[j], cs, 0.0f, e - e0);
                 }
@@ -228,9 +231,8 @@ __device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSm
         __syncwarp();
         const bool last = pcc == g.NPB || iter == g.max_iter - 1;
         /* variable-node phase */
-        auto vnode = [&](int v, auto W) {
+        auto vnode = [&](int v, auto W, int j0, int j1) {
             constexpr int VW = decltype(W)::value;
-            const int j0 = v_off[v], j1 = v_off[v + 1];
             float Qi = llr[v];
             float r[VW];
 #pragma unroll
@@ -246,8 +248,19 @@ __device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSm
                 if (j0 + k < j1) q[j0 + k] = q_store<MODE>(__fsub_rn(Qi, r[k]));
             for (int j = j0 + VW; j < j1; ++j) q[j] = q_store<MODE>(__fsub_rn(Qi, q[j]));
         };
-        for (int v = lane; v < g.v_split; v += 32) vnode(v, std::integral_constant<int, VA>());
-        for (int v = g.v_split + lane; v < g.N; v += 32) vnode(v, std::integral_constant<int, 2>());
+        if (g.v_deg_a > 0)
+            /* every variable below v_split has v_deg_a edges: offsets by arithmetic, no table reads */
+            for (int v = lane; v < g.v_split; v += 32) vnode(v, std::integral_constant<int, VA>(), v * g.v_deg_a, (v + 1) * g.v_deg_a);
+        else
+            for (int v = lane; v < g.v_split; v += 32) vnode(v, std::integral_constant<int, VA>(), v_off[v], v_off[v + 1]);
+        if (g.v_tail_regular) {
+            /* the degree-2 chain of a repeat-accumulate code: two edges each but the last variable */
+            for (int v = g.v_split + lane; v < g.N; v += 32) {
+                const int j0 = g.v_tail_base + 2 * (v - g.v_split);
+                vnode(v, std::integral_constant<int, 2>(), j0, j0 + 2 < g.E ? j0 + 2 : g.E);
+            }
+        } else
+            for (int v = g.v_split + lane; v < g.N; v += 32) vnode(v, std::integral_constant<int, 2>(), v_off[v], v_off[v + 1]);
         __syncwarp();
         if (pcc == g.NPB) {
             result = iter + 1;
@@ -261,8 +274,9 @@ __device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSm
 
 template <int MODE, class Load, class Store>
 __device__ __forceinline__ int ldpc_decode_one(const LdpcGraph &g, const LdpcSmem &m, int lane, Load load, Store store, int *pcc_out) {
-    if (g.max_vdeg <= 4) return ldpc_decode_impl<MODE, 4>(g, m, lane, load, store, pcc_out);
-    return ldpc_decode_impl<MODE, 8>(g, m, lane, load, store, pcc_out);
+    if (g.max_vdeg <= 4 && g.max_cdeg <= 6) return ldpc_decode_impl<MODE, 4, 6>(g, m, lane, load, store, pcc_out);
+    if (g.max_vdeg <= 4) return ldpc_decode_impl<MODE, 4, 8>(g, m, lane, load, store, pcc_out);
+    return ldpc_decode_impl<MODE, 8, 8>(g, m, lane, load, store, pcc_out);
 }
 
 /* Batch decoder: one warp per codeword, up to 8 codewords per CTA, the Tanner graph tables loaded once per CTA; a CTA loops

@@ -263,3 +263,27 @@ def test_fsk_mod_ext_vco_tone_frequencies():
     assert vco.size == 4 * 8
     assert vco.reshape(4, 8).tolist() == [[1200.0] * 8, [2000.0] * 8, [2800.0] * 8, [3600.0] * 8]
     st.close()
+
+
+@pytest.mark.parametrize("nplans,ncap", [(2, 7), (3, 2), (1, 5)])
+def test_multi_device_entry_shards_and_keeps_capture_order(nplans, ncap):
+    """pirip_fsk_demod_batch_multi (one process, several GPUs): plans on every visible device (several on the
+    same device when the box has fewer GPUs than plans), ragged shard sizes, more plans than captures; output in capture order
+    and equal to the single-plan call and to the oracle."""
+    import torch
+
+    import pirip_b200 as pb
+    ndev = torch.cuda.device_count()
+    caps = [synth.capture_u8(500 + c, 1500, 2, 240000, 10000, 10000, 10000, ebno_db=[None, 9.0, 6.0][c % 3])[0] for c in range(ncap)]
+    n = min(x.size for x in caps)
+    iq = np.stack([x[:n] for x in caps])
+    plans = [pb.FskPlan(**C1, device=r % ndev) for r in range(nplans)]
+    out = pb.demod_batch_multi(plans, iq)
+    one = plans[0].demod_batch(iq)
+    assert np.array_equal(out["nframes"], one["nframes"]) and np.array_equal(out["bits"], one["bits"])
+    for c in (0, ncap - 1):
+        ref = orc.fsk_demod_stream(ocfg(C1), iq[c])
+        nf = int(out["nframes"][c])
+        assert nf == ref["nframes"] and np.array_equal(out["bits"][c, :nf * 50], ref["bits"])
+    for p in plans:
+        p.close()
