@@ -142,6 +142,14 @@ void fsk_get_demod_stats(struct FSK *fsk, struct MODEM_STATS *stats);
 void fsk_setup_modem_stats(struct FSK *fsk, struct MODEM_STATS *stats);
 /* replaces codec2 src/fsk.h::fsk_stats_normalise_eye */
 void fsk_stats_normalise_eye(struct FSK *fsk, int normalise_enable);
+/* Stream extension: as many whole modem frames as `n_avail` samples hold, at most max_frames, in ONE launch -
+ * what a receiver front end that hands over fixed-size chunks ([U rtl_fsk.c] USB callback, [R README.md:172]) calls instead of
+ * fsk_demod once per frame.  The struct FSK advances exactly as by that many fsk_demod / fsk_demod_sd calls, outputs are the same
+ * floats.  rx_bits [frames][Nbits], rx_filt [frames][mode * Nsym], stats [frames] may each be NULL.  Returns the frames
+ * demodulated, *consumed the samples they took (the caller keeps the rest for the next call). */
+struct pirip_frame_stats;
+int pirip_fsk_demod_frames(struct FSK *fsk, const COMP *in, size_t n_avail, int max_frames, uint8_t *rx_bits, float *rx_filt,
+                           struct pirip_frame_stats *stats, size_t *consumed);
 /* replaces codec2 src/fsk.h::fsk_mod / fsk_mod_c (Tx side, host only) */
 void fsk_mod(struct FSK *fsk, float fsk_out[], uint8_t tx_bits[], int nbits);
 void fsk_mod_c(struct FSK *fsk, COMP fsk_out[], uint8_t tx_bits[], int nbits);

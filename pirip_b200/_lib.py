@@ -284,6 +284,21 @@ class FskStream:
         self.L.fsk_demod_sd(self.fsk, _ptr(filt), _ptr(samples))
         return filt
 
+    def demod_frames(self, samples, max_frames):
+        """pirip_fsk_demod_frames: every whole frame of `samples` (at most max_frames) in one launch.
+        Returns (bits [nf, Nbits], rx_filt [nf, mode * Nsym], stats [nf], consumed)."""
+        samples = np.ascontiguousarray(samples, np.complex64)
+        L = self.L
+        L.pirip_fsk_demod_frames.restype = C.c_int
+        L.pirip_fsk_demod_frames.argtypes = [C.POINTER(FSK), C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                             C.POINTER(C.c_size_t)]
+        bits = np.zeros((max_frames, self.s.Nbits), np.uint8)
+        filt = np.zeros((max_frames, self.s.mode * self.s.Nsym), np.float32)
+        stats = np.zeros(max_frames, FRAME_STATS_DTYPE)
+        used = C.c_size_t(0)
+        nf = L.pirip_fsk_demod_frames(self.fsk, _ptr(samples), samples.size, max_frames, _ptr(bits), _ptr(filt), _ptr(stats), C.byref(used))
+        return bits[:nf], filt[:nf], stats[:nf], int(used.value)
+
     def clear_estimators(self):
         self.L.fsk_clear_estimators.argtypes = [C.POINTER(FSK)]
         self.L.fsk_clear_estimators(self.fsk)

@@ -935,6 +935,13 @@ struct FskDevice {
     FskDevStateHdr *h_hdr = nullptr;
     int nin_max = 0;
     bool dirty_cfg = false;
+    /* pirip_fsk_demod_frames: many frames per launch */
+    COMP *m_in = nullptr, *mh_in = nullptr; /* device samples, pinned staging ring slot */
+    uint8_t *m_bits = nullptr, *mh_bits = nullptr;
+    float *m_filt = nullptr, *mh_filt = nullptr;
+    pirip_frame_stats *m_stats = nullptr, *mh_stats = nullptr;
+    int32_t *m_nf = nullptr, *mh_nf = nullptr;
+    size_t m_cap_samples = 0, m_cap_frames = 0;
 };
 
 [[noreturn]] void die(const char *what) {
@@ -1142,6 +1149,16 @@ extern "C" void fsk_destroy(struct FSK *fsk) {
         cudaFreeHost(d->h_Sf);
         cudaFreeHost(d->h_stats);
         cudaFreeHost(d->h_hdr);
+        cudaFree(d->m_in);
+        cudaFree(d->m_bits);
+        cudaFree(d->m_filt);
+        cudaFree(d->m_stats);
+        cudaFree(d->m_nf);
+        cudaFreeHost(d->mh_in);
+        cudaFreeHost(d->mh_bits);
+        cudaFreeHost(d->mh_filt);
+        cudaFreeHost(d->mh_stats);
+        cudaFreeHost(d->mh_nf);
         if (d->stream) cudaStreamDestroy(d->stream);
         plan_free(d->plan);
         delete d;
@@ -1218,6 +1235,104 @@ extern "C" void fsk_get_demod_stats(struct FSK *fsk, struct MODEM_STATS *stats) 
 extern "C" void fsk_stats_normalise_eye(struct FSK *fsk, int normalise_enable) {
     assert(fsk != NULL);
     fsk->normalise_eye = normalise_enable;
+}
+
+/* Stream extension (the front end of a live receiver hands over fixed-size chunks, not single frames): as many
+   whole modem frames as `n_avail` samples hold, at most max_frames, in ONE launch - the frame loop, the nin decisions and the
+   state carried from frame to frame stay on the device; samples go through a pinned staging buffer.  The struct FSK advances
+   exactly as by the same number of fsk_demod / fsk_demod_sd calls (same kernel, same state record), so the outputs are the
+   same floats.  rx_bits [frames][Nbits], rx_filt [frames][M * Nsym], stats [frames] may each be NULL.  Returns the number of
+   frames demodulated (0 when n_avail < fsk_nin()), *consumed the samples they took. */
+extern "C" int pirip_fsk_demod_frames(struct FSK *fsk, const COMP *in, size_t n_avail, int max_frames, uint8_t *rx_bits, float *rx_filt,
+                                      struct pirip_frame_stats *stats, size_t *consumed) {
+    assert(fsk != NULL && in != NULL);
+    FskDevice *d = (FskDevice *)fsk->dev;
+    if (consumed) *consumed = 0;
+    if (max_frames < 1 || n_avail < (size_t)fsk->nin) return 0;
+    if (d->dirty_cfg || d->plan->dev.burst_mode != fsk->burst_mode || d->plan->dev.lock_nin != fsk->lock_nin ||
+        d->plan->dev.est_type != fsk->freq_est_type || d->plan->dev.tone_spacing != fsk->tone_spacing)
+        rebuild_plan(fsk);
+    ck(cudaSetDevice(d->plan->device), "cudaSetDevice");
+    const int M = fsk->mode, Nsym = fsk->Nsym, Nbits = fsk->Nbits;
+    const size_t nin_min = (size_t)(fsk->N - fsk->Ts / 4);
+    size_t K = n_avail / nin_min + 1;
+    if (K > (size_t)max_frames) K = (size_t)max_frames;
+    if (n_avail > d->m_cap_samples) {
+        cudaFree(d->m_in);
+        cudaFreeHost(d->mh_in);
+        ck(cudaMalloc(&d->m_in, sizeof(COMP) * n_avail), "cudaMalloc samples");
+        ck(cudaHostAlloc(&d->mh_in, sizeof(COMP) * n_avail, cudaHostAllocDefault), "cudaHostAlloc samples");
+        d->m_cap_samples = n_avail;
+    }
+    if (K > d->m_cap_frames) {
+        cudaFree(d->m_bits), cudaFree(d->m_filt), cudaFree(d->m_stats);
+        cudaFreeHost(d->mh_bits), cudaFreeHost(d->mh_filt), cudaFreeHost(d->mh_stats);
+        ck(cudaMalloc(&d->m_bits, K * (size_t)Nbits), "cudaMalloc bits");
+        ck(cudaMalloc(&d->m_filt, sizeof(float) * K * (size_t)(M * Nsym)), "cudaMalloc rx_filt");
+        ck(cudaMalloc(&d->m_stats, sizeof(pirip_frame_stats) * K), "cudaMalloc stats");
+        ck(cudaHostAlloc(&d->mh_bits, K * (size_t)Nbits, cudaHostAllocDefault), "cudaHostAlloc bits");
+        ck(cudaHostAlloc(&d->mh_filt, sizeof(float) * K * (size_t)(M * Nsym), cudaHostAllocDefault), "cudaHostAlloc rx_filt");
+        ck(cudaHostAlloc(&d->mh_stats, sizeof(pirip_frame_stats) * K, cudaHostAllocDefault), "cudaHostAlloc stats");
+        d->m_cap_frames = K;
+    }
+    if (!d->m_nf) {
+        ck(cudaMalloc(&d->m_nf, sizeof(int32_t)), "cudaMalloc nframes");
+        ck(cudaHostAlloc(&d->mh_nf, sizeof(int32_t), cudaHostAllocDefault), "cudaHostAlloc nframes");
+    }
+    const int nin0 = fsk->nin;
+    memcpy(d->mh_in, in, sizeof(COMP) * n_avail);
+    ck(cudaMemcpyAsync(d->m_in, d->mh_in, sizeof(COMP) * n_avail, cudaMemcpyHostToDevice, d->stream), "H2D samples");
+    FskBatchArgs a;
+    memset(&a, 0, sizeof a);
+    a.iq = (const unsigned char *)d->m_in;
+    a.capture_stride_bytes = sizeof(COMP) * n_avail;
+    a.samples_per_capture = n_avail;
+    a.max_frames = K;
+    a.n_captures = 1;
+    a.tma_ok = 0;
+    a.bits = d->m_bits;
+    a.rx_filt = d->m_filt;
+    a.stats = d->m_stats;
+    a.nframes = d->m_nf;
+    a.state = d->d_state;
+    a.state_stride_floats = fsk_state_floats(fsk->Ndft, M, fsk->Nmem);
+    a.Sf_out = d->d_Sf;
+    ck(fsk_launch_demod(d->plan->dev, a, 1, d->stream), "fsk_demod_kernel launch");
+    pirip::count_launch();
+    ck(cudaMemcpyAsync(d->mh_nf, d->m_nf, sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream), "D2H nframes");
+    ck(cudaMemcpyAsync(d->mh_bits, d->m_bits, K * (size_t)Nbits, cudaMemcpyDeviceToHost, d->stream), "D2H bits");
+    ck(cudaMemcpyAsync(d->mh_filt, d->m_filt, sizeof(float) * K * (size_t)(M * Nsym), cudaMemcpyDeviceToHost, d->stream), "D2H rx_filt");
+    ck(cudaMemcpyAsync(d->mh_stats, d->m_stats, sizeof(pirip_frame_stats) * K, cudaMemcpyDeviceToHost, d->stream), "D2H stats");
+    ck(cudaMemcpyAsync(d->h_Sf, d->d_Sf, sizeof(float) * (size_t)fsk->Ndft, cudaMemcpyDeviceToHost, d->stream), "D2H Sf");
+    ck(cudaMemcpyAsync(d->h_hdr, d->d_state, sizeof(FskDevStateHdr), cudaMemcpyDeviceToHost, d->stream), "D2H state");
+    ck(cudaStreamSynchronize(d->stream), "fsk_demod kernel");
+    const int nf = *d->mh_nf;
+    if (nf <= 0) return 0;
+    if (rx_bits) memcpy(rx_bits, d->mh_bits, (size_t)nf * (size_t)Nbits);
+    if (rx_filt) memcpy(rx_filt, d->mh_filt, sizeof(float) * (size_t)nf * (size_t)(M * Nsym));
+    if (stats) memcpy(stats, d->mh_stats, sizeof(pirip_frame_stats) * (size_t)nf);
+    memcpy(fsk->Sf, d->h_Sf, sizeof(float) * (size_t)fsk->Ndft);
+    const pirip_frame_stats &s = d->mh_stats[nf - 1];
+    for (int m = 0; m < M; ++m) {
+        fsk->f_est[m] = s.f_est[m];
+        fsk->f2_est[m] = s.f2_est[m];
+        fsk->phi_c[m].real = d->h_hdr->phi_c[m].x;
+        fsk->phi_c[m].imag = d->h_hdr->phi_c[m].y;
+    }
+    fsk->norm_rx_timing = s.norm_rx_timing;
+    fsk->ppm = s.ppm;
+    fsk->SNRest = s.SNRest;
+    fsk->v_est = s.v_est;
+    fsk->rx_sig_pow = s.rx_sig_pow;
+    fsk->rx_nse_pow = s.rx_nse_pow;
+    fsk->EbNodB = s.EbNodB;
+    fsk->nin = s.nin_next;
+    fsk->stats->snr_est = s.snr_est;
+    fsk->stats->foff = s.foff;
+    fsk->stats->rx_timing = s.rx_timing;
+    fsk->stats->clock_offset = s.ppm;
+    if (consumed) *consumed = (size_t)s.sample_offset + (size_t)(nf > 1 ? d->mh_stats[nf - 2].nin_next : nin0);
+    return nf;
 }
 
 /* Tx side, host only: continuous-phase M-FSK by a recursive complex oscillator

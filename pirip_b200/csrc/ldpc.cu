@@ -205,7 +205,7 @@ bool build_graph(const struct LDPC *l, std::vector<uint16_t> &c_off, std::vector
         c_off[(size_t)p] = (uint16_t)E;
         E += cvars[(size_t)p].size();
     }
-    if (E > 65535) {
+    if (E >= 65535) { /* 0xffff marks a missing edge in the per-check index records */
         why = "too many edges";
         return false;
     }
@@ -259,7 +259,7 @@ struct pirip_ldpc_plan {
     int device, smem;
     int mode = LDPC_SP_EXACT;
     int num_sms = 148;
-    uint16_t *d_c_off = nullptr, *d_v_off = nullptr, *d_c_vpos = nullptr;
+    uint16_t *d_c_off = nullptr, *d_v_off = nullptr, *d_c_vpos = nullptr, *d_c_idx8 = nullptr;
     float *d_llr = nullptr;
     unsigned char *d_bits = nullptr;
     int *d_iter = nullptr, *d_pcc = nullptr;
@@ -296,6 +296,8 @@ extern "C" pirip_ldpc_plan *pirip_ldpc_plan_create(const struct LDPC *l, int dev
         o += al((g.N + 1) * 2);
         g.off_vedge = o;
         o += al(g.E * 2);
+        g.off_idx8 = o;
+        o += al(g.NPB * 16);
         g.tables_bytes = o;
         int w = 0;
         g.w_q = w;
@@ -349,7 +351,12 @@ extern "C" pirip_ldpc_plan *pirip_ldpc_plan_create(const struct LDPC *l, int dev
         if (!strcmp(e, "minsum")) p->mode = LDPC_MINSUM;
         else if (!strcmp(e, "fast")) p->mode = LDPC_SP_FAST;
     }
+    std::vector<uint16_t> c_idx8((size_t)p->g.NPB * 8, (uint16_t)0xffff);
+    for (int c = 0; c < p->g.NPB; ++c)
+        for (int e = c_off[(size_t)c], k = 0; e < c_off[(size_t)c + 1] && k < 8; ++e, ++k) c_idx8[(size_t)c * 8 + (size_t)k] = c_vpos[(size_t)e];
     if (!pirip::cuda_ok(cudaSetDevice(device), "cudaSetDevice") ||
+        !pirip::cuda_ok(cudaMalloc(&p->d_c_idx8, 2 * c_idx8.size()), "cudaMalloc") ||
+        !pirip::cuda_ok(cudaMemcpy(p->d_c_idx8, c_idx8.data(), 2 * c_idx8.size(), cudaMemcpyHostToDevice), "copy") ||
         !pirip::cuda_ok(cudaMalloc(&p->d_c_off, 2 * c_off.size()), "cudaMalloc") ||
         !pirip::cuda_ok(cudaMalloc(&p->d_v_off, 2 * v_off.size()), "cudaMalloc") ||
         !pirip::cuda_ok(cudaMalloc(&p->d_c_vpos, 2 * c_vpos.size()), "cudaMalloc") ||
@@ -365,6 +372,7 @@ extern "C" pirip_ldpc_plan *pirip_ldpc_plan_create(const struct LDPC *l, int dev
     p->g.c_off = p->d_c_off;
     p->g.v_off = p->d_v_off;
     p->g.c_vpos = p->d_c_vpos;
+    p->g.c_idx8 = p->d_c_idx8;
     return p;
 }
 
@@ -383,6 +391,7 @@ extern "C" void pirip_ldpc_plan_destroy(pirip_ldpc_plan *p) {
     cudaFree(p->d_c_off);
     cudaFree(p->d_v_off);
     cudaFree(p->d_c_vpos);
+    cudaFree(p->d_c_idx8);
     cudaFree(p->d_llr);
     cudaFree(p->d_bits);
     cudaFree(p->d_iter);

@@ -17,8 +17,9 @@ struct LdpcGraph {
     const uint16_t *c_off;  /* [NPB+1] first edge of every check */
     const uint16_t *v_off;  /* [N+1] first entry of every variable in v_edge */
     const uint16_t *c_vpos; /* [E] check order: position of the edge in variable order */
+    const uint16_t *c_idx8; /* [NPB][8] the same positions, one 16-byte record per check, 0xffff where a check has fewer edges */
     /* shared-memory layout of the decoder kernel (bytes): tables once per CTA, then one block per warp (codeword) */
-    int off_voff, off_vedge, tables_bytes;
+    int off_voff, off_vedge, off_idx8, tables_bytes;
     int w_q, w_llr, w_scr, warp_bytes;
     int warps;  /* codewords per CTA */
     int max_vdeg; /* largest number of edges of a variable */
@@ -90,6 +91,7 @@ __device__ __forceinline__ float q_store(float t) {
 /* Per-CTA view of the graph tables in shared memory and one warp's message storage */
 struct LdpcSmem {
     const uint16_t *c_off, *v_off, *c_vpos;
+    const uint4 *c_idx8;
     float *q;      /* [E] variable order: q on the way to the checks, r on the way back */
     float *llr;    /* [N] */
     unsigned *scr; /* [256] scratch words (receive-chain kernel) */
@@ -103,12 +105,15 @@ __device__ __forceinline__ void ldpc_load_tables(const LdpcGraph &g, unsigned ch
     for (int i = threadIdx.x; i <= g.NPB; i += blockDim.x) c_off[i] = g.c_off[i];
     for (int i = threadIdx.x; i <= g.N; i += blockDim.x) v_off[i] = g.v_off[i];
     for (int i = threadIdx.x; i < g.E; i += blockDim.x) c_vpos[i] = g.c_vpos[i];
+    uint16_t *idx8 = reinterpret_cast<uint16_t *>(smem_raw + g.off_idx8);
+    for (int i = threadIdx.x; i < 8 * g.NPB; i += blockDim.x) idx8[i] = g.c_idx8[i];
 }
 __device__ __forceinline__ LdpcSmem ldpc_smem_view(const LdpcGraph &g, unsigned char *smem_raw, int warp) {
     LdpcSmem m;
     m.c_off = reinterpret_cast<const uint16_t *>(smem_raw);
     m.v_off = reinterpret_cast<const uint16_t *>(smem_raw + g.off_voff);
     m.c_vpos = reinterpret_cast<const uint16_t *>(smem_raw + g.off_vedge);
+    m.c_idx8 = reinterpret_cast<const uint4 *>(smem_raw + g.off_idx8);
     unsigned char *wb = smem_raw + g.tables_bytes + (size_t)warp * g.warp_bytes;
     m.q = reinterpret_cast<float *>(wb + g.w_q);
     m.llr = reinterpret_cast<float *>(wb + g.w_llr);
@@ -156,52 +161,54 @@ __device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSm
     for (int iter = 0; iter < g.max_iter; ++iter) {
         /* check-node phase */
         int local = 0;
+#pragma unroll(MODE == LDPC_SP_EXACT ? 1 : 2)
         for (int c = lane; c < g.NPB; c += 32) {
-            const int e0 = c_off[c], e1 = c_off[c + 1];
             const float pad = MODE == LDPC_MINSUM ? 3.0e38f : 0.0f;
             int idx[CD];
             float v[CD];
+            /* the positions of the check's first eight edges in one 16-byte load */
+            const uint4 rec = m.c_idx8[c];
+            const unsigned w[4] = { rec.x, rec.y, rec.z, rec.w };
 #pragma unroll
-            for (int k = 0; k < CD; ++k) idx[k] = (e0 + k < e1) ? c_vpos[e0 + k] : -1;
+            for (int k = 0; k < CD; ++k) {
+                const unsigned u = (k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xffffu);
+                idx[k] = u == 0xffffu ? -1 : (int)u;
+            }
+            int e0 = 0, e1 = 0;
+            if (g.max_cdeg > CD) e0 = c_off[c], e1 = c_off[c + 1]; /* only checks with more edges than the record holds */
 #pragma unroll
             for (int k = 0; k < CD; ++k) v[k] = idx[k] >= 0 ? q[idx[k]] : pad;
             unsigned sign = 0;
             if (MODE == LDPC_MINSUM) {
+                /* smallest and second smallest magnitude without tracking a position: the edge that holds the smallest gets the
+                   second smallest, every other edge the smallest - with a tie both are equal, so the result is the same */
                 float m1 = 3.0e38f, m2 = 3.0e38f;
-                int pos = 0;
 #pragma unroll
                 for (int k = 0; k < CD; ++k) {
                     const float a = fabsf(v[k]);
                     sign ^= __float_as_uint(v[k]) & 0x80000000u;
-                    if (a < m1) {
-                        m2 = m1;
-                        m1 = a;
-                        pos = k;
-                    } else if (a < m2)
-                        m2 = a;
+                    m2 = fminf(m2, fmaxf(m1, a));
+                    m1 = fminf(m1, a);
                 }
                 for (int e = e0 + CD; e < e1; ++e) {
                     const float w = q[c_vpos[e]];
                     const float a = fabsf(w);
                     sign ^= __float_as_uint(w) & 0x80000000u;
-                    if (a < m1) {
-                        m2 = m1;
-                        m1 = a;
-                        pos = e - e0;
-                    } else if (a < m2)
-                        m2 = a;
+                    m2 = fminf(m2, fmaxf(m1, a));
+                    m1 = fminf(m1, a);
                 }
                 const float s1 = m1 * g.ms_scale, s2 = m2 * g.ms_scale;
 #pragma unroll
                 for (int k = 0; k < CD; ++k)
                     if (idx[k] >= 0) {
                         const unsigned neg = (sign ^ __float_as_uint(v[k])) & 0x80000000u;
-                        q[idx[k]] = __uint_as_float(__float_as_uint(k == pos ? s2 : s1) ^ neg);
+                        q[idx[k]] = __uint_as_float(__float_as_uint(fabsf(v[k]) <= m1 ? s2 : s1) ^ neg);
                     }
                 for (int e = e0 + CD; e < e1; ++e) {
                     const int j = c_vpos[e];
-                    const unsigned neg = (sign ^ __float_as_uint(q[j])) & 0x80000000u;
-                    q[j] = __uint_as_float(__float_as_uint((e - e0) == pos ? s2 : s1) ^ neg);
+                    const float w = q[j];
+                    const unsigned neg = (sign ^ __float_as_uint(w)) & 0x80000000u;
+                    q[j] = __uint_as_float(__float_as_uint(fabsf(w) <= m1 ? s2 : s1) ^ neg);
                 }
             } else {
                 float phi_sum = fabsf(v[0]);
@@ -248,7 +255,18 @@ __device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSm
                 if (j0 + k < j1) q[j0 + k] = q_store<MODE>(__fsub_rn(Qi, r[k]));
             for (int j = j0 + VW; j < j1; ++j) q[j] = q_store<MODE>(__fsub_rn(Qi, q[j]));
         };
-        if (g.v_deg_a > 0)
+        if (g.v_deg_a == 4 && VA == 4) {
+            /* every variable below v_split has four edges: one 16-byte load and store per variable (32-bit accesses 16 bytes apart
+               would be 4-way bank conflicts), sums in edge order */
+            for (int v = lane; v < g.v_split; v += 32) {
+                float4 *q4 = reinterpret_cast<float4 *>(q) + v;
+                const float4 r = *q4;
+                const float Qi = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(llr[v], r.x), r.y), r.z), r.w);
+                if (last) store(v, Qi < 0.0f ? 1 : 0);
+                *q4 = make_float4(q_store<MODE>(__fsub_rn(Qi, r.x)), q_store<MODE>(__fsub_rn(Qi, r.y)), q_store<MODE>(__fsub_rn(Qi, r.z)),
+                                  q_store<MODE>(__fsub_rn(Qi, r.w)));
+            }
+        } else if (g.v_deg_a > 0)
             /* every variable below v_split has v_deg_a edges: offsets by arithmetic, no table reads */
             for (int v = lane; v < g.v_split; v += 32) vnode(v, std::integral_constant<int, VA>(), v * g.v_deg_a, (v + 1) * g.v_deg_a);
         else
@@ -257,7 +275,14 @@ __device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSm
             /* the degree-2 chain of a repeat-accumulate code: two edges each but the last variable */
             for (int v = g.v_split + lane; v < g.N; v += 32) {
                 const int j0 = g.v_tail_base + 2 * (v - g.v_split);
-                vnode(v, std::integral_constant<int, 2>(), j0, j0 + 2 < g.E ? j0 + 2 : g.E);
+                if (j0 + 2 <= g.E && (g.v_tail_base & 1) == 0) {
+                    float2 *q2 = reinterpret_cast<float2 *>(q + j0);
+                    const float2 r = *q2;
+                    const float Qi = __fadd_rn(__fadd_rn(llr[v], r.x), r.y);
+                    if (last) store(v, Qi < 0.0f ? 1 : 0);
+                    *q2 = make_float2(q_store<MODE>(__fsub_rn(Qi, r.x)), q_store<MODE>(__fsub_rn(Qi, r.y)));
+                } else
+                    vnode(v, std::integral_constant<int, 2>(), j0, j0 + 2 < g.E ? j0 + 2 : g.E);
             }
         } else
             for (int v = g.v_split + lane; v < g.N; v += 32) vnode(v, std::integral_constant<int, 2>(), v_off[v], v_off[v + 1]);

@@ -131,3 +131,37 @@ def test_many_captures_per_sm_lockstep():
     sub = list(range(0, ncap, max(1, ncap // 10)))
     compare(plan, pk, iq[sub], {k: (v[sub] if isinstance(v, np.ndarray) else v) for k, v in out.items()})
     plan.close()
+
+
+@pytest.mark.parametrize("name", ["c1_2fsk_240k_10k_p24_limits", "c3_4fsk_240k_10k_soft"])
+def test_cuda_exact_path_against_the_glibc_build_of_the_oracle(name):
+    """The oracle and the CUDA kernels share pirip_b200/csrc/exact_math.h, so their bit-for-bit agreement says nothing about those
+    sin / cos / atan2 / exp / log bodies.  Here the CUDA path meets the oracle built with glibc's own functions
+    (liboracle_libm.so, what upstream codec2 links): hard bits, frame counts, nin and tone estimates identical, every float
+    within 1e-4 (norm_rx_timing absolute, rx_filt / LLR relative to the frame's largest value)."""
+    import pirip_b200 as pb
+    pk, gk = CONFIGS[name]
+    iq = make_batch(pk, gk, 6, 1500 if pk["M"] == 2 else 3000, [None, 9.0, 6.0], seed0=4100)
+    plan = pb.FskPlan(**pk)
+    out = plan.demod_batch(iq, want_llr=pk.get("soft", False), want_rx_filt=True, want_stats=True)
+    plan.close()
+    M = pk["M"]
+    for c in range(iq.shape[0]):
+        ref = orc.fsk_demod_stream(oracle_cfg(pk), iq[c], libm=True)
+        nf = int(out["nframes"][c])
+        assert nf == ref["nframes"]
+        nb = ref["bits"].size // nf
+        st = out["stats"][c, :nf]
+        assert np.array_equal(st["nin_next"], ref["stats"]["nin_next"])
+        assert np.array_equal(st["f_est"], ref["stats"]["f_est"])
+        differ = out["bits"][c, :nf * nb] != ref["bits"]
+        assert differ.mean() < 2e-4  # a decision can only flip where the two libms round an energy tie differently
+        d = np.abs(st["norm_rx_timing"].astype(np.float64) - ref["stats"]["norm_rx_timing"])
+        assert np.minimum(d, 1.0 - d).max() < 1e-4
+        gf = out["rx_filt"][c, :nf * M * 50].reshape(nf, -1).astype(np.float64)
+        rf = ref["rx_filt"].reshape(nf, -1).astype(np.float64)
+        assert (np.abs(gf - rf) / np.maximum(rf.max(axis=1, keepdims=True), 1e-30)).max() < 1e-4
+        if pk.get("soft"):
+            gl = out["llr"][c, :nf * nb].reshape(nf, -1).astype(np.float64)
+            rl = ref["llr"].reshape(nf, -1).astype(np.float64)
+            assert (np.abs(gl - rl) / np.maximum(np.abs(rl).max(axis=1, keepdims=True), 1e-30)).max() < 1e-3

@@ -287,3 +287,37 @@ def test_multi_device_entry_shards_and_keeps_capture_order(nplans, ncap):
         assert nf == ref["nframes"] and np.array_equal(out["bits"][c, :nf * 50], ref["bits"])
     for p in plans:
         p.close()
+
+
+@pytest.mark.parametrize("chunk", [7, 64])
+def test_many_frames_per_launch_equal_the_frame_per_call_loop(chunk):
+    """pirip_fsk_demod_frames: chunks of samples, every whole frame of a chunk in one launch, the rest carried
+    over - bits, rx_filt and every per-frame float equal the fsk_demod loop's (and so the oracle's), nin slips included."""
+    import pirip_b200 as pb
+    kw = dict(Fs=240000, Rs=10000, M=2, P=24)
+    u8, _ = synth.capture_u8(77, 9000, 2, 240000, 10000, 10000, 10000, ebno_db=9.0)
+    ref = orc.fsk_demod_stream(ocfg(C1), u8)
+    x = ((u8.astype(np.float32) - 127.0) / 128.0).view(np.complex64)
+    st = pb.FskStream(**kw, limits=(500, 25000))
+    N = st.s.N
+    buf = np.zeros(0, np.complex64)
+    pos, bits, filt, timing = 0, [], [], []
+    while True:
+        want = chunk * N + 40 - buf.size
+        if want > 0 and pos < x.size:
+            buf = np.concatenate([buf, x[pos:pos + want]])
+            pos += want
+        if buf.size < st.nin():
+            break
+        b, f, s, used = st.demod_frames(buf, chunk)
+        assert 1 <= len(b) <= chunk and used <= buf.size
+        bits.append(b.ravel())
+        filt.append(f.ravel())
+        timing.append(s["norm_rx_timing"])
+        buf = buf[used:]
+    st.close()
+    got = np.concatenate(bits)
+    assert got.size == ref["bits"].size and np.array_equal(got, ref["bits"])
+    assert np.array_equal(np.concatenate(filt).view(np.uint32), ref["rx_filt"].view(np.uint32))
+    assert np.array_equal(np.concatenate(timing).view(np.uint32), ref["stats"]["norm_rx_timing"].view(np.uint32))
+    assert len(set(ref["stats"]["nin_next"].tolist())) > 1  # the stream slips: chunks meet frames of different lengths

@@ -229,3 +229,36 @@ def test_reference_command_lines_run_verbatim(args, Fs, Rs, M, tmp_path):
         if "-n" in args.split():
             n = int(args.split()[args.split().index("-n") + 1])
             assert len(r.stdout) <= n // (Fs // Rs)
+
+
+def test_chunked_ingest_writes_the_same_stream_as_one_frame_per_call(tmp_path):
+    """rtl_fsk --chunk K (default 32: K frames per read and per kernel launch) against --chunk 1 (the fsk_demod.c loop), uncoded
+    with the decimating front end and coded with -b records."""
+    build_tools()
+    Fs_in, Fs, Rs = 2400000, 80000, 10000
+    bits = synth.test_bits(6000)
+    x = synth.fsk_mod(bits, 2, Fs_in, Rs, 10000, 10000, timing_offset=33.0, phase0=0.3, ppm=60.0)
+    iq = synth.to_u8(synth.add_awgn(x, 10.0, Fs_in // Rs, 2, synth.rng(78)), amp=70.0)
+    f = tmp_path / "iq.u8"
+    iq.tofile(f)
+    base = [os.path.join(BIN, "rtl_fsk"), "-i", str(f), "-s", str(Fs_in), "-a", str(Fs), "-r", str(Rs), "-m", "2", "-q"]
+    one = subprocess.run(base + ["--chunk", "1", "-"], capture_output=True, check=True).stdout
+    for k in ("5", "32"):
+        many = subprocess.run(base + ["--chunk", k, "-"], capture_output=True, check=True).stdout
+        assert many == one and len(one) >= 5500
+    # coded, record stream
+    import pirip_b200 as pb
+    code = "H_256_512_4"
+    m = pb.FskLdpcModem(code, M=2, Rs=10000, Fs=80000)
+    frames = [m.frame(orc.insert_crc(orc.payload_data_bits(m.data_bits))) for _ in range(4)]
+    m.close()
+    tx = np.concatenate([np.zeros(300, np.uint8), np.array([0, 1] * 25, np.uint8)] + frames + [np.zeros(400, np.uint8)])
+    y = synth.fsk_mod(tx, 2, 80000, 10000, 10000, 10000, timing_offset=2.2)
+    u8 = synth.to_u8(synth.add_awgn(y, 9.0, 8, 2, synth.rng(79)), amp=50.0)
+    g = tmp_path / "coded.u8"
+    u8.tofile(g)
+    cbase = [os.path.join(BIN, "rtl_fsk"), "-i", str(g), "-a", "80000", "-r", "10000", "-m", "2", "--code", code, "-q", "-b"]
+    rec1 = subprocess.run(cbase + ["--chunk", "1", "-"], capture_output=True, check=True).stdout
+    rec32 = subprocess.run(cbase + ["-"], capture_output=True, check=True).stdout
+    assert rec1 == rec32 and len(rec1) % 33 == 0
+    assert sum(1 for i in range(0, len(rec1), 33) if rec1[i] & 4) == 4

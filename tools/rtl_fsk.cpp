@@ -17,6 +17,7 @@
  *                    frame — the clock of tx/frame_repeater.c                            [R tx/frame_repeater.c:55-62]
  *   --filter addr    drop frames whose first payload byte (source address) equals addr   [R README.md:303-304]
  *   -v               per-frame log line with the fields of                               [R README.md:200-208]
+ *   --chunk K        modem frames per ingest chunk and kernel launch (default 32; 1 = one frame per call as fsk_demod.c)
  *   -u host          once per second of signal one JSON line over UDP to host:8001 with the keys script/dash.py reads
  *                    (SfdB, f_est_Hz, fsk_lower_Hz, fsk_upper_Hz, SNRest_lin, norm_rx_timing, Fs_Hz) [R script/dash.py:26-46]
  *
@@ -52,12 +53,14 @@ static void usage(const char *p) {
 int main(int argc, char *argv[]) {
     int Fs_rtl = 0, Fs = 0, Rs = 10000, M = 2, P = 0, lower = -1, upper = -1, mask = 0, filter_addr = -1;
     int burst_records = 0, quiet = 0, verbose = 0, testframes = 0;
+    int chunk_frames = 32; /* --chunk: modem frames per ingest chunk = per launch */
     long long max_samples = -1; /* -n: stop after this many input samples (at the tuner rate) [R README.md:114] */
     const char *code = nullptr, *inname = "-", *dash_host = nullptr;
     static struct option lo[] = { { "code", required_argument, 0, 'c' },      { "mask", required_argument, 0, 'k' },
                                   { "fsk_lower", required_argument, 0, 'l' }, { "fsk_upper", required_argument, 0, 'U' },
                                   { "filter", required_argument, 0, 'F' },    { "testframes", no_argument, 0, 't' },
-                                  { "help", no_argument, 0, 'h' },            { 0, 0, 0, 0 } };
+                                  { "chunk", required_argument, 0, 'C' },     { "help", no_argument, 0, 'h' },
+                                  { 0, 0, 0, 0 } };
     int o;
     while ((o = getopt_long(argc, argv, "i:s:a:r:m:p:f:g:u:n:e:w:L:d:bqvh", lo, NULL)) != -1) {
         switch (o) {
@@ -73,6 +76,7 @@ int main(int argc, char *argv[]) {
             case 'U': upper = atoi(optarg); break;
             case 'F': filter_addr = (int)strtol(optarg, NULL, 0); break;
             case 't': testframes = 1; break;
+            case 'C': chunk_frames = atoi(optarg); break;
             case 'b': burst_records = 1; break;
             case 'q': quiet = 1; break;
             case 'v': verbose = 1; break;
@@ -132,7 +136,7 @@ int main(int argc, char *argv[]) {
     if (mask) fsk_set_freq_est_alg(fsk, 1);
 
     struct freedv *fdv = nullptr;
-    int K = 0;
+    int K_bits = 0;
     if (code) {
         struct freedv_advanced adv;
         memset(&adv, 0, sizeof adv);
@@ -145,10 +149,10 @@ int main(int argc, char *argv[]) {
             fprintf(stderr, "rtl_fsk: unknown LDPC code %s\n", code);
             return 1;
         }
-        K = freedv_get_bits_per_modem_frame(fdv);
+        K_bits = freedv_get_bits_per_modem_frame(fdv);
     }
-    std::vector<uint8_t> test_payload((size_t)(K > 0 ? K : 1));
-    if (testframes && K) ofdm_generate_payload_data_bits(test_payload.data(), K);
+    std::vector<uint8_t> test_payload((size_t)(K_bits > 0 ? K_bits : 1));
+    if (testframes && K_bits) ofdm_generate_payload_data_bits(test_payload.data(), K_bits);
 
     /* csdr front end: convert_u8_f + fir_decimate_cc D with the CLI's default taps (transition 0.05, Hamming) */
     std::vector<float> taps;
@@ -174,117 +178,152 @@ int main(int argc, char *argv[]) {
         }
     }
 
+    /* The sample source delivers CHUNKS (upstream: the USB callback's buffers; here: reads of K frames' worth of the file or
+       pipe).  A chunk goes to the device once and pirip_fsk_demod_frames() demodulates every whole frame in it in ONE launch
+       (SURVEY.md 8f N2); what is left over waits for the next chunk.  --chunk 1 is the frame-per-call loop of fsk_demod.c. */
     const int nmax = fsk->N + fsk->Ts * 2;
-    std::vector<COMP> mod((size_t)nmax);
-    std::vector<uint8_t> bits((size_t)fsk->Nbits), payload((size_t)(K > 0 ? K : 1)), packed((size_t)(K > 0 ? K / 8 : 1));
-    std::vector<float> filt((size_t)(fsk->mode * fsk->Nsym)), llrs((size_t)fsk->Nbits);
+    const size_t K = (size_t)(chunk_frames < 1 ? 1 : chunk_frames);
+    const size_t target = K * (size_t)fsk->N + (size_t)fsk->Ts;
+    std::vector<COMP> cbuf;                 /* modem-rate samples not yet demodulated */
+    cbuf.reserve(target + (size_t)nmax);
+    std::vector<uint8_t> bits_all(K * (size_t)fsk->Nbits), payload((size_t)(K > 0 && code ? freedv_get_bits_per_modem_frame(fdv) : 1)),
+        packed((size_t)(code ? freedv_get_bits_per_modem_frame(fdv) / 8 : 1));
+    std::vector<float> filt_all(K * (size_t)(fsk->mode * fsk->Nsym)), llrs((size_t)fsk->Nbits);
+    std::vector<pirip_frame_stats> st_all(K);
     std::vector<unsigned char> raw;       /* undecimated u8 samples not yet consumed */
     std::vector<float> fbuf;              /* their float form (csdr convention) */
-    std::vector<complexf> dec((size_t)nmax);
+    std::vector<complexf> dec;
     std::vector<float> timing_1s;
     long frames = 0, packets = 0, test_errs = 0, test_bits_n = 0;
     double since_dash = 0.0;
+    long long consumed_in = 0; /* input samples (tuner rate) taken from the source so far */
+    bool eof = false;
 
-    long long consumed = 0; /* input samples handed to the modem chain so far */
-    for (;;) {
-        const int nin = (int)fsk_nin(fsk);
-        if (max_samples >= 0 && consumed + (long long)D * nin > max_samples) break;
-        consumed += (long long)D * nin;
+    /* append up to `want` modem-rate samples to cbuf; fewer at the end of the input */
+    auto pull = [&](size_t want) {
+        if (eof || want == 0) return;
         if (D == 1) {
-            raw.resize((size_t)nin * 2);
-            if (fread(raw.data(), 2, (size_t)nin, fin) != (size_t)nin) break; /* short read ends the loop */
-            for (int i = 0; i < nin; ++i) { /* the fsk_demod -d convention [U fsk_demod.c] */
-                mod[(size_t)i].real = ((float)raw[2 * (size_t)i] - 127.0) / 128.0;
-                mod[(size_t)i].imag = ((float)raw[2 * (size_t)i + 1] - 127.0) / 128.0;
+            if (max_samples >= 0 && consumed_in + (long long)want > max_samples) want = (size_t)(max_samples - consumed_in), eof = true;
+            raw.resize(want * 2);
+            const size_t got = fread(raw.data(), 2, want, fin);
+            if (got < want) eof = true;
+            consumed_in += (long long)got;
+            const size_t o = cbuf.size();
+            cbuf.resize(o + got);
+            for (size_t i = 0; i < got; ++i) { /* the fsk_demod -d convention [U fsk_demod.c] */
+                cbuf[o + i].real = ((float)raw[2 * i] - 127.0) / 128.0;
+                cbuf[o + i].imag = ((float)raw[2 * i + 1] - 127.0) / 128.0;
             }
         } else {
             /* one causal FIR over the continuous stream, phase anchored at stream sample 0 (csdr main loop):
-               nin outputs need D*(nin-1)+L inputs; D*nin of them are consumed */
-            const size_t need = (size_t)D * (size_t)(nin - 1) + (size_t)L;
+               n outputs need D*(n-1)+L inputs; D*n of them are consumed */
+            if (max_samples >= 0 && consumed_in + (long long)(D * want) > max_samples) want = (size_t)((max_samples - consumed_in) / D), eof = true;
+            if (want == 0) return;
+            const size_t need = (size_t)D * (want - 1) + (size_t)L;
             const size_t have = raw.size() / 2;
             if (have < need) {
-                const size_t want = need - have;
-                raw.resize((have + want) * 2);
-                if (fread(raw.data() + have * 2, 2, want, fin) != want) break;
-            }
-            fbuf.resize(need * 2);
-            convert_u8_f(raw.data(), fbuf.data(), (int)(need * 2));
-            const int got = fir_decimate_cc((complexf *)fbuf.data(), dec.data(), (int)need, D, taps.data(), L);
-            if (got < nin) break;
-            for (int i = 0; i < nin; ++i) {
-                mod[(size_t)i].real = dec[(size_t)i].i;
-                mod[(size_t)i].imag = dec[(size_t)i].q;
-            }
-            raw.erase(raw.begin(), raw.begin() + (std::ptrdiff_t)((size_t)D * (size_t)nin * 2));
-        }
-
-        if (!code) {
-            fsk_demod(fsk, bits.data(), mod.data());
-            fwrite(bits.data(), 1, (size_t)fsk->Nbits, fout);
-        } else {
-            fsk_demod_sd(fsk, filt.data(), mod.data());
-            fsk_rx_filt_to_llrs(llrs.data(), filt.data(), fsk->v_est, fsk->SNRest, fsk->mode, fsk->Nsym);
-            int st = freedv_fsk_ldpc_rx_llrs(fdv, llrs.data(), fsk->Nbits, payload.data());
-            bool deliver = (st & FREEDV_RX_BITS) != 0;
-            if (deliver) freedv_pack(packed.data(), payload.data(), K);
-            if (deliver && filter_addr >= 0 && packed[0] == (uint8_t)filter_addr) { /* our own repeater talking */
-                deliver = false;
-                st &= ~FREEDV_RX_BITS;
-            }
-            if (deliver) {
-                packets++;
-                if (testframes) {
-                    for (int i = 0; i < K - 16; ++i) test_errs += payload[(size_t)i] != test_payload[(size_t)i];
-                    test_bits_n += K - 16;
+                raw.resize(need * 2);
+                const size_t got = fread(raw.data() + have * 2, 2, need - have, fin);
+                if (got < need - have) {
+                    eof = true;
+                    raw.resize((have + got) * 2);
                 }
             }
-            if (verbose && (st & (FREEDV_RX_BITS | FREEDV_RX_BIT_ERRORS))) {
-                int info[6];
-                freedv_fsk_ldpc_rx_info(fdv, info);
-                fprintf(stderr, "%3d nbits: %3d state: %d uw_loc: %3d uw_err: %2d snrdB: %4.1f iter: %2d pcc: %3d rxst: %c%c%c%c\n",
-                        (int)packets, info[5], info[0], info[1], info[2], 10.0 * log10((double)fsk->SNRest + 1.0), info[3], info[4],
-                        st & FREEDV_RX_BIT_ERRORS ? 'E' : '-', st & FREEDV_RX_BITS ? 'B' : '-', st & FREEDV_RX_SYNC ? 'S' : '-',
-                        st & FREEDV_RX_TRIAL_SYNC ? 'T' : '-');
+            const size_t avail = raw.size() / 2;
+            if (avail < (size_t)L) return;
+            const size_t nout = (avail - (size_t)L) / (size_t)D + 1 < want ? (avail - (size_t)L) / (size_t)D + 1 : want;
+            const size_t nin_f = (size_t)D * (nout - 1) + (size_t)L;
+            fbuf.resize(nin_f * 2);
+            dec.resize(nout + 1);
+            convert_u8_f(raw.data(), fbuf.data(), (int)(nin_f * 2));
+            const int got = fir_decimate_cc((complexf *)fbuf.data(), dec.data(), (int)nin_f, D, taps.data(), L);
+            const size_t o = cbuf.size();
+            cbuf.resize(o + (size_t)got);
+            for (int i = 0; i < got; ++i) {
+                cbuf[o + (size_t)i].real = dec[(size_t)i].i;
+                cbuf[o + (size_t)i].imag = dec[(size_t)i].q;
             }
-            if (burst_records) {
-                const uint8_t sb = (uint8_t)st;
-                if (!deliver) memset(packed.data(), 0, packed.size());
-                fwrite(&sb, 1, 1, fout);
-                fwrite(packed.data(), 1, (size_t)K / 8, fout);
-            } else if (deliver) {
-                fwrite(packed.data(), 1, (size_t)K / 8, fout);
+            consumed_in += (long long)D * got;
+            raw.erase(raw.begin(), raw.begin() + (std::ptrdiff_t)((size_t)D * (size_t)got * 2));
+        }
+    };
+
+    for (;;) {
+        if (cbuf.size() < target) pull(target - cbuf.size());
+        if (cbuf.size() < (size_t)fsk_nin(fsk)) break; /* a short read ends the loop, as upstream */
+        size_t used = 0;
+        const int nf = pirip_fsk_demod_frames(fsk, cbuf.data(), cbuf.size(), (int)K, bits_all.data(), filt_all.data(), st_all.data(), &used);
+        if (nf <= 0) break;
+        for (int f = 0; f < nf; ++f) {
+            const pirip_frame_stats &fs = st_all[(size_t)f];
+            const uint8_t *bits = bits_all.data() + (size_t)f * (size_t)fsk->Nbits;
+            const float *filt = filt_all.data() + (size_t)f * (size_t)(fsk->mode * fsk->Nsym);
+            if (!code) {
+                fwrite(bits, 1, (size_t)fsk->Nbits, fout);
+            } else {
+                fsk_rx_filt_to_llrs(llrs.data(), (float *)filt, fs.v_est, fs.SNRest, fsk->mode, fsk->Nsym);
+                int st = freedv_fsk_ldpc_rx_llrs(fdv, llrs.data(), fsk->Nbits, payload.data());
+                bool deliver = (st & FREEDV_RX_BITS) != 0;
+                if (deliver) freedv_pack(packed.data(), payload.data(), K_bits);
+                if (deliver && filter_addr >= 0 && packed[0] == (uint8_t)filter_addr) { /* our own repeater talking */
+                    deliver = false;
+                    st &= ~FREEDV_RX_BITS;
+                }
+                if (deliver) {
+                    packets++;
+                    if (testframes) {
+                        for (int i = 0; i < K_bits - 16; ++i) test_errs += payload[(size_t)i] != test_payload[(size_t)i];
+                        test_bits_n += K_bits - 16;
+                    }
+                }
+                if (verbose && (st & (FREEDV_RX_BITS | FREEDV_RX_BIT_ERRORS))) {
+                    int info[6];
+                    freedv_fsk_ldpc_rx_info(fdv, info);
+                    fprintf(stderr, "%3d nbits: %3d state: %d uw_loc: %3d uw_err: %2d snrdB: %4.1f iter: %2d pcc: %3d rxst: %c%c%c%c\n",
+                            (int)packets, info[5], info[0], info[1], info[2], 10.0 * log10((double)fs.SNRest + 1.0), info[3], info[4],
+                            st & FREEDV_RX_BIT_ERRORS ? 'E' : '-', st & FREEDV_RX_BITS ? 'B' : '-', st & FREEDV_RX_SYNC ? 'S' : '-',
+                            st & FREEDV_RX_TRIAL_SYNC ? 'T' : '-');
+                }
+                if (burst_records) {
+                    const uint8_t sb = (uint8_t)st;
+                    if (!deliver) memset(packed.data(), 0, packed.size());
+                    fwrite(&sb, 1, 1, fout);
+                    fwrite(packed.data(), 1, (size_t)K_bits / 8, fout);
+                } else if (deliver) {
+                    fwrite(packed.data(), 1, (size_t)K_bits / 8, fout);
+                }
+            }
+            frames++;
+            /* dashboard telemetry, once per second of signal */
+            timing_1s.push_back(fs.norm_rx_timing);
+            since_dash += (double)(f + 1 < nf ? st_all[(size_t)f + 1].sample_offset - fs.sample_offset : fs.nin_next) / (double)Fs;
+            if (sock >= 0 && since_dash >= 1.0) {
+                std::string js = "{\"SfdB\":[";
+                char num[256];
+                for (int i = 0; i < fsk->Ndft; ++i) {
+                    snprintf(num, sizeof num, "%s%.1f", i ? "," : "", 20.0 * log10((double)fsk->Sf[i] + 1e-9));
+                    js += num;
+                }
+                js += "],\"f_est_Hz\":[";
+                for (int m = 0; m < M; ++m) {
+                    snprintf(num, sizeof num, "%s%.0f", m ? "," : "", (double)(fsk->freq_est_type ? fs.f2_est[m] : fs.f_est[m]));
+                    js += num;
+                }
+                snprintf(num, sizeof num, "],\"fsk_lower_Hz\":%d,\"fsk_upper_Hz\":%d,\"Fs_Hz\":%d,\"SNRest_lin\":%.3f,\"norm_rx_timing\":[",
+                         fsk->est_min, fsk->est_max, Fs, (double)fs.SNRest);
+                js += num;
+                for (size_t i = 0; i < timing_1s.size(); ++i) {
+                    snprintf(num, sizeof num, "%s%.3f", i ? "," : "", (double)timing_1s[i]);
+                    js += num;
+                }
+                js += "]}\n";
+                sendto(sock, js.data(), js.size(), 0, (struct sockaddr *)&dash, sizeof dash);
+                timing_1s.clear();
+                since_dash = 0.0;
             }
         }
         if (fin == stdin || fout == stdout) fflush(fout);
-        frames++;
-
-        /* dashboard telemetry, once per second of signal */
-        timing_1s.push_back(fsk->norm_rx_timing);
-        since_dash += (double)nin / (double)Fs;
-        if (sock >= 0 && since_dash >= 1.0) {
-            std::string js = "{\"SfdB\":[";
-            char num[256];
-            for (int i = 0; i < fsk->Ndft; ++i) {
-                snprintf(num, sizeof num, "%s%.1f", i ? "," : "", 20.0 * log10((double)fsk->Sf[i] + 1e-9));
-                js += num;
-            }
-            js += "],\"f_est_Hz\":[";
-            for (int m = 0; m < M; ++m) {
-                snprintf(num, sizeof num, "%s%.0f", m ? "," : "", (double)(fsk->freq_est_type ? fsk->f2_est[m] : fsk->f_est[m]));
-                js += num;
-            }
-            snprintf(num, sizeof num, "],\"fsk_lower_Hz\":%d,\"fsk_upper_Hz\":%d,\"Fs_Hz\":%d,\"SNRest_lin\":%.3f,\"norm_rx_timing\":[",
-                     fsk->est_min, fsk->est_max, Fs, (double)fsk->SNRest);
-            js += num;
-            for (size_t i = 0; i < timing_1s.size(); ++i) {
-                snprintf(num, sizeof num, "%s%.3f", i ? "," : "", (double)timing_1s[i]);
-                js += num;
-            }
-            js += "]}\n";
-            sendto(sock, js.data(), js.size(), 0, (struct sockaddr *)&dash, sizeof dash);
-            timing_1s.clear();
-            since_dash = 0.0;
-        }
+        cbuf.erase(cbuf.begin(), cbuf.begin() + (std::ptrdiff_t)used);
     }
     if (!quiet) {
         fprintf(stderr, "rtl_fsk: %ld modem frames", frames);
