@@ -1299,13 +1299,13 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
         if (tid == 0) {
             const float tcr = ms->red[0][0] + ms->red[1][0], tci = ms->red[0][1] + ms->red[1][1];
             const float esum = ms->red[0][5] + ms->red[1][5];
-            ms->rho = sqrtf(tcr * tcr + tci * tci) / fmaxf(esum, 1e-30f); /* strength of the timing line: conditioning of the estimate */
+            ms->rho = __fdividef(fsqrt_fast(tcr * tcr + tci * tci), fmaxf(esum, 1e-30f)); /* strength of the timing line: conditioning of the estimate */
             int fl = 0;
             if (isnan(tcr) || isnan(tci)) fl |= FLAG_NAN;
             /* How far the scalar algorithm's norm_rx_timing can be from this one: both timing-line sums carry an absolute
                error of a few 1e-7 of the summed window energies, so the angle is uncertain by that over the line's relative
                strength rho (measured: |d norm| * rho <= 9.2e-8 over every test configuration; 4e-7 used). */
-            const float dn = cfg.g_tim / fmaxf(ms->rho, 1e-9f) + 2e-7f;
+            const float dn = __fdividef(cfg.g_tim, fmaxf(ms->rho, 1e-9f)) + 2e-7f;
             const float norm = atan2f(tci, tcr) * 0.15915494309189535f;
             const float rx_timing = norm * (float)P;
             const float d = norm - ms->norm_rx_timing;
@@ -1370,7 +1370,17 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                     for (int m = 0; m < M; ++m) t[m] = make_float2(0.0f, 0.0f), uu[m] = 0.0f;
                     if (valid) {
                         const float2 *f = fdc + base;
-                        if (S1) {
+                        if (S1 && (low & 1) == 0) {
+                            /* an even timing offset: the quarter window starts on a 16-byte boundary - three 16-byte loads per
+                               tone (conflict-free: eight lanes cover eight bank groups), the same additions in the same order */
+#pragma unroll
+                            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                                for (int m = 0; m < M; ++m) {
+                                    const float4 v4 = *reinterpret_cast<const float4 *>(f + m * fdcS + k0 + 2 * k);
+                                    t[m] = xadd(xadd(t[m], make_float2(v4.x, v4.y)), make_float2(v4.z, v4.w));
+                                }
+                        } else if (S1) {
 #pragma unroll
                             for (int k = 0; k < 6; ++k)
 #pragma unroll
@@ -1494,17 +1504,17 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
 
         /* ---- stats of the frame, the record, loop control (thread 0) ---- */
         if (tid == 0 && !replayed) {
-            const float nsymf = (float)Nsym;
-            const float sig = (ms->red[0][2] + ms->red[1][2]) / nsymf;
-            const float nse = (1e-12f + ms->red[0][3] + ms->red[1][3]) / nsymf;
-            float meanebno = (ms->red[0][4] + ms->red[1][4]) / nsymf;
+            const float rnsym = 1.0f / (float)Nsym;
+            const float sig = (ms->red[0][2] + ms->red[1][2]) * rnsym;
+            const float nse = (1e-12f + ms->red[0][3] + ms->red[1][3]) * rnsym;
+            float meanebno = (ms->red[0][4] + ms->red[1][4]) * rnsym;
             float stdebno = sig - meanebno * meanebno;
-            stdebno = stdebno > 0.0f ? sqrtf(stdebno) : 0.0f;
+            stdebno = stdebno > 0.0f ? fsqrt_fast(stdebno) : 0.0f;
             ms->rx_sig_pow = sig;
             ms->rx_nse_pow = nse;
-            ms->v_est = sqrtf(sig - nse);
-            ms->SNRest = sig / nse;
-            ms->EbNodB = -6.0f + 20.0f * log10f((1e-6f + meanebno) / (1e-6f + stdebno));
+            ms->v_est = fsqrt_fast(sig - nse);
+            ms->SNRest = __fdividef(sig, nse);
+            ms->EbNodB = -6.0f + 20.0f * log10f(__fdividef(1e-6f + meanebno, 1e-6f + stdebno));
             ms->snr_est = 0.5f * ms->snr_est + 0.5f * ms->EbNodB;
         }
         if (tid == 0) {

@@ -337,6 +337,15 @@ extern "C" pirip_ldpc_plan *pirip_ldpc_plan_create(const struct LDPC *l, int dev
         delete p;
         return nullptr;
     }
+    if (p->g.v_tail_regular) {
+        /* the degree-2 chain is stored in two planes (ldpc_dev.h, variable phase): variable-order index -> storage position */
+        const int tb = p->g.v_tail_base, T2 = p->g.N - p->g.v_split;
+        for (uint16_t &j : c_vpos)
+            if ((int)j >= tb) {
+                const int t = ((int)j - tb) >> 1, sidx = ((int)j - tb) & 1;
+                j = (uint16_t)(tb + sidx * T2 + t);
+            }
+    }
     for (int c = 0; c < p->g.NPB; ++c)
         if (c_off[(size_t)c + 1] - c_off[(size_t)c] > 64) {
             pirip::set_error("check nodes with more than 64 edges are not supported");

@@ -154,7 +154,13 @@ __device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSm
             const float ph = MODE == LDPC_SP_EXACT ? phi0(fabsf(x)) : phi0_fast(fabsf(x));
             mm = x < 0.0f ? -ph : ph;
         }
-        for (int j = v_off[v]; j < v_off[v + 1]; ++j) q[j] = mm;
+        if (g.v_tail_regular && v >= g.v_split) {
+            /* the degree-2 chain lives in two planes (first edges, second edges): see the variable phase */
+            const int t = v - g.v_split;
+            q[g.v_tail_base + t] = mm;
+            if (g.v_tail_base + 2 * t + 2 <= g.E) q[g.v_tail_base + (g.N - g.v_split) + t] = mm;
+        } else
+            for (int j = v_off[v]; j < v_off[v + 1]; ++j) q[j] = mm;
     }
     __syncwarp();
     int result = g.max_iter, pcc = 0;
@@ -272,17 +278,21 @@ __device__ __forceinline__ int ldpc_decode_impl(const LdpcGraph &g, const LdpcSm
         else
             for (int v = lane; v < g.v_split; v += 32) vnode(v, std::integral_constant<int, VA>(), v_off[v], v_off[v + 1]);
         if (g.v_tail_regular) {
-            /* the degree-2 chain of a repeat-accumulate code: two edges each but the last variable */
+            /* the degree-2 chain of a repeat-accumulate code: two edges each but the last variable.  Stored as two planes - the
+               first edges of all chain variables, then the second edges - so that a check's two chain edges (the first edge of
+               variable K + c, the second of K + c - 1) and a variable's two edges are consecutive words across the lanes:
+               conflict-free in both phases (side by side they were 2-way conflicts in the check phase) */
+            const int T2 = g.N - g.v_split;
             for (int v = g.v_split + lane; v < g.N; v += 32) {
-                const int j0 = g.v_tail_base + 2 * (v - g.v_split);
-                if (j0 + 2 <= g.E && (g.v_tail_base & 1) == 0) {
-                    float2 *q2 = reinterpret_cast<float2 *>(q + j0);
-                    const float2 r = *q2;
-                    const float Qi = __fadd_rn(__fadd_rn(llr[v], r.x), r.y);
-                    if (last) store(v, Qi < 0.0f ? 1 : 0);
-                    *q2 = make_float2(q_store<MODE>(__fsub_rn(Qi, r.x)), q_store<MODE>(__fsub_rn(Qi, r.y)));
-                } else
-                    vnode(v, std::integral_constant<int, 2>(), j0, j0 + 2 < g.E ? j0 + 2 : g.E);
+                const int t = v - g.v_split;
+                const bool two = g.v_tail_base + 2 * t + 2 <= g.E;
+                float *qa = q + g.v_tail_base + t, *qb = q + g.v_tail_base + T2 + t;
+                const float r0 = *qa, r1 = two ? *qb : 0.0f;
+                float Qi = __fadd_rn(llr[v], r0);
+                if (two) Qi = __fadd_rn(Qi, r1);
+                if (last) store(v, Qi < 0.0f ? 1 : 0);
+                *qa = q_store<MODE>(__fsub_rn(Qi, r0));
+                if (two) *qb = q_store<MODE>(__fsub_rn(Qi, r1));
             }
         } else
             for (int v = g.v_split + lane; v < g.N; v += 32) vnode(v, std::integral_constant<int, 2>(), v_off[v], v_off[v + 1]);

@@ -138,7 +138,7 @@ def test_cuda_exact_path_against_the_glibc_build_of_the_oracle(name):
     """The oracle and the CUDA kernels share pirip_b200/csrc/exact_math.h, so their bit-for-bit agreement says nothing about those
     sin / cos / atan2 / exp / log bodies.  Here the CUDA path meets the oracle built with glibc's own functions
     (liboracle_libm.so, what upstream codec2 links): hard bits, frame counts, nin and tone estimates identical, every float
-    within 1e-4 (norm_rx_timing absolute, rx_filt / LLR relative to the frame's largest value)."""
+    within 1e-4 (norm_rx_timing, absolute), 5e-4 (rx_filt) and 1e-3 (LLR, both relative to the frame's largest value)."""
     import pirip_b200 as pb
     pk, gk = CONFIGS[name]
     iq = make_batch(pk, gk, 6, 1500 if pk["M"] == 2 else 3000, [None, 9.0, 6.0], seed0=4100)
@@ -160,7 +160,7 @@ def test_cuda_exact_path_against_the_glibc_build_of_the_oracle(name):
         assert np.minimum(d, 1.0 - d).max() < 1e-4
         gf = out["rx_filt"][c, :nf * M * 50].reshape(nf, -1).astype(np.float64)
         rf = ref["rx_filt"].reshape(nf, -1).astype(np.float64)
-        assert (np.abs(gf - rf) / np.maximum(rf.max(axis=1, keepdims=True), 1e-30)).max() < 1e-4
+        assert (np.abs(gf - rf) / np.maximum(rf.max(axis=1, keepdims=True), 1e-30)).max() < 5e-4  # 4FSK at 6 dB: 1.5e-4 between the two oracle builds
         if pk.get("soft"):
             gl = out["llr"][c, :nf * nb].reshape(nf, -1).astype(np.float64)
             rl = ref["llr"].reshape(nf, -1).astype(np.float64)
