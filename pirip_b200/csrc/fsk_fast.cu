@@ -98,6 +98,7 @@ struct FastArgs {
     /* launch geometry: the first chain_ctas CTAs run the exact-oscillator chains (chain_wpc warps each), every other CTA
        holds G capture groups */
     int G, chain_ctas, chain_wpc;
+    int cap_index_base; /* added to a capture's index in flag_list: rounds of one call share one list of batch-wide indices */
 };
 
 enum { FLAG_SYM = 1, FLAG_TIM = 2, FLAG_PPM = 4, FLAG_NAN = 8, FLAG_INGEST = 16 };
@@ -815,7 +816,8 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
 
 /* ------------------------------------------------------------------ the kernel */
 /* SPEC = 1: the benchmark shape (config 1 / 5: Ts = P = 24, Nsym = 50, Ndft = 256) with its sizes as compile-time constants, so
-   that the integrator, decision and mixing loops unroll; SPEC = 0: every size from cfg. */
+   that the integrator, decision and mixing loops unroll; SPEC = 2: the same with P = 8 (configs 3 / 4 at Fs = 240 k, Rs = 10 k);
+   SPEC = 0: every size from cfg. */
 template <int M, int FMT, bool STEP1, int SPEC>
 __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const __grid_constant__ FastCfg cfg, const __grid_constant__ FastArgs args) {
     extern __shared__ __align__(128) unsigned char smem_all[];
@@ -838,10 +840,11 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
     float2 *ideal = reinterpret_cast<float2 *>(smem + cfg.off_ideal);
     Misc *ms = reinterpret_cast<Misc *>(smem + cfg.off_misc);
 
-    constexpr bool S1 = SPEC == 1;
-    const int Ndft = S1 ? 256 : cfg.Ndft, half = Ndft >> 1, nb = cfg.nb, Ts = S1 ? 24 : cfg.Ts, P = S1 ? 24 : cfg.P, Nsym = S1 ? 50 : cfg.Nsym;
+    constexpr bool S1 = SPEC != 0;                                   /* Ts = 24, Nsym = 50, Ndft = 256, u8 input compiled in */
+    constexpr int SP = SPEC == 1 ? 24 : (SPEC == 2 ? 8 : 1);         /* ... with P = 24 (config 1 / 5) or P = 8 (configs 3 / 4) */
+    const int Ndft = S1 ? 256 : cfg.Ndft, half = Ndft >> 1, nb = cfg.nb, Ts = S1 ? 24 : cfg.Ts, P = S1 ? SP : cfg.P, Nsym = S1 ? 50 : cfg.Nsym;
     const int Nmem = S1 ? 1248 : cfg.Nmem, fdcS = cfg.fdcS;
-    const int step = S1 ? 1 : cfg.step, nint = S1 ? 1224 : cfg.nint, bps = S1 ? 2 : cfg.bps;
+    const int step = S1 ? 24 / SP : cfg.step, nint = S1 ? 51 * SP : cfg.nint, bps = S1 ? 2 : cfg.bps;
 
     /* per-thread constants: FFT twiddles of the last two levels (256-point path), timing-line correction */
     float2 t3[3], t4[4][3];
@@ -1605,7 +1608,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
         if (args.flags) args.flags[cap] = fl;
         if (fl && args.flag_list && args.flag_count) {
             const int slot = atomicAdd(args.flag_count, 1);
-            args.flag_list[slot] = (int)cap;
+            args.flag_list[slot] = (int)cap + args.cap_index_base;
         }
     }
     } /* captures of this group */
@@ -1666,6 +1669,11 @@ static cudaError_t fast_dispatch(const FskFastPlan *p, const FastArgs &a, cudaSt
     if (s1 && p->M == 2 && p->fmt == PIRIP_FMT_U8 && c.Ts == 24 && c.P == 24 && c.Nsym == 50 && c.Ndft == 256 && c.Nmem == 1248 && c.nint == 1224 &&
         c.bps == 2 && !getenv("PIRIP_FSK_FAST_NO_SPEC"))
         return fast_launch_t<2, PIRIP_FMT_U8, true, 1>(p, a, stream, mode, grid, block, smem, regs);
+    if (!s1 && p->fmt == PIRIP_FMT_U8 && c.Ts == 24 && c.P == 8 && c.Nsym == 50 && c.Ndft == 256 && c.Nmem == 1248 && c.nint == 408 && c.bps == 2 &&
+        !getenv("PIRIP_FSK_FAST_NO_SPEC")) {
+        if (p->M == 2) return fast_launch_t<2, PIRIP_FMT_U8, false, 2>(p, a, stream, mode, grid, block, smem, regs);
+        if (p->M == 4) return fast_launch_t<4, PIRIP_FMT_U8, false, 2>(p, a, stream, mode, grid, block, smem, regs);
+    }
 #define D(MM, FF)                                                                                                   \
     if (p->M == MM && p->fmt == FF)                                                                                 \
         return s1 ? fast_launch_t<MM, FF, true, 0>(p, a, stream, mode, grid, block, smem, regs)                    \
@@ -1952,7 +1960,7 @@ static cudaError_t chain_buffers(FskFastPlan *p, size_t n, size_t max_frames) {
 /* `off` / `total`: position of this launch's captures inside the buffers of a chunked host-buffer call */
 cudaError_t fsk_fast_launch(FskFastPlan *p, const FskBatchArgs &b, int *d_flags, int *d_list, int *d_count, cudaStream_t stream,
                             size_t off, size_t total, size_t slot) {
-    (void)slot;
+    /* slot = index base of this launch's captures in a flag list shared by the rounds of one call (0: the list is the launch's own) */
     FastArgs a;
     memset(&a, 0, sizeof a);
     a.iq = b.iq;
@@ -1972,6 +1980,7 @@ cudaError_t fsk_fast_launch(FskFastPlan *p, const FskBatchArgs &b, int *d_flags,
     a.tma_ok = b.tma_ok;
     a.landed = b.landed;
     a.ckpt_per_frame = p->ckpt_per_frame;
+    a.cap_index_base = (int)slot;
     if (total < off + b.n_captures) total = off + b.n_captures;
     const size_t n = b.n_captures;
     /* geometry: one CTA per SM.  Demodulating CTAs hold up to gmax capture groups; with fewer captures than groups the

@@ -656,20 +656,40 @@ static int batch_dev(pirip_fsk_plan *plan, const void *d_iq, size_t n_captures, 
     a.tma_ok = (reinterpret_cast<size_t>(d_iq) & 15) == 0 && getenv("PIRIP_FSK_NO_TMA") == nullptr;
     a.landed = plan->dev.k2.ok ? d_landed : nullptr;
     if (plan->fast && plan->mode && flag_total == 0 && n_captures > fsk_fast_round_captures(plan->fast)) {
-        /* more captures than one launch keeps resident: rounds of launches, each with its own flag list and counter */
+        /* more captures than one launch keeps resident: rounds of launches that share ONE list of flagged captures (batch-wide
+           indices), then ONE re-run of that list by the exact kernel - a re-run per round cost ~1.4 ms of per-frame latency
+           for every round that had a single flagged capture */
         const size_t R = fsk_fast_round_captures(plan->fast);
-        const size_t rounds = (n_captures + R - 1) / R;
-        if (rounds > 64) return pirip::fail(-6, "too many captures for one call of the fast kernel (64 rounds)");
         const size_t nb = (size_t)plan->dev.Nbits, nfl = (size_t)plan->dev.M * plan->dev.Nsym;
-        plan->last_chunks = rounds;
-        for (size_t r = 0, c0 = 0; c0 < n_captures; ++r, c0 += R) {
-            const size_t nc = c0 + R <= n_captures ? R : n_captures - c0;
-            const int rc = batch_dev(plan, (const unsigned char *)d_iq + c0 * capture_stride_bytes, nc, samples_per_capture, capture_stride_bytes,
-                                     d_bits ? d_bits + c0 * max_frames * nb : nullptr, d_llr ? d_llr + c0 * max_frames * nb : nullptr,
-                                     d_rx_filt ? d_rx_filt + c0 * max_frames * nfl : nullptr, d_stats ? d_stats + c0 * max_frames : nullptr,
-                                     d_nframes + c0, max_frames, stream, d_landed, c0, n_captures, r, phases);
-            if (rc) return rc;
+        int *d_flags = nullptr, *d_list = nullptr, *d_count = nullptr;
+        if (!pirip::cuda_ok(fsk_fast_flag_buffers(plan->fast, n_captures, &d_flags, &d_list, &d_count), "cudaMalloc flags")) return -12;
+        plan->last_chunks = 1;
+        if (phases & 1) {
+            if (!pirip::cuda_ok(cudaMemsetAsync(d_count, 0, sizeof(int), (cudaStream_t)stream), "reset flag count")) return -11;
+            for (size_t c0 = 0; c0 < n_captures; c0 += R) {
+                FskBatchArgs r = a;
+                r.n_captures = c0 + R <= n_captures ? R : n_captures - c0;
+                r.iq = a.iq + c0 * capture_stride_bytes;
+                r.bits = d_bits ? d_bits + c0 * max_frames * nb : nullptr;
+                r.llr = d_llr ? d_llr + c0 * max_frames * nb : nullptr;
+                r.rx_filt = d_rx_filt ? d_rx_filt + c0 * max_frames * nfl : nullptr;
+                r.stats = d_stats ? d_stats + c0 * max_frames : nullptr;
+                r.nframes = d_nframes + c0;
+                r.landed = d_landed;
+                if (!pirip::cuda_ok(fsk_fast_launch(plan->fast, r, d_flags + c0, d_list, d_count, (cudaStream_t)stream, c0, n_captures, c0),
+                                    "fsk_fast_kernel launch"))
+                    return -11;
+                pirip::count_launch();
+            }
         }
+        if (!(phases & 2) || getenv("PIRIP_FSK_FAST_NO_RERUN") != nullptr) return 0;
+        FskBatchArgs x = a;
+        x.landed = nullptr;
+        x.cap_list = d_list;
+        x.cap_count = d_count;
+        x.total_captures = n_captures;
+        if (!pirip::cuda_ok(fsk2_launch_demod(plan->dev, x, n_captures, (cudaStream_t)stream), "fsk2_kernel (flagged captures) launch")) return -11;
+        pirip::count_launch();
         return 0;
     }
     if (plan->fast && plan->mode) {

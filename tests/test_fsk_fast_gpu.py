@@ -188,3 +188,40 @@ def test_fast_full_c5_batch_bits_equal_oracle():
     print("C5 batch: worst", worst, "flagged", nflag, "replays", (ok, failed))
     assert failed == 0 and nflag == 0
     plan.close()
+
+
+def test_fast_more_captures_than_one_resident_round():
+    """Batches larger than the groups one launch keeps resident (1251 at C1 on 148 SMs) run as rounds of launches with one shared
+    list of flagged captures and one exact re-run; called twice (a group that took a second capture inside one launch used to
+    leave the NEXT launch waiting on its bulk-copy barrier).  Low Eb/N0 so that some captures are flagged or replayed."""
+    import torch
+
+    import pirip_b200 as pb
+    pk, gk = CONFIGS["c1_2fsk_240k_10k_p24_limits"]
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    ncap = sms * 9 + 150
+    base = make_batch(pk, gk, 24, 160, [None, 6.0, 3.0, 1.0], seed0=8800)
+    iq = np.ascontiguousarray(base[np.arange(ncap) % base.shape[0]])
+    plan = pb.FskPlan(**pk)
+    assert plan.mode == "fast"
+    out = plan.demod_batch(iq)
+    out2 = plan.demod_batch(iq)
+    plan.close()
+    assert np.array_equal(out["bits"], out2["bits"]) and np.array_equal(out["nframes"], out2["nframes"])
+    refs = oracle_batch(oracle_cfg(pk), base)
+    for c in range(ncap):
+        ref = refs[c % base.shape[0]]
+        nf = ref["nframes"]
+        assert int(out["nframes"][c]) == nf, c
+        assert np.array_equal(out["bits"][c, :nf * 50], ref["bits"]), c
+    # the device-resident entry takes the same path
+    d_iq = torch.from_numpy(iq).cuda()
+    mf = out["max_frames"]
+    bits = torch.zeros((ncap, mf * 50), dtype=torch.uint8, device="cuda")
+    nfr = torch.zeros(ncap, dtype=torch.int32, device="cuda")
+    plan = pb.FskPlan(**pk)
+    for _ in range(2):
+        plan.demod_batch_dev(d_iq.data_ptr(), ncap, iq.shape[1] // 2, d_iq.stride(0), bits.data_ptr(), nfr.data_ptr(), mf)
+    torch.cuda.synchronize()
+    plan.close()
+    assert np.array_equal(bits.cpu().numpy(), out["bits"]) and np.array_equal(nfr.cpu().numpy(), out["nframes"])
