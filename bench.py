@@ -167,7 +167,7 @@ def main():
     ap.add_argument("--seconds", type=float, default=1.0, help="capture length")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary lines (chain_c4, c3_4fsk_llr, c1_single_stream)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary lines (chain_c4, c3_4fsk_llr, c1_single_stream, decim_45, chain_c2, ldpc)")
     args = ap.parse_args()
     assert args.warmup >= 0 and args.steps >= 1
     # stdout carries exactly ONE line, the JSON: libraries that write to file descriptor 1 themselves (NCCL prints its
@@ -219,6 +219,22 @@ def main():
         raise SystemExit("bench.py: no CUDA device; there is no CPU fallback for the product path")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = None
+    if world > 1:
+        # N > 1: every rank streams 600 MB per step from pinned host memory; keep the rank's threads - and with them the first
+        # touch of its pinned buffers - on the CPUs next to its GPU (NVML's affinity mask), so that eight ranks do not pull their
+        # captures across the socket interconnect.  N = 1 keeps every core for the CPU baseline.
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa = "rank threads bound to %d CPUs next to GPU %d" % (len(cpus), local_rank)
+        except Exception as e:  # affinity is an optimisation, never a requirement
+            numa = "not bound (%s)" % type(e).__name__
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -234,20 +250,39 @@ def main():
     bits = torch.zeros((ncap, nbits_cap), dtype=torch.uint8, device=dev)
     bits_dense = bits
     nframes = torch.zeros(ncap, dtype=torch.int32, device=dev)
-    # config 5: the one collective on the path - gather the decoded bit streams.  The batch's bit array is packed 8 bits per
-    # byte on the device first (pirip_pack_bits_dev, the flat [ncap * max_frames * Nbits] array padded to a byte) and gathered
-    # on a side stream, overlapped with the next step's kernel; two buffers, at most two gathers in flight.
+    # config 5: the one exchange on the path - gather the decoded bit streams.  The batch's bit array is packed 8 bits per
+    # byte on the device first (pirip_pack_bits_dev, the flat [ncap * max_frames * Nbits] array padded to a byte); two buffers.
     total_bits = ncap * nbits_cap
     total_bits8 = (total_bits + 7) // 8 * 8
     if world > 1 and total_bits8 != total_bits:
         flat = torch.zeros(total_bits8, dtype=torch.uint8, device=dev)
         bits = flat[:total_bits].view(ncap, nbits_cap)
         bits_dense = bits
-    packed = [torch.empty(total_bits8 // 8, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
-    gathered = [torch.empty((world, total_bits8 // 8), dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
+    nbytes = total_bits8 // 8
+    packed = [torch.empty(nbytes, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
     stream = torch.cuda.current_stream()
     side = torch.cuda.Stream(device=dev) if world > 1 else None
-    pending = []
+    # The gather of the packed bit streams must not need SMs while the next step's kernel runs: the demodulator is persistent
+    # with one CTA per SM and all of its shared memory, so an NCCL kernel on a side stream only gets to run between two launches
+    # and, gated by the slowest rank, stalled every step at N >= 4 (9.5 ms per step against 3.8 ms, measured).  Each rank
+    # therefore PUSHES its packed bits into every peer's gather buffer with copy-engine peer copies over NVLink (torch symmetric
+    # memory: the peers' buffers mapped into this process), on a side stream beside the next kernel.  Where symmetric memory is
+    # not available the NCCL all-gather runs on the compute stream, right after the packing kernel, when the SMs are free.
+    peers, gathered, gather_kind = None, None, None
+    if world > 1:
+        try:
+            if os.environ.get("PIRIP_BENCH_GATHER", "") == "nccl":
+                raise RuntimeError("NCCL gather requested")
+            import torch.distributed._symmetric_memory as symm
+            gathered = [symm.empty((world, nbytes), dtype=torch.uint8, device=dev) for _ in range(2)]
+            handles = [symm.rendezvous(t, dist.group.WORLD) for t in gathered]
+            peers = [[h.get_buffer(p, (world, nbytes), torch.uint8) for p in range(world)] for h in handles]
+            gather_kind = "peer copies over NVLink by the copy engines into every rank's gather buffer (torch symmetric memory), beside the next step's kernel"
+        except Exception as e:
+            peers = None
+            gathered = [torch.empty((world, nbytes), dtype=torch.uint8, device=dev) for _ in range(2)]
+            gather_kind = "NCCL all-gather of the packed bits on the compute stream (%s)" % (str(e)[:80] or type(e).__name__)
+    done = [None, None]  # event: the pushes that read packed[k] have been issued and completed
     step_no = [0]
 
     def demod_into(bits_t):
@@ -259,15 +294,23 @@ def main():
         if world > 1:
             k = step_no[0] & 1
             step_no[0] += 1
-            while len(pending) > 1:  # buffer k was handed to the gather two steps ago
-                pending.pop(0).wait()
+            if done[k] is not None:
+                stream.wait_event(done[k])  # packed[k] is about to be overwritten: its pushes of two steps ago must be through
             pb.pack_bits_dev(ctypes.c_void_p(bits_dense.data_ptr()), total_bits8, ctypes.c_void_p(packed[k].data_ptr()),
                              ctypes.c_void_p(stream.cuda_stream))
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            with torch.cuda.stream(side):
-                side.wait_event(ev)
-                pending.append(dist.all_gather_into_tensor(gathered[k], packed[k], async_op=True))
+            if peers is not None:
+                ev = torch.cuda.Event()
+                ev.record(stream)
+                with torch.cuda.stream(side):
+                    side.wait_event(ev)
+                    for p in range(world):
+                        peers[k][(rank + p) % world][rank].copy_(packed[k], non_blocking=True)
+                    done[k] = torch.cuda.Event()
+                    done[k].record(side)
+            else:
+                dist.all_gather_into_tensor(gathered[k], packed[k])
+
+    pending = []
 
     def sync_all():
         while pending:
@@ -293,6 +336,16 @@ def main():
     sync_all()
     launches = pb.kernel_launches() - l0
     clocks = sampler.stop() if rank == 0 else None
+    gather_ok = None
+    if world > 1:
+        # untimed: what landed in this rank's gather buffer against a plain NCCL all-gather of the same packed streams
+        k_last = (step_no[0] - 1) & 1
+        ref_g = torch.empty((world, nbytes), dtype=torch.uint8, device=dev)
+        dist.all_gather_into_tensor(ref_g, packed[k_last])
+        ok_t = torch.tensor([1 if torch.equal(ref_g, gathered[k_last]) else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(ok_t, op=dist.ReduceOp.MIN)
+        gather_ok = bool(int(ok_t.item()))
+        del ref_g
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -360,7 +413,7 @@ def main():
                "h2d_ceiling": {"ms_per_step": h2d_s * 1e3, "GBps_per_gpu": ncap * nsamp * 2 / h2d_s / 1e9,
                                "Msamples_per_s": total_samples / h2d_s / 1e6,
                                "what": "one cudaMemcpyAsync of the step's captures from pinned host memory on every rank at once, nothing else"},
-               "fraction_of_h2d_ceiling": h2d_s / e2e_s}
+               "fraction_of_h2d_ceiling": h2d_s / e2e_s, "host_affinity": numa}
 
     if rank != 0:
         if world > 1:
@@ -428,14 +481,16 @@ def main():
     line = {"metric": "IQ Msamples/s fsk_demod 2-FSK Fs=240k Rs=10k", "value": value, "unit": "Msamples/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "config": dict(config, **({"gather": gather_kind, "gather_equals_nccl_all_gather": gather_ok,
+                                       "gather_bytes_per_rank_per_step": int(nbytes)} if world > 1 else {})), "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "algorithmic_bytes": ncap * nsamp * BYTES_PER_SAMPLE_ALGO, "peak_source": peak_src,
                          "kernel": kernel_name,
                          "kernel_ms": kernel_ms, "algorithmic_bytes_per_sample": BYTES_PER_SAMPLE_ALGO,
                          "note": "bound by instruction issue (FFT butterflies, mixing, integration), not HBM: DESIGN.md section 6"},
             "fast_mode": {"mode": plan.mode, "captures_left_to_the_exact_kernel_last_step": int(flagged),
-                          "frames_replayed_exactly_in_kernel_total": int(replays_ok), "replays_failed_total": int(replays_failed)},
+                          "frames_replayed_exactly_in_kernel_total": int(replays_ok), "replays_failed_total": int(replays_failed),
+                          "ppm_threshold_near_ties_total": plan.ppm_near_ties()},
             "cpu_baseline": cpu_baseline,
             "parity": {"captures_checked": nchk, "captures_per_gpu": ncap, "captures_mismatching": int(sum(mism)),
                        "bits_and_frames_equal_oracle": bool(ok), "ber_by_ebno_db": ber_by_ebno}}

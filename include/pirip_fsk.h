@@ -241,11 +241,15 @@ int pirip_fsk_plan_set_mode(pirip_fsk_plan *plan, int mode);
 int pirip_fsk_plan_mode(const pirip_fsk_plan *plan);
 /* after a batch call in fast mode: number of captures the guards sent to the exact kernel (synchronises the device);
    flags_out (may be NULL) receives the per-capture flag words of the first n captures: 0 = clean, else
-   reason bits (1 symbol margin, 2 nin threshold, 4 ppm threshold, 8 NaN) | (1 + first flagged frame) << 8 */
+   reason bits (1 symbol margin, 2 nin threshold, 4 unused since round 2 - see pirip_fsk_plan_ppm_near_ties, 8 NaN, 16 ingest time-out) | (1 + first flagged frame) << 8 */
 long pirip_fsk_plan_flagged(pirip_fsk_plan *plan, int32_t *flags_out, size_t n);
 /* frames the fast kernel replayed exactly inside the kernel since the plan was created (out[0]) and replays it had to
    give up (out[1]: those captures are flagged and re-run by the exact kernel); synchronises the device */
 int pirip_fsk_plan_replays(pirip_fsk_plan *plan, int32_t out[2]);
+/* frames whose ppm update decision (|change of norm_rx_timing| < 0.2, [U fsk.c::fsk_demod_core]) lay within the estimates' own
+   error of the threshold and was taken from the fast values (not replayed: it only feeds the ppm statistic, and the scalar
+   algorithm's own decision there depends on the libm in use); synchronises the device */
+long pirip_fsk_plan_ppm_near_ties(pirip_fsk_plan *plan);
 
 /* one-line description of the kernel and launch geometry the batch entry points use for this plan
    (static storage inside the plan; valid until the plan is destroyed) */

@@ -150,6 +150,13 @@ class FskPlan:
             raise _err("pirip_fsk_plan_replays", rc)
         return int(out[0]), int(out[1])
 
+    def ppm_near_ties(self):
+        """frames whose ppm update decision lay inside the estimates' error of its threshold (taken from the fast values)"""
+        L = lib()
+        L.pirip_fsk_plan_ppm_near_ties.restype = C.c_long
+        L.pirip_fsk_plan_ppm_near_ties.argtypes = [C.c_void_p]
+        return int(L.pirip_fsk_plan_ppm_near_ties(self._h))
+
     def flagged(self, n=0):
         """(count, flags[n]) of the last batch call: captures the guards sent to the exact kernel."""
         flags = np.zeros(n, np.int32) if n else None

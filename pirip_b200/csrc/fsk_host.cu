@@ -574,9 +574,21 @@ extern "C" int pirip_fsk_plan_replays(pirip_fsk_plan *plan, int32_t out[2]) {
     out[0] = v[0];
     out[1] = v[1];
     if (getenv("PIRIP_FSK_CHAIN_DIAG"))
-        fprintf(stderr, "side chain: replays %d failed %d, lag at capture end (max frames) %d, replay wait kcycles %d, lag at a replay (max frames) %d\n", v[0],
-                v[1], v[2], v[3], v[4]);
+        fprintf(stderr, "side chain: replays %d failed %d, ppm-threshold near-ties %d, replay wait kcycles %d\n", v[0], v[1], v[2], v[3]);
     return 0;
+}
+
+/* frames whose ppm update decision (|d norm_rx_timing| < 0.2) lay inside the estimates' own error and was taken from the fast
+   values, since the plan was created (synchronises the device); the ppm statistic of those captures may differ from the exact
+   evaluation for the following ~40 frames, nothing else does */
+extern "C" long pirip_fsk_plan_ppm_near_ties(pirip_fsk_plan *plan) {
+    if (!plan) return pirip::fail(-1, "plan is NULL");
+    if (!plan->fast) return 0;
+    if (!pirip::cuda_ok(cudaSetDevice(plan->device), "cudaSetDevice")) return -10;
+    if (!pirip::cuda_ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return -13;
+    int v[8];
+    if (!pirip::cuda_ok(fsk_fast_replay_counts(plan->fast, v), "D2H replay counts")) return -12;
+    return v[2];
 }
 
 extern "C" int pirip_fsk_plan_mode(const pirip_fsk_plan *plan) { return plan ? ((plan->fast && plan->mode) ? 1 : 0) : -1; }

@@ -6,6 +6,8 @@
                    UW sync, LDPC, CRC on the device) -> rx_status + packed payload per modem frame; IQ Msamples/s, roofline
                    at 2 + 33/(544 * 24) = 2.0025 B/sample, the oracle chain on the host cores beside it
   c3_4fsk_llr      config 3: 4FSK Fs=240k Rs=10k, --fsk_lower 500 --fsk_upper 25000, LLRs out (2.3333 B/sample)
+  decim_45 / chain_c2 / ldpc   the csdr stage alone (config 2's front end), config 2 end to end (decimate /45 + demodulate, two
+                   launches) and the LDPC decoder in its three modes: tools/bench_extra.py
   c1_single_stream config 1: ONE 600 k-bit stream [R README.md:101-105] through tools/bin/fsk_demod (GPU, one frame per call as
                    the CLI loop does, and --batch = the whole stream in one launch) beside the CPU port on ONE thread
 
@@ -394,9 +396,16 @@ def note(msg):
 
 def run_all(torch, pb, dev, cores, only="", cpu=True, **kw):
     res = {}
+    def extra(which):
+        # the csdr stage, the config-2 chain (decimate + demodulate, two launches) and the LDPC decoder: tools/bench_extra.py
+        import bench_extra
+        return {"decim_45": lambda: bench_extra.bench_decim(5), "chain_c2": lambda: bench_extra.bench_chain_c2(5),
+                "ldpc": lambda: bench_extra.bench_ldpc(5)}[which]()
+
     for name, fn in (("chain_c4", lambda: chain_c4(torch, pb, dev, cores, cpu=cpu, **kw)),
                      ("c3_4fsk_llr", lambda: c3_4fsk_llr(torch, pb, dev, cores, cpu=cpu, **kw)),
-                     ("c1_single_stream", lambda: c1_single_stream(pb, cores))):
+                     ("c1_single_stream", lambda: c1_single_stream(pb, cores)),
+                     ("decim_45", lambda: extra("decim_45")), ("chain_c2", lambda: extra("chain_c2")), ("ldpc", lambda: extra("ldpc"))):
         if only in ("", name):
             note(name + " ...")
             t0 = time.time()
