@@ -1,3 +1,9 @@
+"""Instruction and stall-sample shares per SASS region of an ncu report (chunks of N instructions in program order, with the
+source lines and opcodes that dominate each chunk): shows which PHASE of a long kernel the instructions belong to when the
+per-line view is blurred by inlined helpers.
+
+usage: ncu_regions.py <report.ncu-rep> <cubin> [chunk=250]
+"""
 import csv, re, subprocess, sys
 from collections import Counter
 rep, cubin = sys.argv[1], sys.argv[2]
