@@ -1233,12 +1233,21 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                     }
                     const int hTs = Ts >> 1;
                     int ip = i0 % P;
+                    /* the samples of the NEXT pair of outputs are fetched before this pair is worked on: the 16-byte loads were
+                       consumed right after issue (half of this loop's stall samples were short-scoreboard) */
+                    float4 ovv[M], nvv[M];
+#pragma unroll
+                    for (int m = 0; m < M; ++m) ovv[m] = r4[m][0], nvv[m] = r4[m][hTs];
 #pragma unroll 2
                     for (int o = 0; o < cnt; o += 2) {
                         float e0, e1;
+                        float4 ovn[M], nvn[M];
+                        const int on = o + 2 < cnt ? (o + 2) >> 1 : o >> 1;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) ovn[m] = r4[m][on], nvn[m] = r4[m][hTs + on];
 #pragma unroll
                         for (int m = 0; m < M; ++m) {
-                            const float4 ov = r4[m][o >> 1], nv = r4[m][hTs + (o >> 1)];
+                            const float4 ov = ovv[m], nv = nvv[m];
                             const float ea = fmaf(S[m].x, S[m].x, S[m].y * S[m].y);
                             const float2 Sn = xadd(S[m], xsub(make_float2(nv.x, nv.y), make_float2(ov.x, ov.y)));
                             const float eb = fmaf(Sn.x, Sn.x, Sn.y * Sn.y);
@@ -1255,6 +1264,8 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                         ti = fmaf(e1, w1.y, ti);
                         ip += 2;
                         if (ip >= P) ip -= P;
+#pragma unroll
+                        for (int m = 0; m < M; ++m) ovv[m] = ovn[m], nvv[m] = nvn[m];
                     }
                 } else {
                     float2 S[M];
