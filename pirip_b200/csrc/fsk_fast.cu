@@ -98,6 +98,7 @@ struct FastArgs {
     /* launch geometry: the first chain_ctas CTAs run the exact-oscillator chains (chain_wpc warps each), every other CTA
        holds G capture groups */
     int G, chain_ctas, chain_wpc;
+    long long *trace;   /* diagnostics (PIRIP_FSK_FAST_TRACE): clock64 at the phase boundaries of frames 20..51 of the first group */
     int cap_index_base; /* added to a capture's index in flag_list: rounds of one call share one list of batch-wide indices */
 };
 
@@ -146,6 +147,11 @@ __host__ __device__ __forceinline__ int ck_of(int nin, int j) { /* chunk holding
    (bar.sync id, 64), so the groups of a CTA run independently of each other. */
 __device__ __forceinline__ void group_sync() { asm volatile("bar.sync %0, %1;" ::"r"((int)(threadIdx.x >> 6) + 1), "r"(64) : "memory"); }
 #define GSYNC() group_sync()
+/* phase time stamps of one group (diagnostics; args.trace is NULL otherwise) */
+#define TR(i)                                                                                                         \
+    do {                                                                                                              \
+        if (args.trace && tid == 0 && grp == 0 && cta_a == 0 && frame >= 20 && frame < 52) args.trace[(frame - 20) * 16 + (i)] = clock64(); \
+    } while (0)
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(u64 *bar, int count) {
@@ -564,14 +570,20 @@ __device__ __noinline__ void osc_chain_role(const FastCfg &cfg, const FastArgs &
    On success: bits / rx_filt of the frame rewritten, ms-> timing, nin_next, interpolation and per-frame statistics set
    from the exact values, `filt` holds the exact magnitudes; the fast baseband memory of the frame's last `tailpad` samples
    is kept (the next frame continues the FAST oscillator phase).  Returns false when the side chain did not deliver. */
-template <int M, int FMT>
+template <int M, int FMT, int SPEC>
 __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastArgs &args, unsigned char *smem, size_t cap, int frame,
                                                 int nin, u64 pos) {
     const int tid = threadIdx.x & (T - 1), lane = tid & 31, warp = tid >> 5;
     float2 *fdc = reinterpret_cast<float2 *>(smem + cfg.off_fdc);
     float *filt = reinterpret_cast<float *>(smem + cfg.off_filt);
     Misc *ms = reinterpret_cast<Misc *>(smem + cfg.off_misc);
-    const int Ts = cfg.Ts, P = cfg.P, Nsym = cfg.Nsym, Nmem = cfg.Nmem, fdcS = cfg.fdcS, step = cfg.step, nint = cfg.nint, bps = cfg.bps;
+    /* the compiled-in shapes (see the kernel): with Ts a constant the 24-term window sums unroll, their loads go out together and
+       only the additions stay serial - a replay cost 295 k cycles with run-time sizes, and the slowest capture's replays are the
+       tail of the whole launch */
+    constexpr bool S1 = SPEC != 0;
+    constexpr int SP = SPEC == 1 ? 24 : (SPEC == 2 ? 8 : 1);
+    const int Ts = S1 ? 24 : cfg.Ts, P = S1 ? SP : cfg.P, Nsym = S1 ? 50 : cfg.Nsym, Nmem = S1 ? 1248 : cfg.Nmem, fdcS = cfg.fdcS;
+    const int step = S1 ? 24 / SP : cfg.step, nint = S1 ? 51 * SP : cfg.nint, bps = S1 ? 2 : cfg.bps;
     const int nold = Nmem - nin;
     const unsigned char *cap_base = args.iq + cap * args.stride;
 
@@ -635,17 +647,28 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
             float2 phi;
             ld_ckpt(ck + ((size_t)(fr_ & 1) * args.ckpt_per_frame + chunk) * 4 + m, 0, &phi); /* validated above */
             const unsigned char *src = cap_base + ((prev ? ms->pos_prev : pos)) * bps;
-            for (int j = jc; j < jhi; ++j) {
-                phi = ocmul(phi, d);
-                if (j >= jlo) {
-                    float2 x = raw_cvt<FMT>(src + (size_t)j * bps);
-                    x.x = __fmul_rn(x.x, cfg.in_scale); /* exact: power of two (1 for s16 / f32) */
-                    x.y = __fmul_rn(x.y, cfg.in_scale);
-                    /* in * conj(phi) as cmult(in, cconj(phi)) evaluates it */
-                    const float2 y = make_float2(__fadd_rn(__fmul_rn(x.x, phi.x), __fmul_rn(x.y, phi.y)),
-                                                 __fadd_rn(__fmul_rn(x.x, -phi.y), __fmul_rn(x.y, phi.x)));
-                    const int idx = prev ? j - jt0 : nold + j;
-                    fdc[m * fdcS + idx] = y;
+            /* eight samples are fetched (global memory: the frame's staging buffer already holds the next frame) before their
+               eight oscillator steps run */
+            for (int j8 = jc; j8 < jhi; j8 += 8) {
+                float2 xs[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) xs[u] = raw_cvt<FMT>(src + (size_t)(j8 + u < jhi ? j8 + u : jhi - 1) * bps);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int j = j8 + u;
+                    if (j < jhi) {
+                        phi = ocmul(phi, d);
+                        if (j >= jlo) {
+                            float2 x = xs[u];
+                            x.x = __fmul_rn(x.x, cfg.in_scale); /* exact: power of two (1 for s16 / f32) */
+                            x.y = __fmul_rn(x.y, cfg.in_scale);
+                            /* in * conj(phi) as cmult(in, cconj(phi)) evaluates it */
+                            const float2 y = make_float2(__fadd_rn(__fmul_rn(x.x, phi.x), __fmul_rn(x.y, phi.y)),
+                                                         __fadd_rn(__fmul_rn(x.x, -phi.y), __fmul_rn(x.y, phi.x)));
+                            const int idx = prev ? j - jt0 : nold + j;
+                            fdc[m * fdcS + idx] = y;
+                        }
+                    }
                 }
             }
         }
@@ -664,7 +687,13 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
                 for (int m = 0; m < M; ++m) {
                     const float2 *f = fdc + m * fdcS + i * step;
                     float2 a = make_float2(0.0f, 0.0f);
-                    for (int k = 0; k < Ts; ++k) a = xadd(a, f[k]);
+                    if (S1) {
+#pragma unroll
+                        for (int k = 0; k < 24; ++k) a = xadd(a, f[k]);
+                    } else {
+#pragma unroll 4
+                        for (int k = 0; k < Ts; ++k) a = xadd(a, f[k]);
+                    }
                     ft1 = __fadd_rn(ft1, __fadd_rn(__fmul_rn(a.x, a.x), __fmul_rn(a.y, a.y)));
                 }
                 const float2 w = cfg.phi_ft[i];
@@ -730,9 +759,18 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
             for (int m = 0; m < M; ++m) {
                 const float2 *fa = fdc + m * fdcS + (st + low) * step, *fb = fdc + m * fdcS + (st + high) * step;
                 float2 a = make_float2(0.0f, 0.0f), b = make_float2(0.0f, 0.0f);
-                for (int k = 0; k < Ts; ++k) {
-                    a = xadd(a, fa[k]);
-                    b = xadd(b, fb[k]);
+                if (S1) {
+#pragma unroll
+                    for (int k = 0; k < 24; ++k) {
+                        a = xadd(a, fa[k]);
+                        b = xadd(b, fb[k]);
+                    }
+                } else {
+#pragma unroll 4
+                    for (int k = 0; k < Ts; ++k) {
+                        a = xadd(a, fa[k]);
+                        b = xadd(b, fb[k]);
+                    }
                 }
                 float2 t = make_float2(__fmul_rn(omf, a.x), __fmul_rn(omf, a.y));
                 t = xadd(t, make_float2(__fmul_rn(fr_w, b.x), __fmul_rn(fr_w, b.y)));
@@ -939,6 +977,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
     while (ms->cont) {
         const int nin = ms->nin, nold = Nmem - nin, frame = ms->frame;
         const u64 pos = ms->pos;
+        TR(0);
         /* ---- raw samples of this frame ---- */
         if (ms->use_tma) {
             if (tid == 0) mbar_wait(&ms->bar, (unsigned)ms->parity); /* the others block in the barrier below: no issue slots */
@@ -952,6 +991,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             for (size_t i = tid; i < nbytes; i += T) raw[ms->roff + i] = __ldcg(g + i);
         }
         GSYNC();
+        TR(1);
         const unsigned char *fr = raw + ms->roff; /* sample 0 of the frame */
 
         /* ---- A7: tone frequency estimate (exact) ---- */
@@ -971,12 +1011,14 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                             fft256_block<FMT>(cfg, tid & 15, fr + (size_t)j * half * bps, hannS, scratch + (tid >> 4) * 272, mag + (size_t)j * nb, t3, t4);
                     }
                     GSYNC();
+                    TR(2);
                     for (int b = tid; b < nb; b += T) {
                         float s = Sf[b];
                         for (int r = 0; r < numffts; ++r) s = __fadd_rn(__fmul_rn(s, c9), __fmul_rn(mag[r * nb + b], tc));
                         Sf[b] = s;
                     }
                     GSYNC();
+                    TR(3);
                 } else
                 for (int j0 = 0; j0 < numffts; j0 += gpr) {
                     const int j = j0 + (tid >> 4);
@@ -1006,6 +1048,11 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             }
             /* peak picking with blanking (warp 0) and the mask correlation (warp 1), on Sf[st, en) */
             float *tmp = mag; /* scratch copy for the blanking */
+            /* This block runs once per frame, straight through, and the frame loop's code does not fit the instruction cache: every
+               128-byte line of it (8 instructions) is fetched from L2 again each frame, ~350 cycles a line - the first version
+               (shuffle trees, an unrolled scan for wide windows) took 6 700 of a frame's 19 000 cycles for 150 executed
+               instructions (PIRIP_FSK_FAST_TRACE).  Hence as few instructions as possible: warp-wide REDUX on the float bit
+               patterns (the values are >= 0, so they order like unsigned integers), ballot + ffs for "first maximum wins". */
             if (warp == 0) {
                 const bool inreg = nb <= 32; /* a window of at most 32 bins: one bin per lane, blanking in registers */
                 float myv = 0.0f;
@@ -1015,89 +1062,86 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                     for (int b = lane; b < nb; b += 32) tmp[b] = Sf[b];
                 __syncwarp();
                 int fq[4];
+#pragma unroll
                 for (int it = 0; it < M; ++it) {
                     float best = 0.0f;
                     int bi = 0;
                     if (inreg) {
-                        if (myv > 0.0f) best = myv, bi = cfg.st + lane;
-                    } else
-                    for (int b = lane; b < nb; b += 32) {
-                        const float v = tmp[b];
-                        if (v > best) {
-                            best = v;
-                            bi = cfg.st + b;
+                        if (myv > 0.0f) best = myv, bi = lane;
+                    } else {
+#pragma unroll 1
+                        for (int b = lane; b < nb; b += 32) {
+                            const float v = tmp[b];
+                            if (v > best) {
+                                best = v;
+                                bi = b;
+                            }
                         }
                     }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-                        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                        if (ov > best || (ov == best && ov > 0.0f && oi < bi)) {
-                            best = ov;
-                            bi = oi;
-                        }
-                    }
-                    const int imax = bi;
+                    /* first maximum wins; nothing above zero leaves bin 0 of the whole spectrum, as the scalar scan does */
+                    const unsigned top = __reduce_max_sync(0xffffffffu, __float_as_uint(best));
+                    const unsigned who = top ? __reduce_min_sync(0xffffffffu, __float_as_uint(best) == top ? (unsigned)bi : 0xffffffffu) : 0u;
+                    const int imax = top ? cfg.st + (int)who : 0;
                     int lo = imax - cfg.f_zero, hi = imax + cfg.f_zero;
                     lo = lo < cfg.st ? cfg.st : lo;
                     hi = hi > cfg.en ? cfg.en : hi;
                     if (inreg) {
                         if (cfg.st + lane >= lo && cfg.st + lane < hi) myv = 0.0f;
                     } else {
+#pragma unroll 1
                         for (int b = lo + lane; b < hi; b += 32) tmp[b - cfg.st] = 0.0f;
                         __syncwarp();
                     }
                     fq[it] = imax - half;
                 }
                 if (lane == 0) {
-                    /* ascending sort as upstream writes it */
-                    int i = 1;
-                    while (i < M) {
-                        if (fq[i] >= fq[i - 1])
-                            i++;
-                        else {
-                            const int j = fq[i];
-                            fq[i] = fq[i - 1];
-                            fq[i - 1] = j;
-                            if (i > 1) i--;
-                        }
+                    /* ascending sort (upstream writes an insertion sort; the result is the same), static indices: registers */
+                    auto cswap = [](int &a, int &b) {
+                        const int lo = a < b ? a : b, hi = a < b ? b : a;
+                        a = lo;
+                        b = hi;
+                    };
+                    if (M == 2)
+                        cswap(fq[0], fq[1]);
+                    else {
+                        cswap(fq[0], fq[1]);
+                        cswap(fq[2], fq[3]);
+                        cswap(fq[0], fq[2]);
+                        cswap(fq[1], fq[3]);
+                        cswap(fq[1], fq[2]);
                     }
+#pragma unroll
                     for (int m = 0; m < M; ++m) {
                         ms->freqi[m] = fq[m];
                         ms->f_est[m] = __fmul_rn((float)fq[m], cfg.fs_over_ndft);
                     }
                 }
+                TR(12);
             } else if (warp == 1) {
                 float best = 0.0f;
-                int bi = cfg.st;
-                bool found = false;
+                int bi = 0x7fffffff;
+#pragma unroll 1
                 for (int b = cfg.st + lane; b < cfg.en - cfg.len_mask; b += 32) {
                     float corr = 0.0f;
+#pragma unroll 1
                     for (int k = 0; k < cfg.nmask; ++k) corr = __fadd_rn(corr, Sf[b - cfg.st + cfg.mask_pos[k]]);
                     if (corr > best) {
                         best = corr;
                         bi = b;
-                        found = true;
                     }
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
-                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                    const bool of = __shfl_xor_sync(0xffffffffu, (int)found, o) != 0;
-                    if (of && (!found || ov > best || (ov == best && oi < bi))) {
-                        best = ov;
-                        bi = oi;
-                        found = true;
-                    }
-                }
+                /* the largest correlation above zero, the lowest bin among equals; none: the window's first bin */
+                const unsigned top = __reduce_max_sync(0xffffffffu, __float_as_uint(best));
+                const unsigned who = __reduce_min_sync(0xffffffffu, (top && __float_as_uint(best) == top) ? (unsigned)bi : 0x7fffffffu);
                 if (lane == 0) {
-                    ms->bmax = found ? bi : cfg.st;
+                    ms->bmax = top ? (int)who : cfg.st;
                     const float foff = (float)((ms->bmax - half) * cfg.Fs / Ndft);
+#pragma unroll
                     for (int m = 0; m < M; ++m) ms->f2_est[m] = __fadd_rn(foff, (float)(m * cfg.tone_spacing));
                 }
             }
             GSYNC();
+            TR(4);
             if (tid < M) {
                 const int m = tid;
                 const int ei = cfg.est_type ? ms->bmax * 4 + m : (ms->freqi[m] + half) * 4;
@@ -1110,6 +1154,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                 ms->osc_idx[m] = ei;
             }
             GSYNC();
+            TR(5);
             if (tid == 0 && args.mbox) {
                 /* tell the exact-oscillator side chain what this frame is */
                 u64 w = MBOX_VALID | ((u64)(nin == cfg.nin_min ? 0 : (nin == cfg.N ? 1 : 2)) << 48);
@@ -1197,6 +1242,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             }
         }
         GSYNC();
+        TR(6);
         /* raw is free: fetch the next frame (its start is known, its length is not: fetch the longest) */
         if (tid == 0) {
             const u64 npos = pos + (u64)nin;
@@ -1309,6 +1355,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             }
         }
         GSYNC();
+        TR(7);
 
         /* ---- A10: timing estimate, nin for the next call, interpolation weights (thread 0) ---- */
         if (tid == 0) {
@@ -1354,6 +1401,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             ms->fflags = fl;
         }
         GSYNC();
+        TR(8);
 
         /* ---- A11: resample at the timing instant, decide, per-symbol statistics (fast, guarded) ---- */
         {
@@ -1378,7 +1426,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                 float E[M], U[M]; /* this lane's symbol of the round: tone energies, |dt/dfract|^2 */
 #pragma unroll
                 for (int m = 0; m < M; ++m) E[m] = U[m] = 0.0f;
-#pragma unroll
+#pragma unroll 1 /* a real loop: four unrolled copies, each run once per frame, cost more in instruction fetch than they saved */
                 for (int pass = 0; pass < 4; ++pass) {
                     if (sym0 + 16 * pass >= Nsym) break; /* uniform */
                     const int sym = sym0 + 16 * pass + (tid >> 2);
@@ -1514,12 +1562,15 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             if (fl) atomicOr(&ms->fflags, fl);
         }
         GSYNC();
+        TR(9);
 
         /* ---- a decision inside its margin: replay the frame exactly (rare) ---- */
         bool replayed = false;
         if (ms->fflags && args.mbox) {
-            replayed = exact_frame_replay<M, FMT>(cfg, args, smem, cap, frame, nin, pos);
+            const long long t_rp = clock64();
+            replayed = exact_frame_replay<M, FMT, SPEC>(cfg, args, smem, cap, frame, nin, pos);
             if (!replayed && tid == 0 && args.replays) atomicAdd(args.replays + 1, 1);
+            if (tid == 0 && args.replays) atomicAdd(args.replays + 4, (int)((clock64() - t_rp) >> 10)); /* diagnostics: kcycles spent in replays */
         }
 
         /* ---- stats of the frame, the record, loop control (thread 0) ---- */
@@ -1575,6 +1626,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             ms->cont = cont;
         }
         GSYNC();
+        TR(10);
 
         /* ---- A12: LLRs (fast) ---- */
         if (cfg.soft && args.llr) {
@@ -1610,6 +1662,7 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                 for (int k = tid; k < nold2; k += T) fdc[m * fdcS + k] = fdc[m * fdcS + (Nmem - nold2) + k];
         }
         GSYNC();
+        TR(11);
     }
 
     /* a bulk copy still in flight must land before the CTA retires */
@@ -1653,6 +1706,7 @@ struct FskFastPlan {
     u64 *d_mbox = nullptr;
     float4 *d_ckpt = nullptr;
     int *d_afin = nullptr, *d_replays = nullptr;
+    long long *d_trace = nullptr; /* PIRIP_FSK_FAST_TRACE */
     size_t cap_mbox = 0, cap_chain = 0;
     int ckpt_per_frame = 0;
     bool chain = true;
@@ -1718,6 +1772,7 @@ void fsk_fast_plan_destroy(FskFastPlan *p) {
     cudaFree(p->d_ckpt);
     cudaFree(p->d_afin);
     cudaFree(p->d_replays);
+    cudaFree(p->d_trace);
     delete p;
 }
 
@@ -2041,6 +2096,36 @@ cudaError_t fsk_fast_launch(FskFastPlan *p, const FskBatchArgs &b, int *d_flags,
        (the chain lanes and the replays wait for each other across CTAs) */
     size_t smem = (size_t)block_groups * p->cfg.group_stride;
     if (smem < 116 * 1024) smem = 116 * 1024;
+    if (getenv("PIRIP_FSK_FAST_TRACE")) {
+        /* diagnostics: cycles between the phase boundaries of frames 20..51 of the first group, averaged, to stderr (synchronous) */
+        if (!p->d_trace && (e = cudaMalloc(&p->d_trace, sizeof(long long) * 32 * 16)) != cudaSuccess) return e;
+        cudaMemsetAsync(p->d_trace, 0, sizeof(long long) * 32 * 16, stream);
+        a.trace = p->d_trace;
+        e = fast_dispatch(p, a, stream, 0, (unsigned)(n_a + chain_ctas), (unsigned)(block_groups * T), smem);
+        if (e != cudaSuccess) return e;
+        long long h[32 * 16];
+        cudaStreamSynchronize(stream);
+        cudaMemcpy(h, p->d_trace, sizeof h, cudaMemcpyDeviceToHost);
+        static const char *names[12] = { "", "raw wait", "FFT", "IIR", "peak / mask", "osc set-up", "mix", "integrate", "timing (tid 0)", "decide",
+                                         "replay / stats / record", "LLR + tail copy" };
+        double sum[12] = { 0 };
+        int nfr = 0;
+        for (int f = 0; f < 32; ++f) {
+            if (!h[f * 16 + 11] || !h[f * 16]) continue;
+            ++nfr;
+            for (int i = 1; i < 12; ++i) sum[i] += (double)(h[f * 16 + i] - h[f * 16 + i - 1]);
+        }
+        if (nfr) {
+            double tot = 0;
+            for (int i = 1; i < 12; ++i) tot += sum[i] / nfr;
+            double w0 = 0;
+            for (int f = 0; f < 32; ++f)
+                if (h[f * 16 + 11] && h[f * 16] && h[f * 16 + 12]) w0 += (double)(h[f * 16 + 12] - h[f * 16 + 3]) / nfr;
+            fprintf(stderr, "fast kernel trace (%d frames of group 0, G = %d): %.0f cycles per frame; peak pick (warp 0) alone %.0f\n", nfr, G, tot, w0);
+            for (int i = 1; i < 12; ++i) fprintf(stderr, "  %-26s %7.0f cycles  %5.1f %%\n", names[i], sum[i] / nfr, 100.0 * sum[i] / nfr / tot);
+        }
+        return cudaSuccess;
+    }
     return fast_dispatch(p, a, stream, 0, (unsigned)(n_a + chain_ctas), (unsigned)(block_groups * T), smem);
 }
 

@@ -574,7 +574,8 @@ extern "C" int pirip_fsk_plan_replays(pirip_fsk_plan *plan, int32_t out[2]) {
     out[0] = v[0];
     out[1] = v[1];
     if (getenv("PIRIP_FSK_CHAIN_DIAG"))
-        fprintf(stderr, "side chain: replays %d failed %d, ppm-threshold near-ties %d, replay wait kcycles %d\n", v[0], v[1], v[2], v[3]);
+        fprintf(stderr, "side chain: replays %d failed %d, ppm-threshold near-ties %d, kcycles waiting for checkpoints %d, kcycles in replays %d\n", v[0], v[1],
+                v[2], v[3], v[4]);
     return 0;
 }
 
