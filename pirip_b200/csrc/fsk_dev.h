@@ -210,7 +210,7 @@ const char *fsk_fast_plan_desc(const FskFastPlan *p);
 cudaError_t fsk_fast_flag_buffers(FskFastPlan *p, size_t n, int **flags, int **list, int **count);
 cudaError_t fsk_fast_launch(FskFastPlan *p, const FskBatchArgs &b, int *d_flags, int *d_list, int *d_count, cudaStream_t stream,
                             size_t off, size_t total, size_t slot);
-cudaError_t fsk_fast_replay_counts(FskFastPlan *p, int out[8]);
+cudaError_t fsk_fast_replay_counts(FskFastPlan *p, int out[64]);
 int fsk_fast_uses_chain(const FskFastPlan *p);
 size_t fsk_fast_round_captures(const FskFastPlan *p);
 #endif

@@ -98,6 +98,8 @@ struct FastArgs {
     /* launch geometry: the first chain_ctas CTAs run the exact-oscillator chains (chain_wpc warps each), every other CTA
        holds G capture groups */
     int G, chain_ctas, chain_wpc;
+    int chain_cpi;      /* PIRIP_FSK_CHAIN_CPI: checkpoint chunks per side-chain iteration (0: the built-in choice) */
+    int chain_diag;     /* diagnostics (PIRIP_FSK_CHAIN_DIAG): mailbox words carry their posting time, the chain sums its lag */
     long long *trace;   /* diagnostics (PIRIP_FSK_FAST_TRACE): clock64 at the phase boundaries of frames 20..51 of the first group */
     int cap_index_base; /* added to a capture's index in flag_list: rounds of one call share one list of batch-wide indices */
 };
@@ -448,6 +450,21 @@ __device__ __forceinline__ float2 ocmul(float2 a, float2 b) {
     return make_float2(__fsub_rn(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)), __fadd_rn(__fmul_rn(a.x, b.y), __fmul_rn(a.y, b.x)));
 }
 
+/* the same product with its four multiplications as two packed ones: dxx = (d.x, d.x), dyn = (d.y, -d.y);
+   (a.x d.x, a.y d.x) and (a.x d.y, -a.y d.y), then x = p1.x + p2.y, y = p1.y + p2.x.  Packed multiplies round each half like the
+   scalar instruction (tools/micro/f32x2_exact.cu), a * (-b) is -(a * b) exactly, and the additions stay SCALAR: ptxas would
+   contract a packed add with the multiply that feeds it into FFMA2 (tests/test_sass_contract_cpu.py: none in this object).
+   Four instructions instead of six - measured on the side chain's SMs: 7.7 cycles of a scheduler per warp and step against 9.4
+   for the scalar form, but ~14 cycles of dependent latency against 8.  (A third form - two packed multiplies and a packed fma by
+   a run-time 1.0, exact as well, tools/micro/ocmul_pk3.cu - is three instructions and slower than both: 8.3 cycles, 21 of latency.) */
+__device__ __forceinline__ float2 ocmul_pk(float2 a, float2 dxx, float2 dyn) {
+    u64 p1, p2;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p1) : "l"(pk(a)), "l"(pk(dxx)));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p2) : "l"(pk(a)), "l"(pk(dyn)));
+    const float2 q1 = upk(p1), q2 = upk(p2);
+    return make_float2(__fadd_rn(q1.x, q2.y), __fadd_rn(q1.y, q2.x));
+}
+
 /* The one computation of the path that cannot be reformulated without changing its floats: the recursive oscillator
    phi_c[m] *= dphi_m of [U fsk.c::fsk_demod_core] (one rounding per sample, renormalised once per frame).  The fast kernel
    mixes with a closed-form phase and needs the scalar algorithm's exact phases only when a frame has to be replayed
@@ -476,51 +493,89 @@ __device__ __noinline__ void osc_chain_role(const FastCfg &cfg, const FastArgs &
     float4 *ck = args.ckpt + (done ? 0 : cap * (size_t)(2 * args.ckpt_per_frame * 4)) + m;
     const int *afin = args.afin + (done ? 0 : cap);
     unsigned idle = 0;
+    int d_work = 0, d_idle = 0;
+    long long d_cw = 0;
+    const long long d_t0 = clock64();
+    /* step counts of a chunk: base or base + 1 for each of the three frame lengths; every lane runs the smallest count with no
+       predicate at all and the few steps by which the counts differ under a per-lane select - no vote across the warp */
+    int nlo, nhi;
+    {
+        const int b0 = cfg.nin_min / ck_chunks(cfg.nin_min), b1 = cfg.N / ck_chunks(cfg.N), b2 = cfg.nin_max / ck_chunks(cfg.nin_max);
+        nlo = min(b0, min(b1, b2));
+        nhi = max(b0, max(b1, b2)) + 1;
+    }
+    /* the CTA's nine active warps sit three, two, two and two on the four schedulers, and the chain is bound by the issue rate of
+       the fma pipe: measured per oscillator step, two warps of scalar steps share a scheduler at 18.8 cycles, three would at 28;
+       the three run the packed form (ocmul_pk) at 23.  The demodulating groups ask for a frame of 1200 steps every ~26 k cycles,
+       21.7 cycles a step: the lanes of those three warps still fall behind slowly, which is what a replay waits for. */
+    const bool packed = ((threadIdx.x >> 5) & 3) == 0 && args.chain_wpc > 8;
+    /* chunks per iteration: half a frame when every frame length has the same even chunk count, else one */
+    int CPI = 1;
+    {
+        const int k0 = ck_chunks(cfg.nin_min), k1 = ck_chunks(cfg.N), k2 = ck_chunks(cfg.nin_max);
+        if (k0 == k1 && k1 == k2 && (k0 & 1) == 0) CPI = k0 / 2;
+        if (args.chain_cpi > 0) CPI = args.chain_cpi;
+    }
     while (true) {
         if (__all_sync(0xffffffffu, done)) break;
-        /* Poll first, look at the answers last: a lane waiting for its next frame reads its mailbox word, a working lane the
-           capture's "finished" flag; both words are consumed after the steps below, whose operands (dphi, have) they would
-           change - so the loads' latency hides behind a chunk of steps.  The words are self-contained: relaxed loads. */
+        const long long d_ti = clock64();
+        /* Poll first, look at the answers last: a lane without a frame reads its mailbox word, a lane on the last chunk of a frame
+           the word of the NEXT frame (a lane that is behind goes straight on), any other working lane the capture's "finished"
+           flag; the words are consumed after the steps below, whose operands (dphi, have) they would change - so the loads'
+           latency hides behind a chunk of steps.  The words are self-contained: relaxed loads. */
         u64 w = 0;
         int fin = 0;
-        const bool poll_box = !done && !have, poll_fin = !done && have;
-        if (poll_box) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(box + f) : "memory");
+        const bool last = have && K - k <= CPI; /* the frame ends inside this iteration */
+        const bool poll_box = !done && (!have || last), poll_fin = !done && have && !last;
+        if (poll_box) asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(box + f + (last ? 1 : 0)) : "memory");
         if (poll_fin) asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(fin) : "l"(afin) : "memory");
         if (__any_sync(0xffffffffu, have)) {
             idle = 0;
-            if (have) {
-                const int tag = ((f + 1) << 8) | k;
-                ck[((size_t)(f & 1) * args.ckpt_per_frame + k) * 4] = make_float4(phi.x, phi.y, __int_as_float(tag), __int_as_float(~tag));
-            }
-            const int n = have ? base + (k < rem ? 1 : 0) : 0;
-            /* the warp runs the shortest count of its working lanes without any predicate (a lane without work steps a scratch
-               copy), then the one or two steps by which the counts differ with a per-lane select */
-            int nmin = have ? n : 0x7fffffff, nmax = n;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const int a = __shfl_xor_sync(0xffffffffu, nmin, o), b = __shfl_xor_sync(0xffffffffu, nmax, o);
-                nmin = a < nmin ? a : nmin;
-                nmax = b > nmax ? b : nmax;
-            }
-            float2 wp = phi;
-#pragma unroll 8
-            for (int it = 0; it < nmin; ++it) wp = ocmul(wp, dphi);
-            for (int it = nmin; it < nmax; ++it) {
-                const float2 r = ocmul(wp, dphi);
-                if (it < n) wp = r;
-            }
-            if (have) {
-                phi = wp;
-                if (++k == K) {
-                    /* [U comp_prim.h::comp_normalize] */
-                    const float av = __fsqrt_rn(__fadd_rn(__fmul_rn(phi.x, phi.x), __fmul_rn(phi.y, phi.y)));
-                    phi = make_float2(__fdiv_rn(phi.x, av), __fdiv_rn(phi.y, av));
-                    ++f;
-                    have = false;
+            /* CPI chunks per iteration: the polls, the votes and the frame-end normalisation (an IEEE square root and two
+               divisions, ~200 issue cycles that the whole warp pays whenever one lane ends a frame) cost 265 cycles per
+               iteration - with one chunk per iteration that was a tenth of the chain's time, and the slowest warps could not
+               keep the demodulators' pace */
+#pragma unroll 1
+            for (int kk = 0; kk < CPI; ++kk) {
+                if (have) {
+                    const int tag = ((f + 1) << 8) | k;
+                    ck[((size_t)(f & 1) * args.ckpt_per_frame + k) * 4] = make_float4(phi.x, phi.y, __int_as_float(tag), __int_as_float(~tag));
                 }
+                const int n = have ? base + (k < rem ? 1 : 0) : 0;
+                float2 wp = phi;
+                if (packed) {
+                    const float2 dxx = make_float2(dphi.x, dphi.x), dyn = make_float2(dphi.y, -dphi.y);
+#pragma unroll 8
+                    for (int it = 0; it < nlo; ++it) wp = ocmul_pk(wp, dxx, dyn);
+                    for (int it = nlo; it < nhi; ++it) {
+                        const float2 r = ocmul_pk(wp, dxx, dyn);
+                        if (it < n) wp = r;
+                    }
+                } else {
+#pragma unroll 8
+                    for (int it = 0; it < nlo; ++it) wp = ocmul(wp, dphi);
+                    for (int it = nlo; it < nhi; ++it) {
+                        const float2 r = ocmul(wp, dphi);
+                        if (it < n) wp = r;
+                    }
+                }
+                if (have) {
+                    phi = wp;
+                    if (++k == K) {
+                        /* [U comp_prim.h::comp_normalize] */
+                        const float av = __fsqrt_rn(__fadd_rn(__fmul_rn(phi.x, phi.x), __fmul_rn(phi.y, phi.y)));
+                        phi = make_float2(__fdiv_rn(phi.x, av), __fdiv_rn(phi.y, av));
+                        ++f;
+                        have = false;
+                    }
+                }
+                if (!__any_sync(0xffffffffu, have)) break;
             }
+            ++d_work;
+            d_cw += clock64() - d_ti;
         } else {
             __nanosleep(500);
+            ++d_idle;
             if (++idle > 200000u) break;
         }
         /* the answers.  Tied to the chain's result (never a NaN) so that neither compiler hoists the tests - and with them the
@@ -542,11 +597,21 @@ __device__ __noinline__ void osc_chain_role(const FastCfg &cfg, const FastArgs &
                 base = nin / K;
                 rem = nin - base * K;
                 dphi = cfg.osc[(w >> (12 * m)) & 0xfff].dphi;
+                if (args.chain_diag && m == 0) {
+                    /* diagnostics: how long the word waited for this lane (replays[5] sum, [6] max, [7] count; ~microseconds) */
+                    u64 gt;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                    const int lag = (int)(((gt >> 10) - (w >> 50)) & 0xfffull);
+                    atomicAdd(args.replays + 5, lag);
+                    atomicMax(args.replays + 6, lag);
+                    atomicAdd(args.replays + 7, 1);
+                }
                 have = true;
                 k = 0;
             }
         }
         if (next) {
+            have = false;
             cap += LB;
             if (cap >= args.n_captures)
                 done = true;
@@ -558,6 +623,14 @@ __device__ __noinline__ void osc_chain_role(const FastCfg &cfg, const FastArgs &
                 afin = args.afin + cap;
             }
         }
+    }
+    if (args.chain_diag && lane == 0) { /* diagnostics: iterations with / without work, kcycles in the former / in all */
+        atomicAdd(args.replays + 8, d_work);
+        atomicAdd(args.replays + 9, d_idle);
+        atomicAdd(args.replays + 10, (int)(d_cw >> 10));
+        atomicAdd(args.replays + 11, (int)((clock64() - d_t0) >> 10));
+        atomicAdd(args.replays + 16 + (threadIdx.x >> 5), (int)(d_cw >> 10)); /* per warp slot of the CTA (<= 18) */
+        atomicAdd(args.replays + 40 + (threadIdx.x >> 5), d_work);
     }
 }
 
@@ -1159,6 +1232,12 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                 /* tell the exact-oscillator side chain what this frame is */
                 u64 w = MBOX_VALID | ((u64)(nin == cfg.nin_min ? 0 : (nin == cfg.N ? 1 : 2)) << 48);
                 for (int m = 0; m < M; ++m) w |= (u64)ms->osc_idx[m] << (12 * m);
+                if (args.chain_diag) {
+                    /* diagnostics: when this word was posted, microseconds modulo 4096 (bits 50..61) */
+                    u64 gt;
+                    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                    w |= ((gt >> 10) & 0xfffull) << 50;
+                }
                 st_relaxed_u64(args.mbox + cap * (args.max_frames + 1) + frame, w); /* self-contained word: no fence */
             }
         }
@@ -1423,19 +1502,19 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             const int sub = tid & 3;
             const int k0 = sub * per, k1 = (k0 + per < Ts) ? k0 + per : Ts;
             for (int sym0 = 0; sym0 < Nsym; sym0 += 64) {
-                float E[M], U[M]; /* this lane's symbol of the round: tone energies, |dt/dfract|^2 */
+                float E[M], U[M], Cc[M]; /* this lane's symbol of the round: tone energies, |dt/dfract|^2, Re(t conj dt/dfract) */
 #pragma unroll
-                for (int m = 0; m < M; ++m) E[m] = U[m] = 0.0f;
+                for (int m = 0; m < M; ++m) E[m] = U[m] = Cc[m] = 0.0f;
 #pragma unroll 1 /* a real loop: four unrolled copies, each run once per frame, cost more in instruction fetch than they saved */
                 for (int pass = 0; pass < 4; ++pass) {
                     if (sym0 + 16 * pass >= Nsym) break; /* uniform */
                     const int sym = sym0 + 16 * pass + (tid >> 2);
                     const bool valid = sym < Nsym;
                     const int base = ((sym + 1) * P + low) * step;
-                    float2 t[M];
+                    float2 t[M], u[M];
                     float uu[M];
 #pragma unroll
-                    for (int m = 0; m < M; ++m) t[m] = make_float2(0.0f, 0.0f), uu[m] = 0.0f;
+                    for (int m = 0; m < M; ++m) t[m] = u[m] = make_float2(0.0f, 0.0f), uu[m] = 0.0f;
                     if (valid) {
                         const float2 *f = fdc + base;
                         if (S1 && (low & 1) == 0) {
@@ -1460,9 +1539,6 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                                 for (int m = 0; m < M; ++m) t[m] = xadd(t[m], f[m * fdcS + k]);
                         }
                         if (sub == 3 && two) {
-                            float2 u[M];
-#pragma unroll
-                            for (int m = 0; m < M; ++m) u[m] = make_float2(0.0f, 0.0f);
                             for (int k = 0; k < step; ++k)
 #pragma unroll
                                 for (int m = 0; m < M; ++m) u[m] = xadd(u[m], xsub(f[m * fdcS + Ts + k], f[m * fdcS + k]));
@@ -1497,8 +1573,11 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
                         const float e = fmaf(t[m].x, t[m].x, t[m].y * t[m].y);
+                        /* Re(t conj u) = half of d|t|^2 / dfract: only the symbol's lane 3 holds u (zero elsewhere) */
+                        const float c = fmaf(t[m].x, u[m].x, t[m].y * u[m].y);
                         const float ge = __shfl_sync(0xffffffffu, e, src), gu = __shfl_sync(0xffffffffu, uu[m], src + 3);
-                        if ((lane >> 3) == pass) E[m] = ge, U[m] = gu;
+                        const float gc = __shfl_sync(0xffffffffu, c, src + 3);
+                        if ((lane >> 3) == pass) E[m] = ge, U[m] = gu, Cc[m] = gc;
                     }
                 }
                 const int sym = sym0 + 16 * (lane >> 3) + 8 * warp + (lane & 7);
@@ -1513,22 +1592,33 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
                             mx = E[m];
                             symv = m;
                         }
-                    float uub = U[0], uus = 0.0f;
+                    float uub = U[0], cb = Cc[0];
 #pragma unroll
                     for (int m = 0; m < M; ++m) {
-                        if (m == symv) uub = U[m];
-                        if (m != symv && E[m] > second) second = E[m], uus = U[m];
+                        if (m == symv) uub = U[m], cb = Cc[m];
+                        if (m != symv && E[m] > second) second = E[m];
                     }
                     /* the scalar algorithm's energies differ from these by rounding (g_sym, relative) and by the uncertainty dfr
-                       of the interpolation weight: d|t|^2 <= dfr (2 |t| |u| + |u|^2 dfr).  2 sqrt(a b) <= a + b gives a bound
-                       without square roots that clears nearly every symbol; the tight bound decides the rest. */
-                    const float gs = cfg.g_sym * (mx + second);
-                    if (mx - second <= gs + dfr * ((mx + second) + (uub + uus) * (1.0f + dfr)) && mx > 0.0f) {
-                        const float slack = gs + dfr * (2.0f * (sqrtf(mx * uub) + sqrtf(second * uus)) + (uub + uus) * dfr);
-                        if (mx - second <= slack) { /* a 0 == 0 tie (zero input) is exact */
-                            fl |= FLAG_SYM;
-                            atomicAdd(&ms->nflag_sym, 1);
+                       of the interpolation weight.  All tones are resampled with the SAME weight, so what a decision sees is the
+                       change of a DIFFERENCE: |t + d u|^2 = |t|^2 + 2 d Re(t conj u) + d^2 |u|^2 gives, against every other tone m,
+                       |change of (e_best - e_m)| <= 2 dfr |c_best - c_m| + dfr^2 (|u_best|^2 + |u_m|^2) with c = Re(t conj u) - far
+                       below the sum of the tones' own worst cases 2 dfr |t| |u|, which flagged several times as many frames.
+                       Next to an integer timing offset (near != 0) the scalar algorithm may interpolate the neighbouring pair;
+                       there the tones' own worst cases stay (2 sqrt(a b) <= a + b first, without square roots). */
+                    bool tie = false;
+#pragma unroll
+                    for (int m = 0; m < M; ++m) {
+                        if (m == symv) continue;
+                        const float gs = cfg.g_sym * (mx + E[m]);
+                        const float lin = near == 0 ? 2.0f * fabsf(cb - Cc[m]) : (mx + E[m]) + (uub + U[m]);
+                        if (mx - E[m] <= gs + dfr * (lin + (uub + U[m]) * dfr) && mx > 0.0f) { /* a 0 == 0 tie (zero input) is exact */
+                            const float tight = near == 0 ? lin : 2.0f * (sqrtf(mx * uub) + sqrtf(E[m] * U[m]));
+                            tie = tie || mx - E[m] <= gs + dfr * (tight + (uub + U[m]) * dfr);
                         }
+                    }
+                    if (tie) {
+                        fl |= FLAG_SYM;
+                        atomicAdd(&ms->nflag_sym, 1);
                     }
                     if (bo) {
                         if (M == 2)
@@ -1943,8 +2033,8 @@ FskFastPlan *fsk_fast_plan_create(const pirip_fsk_cfg &c, const FskDevCfg &d, co
     f.phi_ft = d.phi_ft;
     p->ckpt_per_frame = ck_chunks(f.nin_max) + 1;
     p->chain = getenv("PIRIP_FSK_NO_CHAIN") == nullptr;
-    ok = ok && pirip::cuda_ok(cudaMalloc(&p->d_replays, sizeof(int) * 8), "cudaMalloc replays") &&
-         pirip::cuda_ok(cudaMemset(p->d_replays, 0, sizeof(int) * 8), "memset replays");
+    ok = ok && pirip::cuda_ok(cudaMalloc(&p->d_replays, sizeof(int) * 64), "cudaMalloc replays") &&
+         pirip::cuda_ok(cudaMemset(p->d_replays, 0, sizeof(int) * 64), "memset replays");
     FastArgs dummy;
     memset(&dummy, 0, sizeof dummy);
     ok = ok && pirip::cuda_ok(fast_dispatch(p, dummy, nullptr, 1), "cudaFuncSetAttribute (fast kernel)");
@@ -2002,7 +2092,7 @@ cudaError_t fsk_fast_flag_buffers(FskFastPlan *p, size_t n, int **flags, int **l
 }
 
 /* replays of the plan so far: [0] frames replayed exactly, [1] replays that could not be done (side chain late / absent) */
-cudaError_t fsk_fast_replay_counts(FskFastPlan *p, int out[8]) { return cudaMemcpy(out, p->d_replays, sizeof(int) * 8, cudaMemcpyDeviceToHost); }
+cudaError_t fsk_fast_replay_counts(FskFastPlan *p, int out[64]) { return cudaMemcpy(out, p->d_replays, sizeof(int) * 64, cudaMemcpyDeviceToHost); }
 
 static cudaError_t chain_buffers(FskFastPlan *p, size_t n, size_t max_frames) {
     const size_t need_mbox = n * (max_frames + 1);
@@ -2088,6 +2178,8 @@ cudaError_t fsk_fast_launch(FskFastPlan *p, const FskBatchArgs &b, int *d_flags,
         a.ckpt = p->d_ckpt + off * (size_t)(2 * p->ckpt_per_frame * 4);
         a.afin = p->d_afin + off;
         a.replays = p->d_replays;
+        a.chain_diag = getenv("PIRIP_FSK_CHAIN_DIAG") ? 1 : 0;
+        if (const char *ev = getenv("PIRIP_FSK_CHAIN_CPI")) a.chain_cpi = atoi(ev) > 0 && atoi(ev) <= 64 ? atoi(ev) : 0;
         if ((e = cudaMemsetAsync(a.mbox, 0, sizeof(u64) * n * (b.max_frames + 1), stream)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(a.ckpt, 0, sizeof(float4) * n * 2 * p->ckpt_per_frame * 4, stream)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(a.afin, 0, sizeof(int) * n, stream)) != cudaSuccess) return e;

@@ -569,13 +569,22 @@ extern "C" int pirip_fsk_plan_replays(pirip_fsk_plan *plan, int32_t out[2]) {
     if (!plan->fast) return 0;
     if (!pirip::cuda_ok(cudaSetDevice(plan->device), "cudaSetDevice")) return -10;
     if (!pirip::cuda_ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return -13;
-    int v[8];
+    int v[64];
     if (!pirip::cuda_ok(fsk_fast_replay_counts(plan->fast, v), "D2H replay counts")) return -12;
     out[0] = v[0];
     out[1] = v[1];
     if (getenv("PIRIP_FSK_CHAIN_DIAG"))
-        fprintf(stderr, "side chain: replays %d failed %d, ppm-threshold near-ties %d, kcycles waiting for checkpoints %d, kcycles in replays %d\n", v[0], v[1],
-                v[2], v[3], v[4]);
+        fprintf(stderr, "side chain: replays %d failed %d, ppm-threshold near-ties %d, kcycles waiting for checkpoints %d, kcycles in replays %d; mailbox lag: mean %.1f us, max %d us over %d frames\n", v[0], v[1],
+                v[2], v[3], v[4], v[7] ? (double)v[5] / v[7] : 0.0, v[6], v[7]);
+    if (getenv("PIRIP_FSK_CHAIN_DIAG"))
+        fprintf(stderr, "side chain warps: %d iterations with work (%.0f cycles each), %d without; %d kcycles in all\n", v[8],
+                v[8] ? 1024.0 * v[10] / v[8] : 0.0, v[9], v[11]);
+    if (getenv("PIRIP_FSK_CHAIN_DIAG")) {
+        fprintf(stderr, "side chain cycles per iteration by warp slot:");
+        for (int w = 0; w < 18; ++w)
+            if (v[40 + w]) fprintf(stderr, " %d:%.0f", w, 1024.0 * v[16 + w] / v[40 + w]);
+        fprintf(stderr, "\n");
+    }
     return 0;
 }
 
@@ -587,7 +596,7 @@ extern "C" long pirip_fsk_plan_ppm_near_ties(pirip_fsk_plan *plan) {
     if (!plan->fast) return 0;
     if (!pirip::cuda_ok(cudaSetDevice(plan->device), "cudaSetDevice")) return -10;
     if (!pirip::cuda_ok(cudaDeviceSynchronize(), "cudaDeviceSynchronize")) return -13;
-    int v[8];
+    int v[64];
     if (!pirip::cuda_ok(fsk_fast_replay_counts(plan->fast, v), "D2H replay counts")) return -12;
     return v[2];
 }

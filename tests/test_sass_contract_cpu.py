@@ -50,3 +50,12 @@ def test_fsk_kernels_fma_only_in_division_and_sqrt_sequences():
         assert mufu > 0 and ffma <= 12 * mufu, (obj, ffma, mufu)
         assert _count(s, r"UBLKCP[\w.]*") > 0  # cp.async.bulk staging of the raw samples
     assert _count(_sass("fsk_kernel2.o"), r"FADD2") > 1000  # packed integrator adds
+
+
+def test_fast_kernel_has_no_packed_fma():
+    # the side chain's complex multiply packs its multiplications (ocmul_pk) and keeps the additions scalar: a packed add would be
+    # contracted with the multiply that feeds it
+    s = _sass("fsk_fast.o")
+    assert _count(s, r"FFMA2") == 0
+    assert _count(s, r"FMUL2") > 0
+    assert _count(s, r"FADD2") > 1000  # packed integrator adds
