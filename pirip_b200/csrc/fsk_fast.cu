@@ -130,8 +130,11 @@ struct Misc {
 
 #define MBOX_VALID (1ull << 63)
 #define MBOX_END (1ull << 62)
-#define CKPT_EVERY 128 /* nominal samples per checkpoint chunk: a frame of nin samples has ceil(nin / 128) chunks of nearly equal length */
-
+#define CKPT_EVERY 128 /* nominal samples per checkpoint chunk: a frame of nin samples has ceil(nin / 128) chunks of nearly equal length.
+                          A replay mixes a frame with one thread per (tone, chunk), so the chunk is the serial length of that phase
+                          (40 k cycles; 22 k with 61-sample chunks) - but every chunk costs the side chain ~100 cycles beside its
+                          steps, and the chain has no cycles to spare: with 20 chunks a frame its lag doubled and the batch took
+                          3.50 ms instead of 3.15. */
 /* checkpoint chunks of a frame of nin samples: K = ceil(nin / CKPT_EVERY) chunks, the first nin % K one sample longer */
 __host__ __device__ __forceinline__ int ck_chunks(int nin) { return (nin + CKPT_EVERY - 1) / CKPT_EVERY; }
 __host__ __device__ __forceinline__ int ck_start(int nin, int k) {
@@ -509,11 +512,11 @@ __device__ __noinline__ void osc_chain_role(const FastCfg &cfg, const FastArgs &
        the three run the packed form (ocmul_pk) at 23.  The demodulating groups ask for a frame of 1200 steps every ~26 k cycles,
        21.7 cycles a step: the lanes of those three warps still fall behind slowly, which is what a replay waits for. */
     const bool packed = ((threadIdx.x >> 5) & 3) == 0 && args.chain_wpc > 8;
-    /* chunks per iteration: half a frame when every frame length has the same even chunk count, else one */
-    int CPI = 1;
+    /* chunks per iteration: half a frame (of the longest form; a lane whose frame ends before the iteration does waits for it) */
+    int CPI;
     {
         const int k0 = ck_chunks(cfg.nin_min), k1 = ck_chunks(cfg.N), k2 = ck_chunks(cfg.nin_max);
-        if (k0 == k1 && k1 == k2 && (k0 & 1) == 0) CPI = k0 / 2;
+        CPI = (max(k0, max(k1, k2)) + 1) / 2;
         if (args.chain_cpi > 0) CPI = args.chain_cpi;
     }
     while (true) {
@@ -659,6 +662,14 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
     const int step = S1 ? 24 / SP : cfg.step, nint = S1 ? 51 * SP : cfg.nint, bps = S1 ? 2 : cfg.bps;
     const int nold = Nmem - nin;
     const unsigned char *cap_base = args.iq + cap * args.stride;
+    /* diagnostics (PIRIP_FSK_CHAIN_DIAG): kcycles per section of the replay, replays[24 + section] */
+    long long rp_t = clock64();
+#define RP(i)                                                                        \
+    if (args.chain_diag && tid == 0) {                                               \
+        const long long rp_n = clock64();                                            \
+        atomicAdd(args.replays + 24 + (i), (int)((rp_n - rp_t) >> 6));               \
+        rp_t = rp_n;                                                                 \
+    }
 
     /* the checkpoint records this frame needs (its own chunks and the chunks of the previous frame's tail) must have been
        written by the side chain: every thread polls one record; all or nothing */
@@ -692,6 +703,7 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
         GSYNC();
         if (!ms->rp_ok) return false;
     }
+    RP(0);
 
     /* keep the fast baseband memory the next frame's tail is taken from */
     constexpr int KEEP = (M * 128 + T - 1) / T; /* tailpad <= 128 */
@@ -747,14 +759,23 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
         }
     }
     GSYNC();
+    RP(1);
 
-    /* window energies and the timing line, accumulated in the scalar order (warp 0; lane 0 carries the sum) */
-    if (warp == 0) {
+    /* window energies and the timing line, accumulated in the scalar order: both warps sum 32 windows each per round, the second
+       hands its products over through `filt` (free until the decisions below), warp 0 adds all 64 in index order (lane 0 carries
+       the sum).  A round costs ~4 k cycles whoever runs it - the replaying group shares its schedulers with eight busy groups and
+       its code is cold - so halving the rounds (39 with warp 0 alone) took 58 k cycles off a replay.  (All 64 threads writing the
+       products to a row in global memory and warp 0 adding them from there with 13 loads in flight was slower: the SM's L1 is
+       ~5 KB beside 223 KB of shared memory, the row comes back from L2.) */
+    {
         float2 tc = make_float2(0.0f, 0.0f);
-        for (int i0 = 0; i0 < nint; i0 += 32) {
-            const int i = i0 + lane;
+        float2 *hand = reinterpret_cast<float2 *>(filt);
+        const bool two = (size_t)M * Nsym * sizeof(float) >= 32 * sizeof(float2);
+        const int per = two ? 64 : 32;
+        for (int i0 = 0; i0 < nint; i0 += per) {
+            const int i = i0 + (two ? tid : lane);
             float2 prod = make_float2(0.0f, 0.0f);
-            if (i < nint) {
+            if (i < nint && (two || warp == 0)) {
                 float ft1 = 0.0f;
 #pragma unroll
                 for (int m = 0; m < M; ++m) {
@@ -772,12 +793,25 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
                 const float2 w = cfg.phi_ft[i];
                 prod = make_float2(__fmul_rn(ft1, w.x), __fmul_rn(ft1, w.y));
             }
-            const int n = nint - i0 < 32 ? nint - i0 : 32;
-            for (int l = 0; l < n; ++l) {
-                const float px = __shfl_sync(0xffffffffu, prod.x, l), py = __shfl_sync(0xffffffffu, prod.y, l);
-                tc = xadd(tc, make_float2(px, py));
+            if (two) {
+                if (warp == 1) hand[lane] = prod;
+                GSYNC();
             }
+            if (warp == 0) {
+                const int n = nint - i0 < 32 ? nint - i0 : 32;
+                for (int l = 0; l < n; ++l) {
+                    const float px = __shfl_sync(0xffffffffu, prod.x, l), py = __shfl_sync(0xffffffffu, prod.y, l);
+                    tc = xadd(tc, make_float2(px, py));
+                }
+                if (two) {
+                    const int n2 = nint - i0 - 32 < 32 ? nint - i0 - 32 : 32;
+                    for (int l = 0; l < n2; ++l) tc = xadd(tc, hand[l]);
+                }
+            }
+            if (two) GSYNC(); /* `hand` is rewritten by the next round */
         }
+        RP(2);
+        if (warp == 0)
         if (lane == 0) {
             ms->xtc = tc;
             int fl = 0;
@@ -807,6 +841,7 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
         }
     }
     GSYNC();
+    RP(3);
     if (ms->fflags) {
         /* not settled (NaN input, ppm threshold): leave the frame flagged */
 #pragma unroll
@@ -879,6 +914,7 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
             sq = __fsqrt_rn(mx);
         }
     }
+    RP(4);
     /* serial sums in symbol order: warp 0 (symbols 0..31), then warp 1 */
     for (int w = 0; w < T / 32; ++w) {
         if (warp == w) {
@@ -901,6 +937,7 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
         }
         GSYNC();
     }
+    RP(5);
     if (tid == 0) {
         const float nsymf = (float)Nsym;
         const float sig = __fdiv_rn(ms->red[1][0], nsymf), nse = __fdiv_rn(ms->red[1][1], nsymf);
@@ -923,6 +960,8 @@ __device__ __noinline__ bool exact_frame_replay(const FastCfg &cfg, const FastAr
         if (m < M) fdc[m * fdcS + Nmem - cfg.tailpad + k] = keep[i];
     }
     GSYNC();
+    RP(6);
+#undef RP
     return true;
 }
 

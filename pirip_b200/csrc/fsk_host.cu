@@ -580,6 +580,9 @@ extern "C" int pirip_fsk_plan_replays(pirip_fsk_plan *plan, int32_t out[2]) {
         fprintf(stderr, "side chain warps: %d iterations with work (%.0f cycles each), %d without; %d kcycles in all\n", v[8],
                 v[8] ? 1024.0 * v[10] / v[8] : 0.0, v[9], v[11]);
     if (getenv("PIRIP_FSK_CHAIN_DIAG")) {
+        fprintf(stderr, "replay sections, k cycles per replay: wait %.1f mix %.1f timing line %.1f atan2/lane 0 %.1f decisions %.1f symbol sums %.1f rest %.1f\n",
+                v[0] ? v[24] / 16.0 / v[0] : 0.0, v[0] ? v[25] / 16.0 / v[0] : 0.0, v[0] ? v[26] / 16.0 / v[0] : 0.0, v[0] ? v[27] / 16.0 / v[0] : 0.0,
+                v[0] ? v[28] / 16.0 / v[0] : 0.0, v[0] ? v[29] / 16.0 / v[0] : 0.0, v[0] ? v[30] / 16.0 / v[0] : 0.0);
         fprintf(stderr, "side chain cycles per iteration by warp slot:");
         for (int w = 0; w < 18; ++w)
             if (v[40 + w]) fprintf(stderr, " %d:%.0f", w, 1024.0 * v[16 + w] / v[40 + w]);
