@@ -1502,6 +1502,10 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             int nn = nin;
             if (!cfg.fixed_nin) {
                 if (fabsf(fabsf(norm) - 0.25f) < dn) fl |= FLAG_TIM;
+                /* the branch cut of atan2: an angle within the error of +-pi may come out with the other sign in the scalar
+                   algorithm - norm_rx_timing +0.5 or -0.5, the opposite nin slip and a sampling instant a whole symbol away
+                   (seen once in 1.9 million captures, in a capture's first frame, before the slips have centred the timing) */
+                if (0.5f - fabsf(norm) < dn) fl |= FLAG_TIM;
                 nn = norm > 0.25f ? cfg.N + Ts / 4 : (norm < -0.25f ? cfg.N - Ts / 4 : cfg.N);
             }
             ms->nin_next = nn;
@@ -1930,7 +1934,10 @@ FskFastPlan *fsk_fast_plan_create(const pirip_fsk_cfg &c, const FskDevCfg &d, co
     f.bps = c.fmt == PIRIP_FMT_U8 ? 2 : (c.fmt == PIRIP_FMT_S16 ? 4 : 8);
     f.fs_over_ndft = d.fs_over_ndft;
     f.in_scale = c.fmt == PIRIP_FMT_U8 ? 0.0078125f : 1.0f;
-    f.g_sym = 4e-6f; /* rounding of the energies at a given timing */
+    f.g_sym = 2e-5f; /* the energies at a given timing: fast mixing (closed-form phasors, FMA) and sliding integrators against the
+                        scalar algorithm's recursive oscillator, whose amplitude drifts within a frame.  4e-6 was the first value:
+                        22 single wrong bits in 1.9e10 (tools/validate_seeds.py, 1.9 million captures against the exact kernel),
+                        hidden until the interpolation term of the guard was tightened; all 22 are flagged at 1e-5 */
     f.g_tim = 4e-7f; /* timing-line sums: absolute error relative to the summed window energies (observed <= 9.2e-8) */
     if (const char *e = getenv("PIRIP_FSK_GUARD_SYM")) f.g_sym = (float)atof(e);
     if (const char *e = getenv("PIRIP_FSK_GUARD_TIM")) f.g_tim = (float)atof(e);
