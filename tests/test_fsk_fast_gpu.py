@@ -190,6 +190,33 @@ def test_fast_full_c5_batch_bits_equal_oracle():
     plan.close()
 
 
+@pytest.mark.parametrize("seed,cap", [(5093, 1115), (5776, 419), (6267, 875), (5230, 943)])
+def test_fast_guard_regressions(seed, cap):
+    """Captures on which the fast kernel once disagreed with the oracle (found by tools/validate_seeds.py over 1.9 million fresh
+    captures of the bench workload; profiles/r02_validate_seeds.json): norm_rx_timing within its error of +-0.5 - the branch cut
+    of atan2, a sampling instant one symbol away and the opposite nin slip, 4555 / 17 / 22 wrong bits - and a symbol decision
+    inside a rounding margin that was too small (one wrong bit).  The captures before them in the batch only advance the
+    generator; the named capture and its neighbours are checked against the oracle."""
+    import torch
+    import bench
+    import pirip_b200 as pb
+    ncap = (cap // 50 + 1) * 50  # gen_captures draws per chunk of 50 captures: the prefix of the 1250-capture batch
+    iq = bench.gen_captures(torch, ncap, 240000, seed=seed, device=torch.device("cuda", 0)).cpu().numpy()
+    pk = dict(Fs=bench.FS, Rs=bench.RS, M=bench.M, P=bench.P, limits=bench.LIMITS)
+    plan = pb.FskPlan(**pk)
+    assert plan.mode == "fast"
+    out = plan.demod_batch(iq)
+    nflag, _ = plan.flagged(ncap)
+    plan.close()
+    assert nflag == 0
+    cfg = oracle_cfg(pk)
+    for c in range(max(cap - 3, 0), min(cap + 4, ncap)):
+        ref = orc.fsk_demod_stream(cfg, iq[c])
+        nf = ref["nframes"]
+        assert int(out["nframes"][c]) == nf, (seed, c)
+        assert np.array_equal(out["bits"][c, :nf * plan.nbits], ref["bits"]), (seed, c)
+
+
 def test_fast_more_captures_than_one_resident_round():
     """Batches larger than the groups one launch keeps resident (1251 at C1 on 148 SMs) run as rounds of launches with one shared
     list of flagged captures and one exact re-run; called twice (a group that took a second capture inside one launch used to
