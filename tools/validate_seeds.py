@@ -49,8 +49,8 @@ def gen_4fsk(torch, ncap, nsamp, seed, dev):
 if os.environ.get("CONFIG") == "c3":  # CONFIG=c3: 4FSK, P = 8
     pk = dict(Fs=240000, Rs=10000, M=4, P=8, Nsym=50, limits=(500, 25000))
     gen = gen_4fsk
-else:
-    pk = dict(Fs=bench.FS, Rs=bench.RS, M=bench.M, P=bench.P, Nsym=bench.NSYM, limits=bench.LIMITS)
+else:  # the bench workload; CONFIG=p8: the same captures demodulated with P = 8 (the shape of config 4's demodulator)
+    pk = dict(Fs=bench.FS, Rs=bench.RS, M=bench.M, P=8 if os.environ.get("CONFIG") == "p8" else bench.P, Nsym=bench.NSYM, limits=bench.LIMITS)
     gen = bench.gen_captures
 fast = pb.FskPlan(pk["Fs"], pk["Rs"], pk["M"], P=pk["P"], Nsym=pk["Nsym"], limits=pk["limits"], device=0)
 exact = pb.FskPlan(pk["Fs"], pk["Rs"], pk["M"], P=pk["P"], Nsym=pk["Nsym"], limits=pk["limits"], device=0)
