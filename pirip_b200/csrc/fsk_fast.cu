@@ -1500,12 +1500,12 @@ __global__ void __launch_bounds__((M == 2 ? 9 : 5) * T, 1) fsk_fast_kernel(const
             if (fabsf(fabsf(d) - 0.2f) < 2.0f * dn && args.replays) atomicAdd(args.replays + 2, 1);
             if (fabsf(d) < 0.2f) ms->ppm = 0.9f * ms->ppm + 0.1f * (1e6f * d / (float)Nsym);
             int nn = nin;
+            /* the branch cut of atan2: an angle within the error of +-pi may come out with the other sign in the scalar
+               algorithm - norm_rx_timing +0.5 or -0.5, a sampling instant a whole symbol away and the opposite nin slip (three
+               captures in 1.9 million; with a locked nin the sampling instant still jumps, so this test stands outside) */
+            if (0.5f - fabsf(norm) < dn) fl |= FLAG_TIM;
             if (!cfg.fixed_nin) {
                 if (fabsf(fabsf(norm) - 0.25f) < dn) fl |= FLAG_TIM;
-                /* the branch cut of atan2: an angle within the error of +-pi may come out with the other sign in the scalar
-                   algorithm - norm_rx_timing +0.5 or -0.5, the opposite nin slip and a sampling instant a whole symbol away
-                   (seen once in 1.9 million captures, in a capture's first frame, before the slips have centred the timing) */
-                if (0.5f - fabsf(norm) < dn) fl |= FLAG_TIM;
                 nn = norm > 0.25f ? cfg.N + Ts / 4 : (norm < -0.25f ? cfg.N - Ts / 4 : cfg.N);
             }
             ms->nin_next = nn;
